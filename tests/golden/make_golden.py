@@ -1,0 +1,154 @@
+"""Generate golden input/output vectors by running the REFERENCE implementation.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports the reference's own ``models._modules`` (unmodified) behind the two-line CPU shim
+from SURVEY.md (the reference hard-codes ``torch.cuda.FloatTensor`` / ``.cuda()``), runs
+``Conv2dLSQCiM`` forward+backward on seeded inputs and stores inputs, outputs, gradients and
+the Function's internals (integer partial sums = ``ctx.ps_int``) as small ``.npz`` fixtures.
+
+Step sizes are snapped to "exact recovery" values: the reference recovers integer
+codes as ``x_q / s`` which is exact only when ``fl(fl(k*s)/s) == k`` for every code ``k``.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("CIMQ_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+torch.cuda.FloatTensor = lambda *a: torch.FloatTensor(*a)  # lsq.py:64,169,215,336 hard-code CUDA allocs
+torch.Tensor.cuda = lambda self, *a, **k: self  # lsq.py:169
+sys.path.insert(0, REF)
+import models._modules as ref_nn  # noqa: E402
+from models._modules import lsq as ref_lsq  # noqa: E402
+
+CASES = {
+    # name: dict(cin, cout, k, stride, pad, hw, batch, nbits_w, nbits_a, wbs, abs, xbar, adc, signed_input)
+    "tern_c16o8_x64": dict(cin=16, cout=8, k=3, stride=1, pad=1, hw=8, batch=2, nbits_w=3, nbits_a=3,
+                           wbs=1, abs=1, xbar=64, adc=1.5),
+    "tern_c16o16_x128_s2": dict(cin=16, cout=16, k=3, stride=2, pad=1, hw=8, batch=3, nbits_w=3, nbits_a=3,
+                                wbs=1, abs=1, xbar=128, adc=1.5),
+    "bin_c16o8_x128": dict(cin=16, cout=8, k=3, stride=1, pad=1, hw=8, batch=2, nbits_w=3, nbits_a=3,
+                           wbs=1, abs=1, xbar=128, adc=1),
+    "adc3_w4a4_c8o16_x32": dict(cin=8, cout=16, k=3, stride=1, pad=1, hw=6, batch=2, nbits_w=4, nbits_a=4,
+                                wbs=1, abs=1, xbar=32, adc=3),
+    "adc4_w2a2_c8o8_x64": dict(cin=8, cout=8, k=3, stride=1, pad=1, hw=6, batch=2, nbits_w=2, nbits_a=2,
+                               wbs=1, abs=1, xbar=64, adc=4),
+    "first_w8a8_c3o8_x128": dict(cin=3, cout=8, k=3, stride=1, pad=1, hw=8, batch=2, nbits_w=8, nbits_a=8,
+                                 wbs=1, abs=1, xbar=128, adc=1.5, signed_input=True),
+    "slice2_w4a4_c8o8_x64": dict(cin=8, cout=8, k=3, stride=1, pad=1, hw=6, batch=2, nbits_w=4, nbits_a=4,
+                                 wbs=2, abs=2, xbar=64, adc=2),
+    "pw_c32o8_x16": dict(cin=32, cout=8, k=1, stride=1, pad=0, hw=4, batch=2, nbits_w=3, nbits_a=3,
+                         wbs=1, abs=1, xbar=16, adc=1.5),
+}
+
+
+def _exact(s, qn, qp):
+    k = torch.arange(qn, qp + 1, dtype=torch.float32)
+    return bool(((k * s) / s == k).all())
+
+
+def _snap_alpha(alpha, g, qn, qp):
+    """Smallest alpha' >= alpha (in ulps) whose grad_scale value gives exact code recovery."""
+    a = alpha.clone()
+    for _ in range(4096):
+        s = ref_lsq.grad_scale(a, g).detach()
+        if _exact(s, qn, qp):
+            return a
+        a = torch.nextafter(a, torch.full_like(a, float("inf")))
+    raise RuntimeError("no exact-recovery step size found")
+
+
+def run_case(name, c, seed):
+    g = torch.Generator().manual_seed(seed)
+    m = ref_nn.Conv2dLSQCiM(c["cin"], c["cout"], (c["k"], c["k"]), (c["stride"],) * 2, (c["pad"],) * 2, (1, 1), 1,
+                            False, nbits_w=c["nbits_w"], nbits_a=c["nbits_a"], nbits_alpha=8,
+                            wbitslice=c["wbs"], abitslice=c["abs"], xbar=c["xbar"], adcbits=c["adc"],
+                            signed_xbar=False, stochastic_quant=False)
+    with torch.no_grad():
+        m.weight.copy_(torch.randn(m.weight.shape, generator=g) * 0.2)
+    x0 = torch.randn(c["batch"], c["cin"], c["hw"], c["hw"], generator=g)
+    x = x0 if c.get("signed_input") else torch.relu(x0)
+    m.train()
+    m(x)  # lazy init of alpha_act / alpha_weight / alpha_cim (lsq.py:532-563)
+    qp_a = 2 ** c["nbits_a"] - 1
+    qn_w, qp_w = -2 ** (c["nbits_w"] - 1), 2 ** (c["nbits_w"] - 1) - 1
+    ga = 1.0 / math.sqrt(x.numel() * qp_a)
+    gw = 1.0 / math.sqrt(m.weight.numel() * qp_w)
+    with torch.no_grad():
+        m.alpha_act.copy_(_snap_alpha(m.alpha_act.data, ga, 0, qp_a))
+        m.alpha_weight.copy_(_snap_alpha(m.alpha_weight.data, gw, qn_w, qp_w))
+    alpha_cim_init = None
+    if m.alpha_cim is not None:
+        m.init_state_cim.fill_(0)
+        m(x)  # re-run the reference's own alpha_cim init with the snapped step sizes
+        alpha_cim_init = m.alpha_cim.detach().clone()
+        with torch.no_grad():  # de-correlate from the init so clipping / all three codes occur
+            m.alpha_cim.mul_(0.6 + 0.8 * torch.rand(m.alpha_cim.shape, generator=g))
+
+    # ---- module-level forward/backward through the reference's autograd
+    xin = x.clone().requires_grad_(True)
+    m.zero_grad()
+    y = m(xin)
+    grad_y = torch.randn(y.shape, generator=g)
+    y.backward(grad_y)
+
+    # ---- Function-level internals, re-derived with the reference's own functions
+    with torch.no_grad():
+        s_a = ref_lsq.grad_scale(m.alpha_act, ga)
+        s_w = ref_lsq.grad_scale(m.alpha_weight, gw)
+        x_q = ref_lsq.round_pass((x / s_a).clamp(0, qp_a)) * s_a
+        w_q = ref_lsq.round_pass((m.weight / s_w).clamp(qn_w, qp_w)) * s_w
+        alpha_q = None
+        if m.alpha_cim is not None:
+            al = m.alpha_cim
+            sc = (al.max() - al.min()) / (255 - 1)
+            alpha_q = ref_lsq.round_pass(al / sc).clamp(1, 255) * sc
+
+        class Ctx:
+            pass
+
+        ctx = Ctx()
+        out = ref_lsq.get_cim_output_signed.forward(
+            ctx, x_q, w_q, m.stride, m.padding, m.dilation, m.nbits_a, m.abitslice, m.nbits_w, m.wbitslice,
+            m.adcbits, m.xbar, m.binary_mask, alpha_q, s_w, s_a, False, m.signed_act)
+        oh = y.shape[-1]
+        go = grad_y.reshape(c["batch"], c["cout"], oh * oh).transpose(1, 2).contiguous()
+        grads = ref_lsq.get_cim_output_signed.backward(ctx, go)
+    x_codes = (x_q / s_a)
+    w_codes = (w_q / s_w)
+    assert (x_codes == x_codes.round()).all() and (w_codes == w_codes.round()).all(), "inexact recovery"
+    ps_int = ctx.ps_int.float()
+    assert (ps_int == ps_int.round()).all()
+
+    d = dict(
+        cfg=np.array([c["cin"], c["cout"], c["k"], c["stride"], c["pad"], c["hw"], c["batch"], c["nbits_w"],
+                      c["nbits_a"], c["wbs"], c["abs"], c["xbar"]], dtype=np.int64),
+        adcbits=np.float64(c["adc"]),
+        x=x.numpy(), weight=m.weight.detach().numpy(), alpha_act=m.alpha_act.detach().numpy(),
+        alpha_weight=m.alpha_weight.detach().numpy(), grad_y=grad_y.numpy(),
+        signed_act=m.signed_act.numpy(),
+        y=y.detach().numpy(), grad_x=xin.grad.numpy(), grad_weight=m.weight.grad.numpy(),
+        grad_alpha_act=m.alpha_act.grad.numpy(), grad_alpha_weight=m.alpha_weight.grad.numpy(),
+        s_a=s_a.numpy(), s_w=s_w.numpy(),
+        x_codes=x_codes.round().to(torch.int16).numpy(), w_codes=w_codes.round().to(torch.int16).numpy(),
+        ps_int=ps_int.to(torch.int16).numpy(), fn_out=out.numpy(),
+        fn_grad_xq=grads[0].numpy(), fn_grad_wq=grads[1].numpy(),
+    )
+    if m.alpha_cim is not None:
+        d.update(alpha_cim=m.alpha_cim.detach().numpy(), alpha_cim_init=alpha_cim_init.numpy(),
+                 alpha_q=alpha_q.numpy(), grad_alpha_cim=m.alpha_cim.grad.numpy(),
+                 fn_grad_alpha_q=grads[12].numpy())
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    print(f"{name}: y{tuple(y.shape)} ps_int{tuple(ps_int.shape)} |ps|max={int(ps_int.abs().max())}")
+
+
+if __name__ == "__main__":
+    for n, (name, c) in enumerate(CASES.items()):
+        run_case(name, c, seed=1234 + n)

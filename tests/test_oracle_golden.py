@@ -1,0 +1,87 @@
+"""Pin the numpy oracle against vectors produced by the reference itself (tests/golden)."""
+import numpy as np
+import pytest
+
+from oracle import cim_oracle as O
+from tests._util import golden_names, load_golden, rel_err
+
+TOL = 1e-5  # north_star: outputs and gradients within 1e-5 relative in fp32
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_codes_and_psums_bit_exact(name):
+    cfg, d, hw, batch = load_golden(name)
+    s_a = O.grad_scale_value(d["alpha_act"], 1.0 / np.sqrt(d["x"].size * cfg.qp_a)).reshape(())
+    s_w = O.grad_scale_value(d["alpha_weight"], 1.0 / np.sqrt(d["weight"].size * cfg.qp_w)).reshape(())
+    assert s_a == d["s_a"].reshape(()) and s_w == d["s_w"].reshape(())
+    assert O.recovery_is_exact(s_a, 0, cfg.qp_a) and O.recovery_is_exact(s_w, cfg.qn_w, cfg.qp_w)
+    xc = O.lsq_codes(d["x"], s_a, 0, cfg.qp_a)
+    wc = O.lsq_codes(d["weight"], s_w, cfg.qn_w, cfg.qp_w)
+    np.testing.assert_array_equal(xc, d["x_codes"])
+    np.testing.assert_array_equal(wc, d["w_codes"])
+    ps = O.integer_psums(cfg, xc, wc)
+    np.testing.assert_array_equal(ps, d["ps_int"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_function_forward_backward(name):
+    cfg, d, hw, batch = load_golden(name)
+    aq = d.get("alpha_q")
+    out = O.cim_forward(cfg, d["x_codes"], d["w_codes"], d["s_w"].reshape(()), d["s_a"].reshape(()), aq)
+    assert rel_err(out, d["fn_out"]) < TOL
+    oh = cfg.out_hw(hw)
+    go = d["grad_y"].reshape(batch, cfg.out_channels, oh * oh).transpose(0, 2, 1)
+    gx, gw, ga = O.cim_backward(cfg, go, d["x_codes"], d["w_codes"], d["s_w"].reshape(()), d["s_a"].reshape(()),
+                                aq, hw)
+    assert rel_err(gx, d["fn_grad_xq"]) < TOL
+    assert rel_err(gw, d["fn_grad_wq"]) < TOL
+    if cfg.has_alpha_cim:
+        assert rel_err(ga, d["fn_grad_alpha_q"]) < TOL
+    else:
+        assert ga is None
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_module_forward_backward(name):
+    cfg, d, hw, batch = load_golden(name)
+    r = O.module_forward_backward(cfg, d["x"], d["weight"], d["alpha_act"], d["alpha_weight"],
+                                  d.get("alpha_cim"), d["grad_y"])
+    assert rel_err(r["y"], d["y"]) < TOL
+    assert rel_err(r["grad_x"], d["grad_x"]) < TOL
+    assert rel_err(r["grad_weight"], d["grad_weight"]) < TOL
+    # step-size gradients are sums of cancelling terms: tolerance relative to sum |terms|
+    for key, xs, s, qn, qp, gq in (("grad_alpha_act", d["x"], r["s_a"], 0, cfg.qp_a, r["grad_xq"]),
+                                   ("grad_alpha_weight", d["weight"], r["s_w"], cfg.qn_w, cfg.qp_w, r["grad_wq"])):
+        u = xs / s
+        terms = np.abs(gq * (np.rint(np.clip(u, qn, qp)) - np.where((u >= qn) & (u <= qp), u, 0)))
+        g = 1.0 / np.sqrt(xs.size * qp)
+        assert abs(float(r[key]) - float(d[key].reshape(()))) <= TOL * g * float(terms.sum()) + 1e-12
+    if cfg.has_alpha_cim:
+        assert rel_err(r["alpha_q"], d["alpha_q"]) < 1e-6
+        assert rel_err(r["grad_alpha_cim"], d["grad_alpha_cim"]) < TOL
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "tern" in n or "bin" in n or "first" in n or "pw" in n])
+def test_alpha_cim_init(name):
+    cfg, d, hw, batch = load_golden(name)
+    a0 = O.init_alpha_cim(cfg, d["x_codes"], d["w_codes"], d["s_w"].reshape(()), d["s_a"].reshape(()))
+    assert rel_err(a0, d["alpha_cim_init"]) < TOL
+
+
+def test_wide_adc_equals_plain_conv():
+    """Property P1 (reference test/test_cim.py:39-57): with a wide ADC the CiM conv equals a dense
+    integer convolution exactly, and its gradients equal the plain conv gradients."""
+    rng = np.random.default_rng(0)
+    cfg = O.CimConfig(in_channels=6, out_channels=5, kernel=3, stride=1, padding=1, nbits_w=4, nbits_a=4,
+                      wbitslice=1, abitslice=1, xbar=16, adcbits=12)
+    xc = rng.integers(0, 16, size=(2, 6, 5, 5))
+    wc = rng.integers(-8, 8, size=(5, 6, 3, 3))
+    out = O.cim_forward(cfg, xc, wc, np.float32(1), np.float32(1), None)
+    dense = np.matmul(O.unfold(xc.astype(np.float32), 3, 1, 1), wc.reshape(5, -1).T.astype(np.float32))
+    np.testing.assert_array_equal(out, dense)
+    go = rng.standard_normal(out.shape).astype(np.float32)
+    gx, gw, ga = O.cim_backward(cfg, go, xc, wc, np.float32(1), np.float32(1), None, 5)
+    gw_ref = np.einsum("blf,blc->cf", O.unfold(xc.astype(np.float32), 3, 1, 1), go).reshape(wc.shape)
+    gcols = np.matmul(go, wc.reshape(5, -1).astype(np.float32))
+    gx_ref = O.fold(np.ascontiguousarray(gcols.transpose(0, 2, 1)), (5, 5), 3, 1, 1)
+    assert rel_err(gw, gw_ref) < TOL and rel_err(gx, gx_ref) < TOL and ga is None
