@@ -1,0 +1,246 @@
+"""ctypes binding of ``libcimq.so`` (C ABI declared in ``include/cimq.h``).
+
+There is no CPU fallback: importing this module without the built library raises, and every
+compute wrapper requires CUDA tensors.  All wrappers enqueue on the current torch CUDA stream and
+never synchronise, so they can be captured in CUDA graphs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcimq.so")
+
+ADC_MULTIBIT, ADC_BINARY, ADC_TERNARY = 0, 1, 2
+FLAG_FORCE_SIMT = 1
+
+
+class CimqLayer(C.Structure):
+    """``cimq_layer_t``."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "batch", "in_channels", "in_hw", "out_channels", "kernel", "stride", "padding",
+        "nbits_a", "abitslice", "nbits_w", "wbitslice", "xbar", "adc_mode", "adc_qn", "adc_qp")]
+
+
+class CimqInfo(C.Structure):
+    """``cimq_info_t``."""
+    _fields_ = ([(n, C.c_int32) for n in ("out_hw", "L", "M", "F", "NX", "NSW", "NSA", "pairs", "state_words",
+                                          "tc_forward")] +
+                [(n, C.c_int64) for n in ("state_bytes", "table_bytes", "wdigits_bytes", "wtiles_bytes",
+                                          "bwd_workspace_bytes", "psum_count")])
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "cimq_version": (C.c_int, []),
+    "cimq_last_error": (C.c_char_p, []),
+    "cimq_layer_info": (C.c_int, [C.POINTER(CimqLayer), C.POINTER(CimqInfo)]),
+    "cimq_step_sizes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "cimq_lsq_quantize": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_void_p]),
+    "cimq_codes_from_fakequant": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                            C.c_void_p]),
+    "cimq_lsq_fakequant": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p]),
+    "cimq_lsq_backward_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "cimq_lsq_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cimq_adc_table": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "cimq_weight_prepare": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cimq_conv_forward": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "cimq_conv_backward": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_uint32, C.c_void_p]),
+    "cimq_conv_psums": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cimq_conv_psum_abs_sums": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load ``libcimq.so`` (built in-tree by ``make`` / ``__graft_entry__.build()``).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `make` (or __graft_entry__.build()); "
+                           "cim_quantization_b200 has no CPU / PyTorch fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RuntimeError("libcimq: " + load().cimq_last_error().decode())
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libcimq operates on CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("libcimq expects contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def adc_mode_of(adcbits) -> tuple[int, int, int]:
+    """Map the reference's ``adcbits`` (a float from protobuf) to (mode, qn, qp) -- lsq.py:125-129."""
+    if adcbits == 1:
+        return ADC_BINARY, -1, 1
+    if adcbits == 1.5:
+        return ADC_TERNARY, -1, 1
+    if adcbits <= 0:
+        raise ValueError("adcbits == 0 (no ADC) is the plain F.conv2d path, not a CiM layer")
+    qp = int(2 ** (adcbits - 1) - 1)
+    qn = int(-(2 ** (adcbits - 1)))
+    return ADC_MULTIBIT, qn, qp
+
+
+@dataclass(frozen=True)
+class LayerSpec:
+    """Hashable description of a CiM conv layer instance (one batch size / image size)."""
+    batch: int
+    in_channels: int
+    in_hw: int
+    out_channels: int
+    kernel: int
+    stride: int
+    padding: int
+    nbits_a: int
+    abitslice: int
+    nbits_w: int
+    wbitslice: int
+    xbar: int
+    adcbits: float
+
+    def c_layer(self) -> CimqLayer:
+        mode, qn, qp = adc_mode_of(self.adcbits)
+        return CimqLayer(self.batch, self.in_channels, self.in_hw, self.out_channels, self.kernel, self.stride,
+                         self.padding, self.nbits_a, self.abitslice, self.nbits_w, self.wbitslice, self.xbar,
+                         mode, qn, qp)
+
+
+_info_cache: dict = {}
+
+
+def layer_info(spec: LayerSpec) -> CimqInfo:
+    info = _info_cache.get(spec)
+    if info is None:
+        info = CimqInfo()
+        layer = spec.c_layer()
+        _check(load().cimq_layer_info(C.byref(layer), C.byref(info)))
+        _info_cache[spec] = info
+    return info
+
+
+# ---- thin wrappers (tensors in, tensors out; all allocation happens here, in torch) ------------------
+def step_sizes(alpha_act, alpha_weight, ga: float, gw: float):
+    s = torch.empty(2, dtype=torch.float32, device=alpha_act.device)
+    _check(load().cimq_step_sizes(_ptr(alpha_act), _ptr(alpha_weight), ga, gw, _ptr(s), _stream()))
+    return s
+
+
+def lsq_quantize(x, s_elem, qn: int, qp: int, from_fakequant: bool = False):
+    """x fp32 (contiguous) -> one-byte codes (uint8 if qn >= 0 else int8); s_elem: 1-element CUDA tensor."""
+    codes = torch.empty(x.shape, dtype=torch.uint8 if qn >= 0 else torch.int8, device=x.device)
+    fn = load().cimq_codes_from_fakequant if from_fakequant else load().cimq_lsq_quantize
+    _check(fn(_ptr(x), x.numel(), _ptr(s_elem), qn, qp, _ptr(codes), _stream()))
+    return codes
+
+
+def lsq_fakequant(x, s_elem, qn: int, qp: int, rescale: bool):
+    y = torch.empty_like(x)
+    _check(load().cimq_lsq_fakequant(_ptr(x), x.numel(), _ptr(s_elem), qn, qp, int(rescale), _ptr(y), _stream()))
+    return y
+
+
+def lsq_backward(grad_xq, x, s_elem, qn: int, qp: int, g: float):
+    gx = torch.empty_like(x)
+    galpha = torch.empty(1, dtype=torch.float32, device=x.device)
+    ws = torch.empty(load().cimq_lsq_backward_workspace_bytes(x.numel()), dtype=torch.uint8, device=x.device)
+    _check(load().cimq_lsq_backward(_ptr(grad_xq), _ptr(x), x.numel(), _ptr(s_elem), qn, qp, g, _ptr(gx),
+                                    _ptr(galpha), _ptr(ws), _stream()))
+    return gx, galpha
+
+
+def adc_table(spec: LayerSpec, s, alpha_q, binary_mask, status=None):
+    info = layer_info(spec)
+    table = torch.empty(info.table_bytes, dtype=torch.uint8, device=s.device)
+    layer = spec.c_layer()
+    _check(load().cimq_adc_table(C.byref(layer), _ptr(s), _ptr(alpha_q), _ptr(binary_mask), _ptr(table),
+                                 _ptr(status), _stream()))
+    return table
+
+
+def weight_prepare(spec: LayerSpec, wcodes, want_digits=True, want_tiles=True):
+    info = layer_info(spec)
+    dev = wcodes.device
+    wdigits = torch.empty(info.wdigits_bytes // 4, dtype=torch.float32, device=dev) if want_digits else None
+    wtiles = (torch.empty(info.wtiles_bytes, dtype=torch.uint8, device=dev)
+              if (want_tiles and info.wtiles_bytes > 0) else None)
+    layer = spec.c_layer()
+    _check(load().cimq_weight_prepare(C.byref(layer), _ptr(wcodes), _ptr(wdigits), _ptr(wtiles), _stream()))
+    return wdigits, wtiles
+
+
+def conv_forward(spec: LayerSpec, xcodes, wcodes, wtiles, table, s, binary_mask, save_state: bool, flags: int = 0):
+    info = layer_info(spec)
+    dev = xcodes.device
+    out = torch.empty((spec.batch, spec.out_channels, info.L), dtype=torch.float32, device=dev)
+    state = torch.empty(info.state_bytes // 4, dtype=torch.int32, device=dev) if save_state else None
+    layer = spec.c_layer()
+    _check(load().cimq_conv_forward(C.byref(layer), _ptr(xcodes), _ptr(wcodes), _ptr(wtiles), _ptr(table), _ptr(s),
+                                    _ptr(binary_mask), _ptr(out), _ptr(state), flags, _stream()))
+    return out, state
+
+
+def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, state, s, binary_mask, need_alpha: bool,
+                  need_input: bool = True, flags: int = 0):
+    info = layer_info(spec)
+    dev = grad_out.device
+    gxq = (torch.empty((spec.batch, spec.in_channels, spec.in_hw, spec.in_hw), dtype=torch.float32, device=dev)
+           if need_input else None)
+    gwq = torch.empty((spec.out_channels, info.F), dtype=torch.float32, device=dev)
+    galpha = (torch.empty((1, info.NX, info.NSW, info.NSA, 1, spec.out_channels), dtype=torch.float32, device=dev)
+              if need_alpha else None)
+    ws = torch.empty(info.bwd_workspace_bytes, dtype=torch.uint8, device=dev)
+    layer = spec.c_layer()
+    _check(load().cimq_conv_backward(C.byref(layer), _ptr(grad_out), _ptr(xcodes), _ptr(wdigits), _ptr(state),
+                                     _ptr(s), _ptr(binary_mask), _ptr(gxq), _ptr(gwq), _ptr(galpha), _ptr(ws),
+                                     flags, _stream()))
+    return gxq, gwq, galpha
+
+
+def conv_psums(spec: LayerSpec, xcodes, wcodes):
+    info = layer_info(spec)
+    ps = torch.empty((spec.batch, info.NX, info.NSW, info.NSA, info.L, spec.out_channels), dtype=torch.int32,
+                     device=xcodes.device)
+    layer = spec.c_layer()
+    _check(load().cimq_conv_psums(C.byref(layer), _ptr(xcodes), _ptr(wcodes), _ptr(ps), _stream()))
+    return ps
+
+
+def conv_psum_abs_sums(spec: LayerSpec, xcodes, wcodes):
+    info = layer_info(spec)
+    sums = torch.zeros((1, info.NX, info.NSW, info.NSA, 1, spec.out_channels), dtype=torch.int64,
+                       device=xcodes.device)
+    layer = spec.c_layer()
+    _check(load().cimq_conv_psum_abs_sums(C.byref(layer), _ptr(xcodes), _ptr(wcodes), _ptr(sums), _stream()))
+    return sums

@@ -1,0 +1,356 @@
+// Backward of the CiM convolution (get_cim_output_signed.backward, lsq.py:244-386) on CUDA cores.
+//
+// The reference broadcasts grad_out to the 6-D partial-sum shape, zeroes clipped entries and runs
+// 2*NX*NSA*NSW small GEMMs.  Here the STE clip mask comes from the ADC state the forward stored
+// (1 clip bit per partial sum) and the slice loops are pre-reduced algebraically:
+//
+//   grad_xunf[m, f] = s_w/NSA * sum_{k,co} go[m,co] * PW[m,i(f),k,co] * wdig_k[f,co]
+//                     PW = sum_j pass[k,j] * mask[k,j] * 2^(-abs*j)
+//   grad_w[f, co]   = s_a/NSW * sum_{m,j} xdig_j[m,f] * go[m,co] * PV[m,i(f),j,co]
+//                     PV = sum_k pass[k,j] * mask[k,j] * 2^(-wbs*k)
+//   grad_alpha[i,k,j,co] = mask[k,j]/sqrt(numel*Qp) * sum_m code[m,i,k,j,co] * go[m,co]
+//
+// which is the same arithmetic in a different summation order (results agree to fp32 rounding).
+#include "cimq_common.cuh"
+
+namespace cimq {
+
+namespace {
+
+constexpr int kMaxPairs = 64;
+
+__device__ __forceinline__ uint32_t state_bit(const uint32_t *__restrict__ state, const Geo &g, int i, int c,
+                                              int64_t m, int bit) {
+  return (state[(((int64_t)i * g.Cout + c) * g.state_words + (bit >> 5)) * g.M + m] >> (bit & 31)) & 1u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grad_alpha: partial[ms][e] = sum over a range of pixels of code * go
+// grid (Cout, NX, MS), block 256
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bwd_alpha_partial_kernel(Geo g, int m_per_split,
+                                                                const float *__restrict__ go,
+                                                                const uint32_t *__restrict__ state,
+                                                                float *__restrict__ partial) {
+  __shared__ float red[8][8];
+  const int c = blockIdx.x, i = blockIdx.y, ms = blockIdx.z;
+  const int64_t mbeg = (int64_t)ms * m_per_split;
+  const int64_t mend = min((int64_t)g.M, mbeg + m_per_split);
+  for (int q0 = 0; q0 < g.pairs; q0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
+    for (int64_t m = mbeg + threadIdx.x; m < mend; m += 256) {
+      int b = (int)(m / g.L), l = (int)(m % g.L);
+      float gv = go[((int64_t)b * g.Cout + c) * g.L + l];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        int q = q0 + t;
+        if (q < g.pairs) {
+          uint32_t pos = state_bit(state, g, i, c, m, q), neg = state_bit(state, g, i, c, m, g.pairs + q);
+          acc[t] += pos ? gv : (neg ? -gv : 0.0f);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float v = acc[t];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && q0 + threadIdx.x < g.pairs) {
+      float v = 0.0f;
+      for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+      int64_t e = ((int64_t)i * g.pairs + q0 + threadIdx.x) * g.Cout + c;
+      partial[(int64_t)ms * table_entries(g) + e] = v;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void bwd_alpha_finish_kernel(Geo g, int nsplit, float gfac, const int8_t *__restrict__ mask,
+                                        const float *__restrict__ partial, float *__restrict__ galpha) {
+  const int64_t n = table_entries(g);
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.0f;
+    for (int sidx = 0; sidx < nsplit; ++sidx) v += partial[(int64_t)sidx * n + e];
+    int q = (int)((e / g.Cout) % g.pairs);
+    galpha[e] = v * gfac * (float)mask[q];  // lsq.py:306, 323-325 / 330-332
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// grad wrt the unfolded input, transposed: gxuT[f][m]
+// grid (ceil(M/32), NX, ceil(rowsmax/128)), block 128; smem Ap[NSW*Cout][32]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bwd_input_kernel(Geo g, const float *__restrict__ go,
+                                                        const float *__restrict__ wdigits,
+                                                        const uint32_t *__restrict__ state,
+                                                        const float *__restrict__ s,
+                                                        const int8_t *__restrict__ mask,
+                                                        float *__restrict__ gxuT) {
+  extern __shared__ __align__(16) float Ap[];  // [NSW*Cout][32]
+  __shared__ float wx[kMaxPairs];              // mask[k][j] * 2^(-abs*j)
+  const int i = blockIdx.y;
+  const int lo = i * g.xbar, hi = min(lo + g.xbar, g.F);
+  const int f = lo + blockIdx.z * 128 + threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * 32;
+  if (lo + blockIdx.z * 128 >= hi) return;  // block-uniform
+  if (threadIdx.x < g.pairs) {
+    int j = threadIdx.x % g.NSA;
+    wx[threadIdx.x] = (float)mask[threadIdx.x] * exp2f(-(float)(g.abs_ * j));
+  }
+  __syncthreads();
+  const int nkc = g.NSW * g.Cout;
+  for (int idx = threadIdx.x; idx < nkc * 32; idx += 128) {
+    int p = idx & 31, kc = idx >> 5;
+    int k = kc / g.Cout, co = kc % g.Cout;
+    int64_t m = m0 + p;
+    float v = 0.0f;
+    if (m < g.M) {
+      float pw = 0.0f;
+      for (int j = 0; j < g.NSA; ++j) {
+        int q = k * g.NSA + j;
+        if (!state_bit(state, g, i, co, m, state_clip_bit(g, q))) pw += wx[q];
+      }
+      int b = (int)(m / g.L), l = (int)(m % g.L);
+      v = go[((int64_t)b * g.Cout + co) * g.L + l] * pw;
+    }
+    Ap[kc * 32 + p] = v;
+  }
+  __syncthreads();
+  float acc[32];
+#pragma unroll
+  for (int p = 0; p < 32; ++p) acc[p] = 0.0f;
+  const bool active = f < hi;
+  for (int kc = 0; kc < nkc; ++kc) {
+    float bv = active ? __ldg(&wdigits[(int64_t)kc * g.F + f]) : 0.0f;  // wdigits is [NSW][Cout][F]
+    const float4 *a4 = reinterpret_cast<const float4 *>(Ap + kc * 32);
+#pragma unroll
+    for (int p4 = 0; p4 < 8; ++p4) {
+      float4 a = a4[p4];
+      acc[4 * p4 + 0] = fmaf(a.x, bv, acc[4 * p4 + 0]);
+      acc[4 * p4 + 1] = fmaf(a.y, bv, acc[4 * p4 + 1]);
+      acc[4 * p4 + 2] = fmaf(a.z, bv, acc[4 * p4 + 2]);
+      acc[4 * p4 + 3] = fmaf(a.w, bv, acc[4 * p4 + 3]);
+    }
+  }
+  if (active) {
+    const float scale = s[1] / (float)g.NSA;  // w_sl * s_w (lsq.py:252), mean over act slices (lsq.py:376)
+    float *dst = gxuT + (int64_t)f * g.M + m0;
+#pragma unroll
+    for (int p = 0; p < 32; ++p)
+      if (m0 + p < g.M) dst[p] = acc[p] * scale;
+  }
+}
+
+// col2im (nn.Fold, lsq.py:380-382) as a gather: one thread per input element.
+__global__ void col2im_kernel(Geo g, const float *__restrict__ gxuT, float *__restrict__ gx) {
+  const int64_t n = (int64_t)g.B * g.Cin * g.H * g.W;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int ix = (int)(idx % g.W), iy = (int)((idx / g.W) % g.H);
+    int ci = (int)((idx / ((int64_t)g.W * g.H)) % g.Cin), b = (int)(idx / ((int64_t)g.W * g.H * g.Cin));
+    float v = 0.0f;
+    for (int ky = 0; ky < g.K; ++ky) {
+      int ty = iy + g.pad - ky;
+      if (ty < 0 || ty % g.stride) continue;
+      int oy = ty / g.stride;
+      if (oy >= g.OH) continue;
+      for (int kx = 0; kx < g.K; ++kx) {
+        int tx = ix + g.pad - kx;
+        if (tx < 0 || tx % g.stride) continue;
+        int ox = tx / g.stride;
+        if (ox >= g.OW) continue;
+        int f = ci * g.KK + ky * g.K + kx;
+        v += gxuT[(int64_t)f * g.M + (int64_t)b * g.L + oy * g.OW + ox];
+      }
+    }
+    gx[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// grad wrt the weight codes: partial[ms][f][co]
+// grid (NX * ceil(rowsmax/128), ceil(Cout/32), SPLITS), block 128; thread <-> crossbar row f
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bwd_weight_kernel(Geo g, int ftiles, int m_per_split,
+                                                         const float *__restrict__ go,
+                                                         const uint8_t *__restrict__ xcodes,
+                                                         const uint32_t *__restrict__ state,
+                                                         const float *__restrict__ s,
+                                                         const int8_t *__restrict__ mask,
+                                                         float *__restrict__ partial) {
+  extern __shared__ __align__(16) float Bs[];  // [32 pixels][NSA][32 channels]
+  __shared__ float wv[kMaxPairs];              // mask[k][j] * 2^(-wbs*k)
+  const int i = blockIdx.x / ftiles, ft = blockIdx.x % ftiles;
+  const int lo = i * g.xbar, hi = min(lo + g.xbar, g.F);
+  if (lo + ft * 128 >= hi) return;  // block-uniform
+  const int f = lo + ft * 128 + threadIdx.x;
+  const bool active = f < hi;
+  const int co0 = blockIdx.y * 32;
+  const int64_t mbeg = (int64_t)blockIdx.z * m_per_split;
+  const int64_t mend = min((int64_t)g.M, mbeg + m_per_split);
+  if (threadIdx.x < g.pairs) {
+    int k = threadIdx.x / g.NSA;
+    wv[threadIdx.x] = (float)mask[threadIdx.x] * exp2f(-(float)(g.wbs * k));
+  }
+  int ci = 0, ky = 0, kx = 0;
+  if (active) { ci = f / g.KK; int tap = f % g.KK; ky = tap / g.K; kx = tap % g.K; }
+  float acc[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) acc[t] = 0.0f;
+
+  for (int64_t mb = mbeg; mb < mend; mb += 32) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * g.NSA * 32; idx += 128) {
+      int p = idx & 31, col = (idx >> 5) & 31, j = idx >> 10;  // pixel fastest: coalesced go / state reads
+      int64_t m = mb + p;
+      int co = co0 + col;
+      float v = 0.0f;
+      if (m < mend && co < g.Cout) {
+        float pv = 0.0f;
+        for (int k = 0; k < g.NSW; ++k) {
+          int q = k * g.NSA + j;
+          if (!state_bit(state, g, i, co, m, state_clip_bit(g, q))) pv += wv[q];
+        }
+        int b = (int)(m / g.L), l = (int)(m % g.L);
+        v = go[((int64_t)b * g.Cout + co) * g.L + l] * pv;
+      }
+      Bs[(p * g.NSA + j) * 32 + col] = v;
+    }
+    __syncthreads();
+    if (active) {
+      for (int p = 0; p < 32; ++p) {
+        int64_t m = mb + p;
+        if (m >= mend) break;
+        int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
+        int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
+        int code = 0;
+        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+          code = xcodes[(((int64_t)b * g.Cin + ci) * g.H + iy) * g.W + ix];
+        if (code == 0) continue;
+        for (int j = 0; j < g.NSA; ++j) {
+          float d = (float)((code >> (g.abs_ * j)) & g.amask);
+          if (d == 0.0f) continue;
+          const float4 *b4 = reinterpret_cast<const float4 *>(Bs + (p * g.NSA + j) * 32);
+#pragma unroll
+          for (int t4 = 0; t4 < 8; ++t4) {
+            float4 bv = b4[t4];
+            acc[4 * t4 + 0] = fmaf(d, bv.x, acc[4 * t4 + 0]);
+            acc[4 * t4 + 1] = fmaf(d, bv.y, acc[4 * t4 + 1]);
+            acc[4 * t4 + 2] = fmaf(d, bv.z, acc[4 * t4 + 2]);
+            acc[4 * t4 + 3] = fmaf(d, bv.w, acc[4 * t4 + 3]);
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+    const float scale = s[0] / (float)g.NSW;  // x_sl * s_a (lsq.py:295), mean over weight slices (lsq.py:366)
+    float *dst = partial + ((int64_t)blockIdx.z * g.F + f) * g.Cout + co0;
+#pragma unroll
+    for (int t = 0; t < 32; ++t)
+      if (co0 + t < g.Cout) dst[t] = acc[t] * scale;
+  }
+}
+
+__global__ void bwd_weight_finish_kernel(Geo g, int nsplit, const float *__restrict__ partial,
+                                         float *__restrict__ gw) {
+  const int64_t n = (int64_t)g.Cout * g.F;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int f = (int)(idx % g.F), co = (int)(idx / g.F);
+    float v = 0.0f;
+    for (int sidx = 0; sidx < nsplit; ++sidx) v += partial[((int64_t)sidx * g.F + f) * g.Cout + co];
+    gw[idx] = v;  // [Cout, F] == weight layout, lsq.py:369
+  }
+}
+
+struct BwdPlan {
+  int alpha_splits, alpha_m_per_split;
+  int w_splits, w_m_per_split, ftiles;
+  int64_t off_gxu, off_wpart, off_apart, total;
+};
+
+inline BwdPlan make_plan(const Geo &g) {
+  BwdPlan p;
+  const int target_blocks = 148 * 4;
+  // alpha: grid (Cout, NX, splits)
+  int as = (target_blocks + g.Cout * g.NX - 1) / (g.Cout * g.NX);
+  int max_as = (g.M + 1023) / 1024;
+  as = as < 1 ? 1 : as; if (as > max_as) as = max_as; if (as > 64) as = 64;
+  p.alpha_splits = as;
+  p.alpha_m_per_split = (g.M + as - 1) / as;
+  int rowsmax = g.xbar < g.F ? g.xbar : g.F;
+  p.ftiles = (rowsmax + 127) / 128;
+  int base = g.NX * p.ftiles * ((g.Cout + 31) / 32);
+  int ws = (target_blocks + base - 1) / base;
+  int max_ws = (g.M + 255) / 256;
+  ws = ws < 1 ? 1 : ws; if (ws > max_ws) ws = max_ws; if (ws > 256) ws = 256;
+  int mps = (g.M + ws - 1) / ws;
+  mps = (mps + 31) & ~31;
+  p.w_m_per_split = mps;
+  p.w_splits = (g.M + mps - 1) / mps;
+  auto align = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
+  p.off_gxu = 0;
+  p.off_wpart = align((int64_t)g.F * g.M * 4);
+  p.off_apart = p.off_wpart + align((int64_t)p.w_splits * g.F * g.Cout * 4);
+  p.total = p.off_apart + align((int64_t)p.alpha_splits * table_entries(g) * 4);
+  return p;
+}
+
+}  // namespace
+
+int64_t conv_backward_ws_bytes(const Geo &g) { return make_plan(g).total; }
+
+int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, const float *wdigits,
+                         const uint32_t *state, const float *s, const int8_t *mask, float *gxq, float *gwq,
+                         float *galpha, void *ws, uint32_t, cudaStream_t st) {
+  CIMQ_REQUIRE(go && xcodes && wdigits && state && s && mask && ws, "conv_backward: NULL argument");
+  CIMQ_REQUIRE(g.pairs <= kMaxPairs, "too many slice pairs");
+  const BwdPlan p = make_plan(g);
+  char *base = reinterpret_cast<char *>(ws);
+  float *gxuT = reinterpret_cast<float *>(base + p.off_gxu);
+  float *wpart = reinterpret_cast<float *>(base + p.off_wpart);
+  float *apart = reinterpret_cast<float *>(base + p.off_apart);
+
+  if (galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
+    dim3 grid(g.Cout, g.NX, p.alpha_splits);
+    bwd_alpha_partial_kernel<<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
+    CIMQ_CUDA_OK(cudaGetLastError());
+    // 1/sqrt(ps.numel() * Qp_adc) with Qp_adc = 1 (lsq.py:323, 330)
+    double numel = (double)g.B * g.NX * g.NSW * g.NSA * g.L * g.Cout;
+    float gfac = (float)(1.0 / sqrt(numel));
+    int64_t n = table_entries(g);
+    bwd_alpha_finish_kernel<<<(int)((n + 127) / 128), 128, 0, st>>>(g, p.alpha_splits, gfac, mask, apart, galpha);
+    CIMQ_CUDA_OK(cudaGetLastError());
+  }
+  if (gxq != nullptr) {
+    size_t smem = (size_t)g.NSW * g.Cout * 32 * sizeof(float);
+    CIMQ_REQUIRE(smem <= 200 * 1024, "conv_backward: NSW*Cout too large for the SIMT kernel");
+    CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((g.M + 31) / 32, g.NX, p.ftiles);
+    bwd_input_kernel<<<grid, 128, smem, st>>>(g, go, wdigits, state, s, mask, gxuT);
+    CIMQ_CUDA_OK(cudaGetLastError());
+    int64_t n = (int64_t)g.B * g.Cin * g.H * g.W;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    col2im_kernel<<<blocks, 256, 0, st>>>(g, gxuT, gxq);
+    CIMQ_CUDA_OK(cudaGetLastError());
+  }
+  if (gwq != nullptr) {
+    size_t smem = (size_t)32 * g.NSA * 32 * sizeof(float);
+    CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(g.NX * p.ftiles, (g.Cout + 31) / 32, p.w_splits);
+    bwd_weight_kernel<<<grid, 128, smem, st>>>(g, p.ftiles, p.w_m_per_split, go, xcodes, state, s, mask, wpart);
+    CIMQ_CUDA_OK(cudaGetLastError());
+    int64_t n = (int64_t)g.Cout * g.F;
+    bwd_weight_finish_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, p.w_splits, wpart, gwq);
+    CIMQ_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace cimq

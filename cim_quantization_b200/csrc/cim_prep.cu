@@ -1,0 +1,124 @@
+// Per-step preparation kernels (tiny): ADC decision table and weight digit planes.
+#include "cim_tc_layout.cuh"
+
+namespace cimq {
+
+namespace {
+
+constexpr int kNever = 0x3fffffff;  // threshold that no partial sum reaches
+
+// Scaled partial sum seen by the ADC: fp16 storage, * s_w, * s_a, / alpha_q -- one IEEE op at a
+// time (lsq.py:169, 195, 223 / 257-264).
+__device__ __forceinline__ float adc_input(int p, float sw, float sa, float aq) {
+  float v = __fmul_rn(__fmul_rn(psum_as_stored(p), sw), sa);
+  return __fdiv_rn(v, aq);
+}
+
+// smallest p in [1, 65536] with pred(p), assuming pred is monotone; kNever if none.
+template <class Pred>
+__device__ __forceinline__ int first_true(Pred pred) {
+  int lo = 1, hi = 65537;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (pred(mid)) hi = mid; else lo = mid + 1;
+  }
+  return lo > 65536 ? kNever : lo;
+}
+
+// table entry e = ((i*NSW + k)*NSA + j)*Cout + c  ->  int4 {tp, tg, amp bits, 0}
+__global__ void adc_table_kernel(Geo g, const float *__restrict__ s, const float *__restrict__ alpha_q,
+                                 const int8_t *__restrict__ mask, int4 *__restrict__ table,
+                                 int32_t *__restrict__ status) {
+  const int64_t n = table_entries(g);
+  const float sa = s[0], sw = s[1];
+  bool bad = !(sa > 0.0f) || !(sw > 0.0f) || isinf(sa) || isinf(sw);
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    int q = (int)((e / g.Cout) % g.pairs);
+    float mk = (float)mask[q];  // mask is [NSW, NSA] row-major: index k*NSA + j == q
+    int tp = kNever, tg = kNever;
+    float amp = mk;
+    if (g.adc_mode != CIMQ_ADC_MULTIBIT) {
+      float aq = alpha_q[e];
+      if (!(aq > 0.0f) || isinf(aq)) bad = true;
+      amp = __fmul_rn(aq, mk);  // code * alpha_q * binary_mask with code = +-1 (lsq.py:225, 233)
+      tg = first_true([&](int p) { return adc_input(p, sw, sa, aq) >= 1.00001f; });  // lsq.py:310
+      if (g.adc_mode == CIMQ_ADC_TERNARY)
+        tp = first_true([&](int p) { return rintf(adc_input(p, sw, sa, aq)) >= 1.0f; });  // lsq.py:224
+      else
+        tp = 1;  // sign(p)
+    }
+    table[e] = make_int4(tp, tg, __float_as_int(amp), 0);
+  }
+  if (bad && status != nullptr) atomicOr(status, 1);
+}
+
+__global__ void weight_digits_kernel(Geo g, const int8_t *__restrict__ wcodes, float *__restrict__ wdigits) {
+  const int64_t n = (int64_t)g.Cout * g.F;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int code = wcodes[idx];
+    int mag = code < 0 ? -code : code, sgn = code < 0 ? -1 : 1;
+    for (int k = 0; k < g.NSW; ++k)  // sign-magnitude digits, slicing_weights_signed lsq.py:438-464
+      wdigits[(int64_t)k * n + idx] = (float)(sgn * ((mag >> (g.wbs * k)) & g.wmask));
+  }
+}
+
+// int8 digit tiles for the tcgen05 kernel: tile (ct, i) = NSW*CT rows x Kp bytes, row = k*CT + c_local.
+__global__ void weight_tiles_kernel(Geo g, int CT, int Kp, const int8_t *__restrict__ wcodes,
+                                    int8_t *__restrict__ wtiles) {
+  const int nct = g.Cout / CT;
+  const int rows = g.NSW * CT;
+  const int64_t tile_bytes = (int64_t)rows * Kp;
+  const int64_t n = (int64_t)nct * g.NX * tile_bytes;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t tile = idx / tile_bytes;
+    int within = (int)(idx % tile_bytes);
+    int r = within / Kp, kk = within % Kp;  // logical (row, k-byte); scattered to its layout slot
+    int ct = (int)(tile / g.NX), i = (int)(tile % g.NX);
+    int k = r / CT, c = ct * CT + r % CT;
+    int f = i * g.xbar + kk;
+    int hi = min((i + 1) * g.xbar, g.F);
+    int digit = 0;
+    if (f < hi) {
+      int code = wcodes[(int64_t)c * g.F + f];
+      int mag = code < 0 ? -code : code;
+      digit = (mag >> (g.wbs * k)) & g.wmask;
+      if (code < 0) digit = -digit;
+    }
+    wtiles[tile * tile_bytes + tc_tile_offset(r, kk, Kp)] = (int8_t)digit;
+  }
+}
+
+}  // namespace
+
+int launch_adc_table(const Geo &g, const float *s, const float *alpha_q, const int8_t *mask, void *table,
+                     int32_t *status, cudaStream_t st) {
+  CIMQ_REQUIRE(g.adc_mode == CIMQ_ADC_MULTIBIT || alpha_q != nullptr, "adc_table: alpha_q is NULL");
+  int64_t n = table_entries(g);
+  int blocks = (int)((n + 127) / 128);
+  adc_table_kernel<<<blocks, 128, 0, st>>>(g, s, alpha_q, mask, reinterpret_cast<int4 *>(table), status);
+  CIMQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int64_t wtiles_bytes(const Geo &g) { return tc_forward_supported(g) ? wtiles_total_bytes(g) : 0; }
+
+int launch_weight_prepare(const Geo &g, const int8_t *wcodes, float *wdigits, void *wtiles, cudaStream_t st) {
+  if (wdigits != nullptr) {
+    int64_t n = (int64_t)g.Cout * g.F;
+    weight_digits_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, wcodes, wdigits);
+    CIMQ_CUDA_OK(cudaGetLastError());
+  }
+  if (wtiles != nullptr && tc_forward_supported(g)) {
+    const int CT = tc_channel_tile_for(g);
+    int64_t n = (int64_t)(g.Cout / CT) * g.NX * g.NSW * CT * tc_kp(g);
+    weight_tiles_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, CT, tc_kp(g), wcodes,
+                                                               reinterpret_cast<int8_t *>(wtiles));
+    CIMQ_CUDA_OK(cudaGetLastError());
+    if (launch_im2col_lut(g, wtiles, st)) return 1;
+  }
+  return 0;
+}
+
+}  // namespace cimq

@@ -1,0 +1,140 @@
+// extern "C" entry points of libcimq.so (see include/cimq.h).  Argument checking and dispatch only;
+// every call enqueues kernels on the caller's stream and returns.
+#include <stdarg.h>
+#include <string.h>
+
+#include "cimq_common.cuh"
+
+namespace cimq {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace cimq
+
+using namespace cimq;
+
+extern "C" {
+
+int cimq_version(void) { return CIMQ_VERSION; }
+
+const char *cimq_last_error(void) { return g_error; }
+
+int cimq_layer_info(const cimq_layer_t *layer, cimq_info_t *info) {
+  Geo g;
+  if (make_geo(layer, &g)) return 1;
+  CIMQ_REQUIRE(info != nullptr, "info is NULL");
+  memset(info, 0, sizeof(*info));
+  info->out_hw = g.OH; info->L = g.L; info->M = g.M; info->F = g.F;
+  info->NX = g.NX; info->NSW = g.NSW; info->NSA = g.NSA; info->pairs = g.pairs;
+  info->state_words = g.state_words;
+  info->tc_forward = tc_forward_supported(g) ? 1 : 0;
+  info->state_bytes = (int64_t)g.NX * g.Cout * g.state_words * g.M * 4;
+  info->table_bytes = table_entries(g) * 16;
+  info->wdigits_bytes = (int64_t)g.NSW * g.Cout * g.F * 4;
+  info->wtiles_bytes = wtiles_bytes(g);
+  info->bwd_workspace_bytes = conv_backward_ws_bytes(g);
+  info->psum_count = (int64_t)g.B * g.NX * g.NSW * g.NSA * g.L * g.Cout;
+  return 0;
+}
+
+int cimq_step_sizes(const float *alpha_act, const float *alpha_weight, float ga, float gw, float *s_out,
+                    void *stream) {
+  CIMQ_REQUIRE(alpha_act && alpha_weight && s_out, "step_sizes: NULL argument");
+  return launch_step_sizes(alpha_act, alpha_weight, ga, gw, s_out, as_stream(stream));
+}
+
+int cimq_lsq_quantize(const float *x, int64_t n, const float *s, int32_t qn, int32_t qp, void *codes,
+                      void *stream) {
+  CIMQ_REQUIRE(n >= 0 && (n == 0 || (x && s && codes)), "lsq_quantize: NULL argument");
+  CIMQ_REQUIRE(qn <= qp && qn >= -128 && qp <= 255 && (qn >= 0 || qp <= 127), "lsq_quantize: codes must fit a byte");
+  return launch_lsq_quantize(x, n, s, qn, qp, codes, false, as_stream(stream));
+}
+
+int cimq_codes_from_fakequant(const float *xq, int64_t n, const float *s, int32_t qn, int32_t qp, void *codes,
+                              void *stream) {
+  CIMQ_REQUIRE(n >= 0 && (n == 0 || (xq && s && codes)), "codes_from_fakequant: NULL argument");
+  CIMQ_REQUIRE(qn <= qp && qn >= -128 && qp <= 255 && (qn >= 0 || qp <= 127),
+               "codes_from_fakequant: codes must fit a byte");
+  return launch_lsq_quantize(xq, n, s, qn, qp, codes, true, as_stream(stream));
+}
+
+int cimq_lsq_fakequant(const float *x, int64_t n, const float *s, int32_t qn, int32_t qp, int32_t rescale, float *y,
+                       void *stream) {
+  CIMQ_REQUIRE(n >= 0 && (n == 0 || (x && s && y)), "lsq_fakequant: NULL argument");
+  return launch_lsq_fakequant(x, n, s, qn, qp, rescale, y, as_stream(stream));
+}
+
+int64_t cimq_lsq_backward_workspace_bytes(int64_t n) { return lsq_backward_ws_bytes(n); }
+
+int cimq_lsq_backward(const float *grad_xq, const float *x, int64_t n, const float *s, int32_t qn, int32_t qp,
+                      float g, float *grad_x, float *grad_alpha, void *workspace, void *stream) {
+  CIMQ_REQUIRE(n > 0 && grad_xq && x && s && grad_x && grad_alpha, "lsq_backward: NULL argument");
+  return launch_lsq_backward(grad_xq, x, n, s, qn, qp, g, grad_x, grad_alpha, workspace, as_stream(stream));
+}
+
+int cimq_adc_table(const cimq_layer_t *layer, const float *s, const float *alpha_q, const int8_t *binary_mask,
+                   void *table, int32_t *status, void *stream) {
+  Geo g;
+  if (make_geo(layer, &g)) return 1;
+  CIMQ_REQUIRE(s && binary_mask && table, "adc_table: NULL argument");
+  return launch_adc_table(g, s, alpha_q, binary_mask, table, status, as_stream(stream));
+}
+
+int cimq_weight_prepare(const cimq_layer_t *layer, const int8_t *wcodes, float *wdigits, void *wtiles,
+                        void *stream) {
+  Geo g;
+  if (make_geo(layer, &g)) return 1;
+  CIMQ_REQUIRE(wcodes != nullptr, "weight_prepare: wcodes is NULL");
+  return launch_weight_prepare(g, wcodes, wdigits, wtiles, as_stream(stream));
+}
+
+int cimq_conv_forward(const cimq_layer_t *layer, const uint8_t *xcodes, const int8_t *wcodes, const void *wtiles,
+                      const void *table, const float *s, const int8_t *binary_mask, float *out, uint32_t *state,
+                      uint32_t flags, void *stream) {
+  Geo g;
+  if (make_geo(layer, &g)) return 1;
+  CIMQ_REQUIRE(xcodes && wcodes && table && s && out, "conv_forward: NULL argument");
+  if (!(flags & CIMQ_FLAG_FORCE_SIMT) && wtiles != nullptr && tc_forward_supported(g))
+    return launch_conv_tc_forward(g, xcodes, wtiles, table, s, binary_mask, out, state, as_stream(stream));
+  return launch_conv_simt(g, SIMT_FORWARD, xcodes, wcodes, table, s, binary_mask, out, state, nullptr, nullptr,
+                          as_stream(stream));
+}
+
+int cimq_conv_backward(const cimq_layer_t *layer, const float *grad_out, const uint8_t *xcodes,
+                       const float *wdigits, const uint32_t *state, const float *s, const int8_t *binary_mask,
+                       float *grad_xq, float *grad_wq, float *grad_alpha_q, void *workspace, uint32_t flags,
+                       void *stream) {
+  Geo g;
+  if (make_geo(layer, &g)) return 1;
+  return launch_conv_backward(g, grad_out, xcodes, wdigits, state, s, binary_mask, grad_xq, grad_wq,
+                              grad_alpha_q, workspace, flags, as_stream(stream));
+}
+
+int cimq_conv_psums(const cimq_layer_t *layer, const uint8_t *xcodes, const int8_t *wcodes, int32_t *psums,
+                    void *stream) {
+  Geo g;
+  if (make_geo(layer, &g)) return 1;
+  CIMQ_REQUIRE(xcodes && wcodes, "conv_psums: NULL argument");
+  return launch_conv_simt(g, SIMT_PSUMS, xcodes, wcodes, nullptr, nullptr, nullptr, nullptr, nullptr, psums,
+                          nullptr, as_stream(stream));
+}
+
+int cimq_conv_psum_abs_sums(const cimq_layer_t *layer, const uint8_t *xcodes, const int8_t *wcodes,
+                            unsigned long long *sums, void *stream) {
+  Geo g;
+  if (make_geo(layer, &g)) return 1;
+  CIMQ_REQUIRE(xcodes && wcodes, "conv_psum_abs_sums: NULL argument");
+  return launch_conv_simt(g, SIMT_ABS_SUMS, xcodes, wcodes, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          sums, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// Shared declarations of libcimq (internal).  See include/cimq.h for the public C ABI.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cimq.h"
+
+namespace cimq {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+
+#define CIMQ_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::cimq::set_error(__VA_ARGS__);  \
+      return 1;                        \
+    }                                  \
+  } while (0)
+
+#define CIMQ_CUDA_OK(expr)                                                                \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      ::cimq::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                        \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+// ---- derived layer geometry -------------------------------------------------------------------
+// Plain-old-data copy of the layer with everything the kernels need; passed by value.
+struct Geo {
+  int B, Cin, H, W, Cout, K, stride, pad;
+  int OH, OW, L, M, F, KK;          // KK = K*K
+  int NX, NSW, NSA, pairs;          // crossbars, weight / act digit planes, NSW*NSA
+  int abits, abs_, wbits, wbs;      // activation / weight bits and bits per slice
+  int amask, wmask;                 // (1<<abs_)-1, (1<<wbs)-1
+  int xbar;
+  int adc_mode, qn, qp;
+  int state_bits, state_words;      // bits of ADC state per (crossbar, channel, pixel)
+};
+
+inline int make_geo(const cimq_layer_t *l, Geo *g) {
+  CIMQ_REQUIRE(l != nullptr, "layer is NULL");
+  CIMQ_REQUIRE(l->batch > 0 && l->in_channels > 0 && l->in_hw > 0 && l->out_channels > 0, "bad layer shape");
+  CIMQ_REQUIRE(l->kernel > 0 && l->stride > 0 && l->padding >= 0, "bad kernel/stride/padding");
+  CIMQ_REQUIRE(l->abitslice > 0 && l->wbitslice > 0 && l->nbits_a >= l->abitslice && l->nbits_w >= l->wbitslice,
+               "bad bit widths");
+  CIMQ_REQUIRE(l->nbits_a <= 8 && l->nbits_w <= 8, "codes are one byte: nbits_a, nbits_w <= 8");
+  CIMQ_REQUIRE(l->xbar > 0, "xbar must be positive");
+  CIMQ_REQUIRE(l->adc_mode >= 0 && l->adc_mode <= 2, "bad adc_mode");
+  g->B = l->batch; g->Cin = l->in_channels; g->H = l->in_hw; g->W = l->in_hw;
+  g->Cout = l->out_channels; g->K = l->kernel; g->stride = l->stride; g->pad = l->padding;
+  g->OH = (g->H + 2 * g->pad - g->K) / g->stride + 1;
+  g->OW = g->OH;
+  CIMQ_REQUIRE(g->OH > 0, "empty output");
+  g->L = g->OH * g->OW; g->M = g->B * g->L;
+  g->KK = g->K * g->K; g->F = g->Cin * g->KK;
+  g->xbar = l->xbar;
+  g->NX = (g->F + g->xbar - 1) / g->xbar;
+  g->abits = l->nbits_a; g->abs_ = l->abitslice; g->wbits = l->nbits_w; g->wbs = l->wbitslice;
+  g->NSA = g->abits / g->abs_; g->NSW = g->wbits / g->wbs;   // int(bits/bit_slice), _quan_base.py:203-204
+  g->pairs = g->NSA * g->NSW;
+  g->amask = (1 << g->abs_) - 1; g->wmask = (1 << g->wbs) - 1;
+  g->adc_mode = l->adc_mode; g->qn = l->adc_qn; g->qp = l->adc_qp;
+  g->state_bits = (g->adc_mode == CIMQ_ADC_MULTIBIT ? 1 : 3) * g->pairs;
+  g->state_words = (g->state_bits + 31) / 32;
+  return 0;
+}
+
+// ---- ADC state bit layout ------------------------------------------------------------------------
+// Per (crossbar i, channel c, pixel m) the forward stores `state_words` uint32 at
+//   state[((i*Cout + c)*state_words + w)*M + m]
+// holding, for slice pair q = k*NSA + j:
+//   binary / ternary ADC : bit q = code is +1, bit pairs+q = code is -1, bit 2*pairs+q = clipped (STE mask off)
+//   multi-bit ADC        : bit q = clipped
+__host__ __device__ inline int state_pos_bit(int pairs, int q) { return q; }
+__host__ __device__ inline int state_neg_bit(int pairs, int q) { return pairs + q; }
+__host__ __device__ inline int state_clip_bit(const Geo &g, int q) {
+  return g.adc_mode == CIMQ_ADC_MULTIBIT ? q : 2 * g.pairs + q;
+}
+
+// fp16 round trip of an integer partial sum (the reference stores psums as fp16, lsq.py:169).
+__device__ __forceinline__ float psum_as_stored(int p) {
+  return __half2float(__float2half_rn((float)p));
+}
+
+// ---- kernel launchers (one per .cu file) ---------------------------------------------------------
+int launch_step_sizes(const float *aa, const float *aw, float ga, float gw, float *s, cudaStream_t st);
+int launch_lsq_quantize(const float *x, int64_t n, const float *s, int qn, int qp, void *codes, bool from_fq,
+                        cudaStream_t st);
+int launch_lsq_fakequant(const float *x, int64_t n, const float *s, int qn, int qp, int rescale, float *y,
+                         cudaStream_t st);
+int launch_lsq_backward(const float *gq, const float *x, int64_t n, const float *s, int qn, int qp, float g,
+                        float *gx, float *galpha, void *ws, cudaStream_t st);
+int64_t lsq_backward_ws_bytes(int64_t n);
+
+int launch_adc_table(const Geo &g, const float *s, const float *alpha_q, const int8_t *mask, void *table,
+                     int32_t *status, cudaStream_t st);
+int launch_weight_prepare(const Geo &g, const int8_t *wcodes, float *wdigits, void *wtiles, cudaStream_t st);
+int64_t wtiles_bytes(const Geo &g);
+bool tc_forward_supported(const Geo &g);
+int tc_channel_tile_for(const Geo &g);          // output channels per CTA of the tcgen05 kernel (0: unsupported)
+int64_t wtiles_total_bytes(const Geo &g);       // weight digit tiles + im2col LUT
+int launch_im2col_lut(const Geo &g, void *wtiles, cudaStream_t st);
+
+enum SimtMode { SIMT_FORWARD = 0, SIMT_PSUMS = 1, SIMT_ABS_SUMS = 2 };
+int launch_conv_simt(const Geo &g, int mode, const uint8_t *xcodes, const int8_t *wcodes, const void *table,
+                     const float *s, const int8_t *mask, float *out, uint32_t *state, int32_t *psums,
+                     unsigned long long *sums, cudaStream_t st);
+int launch_conv_tc_forward(const Geo &g, const uint8_t *xcodes, const void *wtiles, const void *table,
+                           const float *s, const int8_t *mask, float *out, uint32_t *state, cudaStream_t st);
+
+int64_t conv_backward_ws_bytes(const Geo &g);
+int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, const float *wdigits,
+                         const uint32_t *state, const float *s, const int8_t *mask, float *gxq, float *gwq,
+                         float *galpha, void *ws, uint32_t flags, cudaStream_t st);
+
+// table = NX*pairs*Cout entries of 16 bytes: int4 {tp, tg, amp (fp32 bits), 0}
+__host__ __device__ inline int64_t table_entries(const Geo &g) { return (int64_t)g.NX * g.pairs * g.Cout; }
+
+}  // namespace cimq

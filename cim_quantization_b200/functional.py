@@ -1,0 +1,200 @@
+"""autograd.Function surface of the CiM conv path, backed by ``libcimq.so``.
+
+* ``get_cim_output_signed`` keeps the reference's 17-argument signature and its 17-tuple of
+  gradients (``models/_modules/lsq.py:89-386``) so existing callers work unchanged.
+* ``cim_conv2d`` is the fused path ``Conv2dLSQCiM.forward`` uses: it goes from fp32 activations /
+  weights and the learned step sizes straight to integer codes (the fake-quant floats of
+  lsq.py:549/555 are never materialised) and its backward also produces the LSQ step-size
+  gradients that the reference obtains through autograd.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import LayerSpec
+
+
+def _pair0(v):
+    return int(v[0]) if isinstance(v, (tuple, list)) else int(v)
+
+
+def _as_mask_2d(binary_mask, nsw, nsa, device):
+    """binary_mask arrives as int8 ``[1,1,NSW,NSA,1,1]`` (``_quan_base.py:207-214``)."""
+    m = binary_mask.to(device=device, dtype=torch.int8).reshape(nsw, nsa).contiguous()
+    return m
+
+
+def _make_spec(x_shape, w_shape, stride, padding, nbits_a, abitslice, nbits_w, wbitslice, xbar, adcbits) -> LayerSpec:
+    b, cin, h, w = x_shape
+    cout, cin_w, kh, kw = w_shape
+    if h != w or kh != kw:
+        raise ValueError("CiM conv supports square images and kernels only (reference envelope, lsq.py:123,369)")
+    if cin_w != cin:
+        raise ValueError("groups != 1 is not supported by the CiM conv (lsq.py:153)")
+    return LayerSpec(batch=int(b), in_channels=int(cin), in_hw=int(h), out_channels=int(cout), kernel=int(kh),
+                     stride=_pair0(stride), padding=_pair0(padding), nbits_a=int(nbits_a), abitslice=int(abitslice),
+                     nbits_w=int(nbits_w), wbitslice=int(wbitslice), xbar=int(xbar), adcbits=adcbits)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cim_quantization_b200 runs on CUDA tensors only; there is no CPU fallback")
+
+
+class get_cim_output_signed(Function):
+    """Drop-in for the reference Function (lsq.py:89): same arguments, output ``[B, L, Cout]``,
+    gradients at positions 0 (x_q), 1 (w_q) and 12 (alpha_cim).
+
+    The integer codes are recovered from the fake-quant floats as ``rint(x_q / s)``: identical to
+    the reference wherever its own ``x_q / s`` is exact, and free of its truncation
+    artefacts elsewhere.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w, conv_stride, conv_padding, conv_dilation, act_bits, act_bit_slice, weight_bits,
+                weight_bit_slice, adc_bits, arr, binary_mask, alpha_cim, weight_scaling_factor,
+                act_scaling_factor, stochastic, signed_act):
+        if stochastic:
+            raise NotImplementedError("stochastic near-ADC-less sampling (lsq.py:205-220) is not implemented")
+        if _pair0(conv_dilation) != 1:
+            raise ValueError("dilation != 1 is not supported (the reference's Unfold ignores it, lsq.py:141)")
+        _require_cuda(x, w)
+        spec = _make_spec(x.shape, w.shape, conv_stride, conv_padding, act_bits, act_bit_slice, weight_bits,
+                          weight_bit_slice, arr, adc_bits)
+        info = _lib.layer_info(spec)
+        dev = x.device
+        s = torch.cat([act_scaling_factor.detach().reshape(1), weight_scaling_factor.detach().reshape(1)]).to(
+            device=dev, dtype=torch.float32)
+        qp_a = 2 ** int(act_bits) - 1
+        qn_w, qp_w = -(2 ** (int(weight_bits) - 1)), 2 ** (int(weight_bits) - 1) - 1
+        xcodes = _lib.lsq_quantize(x.detach().contiguous().float(), s[0:1], 0, qp_a, from_fakequant=True)
+        wcodes = _lib.lsq_quantize(w.detach().contiguous().float(), s[1:2], qn_w, qp_w, from_fakequant=True)
+        mask = _as_mask_2d(binary_mask, info.NSW, info.NSA, dev)
+        has_alpha = adc_bits in (1, 1.5)
+        alpha_q = alpha_cim.detach().contiguous().float() if has_alpha else None
+        table = _lib.adc_table(spec, s, alpha_q, mask)
+        need_bwd = any(ctx.needs_input_grad)
+        wdigits, wtiles = _lib.weight_prepare(spec, wcodes, want_digits=need_bwd)
+        out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd)
+        ctx.spec, ctx.has_alpha, ctx.w_shape = spec, has_alpha, tuple(w.shape)
+        ctx.save_for_backward(xcodes, wdigits, state, s, mask)
+        return out.transpose(1, 2)  # [B, L, Cout] like lsq.py:233 (a view of the NCHW buffer)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        xcodes, wdigits, state, s, mask = ctx.saved_tensors
+        go = grad_output.transpose(1, 2).contiguous().float()  # [B, Cout, L]
+        gxq, gwq, galpha = _lib.conv_backward(ctx.spec, go, xcodes, wdigits, state, s, mask,
+                                              need_alpha=ctx.has_alpha and ctx.needs_input_grad[12],
+                                              need_input=ctx.needs_input_grad[0])
+        gwq = gwq.view(ctx.w_shape)
+        return (gxq, gwq, None, None, None, None, None, None, None, None, None, None, galpha, None, None, None,
+                None)
+
+
+class _CimConv2dFused(Function):
+    """Fused ``Conv2dLSQCiM`` hot path: LSQ quantisation of x and w, CiM conv, and the complete
+    backward (grad x, grad w, the three step-size gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, alpha_act, alpha_weight, alpha_q, binary_mask, stride, padding, nbits_a,
+                abitslice, nbits_w, wbitslice, xbar, adcbits, flags):
+        _require_cuda(x, weight, alpha_act, alpha_weight)
+        x = x.contiguous()
+        weight = weight.contiguous()
+        spec = _make_spec(x.shape, weight.shape, stride, padding, nbits_a, abitslice, nbits_w, wbitslice, xbar,
+                          adcbits)
+        info = _lib.layer_info(spec)
+        qp_a = 2 ** spec.nbits_a - 1  # activations always clamp to [0, Qp_a], lsq.py:537-538
+        qn_w, qp_w = -(2 ** (spec.nbits_w - 1)), 2 ** (spec.nbits_w - 1) - 1
+        ga = 1.0 / math.sqrt(x.numel() * qp_a)  # lsq.py:547
+        gw = 1.0 / math.sqrt(weight.numel() * qp_w)  # lsq.py:553
+        s = _lib.step_sizes(alpha_act.detach(), alpha_weight.detach(), ga, gw)
+        xcodes = _lib.lsq_quantize(x.detach(), s[0:1], 0, qp_a)
+        wcodes = _lib.lsq_quantize(weight.detach(), s[1:2], qn_w, qp_w)
+        mask = _as_mask_2d(binary_mask, info.NSW, info.NSA, x.device)
+        has_alpha = alpha_q is not None
+        table = _lib.adc_table(spec, s, alpha_q.detach().contiguous() if has_alpha else None, mask)
+        need_bwd = any(ctx.needs_input_grad)
+        wdigits, wtiles = _lib.weight_prepare(spec, wcodes, want_digits=need_bwd)
+        out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd,
+                                       flags=flags)
+        ctx.spec, ctx.has_alpha, ctx.flags = spec, has_alpha, flags
+        ctx.consts = (qp_a, qn_w, qp_w, ga, gw)
+        ctx.save_for_backward(x, weight, xcodes, wdigits, state, s, mask)
+        return out.view(spec.batch, spec.out_channels, info.out_hw, info.out_hw)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x, weight, xcodes, wdigits, state, s, mask = ctx.saved_tensors
+        spec = ctx.spec
+        qp_a, qn_w, qp_w, ga, gw = ctx.consts
+        go = grad_y.contiguous().float().view(spec.batch, spec.out_channels, -1)
+        need_x = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
+        gxq, gwq, galpha = _lib.conv_backward(spec, go, xcodes, wdigits, state, s, mask,
+                                              need_alpha=ctx.has_alpha and ctx.needs_input_grad[4],
+                                              need_input=need_x, flags=ctx.flags)
+        gx = g_aa = None
+        if need_x:
+            gx, g_aa = _lib.lsq_backward(gxq, x, s[0:1], 0, qp_a, ga)
+        gwt, g_aw = _lib.lsq_backward(gwq.view_as(weight), weight, s[1:2], qn_w, qp_w, gw)
+        return (gx, gwt, g_aa, g_aw, galpha) + (None,) * 10
+
+
+def cim_conv2d(x, weight, alpha_act, alpha_weight, alpha_q, binary_mask, stride, padding, nbits_a, abitslice,
+               nbits_w, wbitslice, xbar, adcbits, flags: int = 0):
+    """Fused CiM convolution of ``Conv2dLSQCiM`` (lsq.py:546-581): returns ``[B, Cout, OH, OW]``."""
+    return _CimConv2dFused.apply(x, weight, alpha_act, alpha_weight, alpha_q, binary_mask, stride, padding, nbits_a,
+                                 abitslice, nbits_w, wbitslice, xbar, adcbits, flags)
+
+
+class _LsqFakeQuant(Function):
+    """``round_pass(clamp(x / grad_scale(alpha, g), qn, qp)) [* s]`` with its STE / step-size backward
+    (lsq.py:23-32 and the ``Method1`` blocks at lsq.py:426-427, 608-609, 653-654)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, g, qn, qp, rescale):
+        _require_cuda(x, alpha)
+        x = x.contiguous()
+        s = _lib.step_sizes(alpha.detach(), alpha.detach(), g, g)
+        y = _lib.lsq_fakequant(x.detach(), s[0:1], qn, qp, rescale)
+        ctx.save_for_backward(x, s)
+        ctx.consts = (g, qn, qp, rescale)
+        ctx.mark_non_differentiable(s)
+        return y, s[0:1]
+
+    @staticmethod
+    def backward(ctx, grad_y, _grad_s):
+        x, s = ctx.saved_tensors
+        g, qn, qp, rescale = ctx.consts
+        gy = grad_y.contiguous().float()
+        if rescale:
+            gx, galpha = _lib.lsq_backward(gy, x, s[0:1], qn, qp, g)
+        else:
+            # y = round_pass(clamp(x/s)):  dy/dx = mask / s,  dy/ds = -(x/s) * mask / s   (tiny-use path: torch ops)
+            u = x / s[0:1]
+            inside = (u >= qn) & (u <= qp)
+            gx = gy * inside / s[0:1]
+            galpha = (-(gy * u * inside).sum() * g / s[0:1]).reshape(1)
+        return gx, galpha, None, None, None, None
+
+
+def lsq_fake_quant(x, alpha, g: float, qn: int, qp: int, rescale: bool = True):
+    """Returns ``(y, s)`` with ``s = grad_scale(alpha, g)`` (value only, as a 1-element tensor)."""
+    return _LsqFakeQuant.apply(x, alpha, g, qn, qp, rescale)
+
+
+def alpha_cim_initial_value(spec: LayerSpec, xcodes, wcodes, s, qp_adc: float = 1.0):
+    """Data-dependent initial ``alpha_cim`` (lsq.py:557-563): ``2*mean|psum*s_w*s_a| / sqrt(Qp_adc)``
+    over (batch, pixel), zeros replaced by ``s_w*s_a``.  The |psum| sums are exact integers."""
+    info = _lib.layer_info(spec)
+    sums = _lib.conv_psum_abs_sums(spec, xcodes, wcodes)  # int64 [1,NX,NSW,NSA,1,Cout]
+    sa, sw = s[0].double(), s[1].double()
+    t = 2.0 * (sums.double() / float(spec.batch * info.L)) * sw * sa / math.sqrt(qp_adc)
+    t = torch.where(t == 0, sw * sa, t)
+    return t.float()

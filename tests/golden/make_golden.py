@@ -44,6 +44,17 @@ CASES = {
                                  wbs=1, abs=1, xbar=128, adc=1.5, signed_input=True),
     "slice2_w4a4_c8o8_x64": dict(cin=8, cout=8, k=3, stride=1, pad=1, hw=6, batch=2, nbits_w=4, nbits_a=4,
                                  wbs=2, abs=2, xbar=64, adc=2),
+    # channel counts the tcgen05 kernel covers (Cout multiple of 16)
+    "tern_c32o32_x64": dict(cin=32, cout=32, k=3, stride=1, pad=1, hw=6, batch=2, nbits_w=3, nbits_a=3,
+                            wbs=1, abs=1, xbar=64, adc=1.5),
+    "tern_c16o64_x128": dict(cin=16, cout=64, k=3, stride=1, pad=1, hw=6, batch=1, nbits_w=3, nbits_a=3,
+                             wbs=1, abs=1, xbar=128, adc=1.5),
+    "bin_w2a2_c16o16_x64": dict(cin=16, cout=16, k=3, stride=1, pad=1, hw=6, batch=2, nbits_w=2, nbits_a=2,
+                                wbs=1, abs=1, xbar=64, adc=1),
+    "first_w8a8_c3o16_x128": dict(cin=3, cout=16, k=3, stride=1, pad=1, hw=8, batch=2, nbits_w=8, nbits_a=8,
+                                  wbs=1, abs=1, xbar=128, adc=1.5, signed_input=True),
+    "tern_w4a4_c16o32_x128": dict(cin=16, cout=32, k=3, stride=1, pad=1, hw=6, batch=2, nbits_w=4, nbits_a=4,
+                                  wbs=1, abs=1, xbar=128, adc=1.5),
     "pw_c32o8_x16": dict(cin=32, cout=8, k=1, stride=1, pad=0, hw=4, batch=2, nbits_w=3, nbits_a=3,
                          wbs=1, abs=1, xbar=16, adc=1.5),
 }
