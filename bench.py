@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Benchmark of the CiM-aware quantized convolution hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--xbar 128] [--adcbits 1.5] [--batch 256]
+
+Workload (BASELINE.json configs[1]): one Conv2dLSQCiM layer, 3x3, 64->64 channels, 32x32 images,
+batch 256 per GPU, w3a3, 1-bit slices; a *step* is one forward + backward of the layer through the
+module surface (LSQ quantisation of x and w, CiM conv forward, backward to x, w and the three step
+sizes).  ``value`` = algorithmic TOPS of the whole job: (2*NSW*NSA + 2*NSW + 2*NSA) * B*L*F*Cout ops
+per step per GPU divided by the device time of K steps, max over ranks.
+
+N > 1 (torchrun, one rank per GPU): every rank runs its own batch shard (weak scaling) and the
+weight / step-size gradients are all-reduced with NCCL inside the timed step, as data-parallel
+training does.
+
+``--impl reference`` times the CPU restatement of the reference algorithm (oracle/cim_oracle.py, numpy)
+on the host cores with the same metric; it is the only place besides the ``cpu_baseline`` leg where
+bench.py executes anything under oracle/.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "cim_conv_fwd_bwd_tops"
+UNIT = "TOPS"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--xbar", type=int, default=128)
+    p.add_argument("--adcbits", type=float, default=1.5)
+    p.add_argument("--batch", type=int, default=256, help="images per GPU")
+    p.add_argument("--nbits", type=int, default=3)
+    p.add_argument("--channels", type=int, default=64)
+    p.add_argument("--hw", type=int, default=32)
+    p.add_argument("--cpu-sample-batch", type=int, default=8)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    return p.parse_args()
+
+
+def layer_ops(batch, channels, hw, nbits):
+    """Algorithmic integer/float ops of one step on one GPU."""
+    mkn = batch * hw * hw * (channels * 9) * channels
+    ns = nbits  # 1-bit slices: NSW = NSA = nbits
+    fwd = 2 * ns * ns * mkn
+    bwd = 2 * ns * mkn + 2 * ns * mkn
+    return fwd, bwd
+
+
+def workload_config(a):
+    adc = int(a.adcbits) if a.adcbits == int(a.adcbits) else a.adcbits
+    return {"workload": f"CiM conv layer microbench 3x3 {a.channels}->{a.channels} {a.hw}x{a.hw} "
+                        f"w{a.nbits}a{a.nbits} xbar{a.xbar} adcbits{adc} fwd+bwd",
+            "batch_per_gpu": a.batch, "xbar": a.xbar, "adcbits": adc,
+            "l2": "working set (x 67 MB, grad 67 MB, ADC state 335 MB) exceeds the 126 MB L2; no extra flush"}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm
+# --------------------------------------------------------------------------------------------------
+def cpu_step_factory(a, batch):
+    import numpy as np
+    from oracle import cim_oracle as O
+    adc = int(a.adcbits) if a.adcbits == int(a.adcbits) else a.adcbits
+    cfg = O.CimConfig(in_channels=a.channels, out_channels=a.channels, kernel=3, stride=1, padding=1,
+                      nbits_w=a.nbits, nbits_a=a.nbits, wbitslice=1, abitslice=1, xbar=a.xbar, adcbits=adc)
+    rng = np.random.default_rng(0)
+    x = np.maximum(rng.standard_normal((batch, a.channels, a.hw, a.hw)), 0).astype(np.float32)
+    w = (rng.standard_normal((a.channels, a.channels, 3, 3)) * math.sqrt(2.0 / (a.channels * 9))).astype(np.float32)
+    gy = rng.standard_normal((batch, a.channels, a.hw, a.hw)).astype(np.float32)
+    aa, aw = O.init_step_size(x, cfg.qp_a), O.init_step_size(w, cfg.qp_w)
+    s_a = O.grad_scale_value(aa, 1.0 / math.sqrt(x.size * cfg.qp_a))
+    s_w = O.grad_scale_value(aw, 1.0 / math.sqrt(w.size * cfg.qp_w))
+    ac = None
+    if cfg.has_alpha_cim:
+        ac = O.init_alpha_cim(cfg, O.lsq_codes(x, s_a, 0, cfg.qp_a), O.lsq_codes(w, s_w, cfg.qn_w, cfg.qp_w), s_w, s_a)
+
+    def step():
+        return O.module_forward_backward(cfg, x, w, aa, aw, ac, gy)
+
+    return step
+
+
+def time_cpu(a, batch, reps):
+    step = cpu_step_factory(a, batch)
+    step()  # warm-up (BLAS threads, page faults)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    fwd, bwd = layer_ops(batch, a.channels, a.hw, a.nbits)
+    return (fwd + bwd) / statistics.median(ts) / 1e12, statistics.median(ts)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    b = a.cpu_sample_batch
+    step = cpu_step_factory(a, b)
+    for _ in range(min(a.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    dt = time.perf_counter() - t0
+    fwd, bwd = layer_ops(b, a.channels, a.hw, a.nbits)
+    value = (fwd + bwd) * a.steps / dt / 1e12
+    sample = f"{b} images per step of the same layer (numpy port of the reference algorithm, all host threads)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": dt / a.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (holding integers)",
+            "data": "synthetic", "config": workload_config(a),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        for row in open(self.path):
+            cols = [c.strip() for c in row.split(",")]
+            if len(cols) < 7:
+                continue
+            try:
+                sm.append(float(cols[0]))
+                mx.append(float(cols[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                               cols[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def event_time_ms(fn, iters, torch):
+    """Average device time of fn() over `iters` launches, CUDA events on the current stream."""
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    for _ in range(iters):
+        fn()
+    stop.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(stop) / iters
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import cim_quantization_b200 as cq
+    from cim_quantization_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+
+    adc = int(a.adcbits) if a.adcbits == int(a.adcbits) else a.adcbits
+    C, HW, B = a.channels, a.hw, a.batch
+    torch.manual_seed(1234 + rank)
+    layer = cq.Conv2dLSQCiM(C, C, (3, 3), (1, 1), (1, 1), (1, 1), 1, False, nbits_w=a.nbits, nbits_a=a.nbits,
+                            nbits_alpha=8, wbitslice=1, abitslice=1, xbar=a.xbar, adcbits=adc).to(dev).train()
+    with torch.no_grad():
+        torch.nn.init.kaiming_normal_(layer.weight)
+    x_host = torch.relu(torch.randn(B, C, HW, HW)).pin_memory()
+    gy_host = torch.randn(B, C, HW, HW).pin_memory()
+    x = x_host.to(dev).requires_grad_(True)
+    gy = gy_host.to(dev)
+    layer(x.detach())  # lazy initialisation of the step sizes (first training batch, lsq.py:532-563)
+    if world > 1:  # identical parameters on every rank, as DDP's initial broadcast does
+        for p in layer.parameters():
+            dist.broadcast(p.data, 0)
+    params = [p for p in layer.parameters()]
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+
+    def step():
+        for p in params:
+            p.grad = None
+        x.grad = None
+        y = layer(x)
+        y.backward(gy)
+        if world > 1:  # one flat all-reduce of all parameter gradients (weights + step sizes)
+            torch.cat([p.grad.reshape(-1) for p in params], out=flat)
+            dist.all_reduce(flat)
+        return y
+
+    L.launch_counter = 0
+    step()
+    launches_per_step = L.launch_counter
+    for _ in range(max(a.warmup, 3) - 1):
+        step()
+    torch.cuda.synchronize()
+
+    runner = step
+    graph = None
+    if not a.no_graph and world == 1:
+        try:  # replay the whole step as one CUDA graph: no launch gaps, no host work in the timed region
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            runner = graph.replay
+            runner()
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] CUDA graph capture failed ({e!r}); timing eager launches", file=sys.stderr)
+            graph, runner = None, step
+
+    # ---- timed region: exactly K steps between barrier + synchronize, CUDA events, max over ranks
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        start.record()
+        for _ in range(a.steps):
+            runner()
+        stop.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    ms = start.elapsed_time(stop)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    fwd_ops, bwd_ops = layer_ops(B, C, HW, a.nbits)
+    ops_step = fwd_ops + bwd_ops
+    value = ops_step * world * a.steps / (ms * 1e-3) / 1e12
+
+    line = None
+    if rank == 0:
+        # ---- per-kernel device times (CUDA events, same process, same resident tensors)
+        spec = layer._spec(x)
+        info = L.layer_info(spec)
+        qp_a, qn_w, qp_w = 2 ** a.nbits - 1, -(2 ** (a.nbits - 1)), 2 ** (a.nbits - 1) - 1
+        with torch.no_grad():
+            s = L.step_sizes(layer.alpha_act.data, layer.alpha_weight.data, 1.0 / math.sqrt(x.numel() * qp_a),
+                             1.0 / math.sqrt(layer.weight.numel() * qp_w))
+            xd, wd = x.detach(), layer.weight.detach().contiguous()
+            xc = L.lsq_quantize(xd, s[0:1], 0, qp_a)
+            wc = L.lsq_quantize(wd, s[1:2], qn_w, qp_w)
+            mask = layer.binary_mask.reshape(info.NSW, info.NSA).contiguous()
+            aq = layer._alpha_q().detach().contiguous() if layer.alpha_cim is not None else None
+            table = L.adc_table(spec, s, aq, mask)
+            wdig, wtiles = L.weight_prepare(spec, wc.view(C, -1))
+            out, state = L.conv_forward(spec, xc, wc.view(C, -1), wtiles, table, s, mask, save_state=True)
+            go = gy.view(B, C, -1)
+            gxq = torch.empty_like(xd)
+            it = max(3, min(a.steps, 10))
+            t_q = event_time_ms(lambda: L.lsq_quantize(xd, s[0:1], 0, qp_a), it, torch)
+            t_qb = event_time_ms(lambda: L.lsq_backward(gxq, xd, s[0:1], 0, qp_a, 1e-3), it, torch)
+            t_f = event_time_ms(lambda: L.conv_forward(spec, xc, wc.view(C, -1), wtiles, table, s, mask,
+                                                       save_state=True), it, torch)
+            t_fi = event_time_ms(lambda: L.conv_forward(spec, xc, wc.view(C, -1), wtiles, table, s, mask,
+                                                        save_state=False), it, torch)
+            t_b = event_time_ms(lambda: L.conv_backward(spec, go, xc, wdig, state, s, mask,
+                                                        need_alpha=aq is not None), it, torch)
+        n = x.numel()
+        int8_peak = 2.0 * bf16_peak  # no measured int8 peak: 2x the measured dense bf16 rate
+        kernels = {
+            "lsq_quantize_x": {"ms": t_q, "GB/s": 5.0 * n / t_q / 1e6, "frac_hbm": 5.0 * n / t_q / 1e6 / hbm_peak},
+            "lsq_backward_x": {"ms": t_qb, "GB/s": 12.0 * n / t_qb / 1e6, "frac_hbm": 12.0 * n / t_qb / 1e6 / hbm_peak},
+            "conv_forward_train(tcgen05=%d)" % info.tc_forward: {"ms": t_f, "TOPS": fwd_ops / t_f / 1e9,
+                                                                 "frac_int8_tc": fwd_ops / t_f / 1e9 / int8_peak},
+            "conv_forward_infer": {"ms": t_fi, "TOPS": fwd_ops / t_fi / 1e9,
+                                   "frac_int8_tc": fwd_ops / t_fi / 1e9 / int8_peak},
+            "conv_backward": {"ms": t_b, "TFLOP/s": bwd_ops / t_b / 1e9, "frac_bf16_tc": bwd_ops / t_b / 1e9 / bf16_peak},
+        }
+        # dominant kernel of the step
+        if t_b >= t_f:
+            roof = {"kernel": "conv_backward (CUDA-core dgrad/wgrad/alpha-grad)", "bound": "tensor",
+                    "achieved": bwd_ops / t_b / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
+                    "frac": bwd_ops / t_b / 1e9 / bf16_peak, "traffic": None, "peak_source": peak_src}
+        else:
+            roof = {"kernel": "conv_forward", "bound": "tensor", "achieved": fwd_ops / t_f / 1e9, "peak": int8_peak,
+                    "unit": "TOPS", "frac": fwd_ops / t_f / 1e9 / int8_peak, "traffic": None,
+                    "peak_source": peak_src + " x2 for int8"}
+
+        # ---- end to end through the module surface with HOST buffers (pinned), copies inside the timed region
+        gw_host = torch.empty_like(layer.weight, device="cpu").pin_memory()
+        small_host = torch.empty(flat.numel() - layer.weight.numel(), device="cpu").pin_memory()
+
+        def e2e_step():
+            xin = x_host.to(dev, non_blocking=True).requires_grad_(True)
+            gyin = gy_host.to(dev, non_blocking=True)
+            for p in params:
+                p.grad = None
+            layer(xin).backward(gyin)
+            gw_host.copy_(layer.weight.grad, non_blocking=True)
+            small_host.copy_(torch.cat([p.grad.reshape(-1) for p in params if p is not layer.weight]),
+                             non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        e2e_iters = max(3, min(a.steps, 10))
+        e2e_ms = event_time_ms(e2e_step, e2e_iters, torch)
+        e2e = {"value": ops_step / (e2e_ms * 1e-3) / 1e12, "unit": UNIT,
+               "h2d_bytes_per_step": int(x_host.numel() * 4 + gy_host.numel() * 4),
+               "d2h_bytes_per_step": int(gw_host.numel() * 4 + small_host.numel() * 4), "n_gpus": 1,
+               "ms_per_step": e2e_ms}
+
+        cpu = None
+        if not a.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, sec = time_cpu(a, a.cpu_sample_batch, 3)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{a.cpu_sample_batch} images of the same layer per step, median of 3 "
+                             f"({sec:.2f} s/step), numpy port of the reference algorithm"}
+        clocks = clk.summary()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8 x s8 -> s32 (forward), f32 (backward)", "data": "synthetic",
+                "config": dict(workload_config(a), cuda_graph=graph is not None,
+                               tcgen05_forward=bool(info.tc_forward)),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps),
+                "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
+                "ops_per_step": {"forward": fwd_ops, "backward": bwd_ops}}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,12 @@ EXPORTS = {
 }
 
 _lib = None
+launch_counter = 0  # kernels launched by this binding since the caller last reset it (bench.py: gpu_launches)
+
+
+def _count(n: int):
+    global launch_counter
+    launch_counter += n
 
 
 def load():
@@ -154,6 +160,7 @@ def layer_info(spec: LayerSpec) -> CimqInfo:
 def step_sizes(alpha_act, alpha_weight, ga: float, gw: float):
     s = torch.empty(2, dtype=torch.float32, device=alpha_act.device)
     _check(load().cimq_step_sizes(_ptr(alpha_act), _ptr(alpha_weight), ga, gw, _ptr(s), _stream()))
+    _count(1)
     return s
 
 
@@ -162,12 +169,14 @@ def lsq_quantize(x, s_elem, qn: int, qp: int, from_fakequant: bool = False):
     codes = torch.empty(x.shape, dtype=torch.uint8 if qn >= 0 else torch.int8, device=x.device)
     fn = load().cimq_codes_from_fakequant if from_fakequant else load().cimq_lsq_quantize
     _check(fn(_ptr(x), x.numel(), _ptr(s_elem), qn, qp, _ptr(codes), _stream()))
+    _count(1 if x.numel() % 16 == 0 else 2)
     return codes
 
 
 def lsq_fakequant(x, s_elem, qn: int, qp: int, rescale: bool):
     y = torch.empty_like(x)
     _check(load().cimq_lsq_fakequant(_ptr(x), x.numel(), _ptr(s_elem), qn, qp, int(rescale), _ptr(y), _stream()))
+    _count(1)
     return y
 
 
@@ -177,6 +186,7 @@ def lsq_backward(grad_xq, x, s_elem, qn: int, qp: int, g: float):
     ws = torch.empty(load().cimq_lsq_backward_workspace_bytes(x.numel()), dtype=torch.uint8, device=x.device)
     _check(load().cimq_lsq_backward(_ptr(grad_xq), _ptr(x), x.numel(), _ptr(s_elem), qn, qp, g, _ptr(gx),
                                     _ptr(galpha), _ptr(ws), _stream()))
+    _count(2)
     return gx, galpha
 
 
@@ -186,6 +196,7 @@ def adc_table(spec: LayerSpec, s, alpha_q, binary_mask, status=None):
     layer = spec.c_layer()
     _check(load().cimq_adc_table(C.byref(layer), _ptr(s), _ptr(alpha_q), _ptr(binary_mask), _ptr(table),
                                  _ptr(status), _stream()))
+    _count(1)
     return table
 
 
@@ -197,6 +208,7 @@ def weight_prepare(spec: LayerSpec, wcodes, want_digits=True, want_tiles=True):
               if (want_tiles and info.wtiles_bytes > 0) else None)
     layer = spec.c_layer()
     _check(load().cimq_weight_prepare(C.byref(layer), _ptr(wcodes), _ptr(wdigits), _ptr(wtiles), _stream()))
+    _count((1 if wdigits is not None else 0) + (2 if wtiles is not None else 0))
     return wdigits, wtiles
 
 
@@ -208,6 +220,7 @@ def conv_forward(spec: LayerSpec, xcodes, wcodes, wtiles, table, s, binary_mask,
     layer = spec.c_layer()
     _check(load().cimq_conv_forward(C.byref(layer), _ptr(xcodes), _ptr(wcodes), _ptr(wtiles), _ptr(table), _ptr(s),
                                     _ptr(binary_mask), _ptr(out), _ptr(state), flags, _stream()))
+    _count(1)
     return out, state
 
 
@@ -225,6 +238,7 @@ def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, state, s, binary_m
     _check(load().cimq_conv_backward(C.byref(layer), _ptr(grad_out), _ptr(xcodes), _ptr(wdigits), _ptr(state),
                                      _ptr(s), _ptr(binary_mask), _ptr(gxq), _ptr(gwq), _ptr(galpha), _ptr(ws),
                                      flags, _stream()))
+    _count(2 + (2 if need_input else 0) + (2 if galpha is not None else 0))
     return gxq, gwq, galpha
 
 

@@ -360,13 +360,16 @@ def test_wide_adc_equals_dense_conv_full_size():
     mask = _mask(cfg)
     table = L.adc_table(spec, s, None, mask)
     wdigits, wtiles = L.weight_prepare(spec, wc.reshape(C, -1))
-    torch.backends.cudnn.allow_tf32 = False  # exact fp32 reference conv
+    # exact reference: im2col + fp32 SGEMM on small integers (cuDNN may pick an inexact Winograd kernel)
+    torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    dense = torch.nn.functional.conv2d(xc.float(), wc.float(), padding=1)
+    cols = torch.nn.functional.unfold(xc.float(), 3, padding=1)  # [B, F, L]
+    dense = torch.matmul(wc.float().view(C, -1), cols).view(B, C, HW, HW)
+    del cols
     for flags in (0, L.FLAG_FORCE_SIMT):
         out, state = L.conv_forward(spec, xc, wc.reshape(C, -1), wtiles, table, s, mask, save_state=True,
                                     flags=flags)
-        assert torch.equal(out.view_as(dense), dense)
+        assert int((out.view_as(dense) != dense).sum()) == 0
         assert int(state.count_nonzero()) == 0  # nothing clipped
     go = torch.randn(B, C, HW * HW, device="cuda", generator=g)
     gxq, gwq, _ = L.conv_backward(spec, go, xc, wdigits, state, s, mask, need_alpha=False)
