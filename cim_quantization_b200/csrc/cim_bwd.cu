@@ -69,6 +69,46 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_kernel(Geo g, int m_per
   }
 }
 
+// Fast path for layers whose code bits fit one state word (pairs <= 10): one state load + one go load
+// per (pixel, crossbar, channel), PAIRS register accumulators, HBM-bound (8 B per element).
+template <int PAIRS>
+__global__ void __launch_bounds__(256) bwd_alpha_partial_w1_kernel(Geo g, int m_per_split,
+                                                                   const float *__restrict__ go,
+                                                                   const uint32_t *__restrict__ state,
+                                                                   float *__restrict__ partial) {
+  __shared__ float red[8][PAIRS];
+  const int c = blockIdx.x, i = blockIdx.y, ms = blockIdx.z;
+  const int64_t mbeg = (int64_t)ms * m_per_split;
+  const int64_t mend = min((int64_t)g.M, mbeg + m_per_split);
+  const uint32_t *st = state + ((int64_t)i * g.Cout + c) * g.M;  // state_words == 1
+  float acc[PAIRS];
+#pragma unroll
+  for (int q = 0; q < PAIRS; ++q) acc[q] = 0.0f;
+  for (int64_t m = mbeg + threadIdx.x; m < mend; m += 256) {
+    const int b = (int)(m / g.L), l = (int)(m % g.L);
+    const float gv = __ldg(&go[((int64_t)b * g.Cout + c) * g.L + l]);
+    const uint32_t w = __ldg(&st[m]);
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) {
+      // +gv if bit q (code +1), -gv if bit PAIRS+q (code -1)
+      const float sgn = (float)((int)((w >> q) & 1u) - (int)((w >> (PAIRS + q)) & 1u));
+      acc[q] = fmaf(sgn, gv, acc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PAIRS; ++q) {
+    float v = acc[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < PAIRS) {
+    float v = 0.0f;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    partial[(int64_t)ms * table_entries(g) + ((int64_t)i * PAIRS + threadIdx.x) * g.Cout + c] = v;
+  }
+}
+
 __global__ void bwd_alpha_finish_kernel(Geo g, int nsplit, float gfac, const int8_t *__restrict__ mask,
                                         const float *__restrict__ partial, float *__restrict__ galpha) {
   const int64_t n = table_entries(g);
@@ -318,7 +358,12 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
 
   if (galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
     dim3 grid(g.Cout, g.NX, p.alpha_splits);
-    bwd_alpha_partial_kernel<<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
+    if (g.state_words == 1 && g.pairs == 9)
+      bwd_alpha_partial_w1_kernel<9><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
+    else if (g.state_words == 1 && g.pairs == 4)
+      bwd_alpha_partial_w1_kernel<4><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
+    else
+      bwd_alpha_partial_kernel<<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
     CIMQ_CUDA_OK(cudaGetLastError());
     // 1/sqrt(ps.numel() * Qp_adc) with Qp_adc = 1 (lsq.py:323, 330)
     double numel = (double)g.B * g.NX * g.NSW * g.NSA * g.L * g.Cout;
