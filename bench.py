@@ -331,7 +331,7 @@ def run_ours(a):
                                                        save_state=True), it, torch)
             t_fi = event_time_ms(lambda: L.conv_forward(spec, xc, wc.view(C, -1), wtiles, table, s, mask,
                                                         save_state=False), it, torch)
-            t_b = event_time_ms(lambda: L.conv_backward(spec, go, xc, wdig, state, s, mask,
+            t_b = event_time_ms(lambda: L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask,
                                                         need_alpha=aq is not None), it, torch)
         n = x.numel()
         int8_peak = 2.0 * bf16_peak  # no measured int8 peak: 2x the measured dense bf16 rate

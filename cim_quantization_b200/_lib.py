@@ -29,7 +29,7 @@ class CimqLayer(C.Structure):
 class CimqInfo(C.Structure):
     """``cimq_info_t``."""
     _fields_ = ([(n, C.c_int32) for n in ("out_hw", "L", "M", "F", "NX", "NSW", "NSA", "pairs", "state_words",
-                                          "tc_forward")] +
+                                          "tc_forward", "tc_backward", "reserved_")] +
                 [(n, C.c_int64) for n in ("state_bytes", "table_bytes", "wdigits_bytes", "wtiles_bytes",
                                           "bwd_workspace_bytes", "psum_count")])
 
@@ -56,7 +56,7 @@ EXPORTS = {
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "cimq_conv_backward": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_uint32, C.c_void_p]),
+                                     C.c_void_p, C.c_uint32, C.c_void_p]),
     "cimq_conv_psums": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cimq_conv_psum_abs_sums": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
@@ -224,7 +224,7 @@ def conv_forward(spec: LayerSpec, xcodes, wcodes, wtiles, table, s, binary_mask,
     return out, state
 
 
-def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, state, s, binary_mask, need_alpha: bool,
+def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, wtiles, state, s, binary_mask, need_alpha: bool,
                   need_input: bool = True, flags: int = 0):
     info = layer_info(spec)
     dev = grad_out.device
@@ -235,8 +235,8 @@ def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, state, s, binary_m
               if need_alpha else None)
     ws = torch.empty(info.bwd_workspace_bytes, dtype=torch.uint8, device=dev)
     layer = spec.c_layer()
-    _check(load().cimq_conv_backward(C.byref(layer), _ptr(grad_out), _ptr(xcodes), _ptr(wdigits), _ptr(state),
-                                     _ptr(s), _ptr(binary_mask), _ptr(gxq), _ptr(gwq), _ptr(galpha), _ptr(ws),
+    _check(load().cimq_conv_backward(C.byref(layer), _ptr(grad_out), _ptr(xcodes), _ptr(wdigits), _ptr(wtiles),
+                                     _ptr(state), _ptr(s), _ptr(binary_mask), _ptr(gxq), _ptr(gwq), _ptr(galpha), _ptr(ws),
                                      flags, _stream()))
     _count(2 + (2 if need_input else 0) + (2 if galpha is not None else 0))
     return gxq, gwq, galpha

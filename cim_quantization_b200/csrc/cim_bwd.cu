@@ -84,15 +84,31 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_w1_kernel(Geo g, int m_
   float acc[PAIRS];
 #pragma unroll
   for (int q = 0; q < PAIRS; ++q) acc[q] = 0.0f;
-  for (int64_t m = mbeg + threadIdx.x; m < mend; m += 256) {
-    const int b = (int)(m / g.L), l = (int)(m % g.L);
-    const float gv = __ldg(&go[((int64_t)b * g.Cout + c) * g.L + l]);
-    const uint32_t w = __ldg(&st[m]);
+  // four independent (state, go) load pairs in flight per thread; the image index advances incrementally
+  // (no per-element division)
+  int64_t m = mbeg + threadIdx.x;
+  int b = (int)(m / g.L), l = (int)(m % g.L);
+  const float *gbase = go + (int64_t)c * g.L;
+  const int64_t gimg = (int64_t)g.Cout * g.L;
+  for (; m < mend; m += 1024) {
+    float gv[4];
+    uint32_t w[4];
 #pragma unroll
-    for (int q = 0; q < PAIRS; ++q) {
-      // +gv if bit q (code +1), -gv if bit PAIRS+q (code -1)
-      const float sgn = (float)((int)((w >> q) & 1u) - (int)((w >> (PAIRS + q)) & 1u));
-      acc[q] = fmaf(sgn, gv, acc[q]);
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = m + u * 256 < mend;
+      gv[u] = ok ? __ldg(gbase + (int64_t)b * gimg + l) : 0.0f;
+      w[u] = ok ? __ldg(st + m + u * 256) : 0u;
+      l += 256;
+      while (l >= g.L) { l -= g.L; ++b; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int q = 0; q < PAIRS; ++q) {
+        // +gv if bit q (code +1), -gv if bit PAIRS+q (code -1)
+        const float sgn = (float)((int)((w[u] >> q) & 1u) - (int)((w[u] >> (PAIRS + q)) & 1u));
+        acc[q] = fmaf(sgn, gv[u], acc[q]);
+      }
     }
   }
 #pragma unroll
@@ -185,30 +201,55 @@ __global__ void __launch_bounds__(128) bwd_input_kernel(Geo g, const float *__re
   }
 }
 
-// col2im (nn.Fold, lsq.py:380-382) as a gather: one thread per input element.
-__global__ void col2im_kernel(Geo g, const float *__restrict__ gxuT, float *__restrict__ gx) {
+// col2im (nn.Fold, lsq.py:380-382) as a gather: one thread per input element, the K*K tap loads are
+// predicated and independent (K is a template parameter so they unroll); reads of one tap are coalesced
+// (consecutive input columns -> consecutive output pixels of one gxuT row).  K == 0: runtime kernel size.
+template <int KT>
+__global__ void __launch_bounds__(256) col2im_kernel(Geo g, const float *__restrict__ gxuT,
+                                                     float *__restrict__ gx) {
+  const int K = KT > 0 ? KT : g.K;
   const int64_t n = (int64_t)g.B * g.Cin * g.H * g.W;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    int ix = (int)(idx % g.W), iy = (int)((idx / g.W) % g.H);
-    int ci = (int)((idx / ((int64_t)g.W * g.H)) % g.Cin), b = (int)(idx / ((int64_t)g.W * g.H * g.Cin));
+    const int ix = (int)(idx % g.W);
+    const int t1 = (int)(idx / g.W);
+    const int iy = t1 % g.H;
+    const int t2 = t1 / g.H;
+    const int ci = t2 % g.Cin, b = t2 / g.Cin;
+    const float *base = gxuT + (int64_t)ci * K * K * g.M + (int64_t)b * g.L;
     float v = 0.0f;
-    for (int ky = 0; ky < g.K; ++ky) {
-      int ty = iy + g.pad - ky;
-      if (ty < 0 || ty % g.stride) continue;
-      int oy = ty / g.stride;
-      if (oy >= g.OH) continue;
-      for (int kx = 0; kx < g.K; ++kx) {
-        int tx = ix + g.pad - kx;
-        if (tx < 0 || tx % g.stride) continue;
-        int ox = tx / g.stride;
-        if (ox >= g.OW) continue;
-        int f = ci * g.KK + ky * g.K + kx;
-        v += gxuT[(int64_t)f * g.M + (int64_t)b * g.L + oy * g.OW + ox];
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int ty = iy + g.pad - ky;
+      int oy = ty;
+      bool oky = ty >= 0;
+      if (g.stride != 1) { oky = oky && (ty % g.stride == 0); oy = ty / g.stride; }
+      oky = oky && oy < g.OH;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int tx = ix + g.pad - kx;
+        int ox = tx;
+        bool ok = oky && tx >= 0;
+        if (g.stride != 1) { ok = ok && (tx % g.stride == 0); ox = tx / g.stride; }
+        ok = ok && ox < g.OW;
+        const float t = ok ? __ldg(base + (int64_t)(ky * K + kx) * g.M + oy * g.OW + ox) : 0.0f;
+        v += t;
       }
     }
     gx[idx] = v;
   }
+}
+
+inline int launch_col2im(const Geo &g, const float *gxuT, float *gx, cudaStream_t st) {
+  const int64_t n = (int64_t)g.B * g.Cin * g.H * g.W;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  if (g.K == 3) col2im_kernel<3><<<(int)blocks, 256, 0, st>>>(g, gxuT, gx);
+  else if (g.K == 1) col2im_kernel<1><<<(int)blocks, 256, 0, st>>>(g, gxuT, gx);
+  else if (g.K == 5) col2im_kernel<5><<<(int)blocks, 256, 0, st>>>(g, gxuT, gx);
+  else col2im_kernel<0><<<(int)blocks, 256, 0, st>>>(g, gxuT, gx);
+  CIMQ_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -318,9 +359,10 @@ inline BwdPlan make_plan(const Geo &g) {
   BwdPlan p;
   const int target_blocks = 148 * 4;
   // alpha: grid (Cout, NX, splits)
-  int as = (target_blocks + g.Cout * g.NX - 1) / (g.Cout * g.NX);
-  int max_as = (g.M + 1023) / 1024;
-  as = as < 1 ? 1 : as; if (as > max_as) as = max_as; if (as > 64) as = 64;
+  // ~16 pixels per thread (256 threads/block): short dependent chains, many blocks
+  int as = (g.M + 4095) / 4096;
+  (void)target_blocks;
+  as = as < 1 ? 1 : as; if (as > 64) as = 64;
   p.alpha_splits = as;
   p.alpha_m_per_split = (g.M + as - 1) / as;
   int rowsmax = g.xbar < g.F ? g.xbar : g.F;
@@ -336,7 +378,9 @@ inline BwdPlan make_plan(const Geo &g) {
   auto align = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
   p.off_gxu = 0;
   p.off_wpart = align((int64_t)g.F * g.M * 4);
-  p.off_apart = p.off_wpart + align((int64_t)p.w_splits * g.F * g.Cout * 4);
+  int64_t wpart = (int64_t)p.w_splits * g.F * g.Cout * 4;
+  if (tc_backward_supported(g) && bwd_tc_partial_bytes(g) > wpart) wpart = bwd_tc_partial_bytes(g);
+  p.off_apart = p.off_wpart + align(wpart);
   p.total = p.off_apart + align((int64_t)p.alpha_splits * table_entries(g) * 4);
   return p;
 }
@@ -346,9 +390,11 @@ inline BwdPlan make_plan(const Geo &g) {
 int64_t conv_backward_ws_bytes(const Geo &g) { return make_plan(g).total; }
 
 int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, const float *wdigits,
-                         const uint32_t *state, const float *s, const int8_t *mask, float *gxq, float *gwq,
-                         float *galpha, void *ws, uint32_t, cudaStream_t st) {
-  CIMQ_REQUIRE(go && xcodes && wdigits && state && s && mask && ws, "conv_backward: NULL argument");
+                         const void *wtiles, const uint32_t *state, const float *s, const int8_t *mask, float *gxq,
+                         float *gwq, float *galpha, void *ws, uint32_t flags, cudaStream_t st) {
+  CIMQ_REQUIRE(go && xcodes && state && s && mask && ws, "conv_backward: NULL argument");
+  const bool use_tc = !(flags & CIMQ_FLAG_FORCE_SIMT) && wtiles != nullptr && tc_backward_supported(g);
+  CIMQ_REQUIRE(use_tc || wdigits != nullptr, "conv_backward: wdigits is NULL");
   CIMQ_REQUIRE(g.pairs <= kMaxPairs, "too many slice pairs");
   const BwdPlan p = make_plan(g);
   char *base = reinterpret_cast<char *>(ws);
@@ -372,20 +418,23 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
     bwd_alpha_finish_kernel<<<(int)((n + 127) / 128), 128, 0, st>>>(g, p.alpha_splits, gfac, mask, apart, galpha);
     CIMQ_CUDA_OK(cudaGetLastError());
   }
-  if (gxq != nullptr) {
+  if (gxq != nullptr && use_tc) {
+    const WtLayout wl = wt_layout(g);
+    if (launch_bwd_input_tc(g, go, state, reinterpret_cast<const uint8_t *>(wtiles) + wl.bwd_off, s, mask, gxuT, st))
+      return 1;
+    if (launch_col2im(g, gxuT, gxq, st)) return 1;
+  } else if (gxq != nullptr) {
     size_t smem = (size_t)g.NSW * g.Cout * 32 * sizeof(float);
     CIMQ_REQUIRE(smem <= 200 * 1024, "conv_backward: NSW*Cout too large for the SIMT kernel");
     CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((g.M + 31) / 32, g.NX, p.ftiles);
     bwd_input_kernel<<<grid, 128, smem, st>>>(g, go, wdigits, state, s, mask, gxuT);
     CIMQ_CUDA_OK(cudaGetLastError());
-    int64_t n = (int64_t)g.B * g.Cin * g.H * g.W;
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    col2im_kernel<<<blocks, 256, 0, st>>>(g, gxuT, gxq);
-    CIMQ_CUDA_OK(cudaGetLastError());
+    if (launch_col2im(g, gxuT, gxq, st)) return 1;
   }
-  if (gwq != nullptr) {
+  if (gwq != nullptr && use_tc) {
+    if (launch_bwd_weight_tc(g, go, xcodes, state, s, mask, wpart, gwq, st)) return 1;
+  } else if (gwq != nullptr) {
     size_t smem = (size_t)32 * g.NSA * 32 * sizeof(float);
     CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(g.NX * p.ftiles, (g.Cout + 31) / 32, p.w_splits);

@@ -1,0 +1,723 @@
+// tcgen05 backward kernels of the CiM convolution (get_cim_output_signed.backward, lsq.py:244-386).
+//
+// Both GEMMs multiply a real-valued operand (grad_out masked by the STE clip bits) with an exact small
+// integer operand (weight or activation digit planes).  fp32-level accuracy (1e-5 tolerance) on bf16
+// tensor cores is obtained by splitting only the real operand into three bf16 terms
+// (v = hi + mid + lo exactly covers the 24-bit fp32 mantissa); the integer operand is exact in bf16 and
+// accumulation is fp32 in TMEM.  The masked operand is built on the fly in shared memory from grad_out
+// and the 1-bit-per-partial-sum clip state the forward stored -- the 6-D tensors of the reference never
+// exist.
+//
+//   dgrad  D[128 pixels x Nf crossbar rows] = sum_k sum_split A'_{k,split}[128 x Cout] * W_k[Nf x Cout]^T
+//          A'_k[m,co] = go[m,co] * sum_j pass[m,i,k,j,co] * mask[k,j] * 2^(-abs*j)
+//          -> gxuT[f][m] (then col2im)
+//   wgrad  D_i[128 crossbar rows x Cout] += sum_j sum_split X_j[128 x 128 pixels] * G'_{j,split}[Cout x 128 pixels]^T
+//          G'_j[m,co] = go[m,co] * sum_k pass[m,i,k,j,co] * mask[k,j] * 2^(-wbs*k),  X_j = activation digit plane
+//          accumulated over all pixel tiles of the CTA in TMEM, one partial [F x Cout] per CTA
+//
+// Warp roles (16 warps): 0-7 producers, 8-11 epilogue (one per TMEM lane quarter), 12 MMA issuer.
+#include <string.h>
+
+#include "cim_tc_layout.cuh"
+#include "tc_ptx.cuh"
+
+namespace cimq {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int kProducerWarps = 8;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kEpilogueWarp0 = 8;
+constexpr int kEpilogueWarps = 4;
+constexpr int kMmaWarp = 12;
+constexpr int kThreads = 512;
+constexpr int kMaxStages = 4;
+constexpr int kMaxPairs = 64;
+constexpr size_t kSmemBudget = 227 * 1024 - 1024;
+constexpr size_t kBarrierBytes = 1024;  // barriers + tmem slot + slice-weight table
+
+struct BwdParams {
+  Geo g;
+  int Kc;           // Cout
+  int Nf;           // dgrad N: padded crossbar rows
+  int mtiles, stages;
+  uint32_t a_bytes, b_bytes, stage_bytes, tmem_cols;
+  int nxg, chunk0;  // wgrad: crossbars handled by this launch's blockIdx.y group
+  const float *go;
+  const uint32_t *state;
+  const uint8_t *xcodes;
+  const uint8_t *wtb;  // dgrad B tiles (bf16)
+  const float *s;
+  const int8_t *mask;
+  float *out;          // dgrad: gxuT [F][M]; wgrad: partial [ctas][F][Cout]
+};
+
+// two fp32 -> packed bf16x2 (first argument in the upper half)
+__device__ __forceinline__ uint32_t cvt_bf16x2(float upper, float lower) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
+  return d;
+}
+// (v0, v1) -> three packed bf16x2 words with hi + mid + lo == v exactly (24-bit mantissa, up to underflow);
+// v0 lands in the low half (lower K index)
+__device__ __forceinline__ void split3x2(float v0, float v1, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
+  hi = cvt_bf16x2(v1, v0);
+  const float r0 = v0 - __uint_as_float(hi << 16), r1 = v1 - __uint_as_float(hi & 0xffff0000u);
+  mid = cvt_bf16x2(r1, r0);
+  const float q0 = r0 - __uint_as_float(mid << 16), q1 = r1 - __uint_as_float(mid & 0xffff0000u);
+  lo = cvt_bf16x2(q1, q0);
+}
+
+struct Carve {
+  uint8_t *stage_base;
+  uint32_t full0, empty0, tfull0, tempty0;
+  uint32_t *tmem_slot;
+  float *wtab;    // [pairs] slice weights
+  int4 *pixtab;   // [2][16] wgrad: {image, output row, first output column, fast-path flag} per 8-pixel group
+};
+
+__device__ __forceinline__ Carve carve_smem(uint8_t *smem_raw, int stages, uint32_t stage_bytes) {
+  Carve c;
+  c.stage_base = smem_raw;
+  uint8_t *aux = smem_raw + (size_t)stages * stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(aux);
+  c.full0 = smem_u32(bars);
+  c.empty0 = c.full0 + 8 * kMaxStages;
+  c.tfull0 = c.empty0 + 8 * kMaxStages;
+  c.tempty0 = c.tfull0 + 16;
+  c.tmem_slot = reinterpret_cast<uint32_t *>(aux + 112);
+  c.wtab = reinterpret_cast<float *>(aux + 128);     // 64 floats
+  c.pixtab = reinterpret_cast<int4 *>(aux + 512);    // 2 x 16 x 16 bytes
+  return c;
+}
+
+// Compile-time description of where the STE clip bits live in the ADC state words.
+template <int NSW, int NSA, bool TERN>
+struct ClipBits {
+  static constexpr int PAIRS = NSW * NSA;
+  static constexpr int SWORDS = ((TERN ? 3 : 1) * PAIRS + 31) / 32;  // state words per (crossbar, channel, pixel)
+  static constexpr int CLIP0 = TERN ? 2 * PAIRS : 0;                 // first clip bit
+  static constexpr int CW0 = CLIP0 >> 5;                             // first word holding clip bits
+  static constexpr int CWN = ((CLIP0 + PAIRS - 1) >> 5) - CW0 + 1;   // words holding clip bits (1 or 2)
+  static constexpr int CB = CLIP0 - 32 * CW0;                        // clip bit 0 inside word CW0
+  static_assert(CWN <= 2, "clip bits span more than two state words");
+};
+// sum over t < N of (clip bit (start + t*stride) set ? 0 : w[t]); the clip bits of one (crossbar, channel,
+// pixel) live in sw[0..CWN)
+template <int N, int CWN>
+__device__ __forceinline__ float pass_weight(const uint32_t (&sw)[CWN], int start, int stride, const float (&w)[N]) {
+  float acc = 0.0f;
+  if constexpr (CWN == 1) {
+    const uint32_t win = sw[0] >> start;  // all clip bits are in one word: one shift, constant bit tests
+#pragma unroll
+    for (int t = 0; t < N; ++t) acc += ((win >> (t * stride)) & 1u) ? 0.0f : w[t];
+  } else {
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+      const int idx = start + t * stride;
+      const uint32_t bit = (idx >= 32 ? (sw[1] >> (idx - 32)) : (sw[0] >> idx)) & 1u;
+      acc += bit ? 0.0f : w[t];
+    }
+  }
+  return acc;
+}
+
+// =====================================================================================================
+// dgrad
+// =====================================================================================================
+template <int NSW, int NSA, bool TERN>
+__global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdParams P) {
+  using CBits = ClipBits<NSW, NSA, TERN>;
+  const Geo &g = P.g;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const Carve cv = carve_smem(smem_raw, P.stages, P.stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Kc = P.Kc, Nf = P.Nf;
+  const uint32_t sbo = (uint32_t)Kc * 16u;  // 8 rows x Kc bf16
+
+  if (threadIdx.x == 0) {
+    for (int sidx = 0; sidx < P.stages; ++sidx) {
+      mbar_init(cv.full0 + 8 * sidx, kProducerThreads + 1);
+      mbar_init(cv.empty0 + 8 * sidx, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(cv.tfull0 + 8 * b, 1);
+      mbar_init(cv.tempty0 + 8 * b, kEpilogueWarps);
+    }
+    fence_barrier_init();
+  }
+  if (threadIdx.x < g.pairs) {  // mask[k][j] * 2^(-abs*j)  (lsq.py:306, 373-374)
+    const int j = threadIdx.x % g.NSA;
+    cv.wtab[threadIdx.x] = (float)P.mask[threadIdx.x] * exp2f(-(float)(g.abs_ * j));
+  }
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(cv.tmem_slot), P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *cv.tmem_slot;
+  const int rows_full = g.xbar < g.F ? g.xbar : g.F;
+
+  if (warp < kProducerWarps) {
+    // ------------------------------------------------------------------ producers
+    // thread = (pixel row r, channel half h); per stage (crossbar i, weight slice k) it builds
+    // A'[r, co] = go[r, co] * sum_j pass * wx[k][j] for its Kc/2 channels in groups of 8 (one 16-byte
+    // store per bf16 term).  Loads of the next group are issued before the current one is processed.
+    const int r = threadIdx.x & 127;
+    const int h = threadIdx.x >> 7;
+    const int cpt = Kc >> 1;          // channels per thread
+    const int G = cpt >> 3;           // groups of 8 channels
+    uint32_t it = 0;
+    for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
+      const int64_t m = (int64_t)mt * kTcTileM + r;
+      const bool live = m < g.M;
+      const int b = live ? (int)(m / g.L) : 0, l = live ? (int)(m % g.L) : 0;
+      const float *gop = P.go + ((int64_t)b * g.Cout + h * cpt) * g.L + l;
+      const uint32_t *stp = P.state + (int64_t)CBits::CW0 * g.M + (live ? m : 0);
+      uint32_t sw_n[8][CBits::CWN];
+      float gv_n[8];
+      auto prefetch = [&](int i, int cg) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int co = h * cpt + cg + e;
+#pragma unroll
+          for (int w = 0; w < CBits::CWN; ++w)
+            sw_n[e][w] = live ? __ldg(stp + ((int64_t)(i * g.Cout + co) * CBits::SWORDS + w) * g.M) : 0xffffffffu;
+          gv_n[e] = live ? __ldg(gop + (int64_t)(cg + e) * g.L) : 0.0f;
+        }
+      };
+      prefetch(0, 0);
+      for (int i = 0; i < g.NX; ++i) {
+        for (int k = 0; k < NSW; ++k, ++it) {
+          const int sidx = it % P.stages;
+          const uint32_t use = it / P.stages;
+          mbar_wait(cv.empty0 + 8 * sidx, (use & 1) ^ 1);
+          uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
+          if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(cv.full0 + 8 * sidx, P.b_bytes);
+            bulk_copy_g2s(smem_u32(st_ptr + 3 * (size_t)P.a_bytes), P.wtb + (size_t)(i * NSW + k) * P.b_bytes,
+                          P.b_bytes, cv.full0 + 8 * sidx);
+          }
+          float wx[NSA];
+#pragma unroll
+          for (int j = 0; j < NSA; ++j) wx[j] = cv.wtab[k * NSA + j];
+          const int start = CBits::CB + k * NSA;
+          for (int cgi = 0; cgi < G; ++cgi) {
+            uint32_t sw[8][CBits::CWN];
+            float gv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              gv[e] = gv_n[e];
+#pragma unroll
+              for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = sw_n[e][w];
+            }
+            {  // next group in (i, k, cgi) order; state words do not depend on k (cache hits)
+              int ni = i, nc = cgi + 1;
+              if (nc == G) { nc = 0; if (k + 1 == NSW) ni = i + 1; }
+              if (ni < g.NX) prefetch(ni, nc * 8);
+            }
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              v[e] = gv[e] * pass_weight<NSA, CBits::CWN>(sw[e], start, 1, wx);
+            }
+            uint32_t hi[4], mid[4], lo[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo[e2]);
+            const uint32_t off = tc_tile_offset16(r, h * cpt + cgi * 8, kTcLBO, sbo);
+            *reinterpret_cast<uint4 *>(st_ptr + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(st_ptr + P.a_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+            *reinterpret_cast<uint4 *>(st_ptr + 2 * (size_t)P.a_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async();
+          mbar_arrive(cv.full0 + 8 * sidx);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_f32(kTcTileM, Nf);
+      const int ksteps = Kc >> 4;
+      uint32_t it = 0, acc_it = 0;
+      for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
+        for (int i = 0; i < g.NX; ++i, ++acc_it) {
+          const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
+          mbar_wait(cv.tempty0 + 8 * buf, (buse & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * Nf;
+          for (int k = 0; k < NSW; ++k, ++it) {
+            const int sidx = it % P.stages;
+            const uint32_t use = it / P.stages;
+            mbar_wait(cv.full0 + 8 * sidx, use & 1);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(cv.stage_base + (size_t)sidx * P.stage_bytes);
+            const uint32_t b0 = a0 + 3 * P.a_bytes;
+            for (int sp = 0; sp < 3; ++sp)
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t adesc = make_smem_desc(a0 + sp * P.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
+                const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
+                umma_f16(d_tmem, adesc, bdesc, idesc, (k | sp | ks) != 0 ? 1u : 0u);
+              }
+            umma_commit(cv.empty0 + 8 * sidx);
+          }
+          umma_commit(cv.tfull0 + 8 * buf);
+        }
+      }
+    }
+  } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + kEpilogueWarps) {
+    // ------------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const float scale = P.s[1] / (float)NSA;  // w_sl * s_w (lsq.py:252), mean over act slices (lsq.py:376)
+    uint32_t acc_it = 0;
+    for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
+      const int64_t m = (int64_t)mt * kTcTileM + r;
+      for (int i = 0; i < g.NX; ++i, ++acc_it) {
+        const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
+        const int lo = i * g.xbar;
+        const int rows = min(rows_full, g.F - lo);
+        mbar_wait(cv.tfull0 + 8 * buf, buse & 1);
+        tc_fence_after();
+        for (int c0 = 0; c0 < rows; c0 += 32) {
+          int v[32];
+          tmem_ld<32>(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * Nf + c0, v);
+          tmem_ld_wait();
+          if (m < g.M) {
+            float *dst = P.out + (int64_t)(lo + c0) * g.M + m;
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc)
+              if (c0 + cc < rows) dst[(int64_t)cc * g.M] = __int_as_float(v[cc]) * scale;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cv.tempty0 + 8 * buf);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, P.tmem_cols);
+  }
+}
+
+// =====================================================================================================
+// wgrad
+// =====================================================================================================
+constexpr int kWgLBO = 144;  // padded K-stride of the G' tiles: producer lanes run along K (bank-conflict free)
+
+template <int NSW, int NSA, bool TERN>
+__global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdParams P) {
+  using CBits = ClipBits<NSW, NSA, TERN>;
+  const Geo &g = P.g;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const Carve cv = carve_smem(smem_raw, P.stages, P.stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Kc = P.Kc;                            // Cout = UMMA N
+  const uint32_t a_sbo = 128u * 16u;              // X tile: 8 rows x 128 pixels bf16, LBO 128
+  const uint32_t b_sbo = 16u * (uint32_t)kWgLBO;  // G' tile: 16 k-groups of 144 bytes per 8 rows
+  const int i_begin = blockIdx.y * P.nxg;
+  const int i_end = min(g.NX, i_begin + P.nxg);
+
+  if (threadIdx.x == 0) {
+    for (int sidx = 0; sidx < P.stages; ++sidx) {
+      mbar_init(cv.full0 + 8 * sidx, kProducerThreads);
+      mbar_init(cv.empty0 + 8 * sidx, 1);
+    }
+    mbar_init(cv.tfull0, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < g.pairs) {  // mask[k][j] * 2^(-wbs*k)  (lsq.py:306, 363-364)
+    const int k = threadIdx.x / g.NSA;
+    cv.wtab[threadIdx.x] = (float)P.mask[threadIdx.x] * exp2f(-(float)(g.wbs * k));
+  }
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(cv.tmem_slot), P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *cv.tmem_slot;
+  const int rows_full = g.xbar < g.F ? g.xbar : g.F;
+  const bool has_work = blockIdx.x < P.mtiles;
+
+  if (warp < kProducerWarps) {
+    // ------------------------------------------------------------------ producers
+    const int tid = threadIdx.x;  // 0..255
+    const int fr = tid & 127;     // X tile: this thread's crossbar row
+    const bool aligned = (g.L % 8) == 0 && (g.OW % 8) == 0;
+    uint32_t it = 0;
+    int tpar = 0;
+    for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
+      const int64_t m0 = (int64_t)mt * kTcTileM;
+      // per 8-pixel group: image, output row, first output column; fast = one image row, fully valid, aligned
+      if (tid < 16) {
+        const int64_t m = m0 + tid * 8;
+        int4 e = make_int4(0, 0, 0, 0);
+        if (m < g.M) {
+          const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
+          e = make_int4(b, oy, ox, (aligned && m + 7 < g.M && ox + 7 < g.OW) ? 1 : 0);
+        } else {
+          e.w = -1;  // entirely past the end
+        }
+        cv.pixtab[tpar * 16 + tid] = e;
+      }
+      named_barrier_sync(1, kProducerThreads);
+      const int4 *ptab = cv.pixtab + tpar * 16;
+      for (int i = i_begin; i < i_end; ++i) {
+        const int lo = i * g.xbar;
+        const int rows = min(rows_full, g.F - lo);
+        const bool frow = fr < rows;
+        int ci = 0, ky = 0, kx = 0;
+        if (frow) { const int f = lo + fr; ci = f / g.KK; const int tap = f % g.KK; ky = tap / g.K; kx = tap % g.K; }
+        for (int j = 0; j < NSA; ++j, ++it) {
+          const int sidx = it % P.stages;
+          const uint32_t use = it / P.stages;
+          mbar_wait(cv.empty0 + 8 * sidx, (use & 1) ^ 1);
+          uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
+          // ---- X_j tile [128 crossbar rows x 128 pixels] (bf16 digits); item = (row fr, 8-pixel group pg)
+          const int sh = g.abs_ * j;
+#pragma unroll 2
+          for (int n = 0; n < 8; ++n) {
+            const int pg = (tid >> 7) + 2 * n;
+            const int4 pt = ptab[pg];
+            uint32_t c[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) c[e] = 0u;
+            if (frow && pt.w >= 0) {
+              if (pt.w == 1) {
+                const int iy = pt.y * g.stride - g.pad + ky;
+                if (iy >= 0 && iy < g.H) {
+                  const uint8_t *row = P.xcodes + (((int64_t)pt.x * g.Cin + ci) * g.H + iy) * g.W;
+                  const int ix0 = pt.z * g.stride - g.pad + kx;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const int ix = ix0 + e * g.stride;
+                    if (ix >= 0 && ix < g.W) c[e] = __ldg(row + ix);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int64_t m = m0 + pg * 8 + e;
+                  if (m < g.M) {
+                    const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
+                    const int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
+                    if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+                      c[e] = P.xcodes[(((int64_t)b * g.Cin + ci) * g.H + iy) * g.W + ix];
+                  }
+                }
+              }
+            }
+            uint32_t d[4];
+            if (g.amask == 1) {  // 1-bit digits: bf16(1) = 0x3F80, two per word with one multiply
+#pragma unroll
+              for (int e2 = 0; e2 < 4; ++e2)
+                d[e2] = (((c[2 * e2] >> sh) & 1u) | (((c[2 * e2 + 1] >> sh) & 1u) << 16)) * 0x3F80u;
+            } else {
+#pragma unroll
+              for (int e2 = 0; e2 < 4; ++e2)
+                d[e2] = cvt_bf16x2((float)((c[2 * e2 + 1] >> sh) & (uint32_t)g.amask),
+                                   (float)((c[2 * e2] >> sh) & (uint32_t)g.amask));
+            }
+            *reinterpret_cast<uint4 *>(st_ptr + tc_tile_offset16(fr, pg * 8, kTcLBO, a_sbo)) =
+                make_uint4(d[0], d[1], d[2], d[3]);
+          }
+          // ---- G'_j tiles (3 bf16 terms) [Cout x 128 pixels]; item = (channel co, 8-pixel group pg), lanes along pixels
+          uint8_t *gb = st_ptr + P.a_bytes;
+          float wv[NSW];
+#pragma unroll
+          for (int k = 0; k < NSW; ++k) wv[k] = cv.wtab[k * NSA + j];
+          const int pg = tid & 15;
+          const int4 pt = ptab[pg];
+          const int64_t mg = m0 + pg * 8;
+          for (int co = tid >> 4; co < Kc; co += 16) {
+            float gv[8];
+            uint32_t sw[8][CBits::CWN];
+            const uint32_t *sp = P.state + ((int64_t)(i * g.Cout + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
+            if (pt.w == 1) {
+              const float4 *gp = reinterpret_cast<const float4 *>(
+                  P.go + ((int64_t)pt.x * g.Cout + co) * g.L + pt.y * g.OW + pt.z);
+              const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+              gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w;
+              gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
+#pragma unroll
+              for (int w = 0; w < CBits::CWN; ++w) {
+                const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(sp + (int64_t)w * g.M));
+                const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(sp + (int64_t)w * g.M) + 1);
+                sw[0][w] = s0.x; sw[1][w] = s0.y; sw[2][w] = s0.z; sw[3][w] = s0.w;
+                sw[4][w] = s1.x; sw[5][w] = s1.y; sw[6][w] = s1.z; sw[7][w] = s1.w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int64_t m = mg + e;
+                gv[e] = 0.0f;
+#pragma unroll
+                for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = 0xffffffffu;
+                if (m < g.M) {
+                  const int b = (int)(m / g.L), l = (int)(m % g.L);
+                  gv[e] = __ldg(&P.go[((int64_t)b * g.Cout + co) * g.L + l]);
+#pragma unroll
+                  for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = __ldg(sp + (int64_t)w * g.M + e);
+                }
+              }
+            }
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              v[e] = gv[e] * pass_weight<NSW, CBits::CWN>(sw[e], CBits::CB + j, NSA, wv);
+            }
+            uint32_t hi[4], mid[4], lo3[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo3[e2]);
+            const uint32_t off = tc_tile_offset16(co, pg * 8, kWgLBO, b_sbo);
+            *reinterpret_cast<uint4 *>(gb + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(gb + P.b_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+            *reinterpret_cast<uint4 *>(gb + 2 * (size_t)P.b_bytes + off) = make_uint4(lo3[0], lo3[1], lo3[2], lo3[3]);
+          }
+          fence_proxy_async();
+          mbar_arrive(cv.full0 + 8 * sidx);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && has_work) {
+      const uint32_t idesc = idesc_bf16_f32(128, Kc);
+      uint32_t it = 0;
+      bool first_tile = true;
+      for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, first_tile = false) {
+        for (int i = i_begin; i < i_end; ++i) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(i - i_begin) * Kc;
+          for (int j = 0; j < NSA; ++j, ++it) {
+            const int sidx = it % P.stages;
+            const uint32_t use = it / P.stages;
+            mbar_wait(cv.full0 + 8 * sidx, use & 1);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(cv.stage_base + (size_t)sidx * P.stage_bytes);
+            const uint32_t b0 = a0 + P.a_bytes;
+            for (int sp = 0; sp < 3; ++sp)
+              for (int ks = 0; ks < 8; ++ks) {  // 128 pixels = 8 x K16
+                const uint64_t adesc = make_smem_desc(a0 + ks * 2 * kTcLBO, kTcLBO, a_sbo);
+                const uint64_t bdesc = make_smem_desc(b0 + sp * P.b_bytes + ks * 2 * kWgLBO, kWgLBO, b_sbo);
+                umma_f16(d_tmem, adesc, bdesc, idesc, (first_tile && j == 0 && sp == 0 && ks == 0) ? 0u : 1u);
+              }
+            umma_commit(cv.empty0 + 8 * sidx);
+          }
+        }
+      }
+      umma_commit(cv.tfull0);  // every accumulation of this CTA is complete
+    }
+  } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + kEpilogueWarps) {
+    // ------------------------------------------------------------------ epilogue (once, at the end)
+    const int quarter = warp & 3;
+    const int frow = quarter * 32 + lane;  // TMEM lane = crossbar row
+    const float scale = P.s[0] / (float)NSW;  // x_sl * s_a (lsq.py:295), mean over weight slices (lsq.py:366)
+    float *part = P.out + (int64_t)blockIdx.x * g.F * g.Cout;
+    if (has_work) {
+      mbar_wait(cv.tfull0, 0);
+      tc_fence_after();
+    }
+    for (int i = i_begin; i < i_end; ++i) {
+      const int lo = i * g.xbar;
+      const int rows = min(rows_full, g.F - lo);
+      for (int c0 = 0; c0 < Kc; c0 += 16) {
+        int v[16];
+        if (has_work) {
+          tmem_ld<16>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i - i_begin) * Kc + c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < 16; ++cc) v[cc] = 0;
+        }
+        if (frow < rows) {
+          float4 *dst = reinterpret_cast<float4 *>(part + (int64_t)(lo + frow) * g.Cout + c0);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            dst[q4] = make_float4(__int_as_float(v[4 * q4]) * scale, __int_as_float(v[4 * q4 + 1]) * scale,
+                                  __int_as_float(v[4 * q4 + 2]) * scale, __int_as_float(v[4 * q4 + 3]) * scale);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, P.tmem_cols);
+  }
+}
+
+__global__ void bwd_weight_tc_finish_kernel(Geo g, int nparts, const float *__restrict__ partial,
+                                            float *__restrict__ gw) {
+  const int64_t n = (int64_t)g.Cout * g.F;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(idx % g.F), co = (int)(idx / g.F);
+    float v = 0.0f;
+    for (int p = 0; p < nparts; ++p) v += partial[((int64_t)p * g.F + f) * g.Cout + co];
+    gw[idx] = v;  // [Cout, F] == weight layout (lsq.py:369)
+  }
+}
+
+// bf16 weight digit tiles for dgrad: tile (i, k) = [Nf rows (crossbar row) x Cout] K-major no-swizzle
+__global__ void weight_tiles_bwd_kernel(Geo g, int Nf, const int8_t *__restrict__ wcodes,
+                                        uint16_t *__restrict__ tiles) {
+  const int64_t tile_elems = (int64_t)Nf * g.Cout;
+  const int64_t n = (int64_t)g.NX * g.NSW * tile_elems;
+  const uint32_t sbo = (uint32_t)g.Cout * 16u;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tile = idx / tile_elems;
+    const int within = (int)(idx % tile_elems);
+    const int fr = within / g.Cout, co = within % g.Cout;
+    const int i = (int)(tile / g.NSW), k = (int)(tile % g.NSW);
+    const int f = i * g.xbar + fr;
+    const int hi = min((i + 1) * g.xbar, g.F);
+    int digit = 0;
+    if (f < hi) {
+      const int code = wcodes[(int64_t)co * g.F + f];
+      const int mag = code < 0 ? -code : code;
+      digit = (mag >> (g.wbs * k)) & g.wmask;
+      if (code < 0) digit = -digit;
+    }
+    tiles[tile * tile_elems + tc_tile_offset16(fr, co, kTcLBO, sbo) / 2] =
+        __bfloat16_as_ushort(__int2bfloat16_rn(digit));
+  }
+}
+
+inline int wgrad_chunks_per_group(const Geo &g) {
+  int n = 512 / g.Cout;
+  return n < g.NX ? n : g.NX;
+}
+
+}  // namespace
+
+inline bool bwd_slices_supported(const Geo &g) {
+  return (g.NSW == g.NSA) && (g.NSW == 2 || g.NSW == 3 || g.NSW == 4 || g.NSW == 8);
+}
+
+#define CIMQ_BWD_DISPATCH(KERNEL, ...)                                                          \
+  do {                                                                                          \
+    const bool tern = g.adc_mode != CIMQ_ADC_MULTIBIT;                                           \
+    if (g.NSW == 2 && tern) { KERNEL(2, 2, true, __VA_ARGS__); }                                 \
+    else if (g.NSW == 2) { KERNEL(2, 2, false, __VA_ARGS__); }                                   \
+    else if (g.NSW == 3 && tern) { KERNEL(3, 3, true, __VA_ARGS__); }                            \
+    else if (g.NSW == 3) { KERNEL(3, 3, false, __VA_ARGS__); }                                   \
+    else if (g.NSW == 4 && tern) { KERNEL(4, 4, true, __VA_ARGS__); }                            \
+    else if (g.NSW == 4) { KERNEL(4, 4, false, __VA_ARGS__); }                                   \
+    else if (g.NSW == 8 && tern) { KERNEL(8, 8, true, __VA_ARGS__); }                            \
+    else { KERNEL(8, 8, false, __VA_ARGS__); }                                                   \
+  } while (0)
+
+bool tc_backward_supported(const Geo &g) {
+  if (!bwd_slices_supported(g)) return false;
+  if (g.Cout % 16 != 0 || g.Cout > 128) return false;
+  if (g.pairs > kMaxPairs) return false;
+  const int rows = g.xbar < g.F ? g.xbar : g.F;
+  if (rows > 128) return false;  // wgrad M tile is one crossbar of <= 128 rows; dgrad N <= 128 keeps 3 stages
+  if ((int64_t)g.B * g.Cin * g.H * g.W >= (1ll << 31)) return false;
+  return true;
+}
+
+int64_t wtiles_bwd_bytes(const Geo &g) {
+  return tc_backward_supported(g) ? (int64_t)g.NX * g.NSW * tc_nf(g) * g.Cout * 2 : 0;
+}
+
+int launch_weight_tiles_bwd(const Geo &g, const int8_t *wcodes, void *tiles, cudaStream_t st) {
+  const int64_t n = (int64_t)g.NX * g.NSW * tc_nf(g) * g.Cout;
+  weight_tiles_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, tc_nf(g), wcodes,
+                                                                 reinterpret_cast<uint16_t *>(tiles));
+  CIMQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int64_t bwd_tc_partial_bytes(const Geo &g) {
+  const int mtiles = (g.M + kTcTileM - 1) / kTcTileM;
+  const int nxg = wgrad_chunks_per_group(g);
+  const int groups = (g.NX + nxg - 1) / nxg;
+  int ctas = 148 / groups;
+  if (ctas > mtiles) ctas = mtiles;
+  if (ctas < 1) ctas = 1;
+  return (int64_t)ctas * g.F * g.Cout * 4;
+}
+
+int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, const void *wtb, const float *s,
+                        const int8_t *mask, float *gxuT, cudaStream_t st) {
+  BwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.g = g;
+  P.Kc = g.Cout;
+  P.Nf = tc_nf(g);
+  P.mtiles = (g.M + kTcTileM - 1) / kTcTileM;
+  P.a_bytes = (uint32_t)(kTcTileM * g.Cout * 2);
+  P.b_bytes = (uint32_t)(P.Nf * g.Cout * 2);
+  P.stage_bytes = 3 * P.a_bytes + P.b_bytes;
+  int stages = (int)((kSmemBudget - kBarrierBytes) / P.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  CIMQ_REQUIRE(stages >= 1, "dgrad tile does not fit shared memory");
+  P.stages = stages;
+  uint32_t cols = 32;
+  while (cols < 2u * P.Nf) cols <<= 1;
+  P.tmem_cols = cols;
+  P.go = go; P.state = state; P.wtb = reinterpret_cast<const uint8_t *>(wtb); P.s = s; P.mask = mask; P.out = gxuT;
+  const size_t smem = (size_t)stages * P.stage_bytes + kBarrierBytes + 1024;
+  const int grid = P.mtiles < 148 ? P.mtiles : 148;
+#define CIMQ_LAUNCH_DGRAD(W, A, T, ...)                                                                         \
+  do {                                                                                                          \
+    CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_input_tc_kernel<W, A, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                              \
+    bwd_input_tc_kernel<W, A, T><<<grid, kThreads, smem, st>>>(P);                                              \
+  } while (0)
+  CIMQ_BWD_DISPATCH(CIMQ_LAUNCH_DGRAD, 0);
+#undef CIMQ_LAUNCH_DGRAD
+  CIMQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, const uint32_t *state,
+                         const float *s, const int8_t *mask, float *partial, float *gw, cudaStream_t st) {
+  BwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.g = g;
+  P.Kc = g.Cout;
+  P.mtiles = (g.M + kTcTileM - 1) / kTcTileM;
+  P.a_bytes = 128u * 128u * 2u;
+  P.b_bytes = (uint32_t)(g.Cout / 8) * 16u * (uint32_t)kWgLBO;  // 8-row groups x 16 k-groups x 144 B
+  P.stage_bytes = P.a_bytes + 3 * P.b_bytes;
+  int stages = (int)((kSmemBudget - kBarrierBytes) / P.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  CIMQ_REQUIRE(stages >= 1, "wgrad tile does not fit shared memory");
+  P.stages = stages;
+  P.nxg = wgrad_chunks_per_group(g);
+  const int groups = (g.NX + P.nxg - 1) / P.nxg;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(P.nxg * g.Cout)) cols <<= 1;
+  P.tmem_cols = cols;
+  int ctas = 148 / groups;
+  if (ctas > P.mtiles) ctas = P.mtiles;
+  if (ctas < 1) ctas = 1;
+  P.go = go; P.state = state; P.xcodes = xcodes; P.s = s; P.mask = mask; P.out = partial;
+  const size_t smem = (size_t)stages * P.stage_bytes + kBarrierBytes + 1024;
+  dim3 grid(ctas, groups);
+#define CIMQ_LAUNCH_WGRAD(W, A, T, ...)                                                                          \
+  do {                                                                                                           \
+    CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_weight_tc_kernel<W, A, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                               \
+    bwd_weight_tc_kernel<W, A, T><<<grid, kThreads, smem, st>>>(P);                                              \
+  } while (0)
+  CIMQ_BWD_DISPATCH(CIMQ_LAUNCH_WGRAD, 0);
+#undef CIMQ_LAUNCH_WGRAD
+  CIMQ_CUDA_OK(cudaGetLastError());
+  const int64_t n = (int64_t)g.Cout * g.F;
+  bwd_weight_tc_finish_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, ctas, partial, gw);
+  CIMQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cimq

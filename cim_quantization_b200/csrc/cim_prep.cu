@@ -102,7 +102,26 @@ int launch_adc_table(const Geo &g, const float *s, const float *alpha_q, const i
   return 0;
 }
 
-int64_t wtiles_bytes(const Geo &g) { return tc_forward_supported(g) ? wtiles_total_bytes(g) : 0; }
+WtLayout wt_layout(const Geo &g) {
+  auto align = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
+  WtLayout w;
+  const bool fwd = tc_forward_supported(g);
+  w.fwd_off = 0;
+  w.fwd_bytes = 0;
+  if (fwd) {
+    const int CT = tc_channel_tile_for(g);
+    w.fwd_bytes = (int64_t)(g.Cout / CT) * g.NX * g.NSW * CT * tc_kp(g);
+  }
+  w.lut_off = align(w.fwd_bytes);
+  w.lut_bytes = fwd ? (int64_t)g.F * 8 : 0;
+  w.bwd_off = align(w.lut_off + w.lut_bytes);
+  w.bwd_bytes = wtiles_bwd_bytes(g);
+  w.total = align(w.bwd_off + w.bwd_bytes);
+  if (w.fwd_bytes == 0 && w.bwd_bytes == 0) w.total = 0;
+  return w;
+}
+
+int64_t wtiles_bytes(const Geo &g) { return wt_layout(g).total; }
 
 int launch_weight_prepare(const Geo &g, const int8_t *wcodes, float *wdigits, void *wtiles, cudaStream_t st) {
   if (wdigits != nullptr) {
@@ -110,13 +129,16 @@ int launch_weight_prepare(const Geo &g, const int8_t *wcodes, float *wdigits, vo
     weight_digits_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, wcodes, wdigits);
     CIMQ_CUDA_OK(cudaGetLastError());
   }
-  if (wtiles != nullptr && tc_forward_supported(g)) {
+  const WtLayout wl = wt_layout(g);
+  if (wtiles != nullptr && wl.fwd_bytes > 0) {
     const int CT = tc_channel_tile_for(g);
-    int64_t n = (int64_t)(g.Cout / CT) * g.NX * g.NSW * CT * tc_kp(g);
-    weight_tiles_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, CT, tc_kp(g), wcodes,
-                                                               reinterpret_cast<int8_t *>(wtiles));
+    weight_tiles_kernel<<<(int)((wl.fwd_bytes + 255) / 256), 256, 0, st>>>(
+        g, CT, tc_kp(g), wcodes, reinterpret_cast<int8_t *>(wtiles) + wl.fwd_off);
     CIMQ_CUDA_OK(cudaGetLastError());
-    if (launch_im2col_lut(g, wtiles, st)) return 1;
+    if (launch_im2col_lut(g, reinterpret_cast<uint8_t *>(wtiles) + wl.lut_off, st)) return 1;
+  }
+  if (wtiles != nullptr && wl.bwd_bytes > 0) {
+    if (launch_weight_tiles_bwd(g, wcodes, reinterpret_cast<uint8_t *>(wtiles) + wl.bwd_off, st)) return 1;
   }
   return 0;
 }

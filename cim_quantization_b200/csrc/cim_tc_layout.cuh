@@ -27,4 +27,17 @@ __host__ __device__ inline uint32_t tc_tile_offset(int r, int kk, int Kp) {
   return (uint32_t)((r >> 3) * (8 * Kp) + (kk >> 4) * kTcLBO + (r & 7) * 16 + (kk & 15));
 }
 
+
+// ---- backward (bf16) tiles --------------------------------------------------------------------------
+// 16-bit operands use the same K-major no-swizzle scheme with 8-element (16-byte) core-matrix rows:
+//   byte offset of (row r, k-element kk) = (r >> 3) * SBO + (kk >> 3) * LBO + (r & 7) * 16 + (kk & 7) * 2
+__host__ __device__ inline uint32_t tc_tile_offset16(int r, int kk, int lbo, int sbo) {
+  return (uint32_t)((r >> 3) * sbo + (kk >> 3) * lbo + (r & 7) * 16 + (kk & 7) * 2);
+}
+// dgrad GEMM N dimension: crossbar rows padded to a multiple of 16
+__host__ __device__ inline int tc_nf(const Geo &g) {
+  int rows = g.xbar < g.F ? g.xbar : g.F;
+  return (rows + 15) & ~15;
+}
+
 }  // namespace cimq

@@ -37,6 +37,7 @@ int cimq_layer_info(const cimq_layer_t *layer, cimq_info_t *info) {
   info->NX = g.NX; info->NSW = g.NSW; info->NSA = g.NSA; info->pairs = g.pairs;
   info->state_words = g.state_words;
   info->tc_forward = tc_forward_supported(g) ? 1 : 0;
+  info->tc_backward = tc_backward_supported(g) ? 1 : 0;
   info->state_bytes = (int64_t)g.NX * g.Cout * g.state_words * g.M * 4;
   info->table_bytes = table_entries(g) * 16;
   info->wdigits_bytes = (int64_t)g.NSW * g.Cout * g.F * 4;
@@ -110,12 +111,12 @@ int cimq_conv_forward(const cimq_layer_t *layer, const uint8_t *xcodes, const in
 }
 
 int cimq_conv_backward(const cimq_layer_t *layer, const float *grad_out, const uint8_t *xcodes,
-                       const float *wdigits, const uint32_t *state, const float *s, const int8_t *binary_mask,
-                       float *grad_xq, float *grad_wq, float *grad_alpha_q, void *workspace, uint32_t flags,
-                       void *stream) {
+                       const float *wdigits, const void *wtiles, const uint32_t *state, const float *s,
+                       const int8_t *binary_mask, float *grad_xq, float *grad_wq, float *grad_alpha_q,
+                       void *workspace, uint32_t flags, void *stream) {
   Geo g;
   if (make_geo(layer, &g)) return 1;
-  return launch_conv_backward(g, grad_out, xcodes, wdigits, state, s, binary_mask, grad_xq, grad_wq,
+  return launch_conv_backward(g, grad_out, xcodes, wdigits, wtiles, state, s, binary_mask, grad_xq, grad_wq,
                               grad_alpha_q, workspace, flags, as_stream(stream));
 }
 

@@ -105,8 +105,22 @@ int launch_weight_prepare(const Geo &g, const int8_t *wcodes, float *wdigits, vo
 int64_t wtiles_bytes(const Geo &g);
 bool tc_forward_supported(const Geo &g);
 int tc_channel_tile_for(const Geo &g);          // output channels per CTA of the tcgen05 kernel (0: unsupported)
-int64_t wtiles_total_bytes(const Geo &g);       // weight digit tiles + im2col LUT
-int launch_im2col_lut(const Geo &g, void *wtiles, cudaStream_t st);
+int launch_im2col_lut(const Geo &g, void *lut, cudaStream_t st);
+bool tc_backward_supported(const Geo &g);
+int64_t wtiles_bwd_bytes(const Geo &g);
+int launch_weight_tiles_bwd(const Geo &g, const int8_t *wcodes, void *tiles, cudaStream_t st);
+int64_t bwd_tc_partial_bytes(const Geo &g);
+int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, const void *wtb, const float *s,
+                        const int8_t *mask, float *gxuT, cudaStream_t st);
+int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, const uint32_t *state,
+                         const float *s, const int8_t *mask, float *partial, float *gw, cudaStream_t st);
+
+// Sections of the prepared-weights buffer ("wtiles"): forward int8 digit tiles, im2col LUT (int2 per crossbar
+// row), backward bf16 digit tiles.  A section the layer does not support has zero bytes.
+struct WtLayout {
+  int64_t fwd_off, fwd_bytes, lut_off, lut_bytes, bwd_off, bwd_bytes, total;
+};
+WtLayout wt_layout(const Geo &g);
 
 enum SimtMode { SIMT_FORWARD = 0, SIMT_PSUMS = 1, SIMT_ABS_SUMS = 2 };
 int launch_conv_simt(const Geo &g, int mode, const uint8_t *xcodes, const int8_t *wcodes, const void *table,
@@ -117,8 +131,8 @@ int launch_conv_tc_forward(const Geo &g, const uint8_t *xcodes, const void *wtil
 
 int64_t conv_backward_ws_bytes(const Geo &g);
 int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, const float *wdigits,
-                         const uint32_t *state, const float *s, const int8_t *mask, float *gxq, float *gwq,
-                         float *galpha, void *ws, uint32_t flags, cudaStream_t st);
+                         const void *wtiles, const uint32_t *state, const float *s, const int8_t *mask, float *gxq,
+                         float *gwq, float *galpha, void *ws, uint32_t flags, cudaStream_t st);
 
 // table = NX*pairs*Cout entries of 16 bytes: int4 {tp, tg, amp (fp32 bits), 0}
 __host__ __device__ inline int64_t table_entries(const Geo &g) { return (int64_t)g.NX * g.pairs * g.Cout; }

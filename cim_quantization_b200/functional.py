@@ -79,17 +79,17 @@ class get_cim_output_signed(Function):
         alpha_q = alpha_cim.detach().contiguous().float() if has_alpha else None
         table = _lib.adc_table(spec, s, alpha_q, mask)
         need_bwd = any(ctx.needs_input_grad)
-        wdigits, wtiles = _lib.weight_prepare(spec, wcodes, want_digits=need_bwd)
+        wdigits, wtiles = _lib.weight_prepare(spec, wcodes, want_digits=need_bwd and not info.tc_backward)
         out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd)
         ctx.spec, ctx.has_alpha, ctx.w_shape = spec, has_alpha, tuple(w.shape)
-        ctx.save_for_backward(xcodes, wdigits, state, s, mask)
+        ctx.save_for_backward(xcodes, wdigits, wtiles, state, s, mask)
         return out.transpose(1, 2)  # [B, L, Cout] like lsq.py:233 (a view of the NCHW buffer)
 
     @staticmethod
     def backward(ctx, grad_output):
-        xcodes, wdigits, state, s, mask = ctx.saved_tensors
+        xcodes, wdigits, wtiles, state, s, mask = ctx.saved_tensors
         go = grad_output.transpose(1, 2).contiguous().float()  # [B, Cout, L]
-        gxq, gwq, galpha = _lib.conv_backward(ctx.spec, go, xcodes, wdigits, state, s, mask,
+        gxq, gwq, galpha = _lib.conv_backward(ctx.spec, go, xcodes, wdigits, wtiles, state, s, mask,
                                               need_alpha=ctx.has_alpha and ctx.needs_input_grad[12],
                                               need_input=ctx.needs_input_grad[0])
         gwq = gwq.view(ctx.w_shape)
@@ -121,22 +121,23 @@ class _CimConv2dFused(Function):
         has_alpha = alpha_q is not None
         table = _lib.adc_table(spec, s, alpha_q.detach().contiguous() if has_alpha else None, mask)
         need_bwd = any(ctx.needs_input_grad)
-        wdigits, wtiles = _lib.weight_prepare(spec, wcodes, want_digits=need_bwd)
+        simt = bool(flags & _lib.FLAG_FORCE_SIMT)
+        wdigits, wtiles = _lib.weight_prepare(spec, wcodes, want_digits=need_bwd and (simt or not info.tc_backward))
         out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd,
                                        flags=flags)
         ctx.spec, ctx.has_alpha, ctx.flags = spec, has_alpha, flags
         ctx.consts = (qp_a, qn_w, qp_w, ga, gw)
-        ctx.save_for_backward(x, weight, xcodes, wdigits, state, s, mask)
+        ctx.save_for_backward(x, weight, xcodes, wdigits, wtiles, state, s, mask)
         return out.view(spec.batch, spec.out_channels, info.out_hw, info.out_hw)
 
     @staticmethod
     def backward(ctx, grad_y):
-        x, weight, xcodes, wdigits, state, s, mask = ctx.saved_tensors
+        x, weight, xcodes, wdigits, wtiles, state, s, mask = ctx.saved_tensors
         spec = ctx.spec
         qp_a, qn_w, qp_w, ga, gw = ctx.consts
         go = grad_y.contiguous().float().view(spec.batch, spec.out_channels, -1)
         need_x = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
-        gxq, gwq, galpha = _lib.conv_backward(spec, go, xcodes, wdigits, state, s, mask,
+        gxq, gwq, galpha = _lib.conv_backward(spec, go, xcodes, wdigits, wtiles, state, s, mask,
                                               need_alpha=ctx.has_alpha and ctx.needs_input_grad[4],
                                               need_input=need_x, flags=ctx.flags)
         gx = g_aa = None

@@ -68,6 +68,8 @@ typedef struct cimq_info {
   int32_t out_hw, L, M, F, NX, NSW, NSA, pairs;
   int32_t state_words;          /* uint32 words of ADC state per (crossbar, channel, pixel) */
   int32_t tc_forward;           /* 1 if the tcgen05 forward kernel covers this layer */
+  int32_t tc_backward;          /* 1 if the tcgen05 dgrad / wgrad kernels cover this layer */
+  int32_t reserved_;
   int64_t state_bytes;          /* NX*Cout*state_words*M*4 */
   int64_t table_bytes;          /* ADC table: NX*pairs*Cout entries of 16 bytes {tp, tg, amp, 0} */
   int64_t wdigits_bytes;        /* fp32 weight digit planes [NSW, Cout, F] */
@@ -125,7 +127,8 @@ int cimq_adc_table(const cimq_layer_t *layer, const float *s, const float *alpha
                    void *table, int32_t *status, void *stream);
 
 /* Sign-magnitude digit planes of the weight codes (slicing_weights_signed, lsq.py:438-464):
- * wdigits fp32 [NSW, Cout, F]; wtiles int8 tiles in tcgen05 smem order (may be NULL). */
+ * wdigits fp32 [NSW, Cout, F] (CUDA-core backward; may be NULL); wtiles (may be NULL): operand tiles in
+ * tcgen05 shared-memory order -- int8 digit tiles + im2col LUT for the forward, bf16 digit tiles for dgrad. */
 int cimq_weight_prepare(const cimq_layer_t *layer, const int8_t *wcodes, float *wdigits, void *wtiles,
                         void *stream);
 
@@ -140,11 +143,12 @@ int cimq_conv_forward(const cimq_layer_t *layer, const uint8_t *xcodes, const in
                       uint32_t flags, void *stream);
 
 /* get_cim_output_signed.backward (lsq.py:244-386): grad_xq [B,Cin,H,W], grad_wq [Cout,F],
- * grad_alpha_q [NX,NSW,NSA,Cout] (NULL for CIMQ_ADC_MULTIBIT). */
+ * grad_alpha_q [NX,NSW,NSA,Cout] (NULL for CIMQ_ADC_MULTIBIT).  wdigits is needed by the CUDA-core kernels,
+ * wtiles by the tcgen05 kernels; pass both to let the library choose. */
 int cimq_conv_backward(const cimq_layer_t *layer, const float *grad_out, const uint8_t *xcodes,
-                       const float *wdigits, const uint32_t *state, const float *s, const int8_t *binary_mask,
-                       float *grad_xq, float *grad_wq, float *grad_alpha_q, void *workspace, uint32_t flags,
-                       void *stream);
+                       const float *wdigits, const void *wtiles, const uint32_t *state, const float *s,
+                       const int8_t *binary_mask, float *grad_xq, float *grad_wq, float *grad_alpha_q,
+                       void *workspace, uint32_t flags, void *stream);
 
 /* Raw integer partial sums int32 [B,NX,NSW,NSA,L,Cout] (= ctx.ps_int, lsq.py:192).  Test / debug. */
 int cimq_conv_psums(const cimq_layer_t *layer, const uint8_t *xcodes, const int8_t *wcodes, int32_t *psums,

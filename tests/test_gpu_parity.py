@@ -167,7 +167,7 @@ def test_conv_forward_backward_cabi(name, force_simt):
     # backward
     oh = cfg.out_hw(hw)
     go = _cuda(d["grad_y"].reshape(batch, cfg.out_channels, oh * oh))
-    gxq, gwq, galpha = L.conv_backward(spec, go, xc, wdigits, state, s, mask, need_alpha=cfg.has_alpha_cim,
+    gxq, gwq, galpha = L.conv_backward(spec, go, xc, wdigits, wtiles, state, s, mask, need_alpha=cfg.has_alpha_cim,
                                        flags=flags)
     assert rel_err(gxq.cpu().numpy(), d["fn_grad_xq"]) < TOL
     assert rel_err(gwq.cpu().numpy().reshape(d["fn_grad_wq"].shape), d["fn_grad_wq"]) < TOL
@@ -334,7 +334,7 @@ def test_random_layer_against_oracle(case):
             np.testing.assert_array_equal(codes, O.adc_codes(cfg, ps_int, s_w, s_a, aq))
         assert rel_err(out.cpu().numpy().transpose(0, 2, 1), ref_out) < TOL
         gxq, gwq, galpha = L.conv_backward(spec, _cuda(np.ascontiguousarray(go.transpose(0, 2, 1))), xcd, wdigits,
-                                           state, s, mask, need_alpha=cfg.has_alpha_cim, flags=flags)
+                                           wtiles, state, s, mask, need_alpha=cfg.has_alpha_cim, flags=flags)
         assert rel_err(gxq.cpu().numpy(), ref_gx) < TOL
         assert rel_err(gwq.cpu().numpy().reshape(ref_gw.shape), ref_gw) < TOL
         if cfg.has_alpha_cim:
@@ -372,12 +372,13 @@ def test_wide_adc_equals_dense_conv_full_size():
         assert int((out.view_as(dense) != dense).sum()) == 0
         assert int(state.count_nonzero()) == 0  # nothing clipped
     go = torch.randn(B, C, HW * HW, device="cuda", generator=g)
-    gxq, gwq, _ = L.conv_backward(spec, go, xc, wdigits, state, s, mask, need_alpha=False)
     xf = xc.float().requires_grad_(True)
     wf = wc.float().requires_grad_(True)
     torch.nn.functional.conv2d(xf, wf, padding=1).backward(go.view(B, C, HW, HW))
-    assert rel_err(gxq.cpu().numpy(), xf.grad.cpu().numpy()) < TOL
-    assert rel_err(gwq.view_as(wf).cpu().numpy(), wf.grad.cpu().numpy()) < TOL
+    for flags in (0, L.FLAG_FORCE_SIMT):  # tcgen05 dgrad/wgrad, then the CUDA-core kernels
+        gxq, gwq, _ = L.conv_backward(spec, go, xc, wdigits, wtiles, state, s, mask, need_alpha=False, flags=flags)
+        assert rel_err(gxq.cpu().numpy(), xf.grad.cpu().numpy()) < TOL
+        assert rel_err(gwq.view_as(wf).cpu().numpy(), wf.grad.cpu().numpy()) < TOL
 
 
 @pytest.mark.parametrize("xbar,adc", [(64, 1.5), (128, 1.5), (128, 1), (128, 3)])

@@ -37,7 +37,7 @@ for it in range(a.iters + 1):
         torch.cuda.synchronize(); ev[0].record()
     out, state = L.conv_forward(spec, xc, wc, wtiles, table, s, mask, save_state=not a.no_state)
     if a.bwd:
-        L.conv_backward(spec, go, xc, wdig, state, s, mask, need_alpha=aq is not None)
+        L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask, need_alpha=aq is not None)
     if a.quant:
         L.lsq_quantize(x, s[0:1], 0, 7)
         L.lsq_backward(go.view_as(x), x, s[0:1], 0, 7, 1e-3)
