@@ -1,0 +1,499 @@
+// tcgen05 (5th-gen tensor core) forward kernel of the CiM convolution for sm_100a -- kernel template.
+// Reference semantics: get_cim_output_signed.forward, lsq.py:92-237.
+//
+// Implicit GEMM, one persistent CTA per SM, warp-specialised (16 warps, registers rebalanced with
+// setmaxnreg):
+//
+//   warps 0-3   producers   per (pixel tile, crossbar chunk): stage the input rows the tile needs in shared
+//                           memory (uint8 codes, coalesced 4-byte loads, zero padding), then every thread
+//                           assembles the im2col row of ITS output pixel -- whole input channels with
+//                           compile-time byte positions, see cim_tc_layout.cuh for the K order -- splits it
+//                           into NSA digit planes and stores them as the K-major A operands (16-byte
+//                           stores, then fence.proxy.async).  One lane bulk-copies the pre-tiled weight digit
+//                           planes of the chunk (cp.async.bulk -> mbarrier complete_tx).
+//   warp  12    MMA issuer  (warps 13-15 idle) one thread: for every activation digit plane j one
+//                           accumulation group D[128 x NSW*CT] (int32, TMEM) = A_j[128 x K] * B[K x NSW*CT]
+//                           with tcgen05.mma.kind::i8 (K = 32 per instruction); TMEM is double buffered so
+//                           the tensor core runs ahead of the epilogue by one digit plane.
+//   warps 4-11  epilogue    tcgen05.ld the partial sums (thread = output pixel, registers = channels),
+//                           quantise each to its ADC code with integer compares against per-(crossbar,
+//                           slice pair, channel) thresholds held in shared memory, accumulate
+//                           code*alpha*2^shift in fp32 registers across slice pairs and crossbar chunks,
+//                           record code/clip bits for the backward.  The partial-sum tensor never exists in
+//                           memory.
+//
+// Pipelines: shared-memory stages (full/empty mbarriers, producers <-> MMA) and two TMEM accumulator
+// buffers (tmem_full/tmem_empty mbarriers, MMA <-> epilogue).
+#pragma once
+
+#include "cim_tc_layout.cuh"
+#include "tc_ptx.cuh"
+
+namespace cimq {
+namespace tcfwd {
+
+using namespace ptx;
+
+constexpr int kProducerWarps = 4;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kEpilogueWarps = 8;
+constexpr int kMmaWarp = kProducerWarps + kEpilogueWarps;
+// 16 warps = 4 warpgroups: registers are allocated per warpgroup, so the fourth warpgroup (MMA issuer
+// + three idle warps) costs nothing extra and setmaxnreg can move its registers to the epilogue.
+constexpr int kThreads = 512;
+constexpr int kRegsProducer = 104, kRegsMma = 40, kRegsEpilogue = 184;  // 4*32*(104+40+2*184) = 65536
+constexpr int kMaxStages = 4;
+constexpr int kMaxSlots = 16;  // staged input channels per chunk: <= 14 complete (K=3, 128 rows) + head + tail
+
+struct TcParams {
+  Geo g;
+  int Kp, CT, nct, mtiles, stages;
+  uint32_t a_bytes, b_bytes, stage_bytes, tmem_cols;
+  // fast producer (input rows staged in shared memory)
+  int fast;          // 1: staged producer, 0: generic per-element gather
+  int owt;           // output pixels per staged row segment (= OW, divides 128)
+  int rpt;           // output rows per tile (128 / OW)
+  int pitch_log2;    // staged row pitch in bytes (power of two)
+  int col0;          // staged column of input column -pad (alignment shift)
+  uint32_t raw_bytes;    // one staging buffer
+  uint32_t ttab_bytes;   // one epilogue table slice per warpgroup
+  const uint8_t *xcodes;
+  const uint8_t *wtiles;   // [nct*NX] tiles of b_bytes
+  const int2 *lut;         // per operand position: {element offset of the tap, tap index}
+  const int4 *table;       // AoS table (generic paths)
+  const uint32_t *ttab;    // tiled SoA table [ct][i][pair][tp|tg|amp][CT]
+  const float *s;
+  float *out;
+  uint32_t *state;
+};
+
+// shared-memory carve-up (all offsets from the dynamic smem base)
+struct Smem {
+  uint8_t *stage_base;   // stages * stage_bytes
+  uint8_t *raw;          // 2 * raw_bytes
+  uint32_t *ttab;        // 2 warpgroups * 2 buffers * ttab_bytes
+  int *rowoff;           // 2 * 128 ints: global offset of staged row (orow, ky) or -1
+  uint32_t full0, empty0, tfull0, tempty0;
+  uint32_t *tmem_slot;
+};
+constexpr size_t kAuxBytes = 2048;  // barriers, tmem slot, rowoff table
+
+__device__ __forceinline__ Smem carve(uint8_t *base, const TcParams &P) {
+  Smem s;
+  s.stage_base = base;
+  uint8_t *p = base + (size_t)P.stages * P.stage_bytes;
+  s.raw = p;
+  p += 2 * (size_t)P.raw_bytes;
+  s.ttab = reinterpret_cast<uint32_t *>(p);
+  p += 4 * (size_t)P.ttab_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(p);
+  s.full0 = smem_u32(bars);
+  s.empty0 = s.full0 + 8 * kMaxStages;
+  s.tfull0 = s.empty0 + 8 * kMaxStages;
+  s.tempty0 = s.tfull0 + 16;
+  s.tmem_slot = reinterpret_cast<uint32_t *>(p + 112);
+  s.rowoff = reinterpret_cast<int *>(p + 128);
+  return s;
+}
+
+// insert the low byte of `b` at byte position POS of w
+template <int POS>
+__device__ __forceinline__ uint32_t put_byte(uint32_t w, uint32_t b) {
+  constexpr uint32_t sel = POS == 0 ? 0x3214u : POS == 1 ? 0x3240u : POS == 2 ? 0x3410u : 0x4210u;
+  return __byte_perm(w, b, sel);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fast producer: one stage = digit planes of 128 im2col rows for crossbar chunk i
+// ---------------------------------------------------------------------------------------------------
+template <int NSA, int KT>
+__device__ __forceinline__ void produce_fast(const TcParams &P, const Smem &sm, int i, uint8_t *st_ptr,
+                                             uint8_t *raw, const int *rowoff, int r, int pix_base) {
+  constexpr int KK = KT * KT;
+  constexpr int NFMAX = 126 / KK < kMaxSlots - 2 ? 126 / KK : kMaxSlots - 2;  // complete channels in 128 bytes
+  const Geo &g = P.g;
+  const ChunkLayout cl = chunk_layout(g, i);
+  const int pitch = 1 << P.pitch_log2;
+  const int slot_bytes = P.rpt * KT * pitch;
+  const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
+  const int HW = g.H * g.W;
+  // ---- 1. stage rows: slot s < nfull -> channel cf0+s, then head channel cf0-1, then tail channel cf0+nfull
+  {
+    const int words_per_slot = slot_bytes >> 2;
+    const int wpr_log2 = P.pitch_log2 - 2;  // words per staged row
+    for (int sl = 0; sl < nslots; ++sl) {
+      int ch = cl.cf0 + sl;
+      if (sl >= cl.nfull) ch = (sl == cl.nfull && cl.nhead > 0) ? cl.cf0 - 1 : cl.cf0 + cl.nfull;
+      const uint8_t *src = P.xcodes + (size_t)ch * HW;
+      uint32_t *dst = reinterpret_cast<uint32_t *>(raw + (size_t)sl * slot_bytes);
+      for (int idx = threadIdx.x; idx < words_per_slot; idx += kProducerThreads) {
+        const int row = idx >> wpr_log2, xw = idx & ((1 << wpr_log2) - 1);
+        const int off = rowoff[row];             // offset of staged column 0 of this row, or -1
+        const int ix = 4 * xw - P.col0 - g.pad;  // input column of the word's first byte
+        uint32_t v = 0;
+        if (off >= 0 && ix >= 0 && ix < g.W) v = __ldg(reinterpret_cast<const uint32_t *>(src + off + 4 * xw));
+        dst[idx] = v;
+      }
+    }
+  }
+  named_barrier_sync(1, kProducerThreads);
+  // ---- 2. assemble this thread's im2col row: complete channels at compile-time byte positions
+  uint32_t w[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) w[t] = 0u;
+  const uint8_t *pb = raw + pix_base;
+#pragma unroll
+  for (int n = 0; n < NFMAX; ++n) {
+    if (n < cl.nfull) {
+      const uint8_t *cb = pb + (size_t)n * slot_bytes;
+#pragma unroll
+      for (int ky = 0; ky < KT; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KT; ++kx) {
+          const int pos = n * KK + ky * KT + kx;  // compile time after unrolling
+          const uint32_t b = cb[ky * pitch + kx];
+          switch (pos & 3) {
+            case 0: w[pos >> 2] = put_byte<0>(w[pos >> 2], b); break;
+            case 1: w[pos >> 2] = put_byte<1>(w[pos >> 2], b); break;
+            case 2: w[pos >> 2] = put_byte<2>(w[pos >> 2], b); break;
+            default: w[pos >> 2] = put_byte<3>(w[pos >> 2], b); break;
+          }
+        }
+    }
+  }
+  // ---- 3. digit planes (LSB first, slicing_act lsq.py:466-480) -> A operands, 16 bytes per store
+  const uint32_t amask4 = (uint32_t)g.amask * 0x01010101u;
+  const int ngroups = ((cl.rows + 31) & ~31) >> 4;
+#pragma unroll
+  for (int gi = 0; gi < 8; ++gi) {
+    if (gi < ngroups) {
+      const uint32_t off = tc_tile_offset(r, gi * 16, P.Kp);
+#pragma unroll
+      for (int j = 0; j < NSA; ++j) {
+        const int sh = g.abs_ * j;
+        *reinterpret_cast<uint4 *>(st_ptr + (size_t)j * P.a_bytes + off) =
+            make_uint4((w[4 * gi] >> sh) & amask4, (w[4 * gi + 1] >> sh) & amask4, (w[4 * gi + 2] >> sh) & amask4,
+                       (w[4 * gi + 3] >> sh) & amask4);
+      }
+    }
+  }
+  // ---- 4. taps of the channels cut by the chunk edges: few elements, byte stores after the vector stores
+  {
+    int pos = cl.nfull * KK;
+    for (int part = 0; part < 2; ++part) {
+      const int cnt = part == 0 ? cl.nhead : cl.ntail;
+      if (cnt == 0) continue;
+      const int sl = cl.nfull + ((part == 1 && cl.nhead > 0) ? 1 : 0);
+      const int tap0 = part == 0 ? cl.head_tap0 : 0;
+      const uint8_t *cb = pb + (size_t)sl * slot_bytes;
+      for (int e = 0; e < cnt; ++e, ++pos) {
+        const int tap = tap0 + e, ky = tap / KT, kx = tap % KT;
+        const uint32_t b = cb[ky * pitch + kx];
+        const uint32_t off = tc_tile_offset(r, pos, P.Kp);
+#pragma unroll
+        for (int j = 0; j < NSA; ++j) st_ptr[(size_t)j * P.a_bytes + off] = (uint8_t)((b >> (g.abs_ * j)) & g.amask);
+      }
+    }
+  }
+}
+
+// generic producer: per-element gather through the position LUT (any geometry)
+template <int NSA>
+__device__ __forceinline__ void produce_generic(const TcParams &P, int i, uint8_t *st_ptr, int r, int base,
+                                                uint32_t vm) {
+  const Geo &g = P.g;
+  const uint32_t amask4 = (uint32_t)g.amask * 0x01010101u;
+  const int lo = i * g.xbar;
+  const int rows = min(g.xbar, g.F - lo);
+  const int ngroups = ((rows + 31) & ~31) >> 4;
+  for (int gi = 0; gi < ngroups; ++gi) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int kk = gi * 16 + e;
+      uint32_t code = 0;
+      if (kk < rows) {
+        const int2 lt = __ldg(&P.lut[lo + kk]);
+        if ((vm >> lt.y) & 1u) code = P.xcodes[base + lt.x];
+      }
+      w[e >> 2] |= code << (8 * (e & 3));
+    }
+    const uint32_t off = tc_tile_offset(r, gi * 16, P.Kp);
+#pragma unroll
+    for (int j = 0; j < NSA; ++j) {
+      const int sh = g.abs_ * j;
+      *reinterpret_cast<uint4 *>(st_ptr + (size_t)j * P.a_bytes + off) =
+          make_uint4((w[0] >> sh) & amask4, (w[1] >> sh) & amask4, (w[2] >> sh) & amask4, (w[3] >> sh) & amask4);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel.  NSW/NSA: weight / activation digit planes; CH: output channels per epilogue thread (CT/2)
+// ---------------------------------------------------------------------------------------------------
+template <int NSW, int NSA, int CH>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) {
+  constexpr int CT = 2 * CH;
+  constexpr int NROWS = NSW * CT;  // UMMA N
+  constexpr int PAIRS = NSW * NSA;
+  constexpr int SWORDS_MAX = (3 * PAIRS + 31) / 32;
+  const Geo &g = P.g;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const Smem sm = carve(smem_raw, P);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int sidx = 0; sidx < P.stages; ++sidx) {
+      mbar_init(sm.full0 + 8 * sidx, kProducerThreads + 1);
+      mbar_init(sm.empty0 + 8 * sidx, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sm.tfull0 + 8 * b, 1);
+      mbar_init(sm.tempty0 + 8 * b, kEpilogueWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(sm.tmem_slot), P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_slot;
+
+  const int ntiles = P.mtiles * P.nct;
+  const int rows_full = g.xbar < g.F ? g.xbar : g.F;
+
+  if (warp < kProducerWarps) {
+    // =========================== producers ===========================
+    reg_dealloc<kRegsProducer>();
+    const int r = threadIdx.x;  // tile row = output pixel
+    uint32_t it = 0;
+    int tpar = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tpar ^= 1) {
+      const int mt = tile / P.nct, ct = tile % P.nct;
+      const int m = mt * kTcTileM + r;
+      int base = 0, pix_base = 0;
+      uint32_t vm = 0;  // generic path: bit t set = tap t of this pixel is inside the image
+      int *rowoff = sm.rowoff + tpar * 128;
+      if (P.fast) {
+        // staged rows of this tile: row index (orow, ky) -> offset of staged column 0 in channel 0 of its image
+        if (r < P.rpt * g.K) {
+          const int orow = r / g.K, ky = r % g.K;
+          const int m_row = mt * kTcTileM + orow * P.owt;
+          int off = -1;
+          if (m_row < g.M) {
+            const int b = m_row / g.L, oy = (m_row % g.L) / g.OW;
+            const int iy = oy * g.stride - g.pad + ky;
+            if (iy >= 0 && iy < g.H) off = (b * g.Cin * g.H + iy) * g.W - g.pad - P.col0;
+          }
+          rowoff[r] = off;
+        }
+        const int orow = r / P.owt, oxl = r % P.owt;
+        pix_base = ((orow * g.K) << P.pitch_log2) + oxl * g.stride + P.col0;
+        named_barrier_sync(1, kProducerThreads);
+      } else if (m < g.M) {
+        const int b = m / g.L, l = m % g.L, oy = l / g.OW, ox = l % g.OW;
+        const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
+        base = (b * g.Cin * g.H + iy0) * g.W + ix0;
+        for (int ky = 0; ky < g.K; ++ky)
+          for (int kx = 0; kx < g.K; ++kx)
+            if (iy0 + ky >= 0 && iy0 + ky < g.H && ix0 + kx >= 0 && ix0 + kx < g.W) vm |= 1u << (ky * g.K + kx);
+      }
+      for (int i = 0; i < g.NX; ++i, ++it) {
+        const int sidx = it % P.stages;
+        const uint32_t use = it / P.stages;
+        mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
+        uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
+        if (threadIdx.x == 0) {
+          mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
+          bulk_copy_g2s(smem_u32(st_ptr + (size_t)NSA * P.a_bytes), P.wtiles + (size_t)(ct * g.NX + i) * P.b_bytes,
+                        P.b_bytes, sm.full0 + 8 * sidx);
+        }
+        if (P.fast) {
+          uint8_t *raw = sm.raw + (size_t)(it & 1) * P.raw_bytes;
+          if (g.K == 3) produce_fast<NSA, 3>(P, sm, i, st_ptr, raw, rowoff, r, pix_base);
+          else if (g.K == 1) produce_fast<NSA, 1>(P, sm, i, st_ptr, raw, rowoff, r, pix_base);
+          else produce_fast<NSA, 5>(P, sm, i, st_ptr, raw, rowoff, r, pix_base);
+        } else {
+          produce_generic<NSA>(P, i, st_ptr, r, base, vm);
+        }
+        fence_proxy_async();
+        mbar_arrive(sm.full0 + 8 * sidx);
+      }
+    }
+  } else if (warp >= kMmaWarp) {
+    // =========================== MMA issuer ===========================
+    reg_dealloc<kRegsMma>();
+    if (warp == kMmaWarp && lane == 0) {
+      const uint32_t idesc = idesc_i8_u8s8(kTcTileM, NROWS);
+      const uint32_t sbo = 8u * (uint32_t)P.Kp;
+      uint32_t it = 0, acc_it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int i = 0; i < g.NX; ++i, ++it) {
+          const int sidx = it % P.stages;
+          const uint32_t use = it / P.stages;
+          const int rows = min(rows_full, g.F - i * g.xbar);
+          const int ksteps = (rows + 31) >> 5;
+          mbar_wait(sm.full0 + 8 * sidx, use & 1);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sm.stage_base + (size_t)sidx * P.stage_bytes);
+          const uint32_t b0 = a0 + NSA * P.a_bytes;
+          for (int j = 0; j < NSA; ++j, ++acc_it) {
+            const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
+            mbar_wait(sm.tempty0 + 8 * buf, (buse & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * NROWS;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t adesc = make_smem_desc(a0 + j * P.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
+              const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
+              umma_i8(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(sm.tfull0 + 8 * buf);  // accumulator of digit plane j complete -> epilogue
+          }
+          umma_commit(sm.empty0 + 8 * sidx);  // all MMAs reading this stage complete -> producers
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue ===========================
+    reg_alloc<kRegsEpilogue>();
+    const int e = warp - kProducerWarps;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = e >> 2;       // which half of the channel tile (= epilogue warpgroup)
+    const int wgt = threadIdx.x - (kProducerWarps + 4 * half) * 32;  // thread index inside the warpgroup
+    const int r = quarter * 32 + lane;
+    const float sa = P.s[0], sw = P.s[1];
+    const int swords = g.state_words;
+    const bool multibit = g.adc_mode == CIMQ_ADC_MULTIBIT;
+    const bool want_state = P.state != nullptr;
+    // per-warpgroup table slice [pair][tp|tg|amp][CH], double buffered by chunk parity
+    constexpr int SLICE_WORDS = PAIRS * 3 * CH;
+    uint32_t *tbuf = sm.ttab + (size_t)half * 2 * (P.ttab_bytes / 4);
+    uint32_t acc_it = 0, chunk_it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int mt = tile / P.nct, ct = tile % P.nct;
+      const int m = mt * kTcTileM + r;
+      const int c_first = ct * CT + half * CH;
+      float acc[CH];
+#pragma unroll
+      for (int cc = 0; cc < CH; ++cc) acc[cc] = 0.0f;
+      for (int i = 0; i < g.NX; ++i, ++chunk_it) {
+        // stage this chunk's thresholds / amplitudes for our channels (the previous use of this buffer was
+        // two chunks ago; the barrier below orders it)
+        uint32_t *tb = tbuf + (size_t)(chunk_it & 1) * (P.ttab_bytes / 4);
+        {
+          const uint32_t *src = P.ttab + ((size_t)(ct * g.NX + i) * PAIRS * 3) * CT + half * CH;
+          for (int idx = wgt; idx < SLICE_WORDS / 4; idx += 128) {
+            const int row = idx / (CH / 4), c4 = idx % (CH / 4);  // row = pair*3 + array
+            *reinterpret_cast<uint4 *>(tb + row * CH + 4 * c4) =
+                __ldg(reinterpret_cast<const uint4 *>(src + (size_t)row * CT + 4 * c4));
+          }
+        }
+        named_barrier_sync(2 + half, 128);
+        uint32_t stw[CH][SWORDS_MAX];
+#pragma unroll
+        for (int cc = 0; cc < CH; ++cc)
+#pragma unroll
+          for (int w = 0; w < SWORDS_MAX; ++w) stw[cc][w] = 0u;
+#pragma unroll
+        for (int j = 0; j < NSA; ++j, ++acc_it) {
+          const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
+          mbar_wait(sm.tfull0 + 8 * buf, buse & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < NSW; ++k) {
+            int v[CH];
+            tmem_ld<CH>(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NROWS + k * CT + half * CH, v);
+            const int q = k * NSA + j;
+            const uint32_t *trow = tb + q * 3 * CH;
+            tmem_ld_wait();
+            if (multibit) {
+#pragma unroll
+              for (int c4 = 0; c4 < CH / 4; ++c4) {
+                const float4 amp4 = *reinterpret_cast<const float4 *>(trow + 2 * CH + 4 * c4);
+                const float ampv[4] = {amp4.x, amp4.y, amp4.z, amp4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int cc = 4 * c4 + u;
+                  const float ph = psum_as_stored(v[cc]);
+                  const float cf = fminf(fmaxf(ph, (float)g.qn), (float)g.qp);
+                  acc[cc] += __fmul_rn(__fmul_rn(cf, sw), sa) * ampv[u];
+                  if (ph > (float)g.qp || ph < (float)g.qn) stw[cc][q >> 5] |= 1u << (q & 31);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int c4 = 0; c4 < CH / 4; ++c4) {
+                const int4 tp4 = *reinterpret_cast<const int4 *>(trow + 4 * c4);
+                const float4 amp4 = *reinterpret_cast<const float4 *>(trow + 2 * CH + 4 * c4);
+                const int tpv[4] = {tp4.x, tp4.y, tp4.z, tp4.w};
+                const float ampv[4] = {amp4.x, amp4.y, amp4.z, amp4.w};
+                int tgv[4] = {0, 0, 0, 0};
+                if (want_state) {
+                  const int4 tg4 = *reinterpret_cast<const int4 *>(trow + CH + 4 * c4);
+                  tgv[0] = tg4.x; tgv[1] = tg4.y; tgv[2] = tg4.z; tgv[3] = tg4.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int cc = 4 * c4 + u;
+                  const int p = v[cc];
+                  const int a = p < 0 ? -p : p;
+                  const bool nz = a >= tpv[u];
+                  // signed amplitude: flip the sign bit of amp when p is negative
+                  const float samp = __uint_as_float(__float_as_uint(ampv[u]) ^ ((uint32_t)p & 0x80000000u));
+                  if (nz) acc[cc] += samp;
+                  if (want_state) {
+                    if (nz && p > 0) stw[cc][q >> 5] |= 1u << (q & 31);
+                    if (nz && p < 0) stw[cc][(PAIRS + q) >> 5] |= 1u << ((PAIRS + q) & 31);
+                    if (a >= tgv[u]) stw[cc][(2 * PAIRS + q) >> 5] |= 1u << ((2 * PAIRS + q) & 31);
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sm.tempty0 + 8 * buf);  // this warp has drained the accumulator
+        }
+        if (want_state && m < g.M) {
+#pragma unroll
+          for (int cc = 0; cc < CH; ++cc)
+#pragma unroll
+            for (int w = 0; w < SWORDS_MAX; ++w)
+              if (w < swords)
+                P.state[(((size_t)i * g.Cout + c_first + cc) * swords + w) * g.M + m] = stw[cc][w];
+        }
+      }
+      if (m < g.M) {
+        const int b = m / g.L, l = m % g.L;
+#pragma unroll
+        for (int cc = 0; cc < CH; ++cc) P.out[((size_t)b * g.Cout + c_first + cc) * g.L + l] = acc[cc];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, P.tmem_cols);
+  }
+}
+
+template <int NSW, int NSA, int CH>
+int launch_instance(const TcParams &P, size_t smem, int grid, cudaStream_t st) {
+  CIMQ_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NSW, NSA, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  conv_tc_kernel<NSW, NSA, CH><<<grid, kThreads, smem, st>>>(P);
+  CIMQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// one translation unit per slice count (parallel compilation)
+int launch_ns2(const TcParams &P, size_t smem, int grid, int ch, cudaStream_t st);
+int launch_ns3(const TcParams &P, size_t smem, int grid, int ch, cudaStream_t st);
+int launch_ns4(const TcParams &P, size_t smem, int grid, int ch, cudaStream_t st);
+int launch_ns8(const TcParams &P, size_t smem, int grid, int ch, cudaStream_t st);
+
+}  // namespace tcfwd
+}  // namespace cimq

@@ -26,9 +26,9 @@ __device__ __forceinline__ int first_true(Pred pred) {
 }
 
 // table entry e = ((i*NSW + k)*NSA + j)*Cout + c  ->  int4 {tp, tg, amp bits, 0}
-__global__ void adc_table_kernel(Geo g, const float *__restrict__ s, const float *__restrict__ alpha_q,
+__global__ void adc_table_kernel(Geo g, int CT, const float *__restrict__ s, const float *__restrict__ alpha_q,
                                  const int8_t *__restrict__ mask, int4 *__restrict__ table,
-                                 int32_t *__restrict__ status) {
+                                 uint32_t *__restrict__ tiled, int32_t *__restrict__ status) {
   const int64_t n = table_entries(g);
   const float sa = s[0], sw = s[1];
   bool bad = !(sa > 0.0f) || !(sw > 0.0f) || isinf(sa) || isinf(sw);
@@ -48,6 +48,14 @@ __global__ void adc_table_kernel(Geo g, const float *__restrict__ s, const float
         tp = 1;  // sign(p)
     }
     table[e] = make_int4(tp, tg, __float_as_int(amp), 0);
+    if (CT > 0) {  // tiled copy for the tcgen05 epilogue: [ct][i][pair][tp | tg | amp][CT]
+      const int c = (int)(e % g.Cout), i = (int)(e / ((int64_t)g.pairs * g.Cout));
+      const int ct = c / CT, cl = c % CT;
+      uint32_t *row = tiled + ((((int64_t)ct * g.NX + i) * g.pairs + q) * 3) * CT + cl;
+      row[0] = (uint32_t)tp;
+      row[CT] = (uint32_t)tg;
+      row[2 * CT] = __float_as_uint(amp);
+    }
   }
   if (bad && status != nullptr) atomicOr(status, 1);
 }
@@ -77,10 +85,10 @@ __global__ void weight_tiles_kernel(Geo g, int CT, int Kp, const int8_t *__restr
     int r = within / Kp, kk = within % Kp;  // logical (row, k-byte); scattered to its layout slot
     int ct = (int)(tile / g.NX), i = (int)(tile % g.NX);
     int k = r / CT, c = ct * CT + r % CT;
-    int f = i * g.xbar + kk;
-    int hi = min((i + 1) * g.xbar, g.F);
+    const ChunkLayout cl = chunk_layout(g, i);
     int digit = 0;
-    if (f < hi) {
+    if (kk < cl.rows) {
+      const int f = chunk_row_at(g, cl, kk);  // K order inside the chunk: see cim_tc_layout.cuh
       int code = wcodes[(int64_t)c * g.F + f];
       int mag = code < 0 ? -code : code;
       digit = (mag >> (g.wbs * k)) & g.wmask;
@@ -97,7 +105,9 @@ int launch_adc_table(const Geo &g, const float *s, const float *alpha_q, const i
   CIMQ_REQUIRE(g.adc_mode == CIMQ_ADC_MULTIBIT || alpha_q != nullptr, "adc_table: alpha_q is NULL");
   int64_t n = table_entries(g);
   int blocks = (int)((n + 127) / 128);
-  adc_table_kernel<<<blocks, 128, 0, st>>>(g, s, alpha_q, mask, reinterpret_cast<int4 *>(table), status);
+  adc_table_kernel<<<blocks, 128, 0, st>>>(
+      g, tc_channel_tile_for(g), s, alpha_q, mask, reinterpret_cast<int4 *>(table),
+      reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(table) + table_tiled_offset(g)), status);
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -39,7 +39,7 @@ int cimq_layer_info(const cimq_layer_t *layer, cimq_info_t *info) {
   info->tc_forward = tc_forward_supported(g) ? 1 : 0;
   info->tc_backward = tc_backward_supported(g) ? 1 : 0;
   info->state_bytes = (int64_t)g.NX * g.Cout * g.state_words * g.M * 4;
-  info->table_bytes = table_entries(g) * 16;
+  info->table_bytes = table_total_bytes(g);
   info->wdigits_bytes = (int64_t)g.NSW * g.Cout * g.F * 4;
   info->wtiles_bytes = wtiles_bytes(g);
   info->bwd_workspace_bytes = conv_backward_ws_bytes(g);

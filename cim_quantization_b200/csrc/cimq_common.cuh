@@ -134,7 +134,10 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
                          const void *wtiles, const uint32_t *state, const float *s, const int8_t *mask, float *gxq,
                          float *gwq, float *galpha, void *ws, uint32_t flags, cudaStream_t st);
 
-// table = NX*pairs*Cout entries of 16 bytes: int4 {tp, tg, amp (fp32 bits), 0}
+// table = NX*pairs*Cout entries of 16 bytes: int4 {tp, tg, amp (fp32 bits), 0}, followed (256-byte aligned) by the
+// same values tiled for the tcgen05 epilogue: uint32 [Cout/CT][NX][pairs][tp | tg | amp][CT]
 __host__ __device__ inline int64_t table_entries(const Geo &g) { return (int64_t)g.NX * g.pairs * g.Cout; }
+__host__ __device__ inline int64_t table_tiled_offset(const Geo &g) { return (table_entries(g) * 16 + 255) & ~(int64_t)255; }
+__host__ __device__ inline int64_t table_total_bytes(const Geo &g) { return table_tiled_offset(g) + table_entries(g) * 12; }
 
 }  // namespace cimq

@@ -71,7 +71,7 @@ typedef struct cimq_info {
   int32_t tc_backward;          /* 1 if the tcgen05 dgrad / wgrad kernels cover this layer */
   int32_t reserved_;
   int64_t state_bytes;          /* NX*Cout*state_words*M*4 */
-  int64_t table_bytes;          /* ADC table: NX*pairs*Cout entries of 16 bytes {tp, tg, amp, 0} */
+  int64_t table_bytes;          /* ADC table: NX*pairs*Cout entries {tp, tg, amp, 0} + a tiled copy for tcgen05 */
   int64_t wdigits_bytes;        /* fp32 weight digit planes [NSW, Cout, F] */
   int64_t wtiles_bytes;         /* int8 weight digit tiles in tcgen05 shared-memory order (0 if !tc_forward) */
   int64_t bwd_workspace_bytes;  /* scratch for cimq_conv_backward */
