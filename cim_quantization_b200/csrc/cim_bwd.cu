@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_kernel(Geo g, int m_per
       for (int t = 0; t < 8; ++t) {
         int q = q0 + t;
         if (q < g.pairs) {
-          uint32_t pos = state_bit(state, g, i, c, m, q), neg = state_bit(state, g, i, c, m, g.pairs + q);
+          const int sq = state_pair(g, q / g.NSA, q % g.NSA);
+          uint32_t pos = state_bit(state, g, i, c, m, sq), neg = state_bit(state, g, i, c, m, g.pairs + sq);
           acc[t] += pos ? gv : (neg ? -gv : 0.0f);
         }
       }
@@ -71,11 +72,12 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_kernel(Geo g, int m_per
 
 // Fast path for layers whose code bits fit one state word (pairs <= 10): one state load + one go load
 // per (pixel, crossbar, channel), PAIRS register accumulators, HBM-bound (8 B per element).
-template <int PAIRS>
+template <int NSW, int NSA>
 __global__ void __launch_bounds__(256) bwd_alpha_partial_w1_kernel(Geo g, int m_per_split,
                                                                    const float *__restrict__ go,
                                                                    const uint32_t *__restrict__ state,
                                                                    float *__restrict__ partial) {
+  constexpr int PAIRS = NSW * NSA;
   __shared__ float red[8][PAIRS];
   const int c = blockIdx.x, i = blockIdx.y, ms = blockIdx.z;
   const int64_t mbeg = (int64_t)ms * m_per_split;
@@ -105,8 +107,9 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_w1_kernel(Geo g, int m_
     for (int u = 0; u < 4; ++u) {
 #pragma unroll
       for (int q = 0; q < PAIRS; ++q) {
-        // +gv if bit q (code +1), -gv if bit PAIRS+q (code -1)
-        const float sgn = (float)((int)((w[u] >> q) & 1u) - (int)((w[u] >> (PAIRS + q)) & 1u));
+        // table pair q = k*NSA + j lives at state pair sq = j*NSW + k: +gv if bit sq, -gv if bit PAIRS+sq
+        const int sq = (q % NSA) * NSW + q / NSA;
+        const float sgn = (float)((int)((w[u] >> sq) & 1u) - (int)((w[u] >> (PAIRS + sq)) & 1u));
         acc[q] = fmaf(sgn, gv[u], acc[q]);
       }
     }
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(128) bwd_input_kernel(Geo g, const float *__re
       float pw = 0.0f;
       for (int j = 0; j < g.NSA; ++j) {
         int q = k * g.NSA + j;
-        if (!state_bit(state, g, i, co, m, state_clip_bit(g, q))) pw += wx[q];
+        if (!state_bit(state, g, i, co, m, state_clip_bit(g, state_pair(g, k, j)))) pw += wx[q];
       }
       int b = (int)(m / g.L), l = (int)(m % g.L);
       v = go[((int64_t)b * g.Cout + co) * g.L + l] * pw;
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(128) bwd_weight_kernel(Geo g, int ftiles, int 
         float pv = 0.0f;
         for (int k = 0; k < g.NSW; ++k) {
           int q = k * g.NSA + j;
-          if (!state_bit(state, g, i, co, m, state_clip_bit(g, q))) pv += wv[q];
+          if (!state_bit(state, g, i, co, m, state_clip_bit(g, state_pair(g, k, j)))) pv += wv[q];
         }
         int b = (int)(m / g.L), l = (int)(m % g.L);
         v = go[((int64_t)b * g.Cout + co) * g.L + l] * pv;
@@ -405,9 +408,9 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
   if (galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
     dim3 grid(g.Cout, g.NX, p.alpha_splits);
     if (g.state_words == 1 && g.pairs == 9)
-      bwd_alpha_partial_w1_kernel<9><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
+      bwd_alpha_partial_w1_kernel<3, 3><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
     else if (g.state_words == 1 && g.pairs == 4)
-      bwd_alpha_partial_w1_kernel<4><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
+      bwd_alpha_partial_w1_kernel<2, 2><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
     else
       bwd_alpha_partial_kernel<<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
     CIMQ_CUDA_OK(cudaGetLastError());

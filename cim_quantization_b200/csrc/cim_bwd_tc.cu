@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
           float wx[NSA];
 #pragma unroll
           for (int j = 0; j < NSA; ++j) wx[j] = cv.wtab[k * NSA + j];
-          const int start = CBits::CB + k * NSA;
+          const int start = CBits::CB + k;  // clip bit of (k, j) = CB + j*NSW + k
           for (int cgi = 0; cgi < G; ++cgi) {
             uint32_t sw[8][CBits::CWN];
             float gv[8];
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              v[e] = gv[e] * pass_weight<NSA, CBits::CWN>(sw[e], start, 1, wx);
+              v[e] = gv[e] * pass_weight<NSA, CBits::CWN>(sw[e], start, NSW, wx);
             }
             uint32_t hi[4], mid[4], lo[4];
 #pragma unroll
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              v[e] = gv[e] * pass_weight<NSW, CBits::CWN>(sw[e], CBits::CB + j, NSA, wv);
+              v[e] = gv[e] * pass_weight<NSW, CBits::CWN>(sw[e], CBits::CB + j * NSW, 1, wv);
             }
             uint32_t hi[4], mid[4], lo3[4];
 #pragma unroll

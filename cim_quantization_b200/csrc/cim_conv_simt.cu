@@ -100,14 +100,15 @@ __global__ void __launch_bounds__(kPix * kCh) conv_simt_kernel(
             float cf = fminf(fmaxf(ph, (float)g.qn), (float)g.qp);  // lsq.py:228-229
             clip = (ph > (float)g.qp) || (ph < (float)g.qn);         // lsq.py:310-311 on integer psums
             acc += __fmul_rn(__fmul_rn(cf, sw), sa) * amp;           // lsq.py:230, 233
-            if (clip) { int bit = q; st[bit >> 5] |= 1u << (bit & 31); }
+            if (clip) { int bit = state_pair(g, k, j); st[bit >> 5] |= 1u << (bit & 31); }
           } else {
             int pos = p >= te.x, neg = p <= -te.x;                   // ternary / sign code
             clip = (p >= te.y) || (p <= -te.y);
             acc += pos ? amp : (neg ? -amp : 0.0f);
-            if (pos) { int bit = q; st[bit >> 5] |= 1u << (bit & 31); }
-            if (neg) { int bit = g.pairs + q; st[bit >> 5] |= 1u << (bit & 31); }
-            if (clip) { int bit = 2 * g.pairs + q; st[bit >> 5] |= 1u << (bit & 31); }
+            const int sq = state_pair(g, k, j);
+            if (pos) { int bit = sq; st[bit >> 5] |= 1u << (bit & 31); }
+            if (neg) { int bit = g.pairs + sq; st[bit >> 5] |= 1u << (bit & 31); }
+            if (clip) { int bit = 2 * g.pairs + sq; st[bit >> 5] |= 1u << (bit & 31); }
           }
         }
       }

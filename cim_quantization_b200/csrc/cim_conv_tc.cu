@@ -78,9 +78,11 @@ bool make_plan(const Geo &g, TcParams &P, size_t &smem) {
 }  // namespace
 
 int tc_channel_tile_for(const Geo &g) {
-  // channels per CTA: multiple of 16, at most 64, NSW*CT <= 256 (UMMA N) and 2*NSW*CT <= 512 (TMEM)
+  // channels per CTA: multiple of 16, at most 64, NSW*CT <= 256 (UMMA N) and 2*NSW*CT <= 512 (TMEM); an
+  // epilogue thread keeps CT/2 * (accumulator + partial sum + 2 floats per state word) in registers
+  const int swords = (3 * g.pairs + 31) / 32;
   for (int ct = 64; ct >= 16; ct >>= 1)
-    if (g.Cout % ct == 0 && g.NSW * ct <= 256) return ct;
+    if (g.Cout % ct == 0 && g.NSW * ct <= 256 && (ct / 2) * (2 * swords + 2) <= 140) return ct;
   return 0;
 }
 

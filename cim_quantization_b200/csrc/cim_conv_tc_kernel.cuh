@@ -43,6 +43,7 @@ constexpr int kMmaWarp = kProducerWarps + kEpilogueWarps;
 constexpr int kThreads = 512;
 constexpr int kRegsProducer = 104, kRegsMma = 40, kRegsEpilogue = 184;  // 4*32*(104+40+2*184) = 65536
 constexpr int kMaxStages = 4;
+constexpr int kNoRow = -2147483647 - 1;  // staged row outside the image / past the last pixel
 constexpr int kMaxSlots = 16;  // staged input channels per chunk: <= 14 complete (K=3, 128 rows) + head + tail
 
 struct TcParams {
@@ -72,7 +73,7 @@ struct Smem {
   uint8_t *stage_base;   // stages * stage_bytes
   uint8_t *raw;          // 2 * raw_bytes
   uint32_t *ttab;        // 2 warpgroups * 2 buffers * ttab_bytes
-  int *rowoff;           // 2 * 128 ints: global offset of staged row (orow, ky) or -1
+  int *rowoff;           // 2 * 128 ints: global offset of staged row (orow, ky) or kNoRow
   uint32_t full0, empty0, tfull0, tempty0;
   uint32_t *tmem_slot;
 };
@@ -128,10 +129,10 @@ __device__ __forceinline__ void produce_fast(const TcParams &P, const Smem &sm, 
       uint32_t *dst = reinterpret_cast<uint32_t *>(raw + (size_t)sl * slot_bytes);
       for (int idx = threadIdx.x; idx < words_per_slot; idx += kProducerThreads) {
         const int row = idx >> wpr_log2, xw = idx & ((1 << wpr_log2) - 1);
-        const int off = rowoff[row];             // offset of staged column 0 of this row, or -1
+        const int off = rowoff[row];             // offset of staged column 0 of this row, or kNoRow
         const int ix = 4 * xw - P.col0 - g.pad;  // input column of the word's first byte
         uint32_t v = 0;
-        if (off >= 0 && ix >= 0 && ix < g.W) v = __ldg(reinterpret_cast<const uint32_t *>(src + off + 4 * xw));
+        if (off != kNoRow && ix >= 0 && ix < g.W) v = __ldg(reinterpret_cast<const uint32_t *>(src + off + 4 * xw));
         dst[idx] = v;
       }
     }
@@ -229,9 +230,10 @@ __device__ __forceinline__ void produce_generic(const TcParams &P, int i, uint8_
 }
 
 // ---------------------------------------------------------------------------------------------------
-// the kernel.  NSW/NSA: weight / activation digit planes; CH: output channels per epilogue thread (CT/2)
+// the kernel.  NSW/NSA: weight / activation digit planes; CH: output channels per epilogue thread (CT/2);
+// MB: multi-bit ADC (clamp) instead of the binary / ternary threshold ADC
 // ---------------------------------------------------------------------------------------------------
-template <int NSW, int NSA, int CH>
+template <int NSW, int NSA, int CH, bool MB>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) {
   constexpr int CT = 2 * CH;
   constexpr int NROWS = NSW * CT;  // UMMA N
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
         if (r < P.rpt * g.K) {
           const int orow = r / g.K, ky = r % g.K;
           const int m_row = mt * kTcTileM + orow * P.owt;
-          int off = -1;
+          int off = kNoRow;
           if (m_row < g.M) {
             const int b = m_row / g.L, oy = (m_row % g.L) / g.OW;
             const int iy = oy * g.stride - g.pad + ky;
@@ -364,7 +366,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
     const int r = quarter * 32 + lane;
     const float sa = P.s[0], sw = P.s[1];
     const int swords = g.state_words;
-    const bool multibit = g.adc_mode == CIMQ_ADC_MULTIBIT;
     const bool want_state = P.state != nullptr;
     // per-warpgroup table slice [pair][tp|tg|amp][CH], double buffered by chunk parity
     constexpr int SLICE_WORDS = PAIRS * 3 * CH;
@@ -390,24 +391,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
           }
         }
         named_barrier_sync(2 + half, 128);
-        uint32_t stw[CH][SWORDS_MAX];
+        // ADC state, accumulated on the FMA pipe: every 32-bit state word is two fp32 accumulators (bits
+        // [0,HB) and [HB,32)) that start at 2^23, so their low mantissa bits are an exact integer, and
+        // receive decision * 2^bit.  State bit of (type t, act slice j, weight slice k) = t*PAIRS + j*NSW + k:
+        // the k loop below is a real loop (small code: the instruction cache matters here), so a group of NSW
+        // consecutive bits must stay inside one accumulator -- HB is a multiple of NSW.
+        constexpr int HB = (16 / NSW) * NSW;
+        float stf[CH][2 * SWORDS_MAX];
 #pragma unroll
         for (int cc = 0; cc < CH; ++cc)
 #pragma unroll
-          for (int w = 0; w < SWORDS_MAX; ++w) stw[cc][w] = 0u;
+          for (int w = 0; w < 2 * SWORDS_MAX; ++w) stf[cc][w] = 8388608.0f;
 #pragma unroll
         for (int j = 0; j < NSA; ++j, ++acc_it) {
           const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
           mbar_wait(sm.tfull0 + 8 * buf, buse & 1);
           tc_fence_after();
+          // first bit of this activation slice in the +1 / -1 / clip groups, its accumulator and weight there
+          constexpr int kTypes = MB ? 1 : 3;
+          int aidx[3];
+          float abase[3];
 #pragma unroll
-          for (int k = 0; k < NSW; ++k) {
+          for (int t = 0; t < kTypes; ++t) {
+            const int b0 = t * PAIRS + j * NSW;
+            const bool hi = (b0 & 31) >= HB;
+            aidx[t] = 2 * (b0 >> 5) + (hi ? 1 : 0);
+            abase[t] = (float)(1u << ((b0 & 31) - (hi ? HB : 0)));
+          }
+          float wk = 1.0f;  // 2^k
+#pragma unroll 1
+          for (int k = 0; k < NSW; ++k, wk *= 2.0f) {
             int v[CH];
             tmem_ld<CH>(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NROWS + k * CT + half * CH, v);
-            const int q = k * NSA + j;
-            const uint32_t *trow = tb + q * 3 * CH;
+            const uint32_t *trow = tb + (k * NSA + j) * 3 * CH;
             tmem_ld_wait();
-            if (multibit) {
+            if constexpr (MB) {
+              const float kBit = abase[0] * wk;
 #pragma unroll
               for (int c4 = 0; c4 < CH / 4; ++c4) {
                 const float4 amp4 = *reinterpret_cast<const float4 *>(trow + 2 * CH + 4 * c4);
@@ -418,34 +437,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
                   const float ph = psum_as_stored(v[cc]);
                   const float cf = fminf(fmaxf(ph, (float)g.qn), (float)g.qp);
                   acc[cc] += __fmul_rn(__fmul_rn(cf, sw), sa) * ampv[u];
-                  if (ph > (float)g.qp || ph < (float)g.qn) stw[cc][q >> 5] |= 1u << (q & 31);
+                  if (ph > (float)g.qp || ph < (float)g.qn) stf[cc][aidx[0]] += kBit;
                 }
               }
             } else {
+              const float kPos = abase[0] * wk, kNeg = abase[1] * wk, kClp = abase[2] * wk;
 #pragma unroll
               for (int c4 = 0; c4 < CH / 4; ++c4) {
-                const int4 tp4 = *reinterpret_cast<const int4 *>(trow + 4 * c4);
+                const float4 tp4 = *reinterpret_cast<const float4 *>(trow + 4 * c4);
                 const float4 amp4 = *reinterpret_cast<const float4 *>(trow + 2 * CH + 4 * c4);
-                const int tpv[4] = {tp4.x, tp4.y, tp4.z, tp4.w};
+                const float tpv[4] = {tp4.x, tp4.y, tp4.z, tp4.w};
                 const float ampv[4] = {amp4.x, amp4.y, amp4.z, amp4.w};
-                int tgv[4] = {0, 0, 0, 0};
+                float tgv[4] = {0.f, 0.f, 0.f, 0.f};
                 if (want_state) {
-                  const int4 tg4 = *reinterpret_cast<const int4 *>(trow + CH + 4 * c4);
+                  const float4 tg4 = *reinterpret_cast<const float4 *>(trow + CH + 4 * c4);
                   tgv[0] = tg4.x; tgv[1] = tg4.y; tgv[2] = tg4.z; tgv[3] = tg4.w;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   const int cc = 4 * c4 + u;
-                  const int p = v[cc];
-                  const int a = p < 0 ? -p : p;
-                  const bool nz = a >= tpv[u];
-                  // signed amplitude: flip the sign bit of amp when p is negative
-                  const float samp = __uint_as_float(__float_as_uint(ampv[u]) ^ ((uint32_t)p & 0x80000000u));
-                  if (nz) acc[cc] += samp;
+                  // int32 partial sum -> fp32 without the conversion unit (exact for |p| < 2^22)
+                  const float pf = __int_as_float(v[cc] + 0x4B400000) - 12582912.0f;
+                  const float tpos = __saturatef(pf - tpv[u]);    // 1 if p >= tp
+                  const float tneg = __saturatef(-pf - tpv[u]);   // 1 if p <= -tp
+                  acc[cc] = fmaf(tpos - tneg, ampv[u], acc[cc]);  // ternary / sign code times alpha*2^shift
                   if (want_state) {
-                    if (nz && p > 0) stw[cc][q >> 5] |= 1u << (q & 31);
-                    if (nz && p < 0) stw[cc][(PAIRS + q) >> 5] |= 1u << ((PAIRS + q) & 31);
-                    if (a >= tgv[u]) stw[cc][(2 * PAIRS + q) >> 5] |= 1u << ((2 * PAIRS + q) & 31);
+                    const float tclp = __saturatef(fabsf(pf) - tgv[u]);  // 1 if |p| >= tg (STE clip, lsq.py:310)
+                    stf[cc][aidx[0]] = fmaf(tpos, kPos, stf[cc][aidx[0]]);
+                    stf[cc][aidx[1]] = fmaf(tneg, kNeg, stf[cc][aidx[1]]);
+                    stf[cc][aidx[2]] = fmaf(tclp, kClp, stf[cc][aidx[2]]);
                   }
                 }
               }
@@ -455,6 +475,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
           __syncwarp();
           if (lane == 0) mbar_arrive(sm.tempty0 + 8 * buf);  // this warp has drained the accumulator
         }
+        uint32_t stw[CH][SWORDS_MAX];
+#pragma unroll
+        for (int cc = 0; cc < CH; ++cc)
+#pragma unroll
+          for (int w = 0; w < SWORDS_MAX; ++w)
+            stw[cc][w] = (__float_as_uint(stf[cc][2 * w]) & 0x7fffffu) |
+                         ((__float_as_uint(stf[cc][2 * w + 1]) & 0x7fffffu) << HB);
         if (want_state && m < g.M) {
 #pragma unroll
           for (int cc = 0; cc < CH; ++cc)
@@ -482,9 +509,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
 
 template <int NSW, int NSA, int CH>
 int launch_instance(const TcParams &P, size_t smem, int grid, cudaStream_t st) {
-  CIMQ_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NSW, NSA, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-  conv_tc_kernel<NSW, NSA, CH><<<grid, kThreads, smem, st>>>(P);
+  if (P.g.adc_mode == CIMQ_ADC_MULTIBIT) {
+    CIMQ_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NSW, NSA, CH, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<NSW, NSA, CH, true><<<grid, kThreads, smem, st>>>(P);
+  } else {
+    CIMQ_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NSW, NSA, CH, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<NSW, NSA, CH, false><<<grid, kThreads, smem, st>>>(P);
+  }
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

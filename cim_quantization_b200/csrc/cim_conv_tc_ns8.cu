@@ -5,7 +5,6 @@ namespace cimq {
 namespace tcfwd {
 
 int launch_ns8(const TcParams &P, size_t smem, int grid, int ch, cudaStream_t st) {
-  if (ch == 16) return launch_instance<8, 8, 16>(P, smem, grid, st);
   if (ch == 8) return launch_instance<8, 8, 8>(P, smem, grid, st);
   CIMQ_REQUIRE(false, "no tcgen05 forward instance for 8 slices, %d channels per thread", ch);
 }

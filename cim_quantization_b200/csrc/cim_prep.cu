@@ -52,8 +52,9 @@ __global__ void adc_table_kernel(Geo g, int CT, const float *__restrict__ s, con
       const int c = (int)(e % g.Cout), i = (int)(e / ((int64_t)g.pairs * g.Cout));
       const int ct = c / CT, cl = c % CT;
       uint32_t *row = tiled + ((((int64_t)ct * g.NX + i) * g.pairs + q) * 3) * CT + cl;
-      row[0] = (uint32_t)tp;
-      row[CT] = (uint32_t)tg;
+      // thresholds as fp32 "threshold - 1" so that sat(|p| - row) is the 0/1 decision (exact: |p| < 2^24)
+      row[0] = __float_as_uint(tp == kNever ? 3.0e38f : (float)(tp - 1));
+      row[CT] = __float_as_uint(tg == kNever ? 3.0e38f : (float)(tg - 1));
       row[2 * CT] = __float_as_uint(amp);
     }
   }

@@ -75,13 +75,14 @@ inline int make_geo(const cimq_layer_t *l, Geo *g) {
 // ---- ADC state bit layout ------------------------------------------------------------------------
 // Per (crossbar i, channel c, pixel m) the forward stores `state_words` uint32 at
 //   state[((i*Cout + c)*state_words + w)*M + m]
-// holding, for slice pair q = k*NSA + j:
-//   binary / ternary ADC : bit q = code is +1, bit pairs+q = code is -1, bit 2*pairs+q = clipped (STE mask off)
-//   multi-bit ADC        : bit q = clipped
-__host__ __device__ inline int state_pos_bit(int pairs, int q) { return q; }
-__host__ __device__ inline int state_neg_bit(int pairs, int q) { return pairs + q; }
-__host__ __device__ inline int state_clip_bit(const Geo &g, int q) {
-  return g.adc_mode == CIMQ_ADC_MULTIBIT ? q : 2 * g.pairs + q;
+// holding, for weight slice k and activation slice j, with the state pair index sq = j*NSW + k:
+//   binary / ternary ADC : bit sq = code is +1, bit pairs+sq = code is -1, bit 2*pairs+sq = clipped (STE mask off)
+//   multi-bit ADC        : bit sq = clipped
+// (sq is activation-slice major so that the forward epilogue, which walks the weight slices of one
+//  activation digit plane in a rolled loop, writes consecutive bits.)
+__host__ __device__ inline int state_pair(const Geo &g, int k, int j) { return j * g.NSW + k; }
+__host__ __device__ inline int state_clip_bit(const Geo &g, int sq) {
+  return g.adc_mode == CIMQ_ADC_MULTIBIT ? sq : 2 * g.pairs + sq;
 }
 
 // fp16 round trip of an integer partial sum (the reference stores psums as fp16, lsq.py:169).

@@ -24,9 +24,10 @@
  *   conv output, grad_out           [B, Cout, L], L = OH*OW   (NCHW; the reference's [B,L,Cout] is its transpose)
  *   per-psum tables                 [NX, NSW, NSA, Cout]      (same flattening as alpha_cim [1,NX,NSW,NSA,1,Cout])
  *   binary_mask                     int8 [NSW, NSA]           (_quan_base.py:207-214, int8 wrap-around included)
- *   ADC state                       uint32 [NX, Cout, NWORDS, M], M = B*L; per slice pair q = k*NSA + j:
- *                                     binary/ternary: bit q = code +1, bit pairs+q = code -1, bit 2*pairs+q = clipped
- *                                     multi-bit     : bit q = clipped (STE mask off)
+ *   ADC state                       uint32 [NX, Cout, NWORDS, M], M = B*L; for weight slice k, activation slice j,
+ *                                   sq = j*NSW + k:
+ *                                     binary/ternary: bit sq = code +1, bit pairs+sq = code -1, bit 2*pairs+sq = clipped
+ *                                     multi-bit     : bit sq = clipped (STE mask off)
  */
 #ifndef CIMQ_H_
 #define CIMQ_H_

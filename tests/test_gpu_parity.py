@@ -50,7 +50,7 @@ def unpack_state(state, cfg, info, batch):
     clip = np.zeros_like(codes)
     for k in range(info.NSW):
         for j in range(info.NSA):
-            q = k * info.NSA + j
+            q = j * info.NSW + k  # state pair index (activation-slice major), see include/cimq.h
             if multibit:
                 cl = bit(q)
                 cd = np.zeros_like(cl)
