@@ -434,9 +434,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           const int pg = tid & 15;
           const int4 pt = ptab[pg];
           const int64_t mg = m0 + pg * 8;
-          for (int co = tid >> 4; co < Kc; co += 16) {
-            float gv[8];
-            uint32_t sw[8][CBits::CWN];
+          // loads of the next channel are issued before the current one is processed (latency hiding)
+          auto load_g = [&](int co, float (&gv)[8], uint32_t (&sw)[8][CBits::CWN]) {
             const uint32_t *sp = P.state + ((int64_t)(i * g.Cout + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
             if (pt.w == 1) {
               const float4 *gp = reinterpret_cast<const float4 *>(
@@ -466,6 +465,20 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
                 }
               }
             }
+          };
+          float gv_n[8];
+          uint32_t sw_n[8][CBits::CWN];
+          if ((tid >> 4) < Kc) load_g(tid >> 4, gv_n, sw_n);
+          for (int co = tid >> 4; co < Kc; co += 16) {
+            float gv[8];
+            uint32_t sw[8][CBits::CWN];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              gv[e] = gv_n[e];
+#pragma unroll
+              for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = sw_n[e][w];
+            }
+            if (co + 16 < Kc) load_g(co + 16, gv_n, sw_n);
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {

@@ -54,7 +54,7 @@ bool make_plan(const Geo &g, TcParams &P, size_t &smem) {
       nslots = n > nslots ? n : nslots;
     }
     const size_t raw = ((size_t)nslots * (kTcTileM / g.OW) * g.K * (1u << pl) + 15) & ~(size_t)15;
-    if (nslots <= kMaxSlots && raw <= 48 * 1024) {
+    if (nslots <= kMaxSlots && raw <= 48 * 1024 && pl <= 9) {
       P.fast = 1; P.owt = g.OW; P.rpt = kTcTileM / g.OW; P.pitch_log2 = pl; P.col0 = col0;
       P.raw_bytes = (uint32_t)raw;
     }

@@ -119,22 +119,39 @@ __device__ __forceinline__ void produce_fast(const TcParams &P, const Smem &sm, 
   const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
   const int HW = g.H * g.W;
   // ---- 1. stage rows: slot s < nfull -> channel cf0+s, then head channel cf0-1, then tail channel cf0+nfull
+  //         A thread owns one 4-byte column of the staged rows and walks the (slot, row) list in steps of
+  //         `rstep` rows; eight independent global loads are issued before the first store (latency).
   {
-    const int words_per_slot = slot_bytes >> 2;
-    const int wpr_log2 = P.pitch_log2 - 2;  // words per staged row
-    for (int sl = 0; sl < nslots; ++sl) {
-      int ch = cl.cf0 + sl;
-      if (sl >= cl.nfull) ch = (sl == cl.nfull && cl.nhead > 0) ? cl.cf0 - 1 : cl.cf0 + cl.nfull;
-      const uint8_t *src = P.xcodes + (size_t)ch * HW;
-      uint32_t *dst = reinterpret_cast<uint32_t *>(raw + (size_t)sl * slot_bytes);
-      for (int idx = threadIdx.x; idx < words_per_slot; idx += kProducerThreads) {
-        const int row = idx >> wpr_log2, xw = idx & ((1 << wpr_log2) - 1);
-        const int off = rowoff[row];             // offset of staged column 0 of this row, or kNoRow
-        const int ix = 4 * xw - P.col0 - g.pad;  // input column of the word's first byte
-        uint32_t v = 0;
-        if (off != kNoRow && ix >= 0 && ix < g.W) v = __ldg(reinterpret_cast<const uint32_t *>(src + off + 4 * xw));
-        dst[idx] = v;
+    const int wpr_log2 = P.pitch_log2 - 2;          // words per staged row (<= 128)
+    const int xw = threadIdx.x & ((1 << wpr_log2) - 1);
+    const int rstep = kProducerThreads >> wpr_log2;  // rows covered per pass
+    const int rk = P.rpt * KT;                       // staged rows per slot
+    const int total_rows = nslots * rk;
+    const int ix = 4 * xw - P.col0 - g.pad;          // input column of this thread's word
+    const bool xok = ix >= 0 && ix < g.W;
+    int row = threadIdx.x >> wpr_log2, sl = 0;
+    while (row >= rk) { row -= rk; ++sl; }
+    for (int r0 = threadIdx.x >> wpr_log2; r0 < total_rows; r0 += 8 * rstep) {
+      uint32_t v[8];
+      int dsto[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v[u] = 0u;
+        dsto[u] = -1;
+        if (r0 + u * rstep < total_rows) {
+          int ch = cl.cf0 + sl;
+          if (sl >= cl.nfull) ch = (sl == cl.nfull && cl.nhead > 0) ? cl.cf0 - 1 : cl.cf0 + cl.nfull;
+          const int off = rowoff[row];  // offset of staged column 0 of this row in channel 0, or kNoRow
+          if (xok && off != kNoRow)
+            v[u] = __ldg(reinterpret_cast<const uint32_t *>(P.xcodes + (size_t)ch * HW + off + 4 * xw));
+          dsto[u] = sl * slot_bytes + (row << P.pitch_log2) + 4 * xw;
+        }
+        row += rstep;
+        while (row >= rk) { row -= rk; ++sl; }
       }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (dsto[u] >= 0) *reinterpret_cast<uint32_t *>(raw + dsto[u]) = v[u];
     }
   }
   named_barrier_sync(1, kProducerThreads);
