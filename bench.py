@@ -192,13 +192,34 @@ class ClockSampler:
         return out
 
 
-def event_time_ms(fn, iters, torch):
-    """Average device time of fn() over `iters` launches, CUDA events on the current stream."""
+def event_time_ms(fn, iters, torch, graph=True):
+    """Average device time of fn() over `iters` launches: CUDA events on the current stream around one replay
+    of a CUDA graph holding `iters` back-to-back calls (no host launch gaps between them)."""
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fn()
+    torch.cuda.synchronize()
+    g = None
+    if graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(iters):
+                    fn()
+            g.replay()
+        except Exception:
+            g = None
     torch.cuda.synchronize()
     start.record()
-    for _ in range(iters):
-        fn()
+    if g is not None:
+        g.replay()
+    else:
+        for _ in range(iters):
+            fn()
     stop.record()
     torch.cuda.synchronize()
     return start.elapsed_time(stop) / iters
@@ -244,7 +265,9 @@ def run_ours(a):
         for p in layer.parameters():
             dist.broadcast(p.data, 0)
     params = [p for p in layer.parameters()]
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    from cim_quantization_b200.distributed import FlatGradAllReducer
+    reducer = FlatGradAllReducer(params)
+    flat = reducer.flat
 
     def step():
         for p in params:
@@ -252,9 +275,8 @@ def run_ours(a):
         x.grad = None
         y = layer(x)
         y.backward(gy)
-        if world > 1:  # one flat all-reduce of all parameter gradients (weights + step sizes)
-            torch.cat([p.grad.reshape(-1) for p in params], out=flat)
-            dist.all_reduce(flat)
+        if world > 1:  # one flat all-reduce of all parameter gradients (weights + step sizes), DDP average
+            reducer.all_reduce_()
         return y
 
     L.launch_counter = 0
@@ -344,15 +366,24 @@ def run_ours(a):
                                    "frac_int8_tc": fwd_ops / t_fi / 1e9 / int8_peak},
             "conv_backward": {"ms": t_b, "TFLOP/s": bwd_ops / t_b / 1e9, "frac_bf16_tc": bwd_ops / t_b / 1e9 / bf16_peak},
         }
-        # dominant kernel of the step
+        # dominant kernel family of the step (by device time); DRAM traffic per launch from the committed ncu
+        # capture of the same kernels (profiles/ncu_traffic.json), when present
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            pass
         if t_b >= t_f:
-            roof = {"kernel": "conv_backward (CUDA-core dgrad/wgrad/alpha-grad)", "bound": "tensor",
+            roof = {"kernel": "conv_backward (bwd_weight_tc + bwd_input_tc + col2im + alpha-grad)", "bound": "tensor",
                     "achieved": bwd_ops / t_b / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
-                    "frac": bwd_ops / t_b / 1e9 / bf16_peak, "traffic": None, "peak_source": peak_src}
+                    "frac": bwd_ops / t_b / 1e9 / bf16_peak, "traffic": traffic.get("conv_backward"),
+                    "peak_source": peak_src,
+                    "note": "algorithmic flops 2*(NSW+NSA)*MKN; the kernels issue 3x that in bf16 (hi/mid/lo split)"}
         else:
-            roof = {"kernel": "conv_forward", "bound": "tensor", "achieved": fwd_ops / t_f / 1e9, "peak": int8_peak,
-                    "unit": "TOPS", "frac": fwd_ops / t_f / 1e9 / int8_peak, "traffic": None,
-                    "peak_source": peak_src + " x2 for int8"}
+            roof = {"kernel": "conv_forward (conv_tc_kernel, tcgen05 kind::i8)", "bound": "tensor",
+                    "achieved": fwd_ops / t_f / 1e9, "peak": int8_peak, "unit": "TOPS",
+                    "frac": fwd_ops / t_f / 1e9 / int8_peak, "traffic": traffic.get("conv_forward"),
+                    "peak_source": peak_src + " x2 for int8 (no measured int8 peak)"}
 
         # ---- end to end through the module surface with HOST buffers (pinned), copies inside the timed region
         gw_host = torch.empty_like(layer.weight, device="cpu").pin_memory()
@@ -371,7 +402,7 @@ def run_ours(a):
         for _ in range(3):
             e2e_step()
         e2e_iters = max(3, min(a.steps, 10))
-        e2e_ms = event_time_ms(e2e_step, e2e_iters, torch)
+        e2e_ms = event_time_ms(e2e_step, e2e_iters, torch, graph=False)
         e2e = {"value": ops_step / (e2e_ms * 1e-3) / 1e12, "unit": UNIT,
                "h2d_bytes_per_step": int(x_host.numel() * 4 + gy_host.numel() * 4),
                "d2h_bytes_per_step": int(gw_host.numel() * 4 + small_host.numel() * 4), "n_gpus": 1,
