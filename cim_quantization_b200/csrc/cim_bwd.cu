@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_w1_kernel(Geo g, int m_
       for (int q = 0; q < PAIRS; ++q) {
         // table pair q = k*NSA + j lives at state pair sq = j*NSW + k: +gv if bit sq, -gv if bit PAIRS+sq
         const int sq = (q % NSA) * NSW + q / NSA;
-        const float sgn = (float)((int)((w[u] >> sq) & 1u) - (int)((w[u] >> (PAIRS + sq)) & 1u));
-        acc[q] = fmaf(sgn, gv[u], acc[q]);
+        if (w[u] & (1u << sq)) acc[q] += gv[u];            // bit test into a predicate + predicated add
+        if (w[u] & (1u << (PAIRS + sq))) acc[q] -= gv[u];
       }
     }
   }

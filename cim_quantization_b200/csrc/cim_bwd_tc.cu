@@ -36,7 +36,9 @@ constexpr int kThreads = 512;
 constexpr int kMaxStages = 4;
 constexpr int kMaxPairs = 64;
 constexpr size_t kSmemBudget = 227 * 1024 - 1024;
-constexpr size_t kBarrierBytes = 1024;  // barriers + tmem slot + slice-weight table
+constexpr size_t kBarrierBytes = 3072;  // barriers, tmem slot, slice-weight table, pixel / row tables, LUT
+constexpr int kWgProducerThreads = 384;  // wgrad: warps 0-11 build operands (8-11 also run the final epilogue)
+constexpr int kNoRow = -2147483647 - 1;
 
 struct BwdParams {
   Geo g;
@@ -45,6 +47,9 @@ struct BwdParams {
   int mtiles, stages;
   uint32_t a_bytes, b_bytes, stage_bytes, tmem_cols;
   int nxg, chunk0;  // wgrad: crossbars handled by this launch's blockIdx.y group
+  // wgrad staged activation rows (same geometry as the forward producer, stride 1 only)
+  int fastx, ow_log2, rpt, pitch_log2, col0;
+  uint32_t raw_bytes;
   const float *go;
   const uint32_t *state;
   const uint8_t *xcodes;
@@ -76,6 +81,9 @@ struct Carve {
   uint32_t *tmem_slot;
   float *wtab;    // [pairs] slice weights
   int4 *pixtab;   // [2][16] wgrad: {image, output row, first output column, fast-path flag} per 8-pixel group
+  int *rowoff;    // [2][128] wgrad: global offset of staged row (output row, ky) or kNoRow
+  float *lut;     // [NSA][16] wgrad: pass weight by clip-bit pattern of the weight slices
+  uint8_t *raw;   // wgrad: 2 staging buffers of raw_bytes (after the stages)
 };
 
 __device__ __forceinline__ Carve carve_smem(uint8_t *smem_raw, int stages, uint32_t stage_bytes) {
@@ -90,6 +98,9 @@ __device__ __forceinline__ Carve carve_smem(uint8_t *smem_raw, int stages, uint3
   c.tmem_slot = reinterpret_cast<uint32_t *>(aux + 112);
   c.wtab = reinterpret_cast<float *>(aux + 128);     // 64 floats
   c.pixtab = reinterpret_cast<int4 *>(aux + 512);    // 2 x 16 x 16 bytes
+  c.rowoff = reinterpret_cast<int *>(aux + 1024);    // 2 x 128 ints
+  c.lut = reinterpret_cast<float *>(aux + 2048);     // 8 x 16 floats
+  c.raw = aux + kBarrierBytes;
   return c;
 }
 
@@ -314,6 +325,7 @@ constexpr int kWgLBO = 144;  // padded K-stride of the G' tiles: producer lanes 
 template <int NSW, int NSA, bool TERN>
 __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdParams P) {
   using CBits = ClipBits<NSW, NSA, TERN>;
+  constexpr bool kLut = NSW <= 4;  // pass weight of one activation slice by table lookup on its NSW clip bits
   const Geo &g = P.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const Carve cv = carve_smem(smem_raw, P.stages, P.stage_bytes);
@@ -326,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
 
   if (threadIdx.x == 0) {
     for (int sidx = 0; sidx < P.stages; ++sidx) {
-      mbar_init(cv.full0 + 8 * sidx, kProducerThreads);
+      mbar_init(cv.full0 + 8 * sidx, kWgProducerThreads);
       mbar_init(cv.empty0 + 8 * sidx, 1);
     }
     mbar_init(cv.tfull0, 1);
@@ -336,6 +348,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     const int k = threadIdx.x / g.NSA;
     cv.wtab[threadIdx.x] = (float)P.mask[threadIdx.x] * exp2f(-(float)(g.wbs * k));
   }
+  if (kLut && threadIdx.x >= 128 && threadIdx.x < 128 + NSA * 16) {
+    const int j = (threadIdx.x - 128) >> 4, pat = (threadIdx.x - 128) & 15;
+    float acc = 0.0f;
+    for (int k = 0; k < NSW; ++k)
+      if (!((pat >> k) & 1)) acc += (float)P.mask[k * NSA + j] * exp2f(-(float)(g.wbs * k));
+    cv.lut[j * 16 + pat] = acc;
+  }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(cv.tmem_slot), P.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -344,35 +363,84 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
   const int rows_full = g.xbar < g.F ? g.xbar : g.F;
   const bool has_work = blockIdx.x < P.mtiles;
 
-  if (warp < kProducerWarps) {
-    // ------------------------------------------------------------------ producers
-    const int tid = threadIdx.x;  // 0..255
+  if (warp < 12) {
+    // ------------------------------------------------------------------ producers (384 threads)
+    const int tid = threadIdx.x;
     const int fr = tid & 127;     // X tile: this thread's crossbar row
     const bool aligned = (g.L % 8) == 0 && (g.OW % 8) == 0;
-    uint32_t it = 0;
+    const int pitch = 1 << P.pitch_log2;
+    const int slot_bytes = P.rpt * g.K * pitch;
+    const int HW = g.H * g.W;
+    uint32_t it = 0, chunk_it = 0;
     int tpar = 0;
     for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
       const int64_t m0 = (int64_t)mt * kTcTileM;
       // per 8-pixel group: image, output row, first output column; fast = one image row, fully valid, aligned
       if (tid < 16) {
         const int64_t m = m0 + tid * 8;
-        int4 e = make_int4(0, 0, 0, 0);
+        int4 e = make_int4(0, 0, 0, -1);  // w = -1: entirely past the end
         if (m < g.M) {
           const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
           e = make_int4(b, oy, ox, (aligned && m + 7 < g.M && ox + 7 < g.OW) ? 1 : 0);
-        } else {
-          e.w = -1;  // entirely past the end
         }
         cv.pixtab[tpar * 16 + tid] = e;
       }
-      named_barrier_sync(1, kProducerThreads);
+      int *rowoff = cv.rowoff + tpar * 128;
+      if (P.fastx && tid >= 128 && tid < 128 + P.rpt * g.K) {  // staged row (output row, ky) -> global offset
+        const int rr = tid - 128, orow = rr / g.K, ky = rr % g.K;
+        const int64_t m_row = m0 + (orow << P.ow_log2);
+        int off = kNoRow;
+        if (m_row < g.M) {
+          const int b = (int)(m_row / g.L), oy = (int)(m_row % g.L) >> P.ow_log2;
+          const int iy = oy - g.pad + ky;  // stride 1
+          if (iy >= 0 && iy < g.H) off = (b * g.Cin * g.H + iy) * g.W - g.pad - P.col0;
+        }
+        rowoff[rr] = off;
+      }
+      named_barrier_sync(1, kWgProducerThreads);
       const int4 *ptab = cv.pixtab + tpar * 16;
-      for (int i = i_begin; i < i_end; ++i) {
+      for (int i = i_begin; i < i_end; ++i, ++chunk_it) {
         const int lo = i * g.xbar;
         const int rows = min(rows_full, g.F - lo);
         const bool frow = fr < rows;
         int ci = 0, ky = 0, kx = 0;
         if (frow) { const int f = lo + fr; ci = f / g.KK; const int tap = f % g.KK; ky = tap / g.K; kx = tap % g.K; }
+        const int c_lo = lo / g.KK;
+        uint8_t *raw = cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes;
+        if (P.fastx) {
+          // stage the input rows of the channels this crossbar touches (once per chunk, shared by all planes)
+          const int nch = (lo + rows - 1) / g.KK - c_lo + 1;
+          const int wpr_log2 = P.pitch_log2 - 2;
+          const int xw = tid & ((1 << wpr_log2) - 1);
+          const int rstep = kWgProducerThreads >> wpr_log2;
+          const int rk = P.rpt * g.K;
+          const int total_rows = nch * rk;
+          const int ix = 4 * xw - P.col0 - g.pad;
+          const bool xok = ix >= 0 && ix < g.W;
+          int row = tid >> wpr_log2, sl = 0;
+          while (row >= rk) { row -= rk; ++sl; }
+          for (int r0 = tid >> wpr_log2; r0 < total_rows; r0 += 4 * rstep) {
+            uint32_t v[4];
+            int dsto[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              v[u] = 0u;
+              dsto[u] = -1;
+              if (r0 + u * rstep < total_rows) {
+                const int off = rowoff[row];
+                if (xok && off != kNoRow)
+                  v[u] = __ldg(reinterpret_cast<const uint32_t *>(P.xcodes + (size_t)(c_lo + sl) * HW + off + 4 * xw));
+                dsto[u] = sl * slot_bytes + (row << P.pitch_log2) + 4 * xw;
+              }
+              row += rstep;
+              while (row >= rk) { row -= rk; ++sl; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (dsto[u] >= 0) *reinterpret_cast<uint32_t *>(raw + dsto[u]) = v[u];
+          }
+          named_barrier_sync(1, kWgProducerThreads);
+        }
         for (int j = 0; j < NSA; ++j, ++it) {
           const int sidx = it % P.stages;
           const uint32_t use = it / P.stages;
@@ -380,48 +448,67 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
           // ---- X_j tile [128 crossbar rows x 128 pixels] (bf16 digits); item = (row fr, 8-pixel group pg)
           const int sh = g.abs_ * j;
-#pragma unroll 2
-          for (int n = 0; n < 8; ++n) {
-            const int pg = (tid >> 7) + 2 * n;
-            const int4 pt = ptab[pg];
-            uint32_t c[8];
+          for (int pg = tid >> 7; pg < 16; pg += 3) {
+            uint32_t lo8 = 0u, hi8 = 0u;  // the 8 activation codes of this item, one per byte
+            if (frow) {
+              if (P.fastx) {
+                const int p0 = pg * 8;
+                const uint8_t *src = raw + (size_t)(ci - c_lo) * slot_bytes +
+                                     ((((p0 >> P.ow_log2) * g.K) + ky) << P.pitch_log2) +
+                                     (p0 & ((1 << P.ow_log2) - 1)) + kx + P.col0;
+                const uint32_t sa = smem_u32(src);
+                const uint32_t *al = reinterpret_cast<const uint32_t *>(src - (sa & 3u));
+                const uint32_t w0 = al[0], w1 = al[1], w2 = al[2];
+                const uint32_t bsh = (sa & 3u) * 8u;
+                lo8 = __funnelshift_r(w0, w1, bsh);
+                hi8 = __funnelshift_r(w1, w2, bsh);
+              } else {
+                const int4 pt = ptab[pg];
+                uint32_t c[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) c[e] = 0u;
-            if (frow && pt.w >= 0) {
-              if (pt.w == 1) {
-                const int iy = pt.y * g.stride - g.pad + ky;
-                if (iy >= 0 && iy < g.H) {
-                  const uint8_t *row = P.xcodes + (((int64_t)pt.x * g.Cin + ci) * g.H + iy) * g.W;
-                  const int ix0 = pt.z * g.stride - g.pad + kx;
+                for (int e = 0; e < 8; ++e) c[e] = 0u;
+                if (pt.w == 1) {
+                  const int iy = pt.y * g.stride - g.pad + ky;
+                  if (iy >= 0 && iy < g.H) {
+                    const uint8_t *row = P.xcodes + (((int64_t)pt.x * g.Cin + ci) * g.H + iy) * g.W;
+                    const int ix0 = pt.z * g.stride - g.pad + kx;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                      const int ix = ix0 + e * g.stride;
+                      if (ix >= 0 && ix < g.W) c[e] = __ldg(row + ix);
+                    }
+                  }
+                } else if (pt.w == 0) {
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
-                    const int ix = ix0 + e * g.stride;
-                    if (ix >= 0 && ix < g.W) c[e] = __ldg(row + ix);
+                    const int64_t m = m0 + pg * 8 + e;
+                    if (m < g.M) {
+                      const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
+                      const int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
+                      if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+                        c[e] = P.xcodes[(((int64_t)b * g.Cin + ci) * g.H + iy) * g.W + ix];
+                    }
                   }
                 }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const int64_t m = m0 + pg * 8 + e;
-                  if (m < g.M) {
-                    const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
-                    const int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
-                    if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
-                      c[e] = P.xcodes[(((int64_t)b * g.Cin + ci) * g.H + iy) * g.W + ix];
-                  }
-                }
+                lo8 = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+                hi8 = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
               }
             }
             uint32_t d[4];
-            if (g.amask == 1) {  // 1-bit digits: bf16(1) = 0x3F80, two per word with one multiply
-#pragma unroll
-              for (int e2 = 0; e2 < 4; ++e2)
-                d[e2] = (((c[2 * e2] >> sh) & 1u) | (((c[2 * e2 + 1] >> sh) & 1u) << 16)) * 0x3F80u;
+            if (g.amask == 1) {  // 1-bit digits: bf16(1) = 0x3F80; spread two bytes to 16-bit lanes, one multiply
+              const uint32_t tl = (lo8 >> sh) & 0x01010101u, th = (hi8 >> sh) & 0x01010101u;
+              d[0] = __byte_perm(tl, 0u, 0x4140) * 0x3F80u;
+              d[1] = __byte_perm(tl, 0u, 0x4342) * 0x3F80u;
+              d[2] = __byte_perm(th, 0u, 0x4140) * 0x3F80u;
+              d[3] = __byte_perm(th, 0u, 0x4342) * 0x3F80u;
             } else {
+              const uint32_t am = (uint32_t)g.amask;
 #pragma unroll
-              for (int e2 = 0; e2 < 4; ++e2)
-                d[e2] = cvt_bf16x2((float)((c[2 * e2 + 1] >> sh) & (uint32_t)g.amask),
-                                   (float)((c[2 * e2] >> sh) & (uint32_t)g.amask));
+              for (int e2 = 0; e2 < 4; ++e2) {
+                const uint32_t wsrc = e2 < 2 ? lo8 : hi8;
+                const uint32_t b0 = (wsrc >> (16 * (e2 & 1) + sh)) & am, b1 = (wsrc >> (16 * (e2 & 1) + 8 + sh)) & am;
+                d[e2] = cvt_bf16x2((float)b1, (float)b0);
+              }
             }
             *reinterpret_cast<uint4 *>(st_ptr + tc_tile_offset16(fr, pg * 8, kTcLBO, a_sbo)) =
                 make_uint4(d[0], d[1], d[2], d[3]);
@@ -431,6 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           float wv[NSW];
 #pragma unroll
           for (int k = 0; k < NSW; ++k) wv[k] = cv.wtab[k * NSA + j];
+          const float *lutj = cv.lut + j * 16;
           const int pg = tid & 15;
           const int4 pt = ptab[pg];
           const int64_t mg = m0 + pg * 8;
@@ -468,8 +556,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           };
           float gv_n[8];
           uint32_t sw_n[8][CBits::CWN];
-          if ((tid >> 4) < Kc) load_g(tid >> 4, gv_n, sw_n);
-          for (int co = tid >> 4; co < Kc; co += 16) {
+          const int co0 = tid >> 4;  // 0..23
+          if (co0 < Kc) load_g(co0, gv_n, sw_n);
+          for (int co = co0; co < Kc; co += 24) {
             float gv[8];
             uint32_t sw[8][CBits::CWN];
 #pragma unroll
@@ -478,11 +567,15 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
 #pragma unroll
               for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = sw_n[e][w];
             }
-            if (co + 16 < Kc) load_g(co + 16, gv_n, sw_n);
+            if (co + 24 < Kc) load_g(co + 24, gv_n, sw_n);
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              v[e] = gv[e] * pass_weight<NSW, CBits::CWN>(sw[e], CBits::CB + j * NSW, 1, wv);
+              if constexpr (kLut && CBits::CWN == 1) {
+                v[e] = gv[e] * lutj[(sw[e][0] >> (CBits::CB + j * NSW)) & ((1u << NSW) - 1u)];
+              } else {
+                v[e] = gv[e] * pass_weight<NSW, CBits::CWN>(sw[e], CBits::CB + j * NSW, 1, wv);
+              }
             }
             uint32_t hi[4], mid[4], lo3[4];
 #pragma unroll
@@ -525,7 +618,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
       }
       umma_commit(cv.tfull0);  // every accumulation of this CTA is complete
     }
-  } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + kEpilogueWarps) {
+  }
+  if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + kEpilogueWarps) {
     // ------------------------------------------------------------------ epilogue (once, at the end)
     const int quarter = warp & 3;
     const int frow = quarter * 32 + lane;  // TMEM lane = crossbar row
@@ -703,7 +797,25 @@ int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, c
   P.a_bytes = 128u * 128u * 2u;
   P.b_bytes = (uint32_t)(g.Cout / 8) * 16u * (uint32_t)kWgLBO;  // 8-row groups x 16 k-groups x 144 B
   P.stage_bytes = P.a_bytes + 3 * P.b_bytes;
-  int stages = (int)((kSmemBudget - kBarrierBytes) / P.stage_bytes);
+  // staged activation rows (stride 1, output width a power of two between 8 and 128, 4-byte aligned rows)
+  P.fastx = 0; P.raw_bytes = 0;
+  if (g.stride == 1 && g.W % 4 == 0 && g.OW >= 8 && g.OW <= kTcTileM && (g.OW & (g.OW - 1)) == 0 &&
+      (kTcTileM / g.OW) * g.K <= 128 && g.pad < g.K) {
+    int owl = 0;
+    while ((1 << owl) < g.OW) ++owl;
+    const int col0 = (4 - g.pad % 4) % 4;
+    const int needp = (g.OW - 1) + g.K + col0 + 4;  // + 4: the unaligned 8-byte window reads one word further
+    int pl = 2;
+    while ((1 << pl) < needp) ++pl;
+    const int rows = g.xbar < g.F ? g.xbar : g.F;
+    const int nch = (rows + g.KK - 2) / g.KK + 1;  // channels one crossbar can touch
+    const size_t raw = ((size_t)nch * (kTcTileM / g.OW) * g.K * (1u << pl) + 8 + 15) & ~(size_t)15;
+    if (pl <= 9 && 2 * raw + 2 * P.stage_bytes + kBarrierBytes <= kSmemBudget) {
+      P.fastx = 1; P.ow_log2 = owl; P.rpt = kTcTileM / g.OW; P.pitch_log2 = pl; P.col0 = col0;
+      P.raw_bytes = (uint32_t)raw;
+    }
+  }
+  int stages = (int)((kSmemBudget - kBarrierBytes - 2 * (size_t)P.raw_bytes) / P.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   CIMQ_REQUIRE(stages >= 1, "wgrad tile does not fit shared memory");
   P.stages = stages;
@@ -716,7 +828,7 @@ int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, c
   if (ctas > P.mtiles) ctas = P.mtiles;
   if (ctas < 1) ctas = 1;
   P.go = go; P.state = state; P.xcodes = xcodes; P.s = s; P.mask = mask; P.out = partial;
-  const size_t smem = (size_t)stages * P.stage_bytes + kBarrierBytes + 1024;
+  const size_t smem = (size_t)stages * P.stage_bytes + kBarrierBytes + 2 * (size_t)P.raw_bytes + 1024;
   dim3 grid(ctas, groups);
 #define CIMQ_LAUNCH_WGRAD(W, A, T, ...)                                                                          \
   do {                                                                                                           \

@@ -9,7 +9,7 @@
 namespace cimq {
 namespace ptx {
 
-constexpr uint32_t kSpinLimit = 1u << 24;  // a dead pipeline traps instead of hanging the GPU
+constexpr uint32_t kSpinLimit = 1u << 22;  // a dead pipeline traps (after ~1 s) instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -32,7 +32,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity), "r"(20000u)  // suspend-time hint (ns): fewer spin iterations
         : "memory");
-    if (!done && ++spins > kSpinLimit) __trap();
+    if (!done) {
+      // back off: a waiting role must not eat the issue slots of the role it waits for
+      if (++spins > 2) __nanosleep(spins < 32 ? 40 : 200);
+      if (spins > kSpinLimit) __trap();
+    }
   } while (!done);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
