@@ -140,7 +140,7 @@ __global__ void bwd_alpha_finish_kernel(Geo g, int nsplit, float gfac, const int
 }
 
 // ---------------------------------------------------------------------------------------------
-// grad wrt the unfolded input, transposed: gxuT[f][m]
+// grad wrt the unfolded input, image-major and transposed: gxu[b][f][l]
 // grid (ceil(M/32), NX, ceil(rowsmax/128)), block 128; smem Ap[NSW*Cout][32]
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) bwd_input_kernel(Geo g, const float *__restrict__ go,
@@ -197,10 +197,11 @@ __global__ void __launch_bounds__(128) bwd_input_kernel(Geo g, const float *__re
   }
   if (active) {
     const float scale = s[1] / (float)g.NSA;  // w_sl * s_w (lsq.py:252), mean over act slices (lsq.py:376)
-    float *dst = gxuT + (int64_t)f * g.M + m0;
 #pragma unroll
-    for (int p = 0; p < 32; ++p)
-      if (m0 + p < g.M) dst[p] = acc[p] * scale;
+    for (int p = 0; p < 32; ++p) {
+      const int64_t m = m0 + p;
+      if (m < g.M) gxuT[((m / g.L) * g.F + f) * g.L + m % g.L] = acc[p] * scale;  // gxu[b][f][l]
+    }
   }
 }
 
@@ -210,16 +211,16 @@ __global__ void __launch_bounds__(128) bwd_input_kernel(Geo g, const float *__re
 template <int KT>
 __global__ void __launch_bounds__(256) col2im_kernel(Geo g, const float *__restrict__ gxuT,
                                                      float *__restrict__ gx) {
+  // block = one (image, input channel) plane: no per-element division by Cin / B, 32-bit offsets inside the
+  // channel's K*K rows of gxuT (K*K*M < 2^31 is checked by the launcher)
   const int K = KT > 0 ? KT : g.K;
-  const int64_t n = (int64_t)g.B * g.Cin * g.H * g.W;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int ix = (int)(idx % g.W);
-    const int t1 = (int)(idx / g.W);
-    const int iy = t1 % g.H;
-    const int t2 = t1 / g.H;
-    const int ci = t2 % g.Cin, b = t2 / g.Cin;
-    const float *base = gxuT + (int64_t)ci * K * K * g.M + (int64_t)b * g.L;
+  const int ci = blockIdx.x % g.Cin, b = blockIdx.x / g.Cin;
+  const float *base = gxuT + ((int64_t)b * g.F + ci * K * K) * g.L;  // gxu[b][f][l]
+  float *dst = gx + (int64_t)blockIdx.x * g.H * g.W;
+  const int HW = g.H * g.W;
+  const int M = g.L;  // stride between the K*K tap rows of one channel
+  for (int idx = blockIdx.y * 256 + threadIdx.x; idx < HW; idx += gridDim.y * 256) {
+    const int iy = idx / g.W, ix = idx - iy * g.W;
     float v = 0.0f;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(Geo g, const float *__restr
       bool oky = ty >= 0;
       if (g.stride != 1) { oky = oky && (ty % g.stride == 0); oy = ty / g.stride; }
       oky = oky && oy < g.OH;
+      const int rowo = oy * g.OW + ky * K * M;
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
         const int tx = ix + g.pad - kx;
@@ -235,22 +237,24 @@ __global__ void __launch_bounds__(256) col2im_kernel(Geo g, const float *__restr
         bool ok = oky && tx >= 0;
         if (g.stride != 1) { ok = ok && (tx % g.stride == 0); ox = tx / g.stride; }
         ok = ok && ox < g.OW;
-        const float t = ok ? __ldg(base + (int64_t)(ky * K + kx) * g.M + oy * g.OW + ox) : 0.0f;
+        const float t = ok ? __ldg(base + (rowo + kx * M + ox)) : 0.0f;
         v += t;
       }
     }
-    gx[idx] = v;
+    dst[idx] = v;
   }
 }
 
 inline int launch_col2im(const Geo &g, const float *gxuT, float *gx, cudaStream_t st) {
-  const int64_t n = (int64_t)g.B * g.Cin * g.H * g.W;
-  int64_t blocks = (n + 255) / 256;
-  if (blocks > 148 * 64) blocks = 148 * 64;
-  if (g.K == 3) col2im_kernel<3><<<(int)blocks, 256, 0, st>>>(g, gxuT, gx);
-  else if (g.K == 1) col2im_kernel<1><<<(int)blocks, 256, 0, st>>>(g, gxuT, gx);
-  else if (g.K == 5) col2im_kernel<5><<<(int)blocks, 256, 0, st>>>(g, gxuT, gx);
-  else col2im_kernel<0><<<(int)blocks, 256, 0, st>>>(g, gxuT, gx);
+  CIMQ_REQUIRE((int64_t)g.KK * g.L < (1ll << 31), "col2im: K*K*L must be below 2^31");
+  const int hw = g.H * g.W;
+  int by = (hw + 1023) / 1024;  // ~4 pixels per thread
+  if (by < 1) by = 1;
+  dim3 grid(g.B * g.Cin, by);
+  if (g.K == 3) col2im_kernel<3><<<grid, 256, 0, st>>>(g, gxuT, gx);
+  else if (g.K == 1) col2im_kernel<1><<<grid, 256, 0, st>>>(g, gxuT, gx);
+  else if (g.K == 5) col2im_kernel<5><<<grid, 256, 0, st>>>(g, gxuT, gx);
+  else col2im_kernel<0><<<grid, 256, 0, st>>>(g, gxuT, gx);
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

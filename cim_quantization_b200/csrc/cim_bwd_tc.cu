@@ -10,7 +10,7 @@
 //
 //   dgrad  D[128 pixels x Nf crossbar rows] = sum_k sum_split A'_{k,split}[128 x Cout] * W_k[Nf x Cout]^T
 //          A'_k[m,co] = go[m,co] * sum_j pass[m,i,k,j,co] * mask[k,j] * 2^(-abs*j)
-//          -> gxuT[f][m] (then col2im)
+//          -> gxu[b][f][l] (then col2im)
 //   wgrad  D_i[128 crossbar rows x Cout] += sum_j sum_split X_j[128 x 128 pixels] * G'_{j,split}[Cout x 128 pixels]^T
 //          G'_j[m,co] = go[m,co] * sum_k pass[m,i,k,j,co] * mask[k,j] * 2^(-wbs*k),  X_j = activation digit plane
 //          accumulated over all pixel tiles of the CTA in TMEM, one partial [F x Cout] per CTA
@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
     uint32_t acc_it = 0;
     for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
       const int64_t m = (int64_t)mt * kTcTileM + r;
+      const int eb = m < g.M ? (int)(m / g.L) : 0, el = m < g.M ? (int)(m % g.L) : 0;
       for (int i = 0; i < g.NX; ++i, ++acc_it) {
         const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
         const int lo = i * g.xbar;
@@ -295,11 +296,11 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
           int v[32];
           tmem_ld<32>(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * Nf + c0, v);
           tmem_ld_wait();
-          if (m < g.M) {
-            float *dst = P.out + (int64_t)(lo + c0) * g.M + m;
+          if (m < g.M) {  // gxu[b][f][l]: image-major so that col2im's nine reads per output stay within one image
+            float *dst = P.out + ((int64_t)eb * g.F + lo + c0) * g.L + el;
 #pragma unroll
             for (int cc = 0; cc < 32; ++cc)
-              if (c0 + cc < rows) dst[(int64_t)cc * g.M] = __int_as_float(v[cc]) * scale;
+              if (c0 + cc < rows) dst[(int64_t)cc * g.L] = __int_as_float(v[cc]) * scale;
           }
         }
         tc_fence_before();

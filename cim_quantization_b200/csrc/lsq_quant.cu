@@ -21,12 +21,49 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
   return r;
 }
 
-// rint(clamp(x / s, qn, qp)): IEEE division, round-half-to-even -- the exact op chain of
-// `(x / s).clamp(qn, qp).round()` (lsq.py:549).
-__device__ __forceinline__ int lsq_code(float x, float s, float qn, float qp) {
-  float u = __fdiv_rn(x, s);
-  u = fminf(fmaxf(u, qn), qp);
-  return __float2int_rn(u);
+// The reference computes `(x / s).clamp(qn, qp).round()` (lsq.py:549) with an IEEE fp32 division.  A
+// correctly-rounded division per element (MUFU.RCP + Newton + range check) makes the kernel
+// instruction-bound, so the quotient is first approximated with the step size's reciprocal hoisted out of
+// the loop (x*r refined by one FMA residual step: error << 1e-3 for |x/s| < 65536) and the exact division is
+// only evaluated when the approximation is within 1e-3 of a point where the result could change (a
+// rounding tie k+0.5, or -- for the backward's inclusive clamp mask -- a clamp bound).  Results are
+// bit-identical to the IEEE chain.
+struct StepSize {
+  float s, r;
+  bool ok;  // s is a positive normal number whose reciprocal is finite: the fast path is valid
+};
+__device__ __forceinline__ StepSize load_step(const float *sp) {
+  StepSize st;
+  st.s = __ldg(sp);
+  st.r = __frcp_rn(st.s);
+  st.ok = st.s >= 1e-30f && st.s <= 1e30f;
+  return st;
+}
+__device__ __forceinline__ float approx_quotient(float x, const StepSize &st) {
+  const float q0 = x * st.r;
+  const float u = fmaf(fmaf(-q0, st.s, x), st.r, q0);
+  return fabsf(q0) < 65536.0f ? u : q0;  // far outside the code range only the sign matters
+}
+// rint (half to even) of a value in (-2^22, 2^22) without the conversion unit
+__device__ __forceinline__ float rint_magic(float u) { return __fadd_rn(__fadd_rn(u, 12582912.0f), -12582912.0f); }
+
+// integer code rint(clamp(x / s, qn, qp)), as the low byte of the result
+__device__ __forceinline__ uint32_t lsq_code(float x, const StepSize &st, float qn, float qp) {
+  float uc = fminf(fmaxf(approx_quotient(x, st), qn), qp);
+  float biased = __fadd_rn(uc, 12582912.0f);  // low mantissa bits = rint(uc) in two's complement
+  const float t = uc - __fadd_rn(biased, -12582912.0f);
+  if (fabsf(fabsf(t) - 0.5f) < 1e-3f || !(fabsf(x) <= 3.0e38f) || !st.ok) {  // near a tie / non-finite: exact
+    uc = fminf(fmaxf(__fdiv_rn(x, st.s), qn), qp);
+    biased = __fadd_rn(uc, 12582912.0f);
+  }
+  return __float_as_uint(biased) & 0xffu;
+}
+__device__ __forceinline__ float lsq_code_f(float x, const StepSize &st, float qn, float qp) {
+  float uc = fminf(fmaxf(approx_quotient(x, st), qn), qp);
+  float c = rint_magic(uc);
+  if (fabsf(fabsf(uc - c) - 0.5f) < 1e-3f || !(fabsf(x) <= 3.0e38f) || !st.ok)
+    c = rint_magic(fminf(fmaxf(__fdiv_rn(x, st.s), qn), qp));
+  return c;
 }
 
 __global__ void step_sizes_kernel(const float *__restrict__ aa, const float *__restrict__ aw, float ga, float gw,
@@ -44,7 +81,7 @@ __global__ void step_sizes_kernel(const float *__restrict__ aa, const float *__r
 __global__ void __launch_bounds__(kThreads) lsq_quantize_vec_kernel(const float4 *__restrict__ x, int64_t n16,
                                                                     const float *__restrict__ sp, float qn,
                                                                     float qp, uint4 *__restrict__ codes) {
-  const float s = __ldg(sp);
+  const StepSize s = load_step(sp);
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n16; i += (int64_t)gridDim.x * kThreads) {
     float4 v[4];
 #pragma unroll
@@ -52,10 +89,10 @@ __global__ void __launch_bounds__(kThreads) lsq_quantize_vec_kernel(const float4
     uint32_t w[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      uint32_t c0 = (uint32_t)lsq_code(v[k].x, s, qn, qp) & 0xffu;
-      uint32_t c1 = (uint32_t)lsq_code(v[k].y, s, qn, qp) & 0xffu;
-      uint32_t c2 = (uint32_t)lsq_code(v[k].z, s, qn, qp) & 0xffu;
-      uint32_t c3 = (uint32_t)lsq_code(v[k].w, s, qn, qp) & 0xffu;
+      uint32_t c0 = lsq_code(v[k].x, s, qn, qp);
+      uint32_t c1 = lsq_code(v[k].y, s, qn, qp);
+      uint32_t c2 = lsq_code(v[k].z, s, qn, qp);
+      uint32_t c3 = lsq_code(v[k].w, s, qn, qp);
       w[k] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
     }
     codes[i] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -65,10 +102,10 @@ __global__ void __launch_bounds__(kThreads) lsq_quantize_vec_kernel(const float4
 __global__ void lsq_quantize_scalar_kernel(const float *__restrict__ x, int64_t begin, int64_t n,
                                            const float *__restrict__ sp, float qn, float qp,
                                            uint8_t *__restrict__ codes) {
-  const float s = __ldg(sp);
+  const StepSize s = load_step(sp);
   for (int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
-    codes[i] = (uint8_t)(lsq_code(x[i], s, qn, qp) & 0xff);
+    codes[i] = (uint8_t)lsq_code(x[i], s, qn, qp);
 }
 
 // Float outputs for the plain LSQ modules (ActLSQ returns codes, LinearLSQ / Conv2dLSQ need
@@ -76,29 +113,36 @@ __global__ void lsq_quantize_scalar_kernel(const float *__restrict__ x, int64_t 
 __global__ void __launch_bounds__(kThreads) lsq_fakequant_kernel(const float *__restrict__ x, int64_t n,
                                                                  const float *__restrict__ sp, float qn, float qp,
                                                                  int rescale, float *__restrict__ y, int vec_ok) {
-  const float s = __ldg(sp);
-  const float m = rescale ? s : 1.0f;
+  const StepSize s = load_step(sp);
+  const float m = rescale ? s.s : 1.0f;
   const int64_t n4 = vec_ok ? n / 4 : 0;
   const float4 *x4 = reinterpret_cast<const float4 *>(x);
   float4 *y4 = reinterpret_cast<float4 *>(y);
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
     float4 v = ldg_stream(x4 + i), o;
-    o.x = __fmul_rn((float)lsq_code(v.x, s, qn, qp), m);
-    o.y = __fmul_rn((float)lsq_code(v.y, s, qn, qp), m);
-    o.z = __fmul_rn((float)lsq_code(v.z, s, qn, qp), m);
-    o.w = __fmul_rn((float)lsq_code(v.w, s, qn, qp), m);
+    o.x = __fmul_rn(lsq_code_f(v.x, s, qn, qp), m);
+    o.y = __fmul_rn(lsq_code_f(v.y, s, qn, qp), m);
+    o.z = __fmul_rn(lsq_code_f(v.z, s, qn, qp), m);
+    o.w = __fmul_rn(lsq_code_f(v.w, s, qn, qp), m);
     y4[i] = o;
   }
   for (int64_t i = n4 * 4 + blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * kThreads)
-    y[i] = __fmul_rn((float)lsq_code(x[i], s, qn, qp), m);
+    y[i] = __fmul_rn(lsq_code_f(x[i], s, qn, qp), m);
 }
 
-__device__ __forceinline__ void lsq_bwd_elem(float g, float x, float s, float qn, float qp, float &gx,
+__device__ __forceinline__ void lsq_bwd_elem(float g, float x, const StepSize &st, float qn, float qp, float &gx,
                                              float &acc) {
-  float u = __fdiv_rn(x, s);
+  float u = approx_quotient(x, st);
+  {
+    const float uc = fminf(fmaxf(u, qn), qp);
+    const float t = uc - rint_magic(uc);
+    // exact division near a rounding tie, near a clamp bound (inclusive mask; x == 0 is exact) or for odd inputs
+    const bool near_bound = (fabsf(u - qn) < 1e-3f || fabsf(u - qp) < 1e-3f) && x != 0.0f;
+    if (fabsf(fabsf(t) - 0.5f) < 1e-3f || near_bound || !(fabsf(x) <= 3.0e38f) || !st.ok) u = __fdiv_rn(x, st.s);
+  }
   bool inside = (u >= qn) && (u <= qp);  // torch.clamp backward mask is inclusive
-  float q = rintf(fminf(fmaxf(u, qn), qp));
+  float q = rint_magic(fminf(fmaxf(u, qn), qp));
   gx = inside ? g : 0.0f;
   acc = fmaf(g, q - (inside ? u : 0.0f), acc);
 }
@@ -120,7 +164,7 @@ __global__ void __launch_bounds__(kThreads) lsq_backward_kernel(const float *__r
                                                                 const float *__restrict__ sp, float qn, float qp,
                                                                 float *__restrict__ gx,
                                                                 double *__restrict__ partials, int vec_ok) {
-  const float s = __ldg(sp);
+  const StepSize s = load_step(sp);
   float acc = 0.0f;
   const int64_t n8 = vec_ok ? n / 8 : 0;
   const float4 *g4 = reinterpret_cast<const float4 *>(gq);

@@ -96,6 +96,33 @@ def test_lsq_quantize_bit_exact(n, signed):
     np.testing.assert_array_equal(codes.cpu().numpy().astype(np.int32), ref)
 
 
+@pytest.mark.parametrize("s", [0.1234567, 0.3333333, 1.0, 7.1e-4, 3.0])
+def test_lsq_quantize_adversarial_ties(s):
+    """Inputs within a few ulps of every rounding tie (k+0.5)*s and of the clamp bounds: the hoisted-reciprocal
+    fast path must fall back to the exact division there and still match the IEEE chain bit-for-bit."""
+    L = _lib()
+    s = np.float32(s)
+    ks = np.arange(-6, 10, dtype=np.float32)
+    base = np.concatenate([(ks + np.float32(0.5)) * s, ks * s])
+    xs = [base]
+    for _ in range(6):  # walk ulps up and down around every critical point
+        xs.append(np.nextafter(xs[-1], np.float32(np.inf), dtype=np.float32))
+    lo = [base]
+    for _ in range(6):
+        lo.append(np.nextafter(lo[-1], np.float32(-np.inf), dtype=np.float32))
+    x = np.concatenate(xs + lo + [np.array([np.inf, -np.inf, 3.4e38, -3.4e38, 1e-45, -1e-45, 0.0, -0.0], np.float32)])
+    x = np.tile(x, 5).astype(np.float32)
+    sd = _cuda(np.array([s], dtype=np.float32))
+    for qn, qp in ((0, 7), (-4, 3), (0, 255), (-128, 127)):
+        codes = L.lsq_quantize(_cuda(x), sd, qn, qp)
+        np.testing.assert_array_equal(codes.cpu().numpy().astype(np.int32), O.lsq_codes(x, s, qn, qp))
+        fin = np.isfinite(x)
+        g = np.ones_like(x)
+        gx, _ = L.lsq_backward(_cuda(g), _cuda(np.where(fin, x, 0).astype(np.float32)), sd, qn, qp, 1.0)
+        u = np.where(fin, x, 0).astype(np.float32) / s
+        np.testing.assert_array_equal(gx.cpu().numpy(), ((u >= qn) & (u <= qp)).astype(np.float32))
+
+
 @pytest.mark.parametrize("n", [37, 1 << 16, (1 << 18) + 5])
 def test_lsq_backward(n):
     L = _lib()
