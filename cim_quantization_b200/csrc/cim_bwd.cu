@@ -70,47 +70,51 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_kernel(Geo g, int m_per
   }
 }
 
-// Fast path for layers whose code bits fit one state word (pairs <= 10): one state load + one go load
-// per (pixel, crossbar, channel), PAIRS register accumulators, HBM-bound (8 B per element).
+// Fast path (compile-time slice counts): one pass over (state words, go) per (pixel, crossbar, channel),
+// PAIRS register accumulators, predicated adds; HBM-bound (state + go bytes).
 template <int NSW, int NSA>
 __global__ void __launch_bounds__(256) bwd_alpha_partial_w1_kernel(Geo g, int m_per_split,
                                                                    const float *__restrict__ go,
                                                                    const uint32_t *__restrict__ state,
                                                                    float *__restrict__ partial) {
   constexpr int PAIRS = NSW * NSA;
+  constexpr int SWORDS = (3 * PAIRS + 31) / 32;  // state words per (crossbar, channel, pixel)
+  constexpr int NW = (2 * PAIRS + 31) / 32;      // words holding the +1 / -1 code bits
+  constexpr int U = PAIRS <= 16 ? 4 : 2;         // independent (state, go) loads in flight per thread
   __shared__ float red[8][PAIRS];
   const int c = blockIdx.x, i = blockIdx.y, ms = blockIdx.z;
   const int64_t mbeg = (int64_t)ms * m_per_split;
   const int64_t mend = min((int64_t)g.M, mbeg + m_per_split);
-  const uint32_t *st = state + ((int64_t)i * g.Cout + c) * g.M;  // state_words == 1
+  const uint32_t *st = state + ((int64_t)i * g.Cout + c) * SWORDS * g.M;
   float acc[PAIRS];
 #pragma unroll
   for (int q = 0; q < PAIRS; ++q) acc[q] = 0.0f;
-  // four independent (state, go) load pairs in flight per thread; the image index advances incrementally
-  // (no per-element division)
+  // the image index advances incrementally (no per-element division)
   int64_t m = mbeg + threadIdx.x;
   int b = (int)(m / g.L), l = (int)(m % g.L);
   const float *gbase = go + (int64_t)c * g.L;
   const int64_t gimg = (int64_t)g.Cout * g.L;
-  for (; m < mend; m += 1024) {
-    float gv[4];
-    uint32_t w[4];
+  for (; m < mend; m += U * 256) {
+    float gv[U];
+    uint32_t w[U][NW];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const bool ok = m + u * 256 < mend;
       gv[u] = ok ? __ldg(gbase + (int64_t)b * gimg + l) : 0.0f;
-      w[u] = ok ? __ldg(st + m + u * 256) : 0u;
+#pragma unroll
+      for (int t = 0; t < NW; ++t) w[u][t] = ok ? __ldg(st + (int64_t)t * g.M + m + u * 256) : 0u;
       l += 256;
       while (l >= g.L) { l -= g.L; ++b; }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
       for (int q = 0; q < PAIRS; ++q) {
         // table pair q = k*NSA + j lives at state pair sq = j*NSW + k: +gv if bit sq, -gv if bit PAIRS+sq
         const int sq = (q % NSA) * NSW + q / NSA;
-        if (w[u] & (1u << sq)) acc[q] += gv[u];            // bit test into a predicate + predicated add
-        if (w[u] & (1u << (PAIRS + sq))) acc[q] -= gv[u];
+        const int bp = sq, bn = PAIRS + sq;
+        if (w[u][bp >> 5] & (1u << (bp & 31))) acc[q] += gv[u];  // bit test into a predicate + predicated add
+        if (w[u][bn >> 5] & (1u << (bn & 31))) acc[q] -= gv[u];
       }
     }
   }
@@ -411,10 +415,14 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
 
   if (galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
     dim3 grid(g.Cout, g.NX, p.alpha_splits);
-    if (g.state_words == 1 && g.pairs == 9)
+    if (g.NSW == 3 && g.NSA == 3)
       bwd_alpha_partial_w1_kernel<3, 3><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
-    else if (g.state_words == 1 && g.pairs == 4)
+    else if (g.NSW == 2 && g.NSA == 2)
       bwd_alpha_partial_w1_kernel<2, 2><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
+    else if (g.NSW == 4 && g.NSA == 4)
+      bwd_alpha_partial_w1_kernel<4, 4><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
+    else if (g.NSW == 8 && g.NSA == 8)
+      bwd_alpha_partial_w1_kernel<8, 8><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
     else
       bwd_alpha_partial_kernel<<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
     CIMQ_CUDA_OK(cudaGetLastError());

@@ -1,0 +1,105 @@
+"""Benchmark / example harness around the hot path (NOT part of the re-implemented scope): a CIFAR ResNet-20
+like the reference's ``models/cifar10/resnet.py`` (option-A shortcuts, ``resnet.py:73-75``) and the model
+surgery of ``utils/wrapper/replace_module.py`` (every ``nn.Conv2d`` -> ``Conv2dLSQCiM``, first conv forced
+to 8-bit weights/activations, ``replace_module.py:83-95``), so that the ResNet-20 configurations of
+BASELINE.json can be run on the GPU box where the reference tree is not available.  When the reference IS
+available, ``cim_quantization_b200.dropin.install()`` lets its own ``main_lsq.py`` drive these kernels.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .modules import Conv2dLSQCiM
+
+
+class _OptionA(nn.Module):
+    def __init__(self, planes):
+        super().__init__()
+        self.pad = planes // 4
+
+    def forward(self, x):
+        return F.pad(x[:, :, ::2, ::2], (0, 0, 0, 0, self.pad, self.pad), "constant", 0)
+
+
+class BasicBlock(nn.Module):
+    def __init__(self, in_planes, planes, stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_planes, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.shortcut = _OptionA(planes) if (stride != 1 or in_planes != planes) else nn.Sequential()
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        return F.relu(out + self.shortcut(x))
+
+
+class ResNetCifar(nn.Module):
+    def __init__(self, num_blocks=(3, 3, 3), width=1, num_classes=10):
+        super().__init__()
+        p = 16 * width
+        self.in_planes = p
+        self.conv1 = nn.Conv2d(3, p, 3, 1, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(p)
+        self.layer1 = self._make_layer(p, num_blocks[0], 1)
+        self.layer2 = self._make_layer(2 * p, num_blocks[1], 2)
+        self.layer3 = self._make_layer(4 * p, num_blocks[2], 2)
+        self.linear = nn.Linear(4 * p, num_classes)
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.kaiming_normal_(m.weight)
+
+    def _make_layer(self, planes, n, stride):
+        layers = []
+        for s in [stride] + [1] * (n - 1):
+            layers.append(BasicBlock(self.in_planes, planes, s))
+            self.in_planes = planes
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.layer3(self.layer2(self.layer1(out)))
+        out = F.adaptive_avg_pool2d(out, 1).flatten(1)
+        return self.linear(out)
+
+
+def resnet20(width=1):
+    """CIFAR ResNet-20 (19 convs + 1 linear); ``width=4`` is the 'wide' variant of BASELINE.json config 5."""
+    return ResNetCifar((3, 3, 3), width)
+
+
+def convert_to_cim(model, nbits_w=3, nbits_a=3, nbits_alpha=8, wbitslice=1, abitslice=1, xbar=128, adcbits=1.5,
+                   stochastic_quant=False):
+    """Replace every ``nn.Conv2d`` by ``Conv2dLSQCiM`` (weights copied), first conv at 8/8 bits -- the
+    behaviour of ``ReplaceModuleTool(model, {'Conv2d': [Conv2dLSQCiM]}, True, ...)`` in the reference."""
+    state = {"first": True}
+
+    def recurse(mod):
+        for name, child in list(mod._modules.items()):
+            if isinstance(child, nn.Conv2d) and not isinstance(child, Conv2dLSQCiM):
+                bw, ba = (8, 8) if state["first"] else (nbits_w, nbits_a)
+                state["first"] = False
+                new = Conv2dLSQCiM(child.in_channels, child.out_channels, child.kernel_size, child.stride,
+                                   child.padding, child.dilation, groups=child.groups, bias=child.bias is not None,
+                                   nbits_w=bw, nbits_a=ba, nbits_alpha=nbits_alpha, wbitslice=wbitslice,
+                                   abitslice=abitslice, xbar=xbar, adcbits=adcbits, signed_xbar=False,
+                                   stochastic_quant=stochastic_quant)
+                new.weight.data.copy_(child.weight.data)
+                if child.bias is not None:
+                    new.bias.data.copy_(child.bias.data)
+                mod._modules[name] = new.to(child.weight.device)
+            elif child is not None and len(child._modules) > 0:
+                recurse(child)
+
+    recurse(model)
+    return model
+
+
+def sgd_param_groups(model, weight_decay=1e-4):
+    """No weight decay on the learned step sizes (names containing 'alpha'), examples/__init__.py:181-196."""
+    decay, no_decay = [], []
+    for n, p in model.named_parameters():
+        (no_decay if "alpha" in n else decay).append(p)
+    return [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}]
