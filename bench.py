@@ -288,7 +288,7 @@ def run_ours(a):
 
     runner = step
     graph = None
-    if not a.no_graph and world == 1:
+    if not a.no_graph and world == 1:  # (N > 1 launches eagerly: NCCL teardown after graph capture is fragile)
         try:  # replay the whole step as one CUDA graph: no launch gaps, no host work in the timed region
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())

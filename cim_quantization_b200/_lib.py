@@ -49,6 +49,9 @@ EXPORTS = {
     "cimq_lsq_backward_workspace_bytes": (C.c_int64, [C.c_int64]),
     "cimq_lsq_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cimq_alpha_quantize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cimq_alpha_quantize_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]),
     "cimq_adc_table": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
     "cimq_weight_prepare": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -188,6 +191,22 @@ def lsq_backward(grad_xq, x, s_elem, qn: int, qp: int, g: float):
                                     _ptr(galpha), _ptr(ws), _stream()))
     _count(2)
     return gx, galpha
+
+
+def alpha_quantize(alpha, qn: int, qp: int):
+    aq = torch.empty_like(alpha)
+    aux = torch.empty(8, dtype=torch.float32, device=alpha.device)
+    _check(load().cimq_alpha_quantize(_ptr(alpha), alpha.numel(), qn, qp, _ptr(aq), _ptr(aux), _stream()))
+    _count(1)
+    return aq, aux
+
+
+def alpha_quantize_backward(alpha, grad_aq, qn: int, qp: int, aux):
+    ga = torch.empty_like(alpha)
+    _check(load().cimq_alpha_quantize_backward(_ptr(alpha), _ptr(grad_aq), alpha.numel(), qn, qp, _ptr(aux), _ptr(ga),
+                                               _stream()))
+    _count(1)
+    return ga
 
 
 def adc_table(spec: LayerSpec, s, alpha_q, binary_mask, status=None):

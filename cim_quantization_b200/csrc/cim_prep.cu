@@ -99,7 +99,100 @@ __global__ void weight_tiles_kernel(Geo g, int CT, int Kp, const int8_t *__restr
   }
 }
 
+// ---- alpha_cim range quantiser (lsq.py:566-571) ---------------------------------------------------------
+// alpha_q = clamp(round_pass(alpha / scale), qn, qp) * scale,  scale = (max(alpha) - min(alpha)) / (qp - qn)
+// One block: the tensor has NX*pairs*Cout elements (a few thousand).  aux = {scale, max, min, #max, #min}.
+constexpr int kAqThreads = 1024;
+
+__device__ __forceinline__ float block_reduce_f(float v, bool is_max, float *sm) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : fminf(v, t);
+  }
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = sm[threadIdx.x & 31];
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : fminf(v, t);
+  }
+  __syncthreads();
+  return v;
+}
+__device__ __forceinline__ double block_reduce_d(double v, double *sm) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = sm[threadIdx.x & 31];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  return v;
+}
+
+__global__ void __launch_bounds__(kAqThreads) alpha_quant_fwd_kernel(const float *__restrict__ alpha, int n, float qn,
+                                                                     float qp, float *__restrict__ aq,
+                                                                     float *__restrict__ aux) {
+  __shared__ float smf[32];
+  __shared__ double smd[32];
+  float mx = -INFINITY, mn = INFINITY;
+  for (int i = threadIdx.x; i < n; i += kAqThreads) { mx = fmaxf(mx, alpha[i]); mn = fminf(mn, alpha[i]); }
+  mx = block_reduce_f(mx, true, smf);
+  mn = block_reduce_f(mn, false, smf);
+  const float scale = __fdiv_rn(__fsub_rn(mx, mn), __fsub_rn(qp, qn));
+  double cmx = 0.0, cmn = 0.0;
+  for (int i = threadIdx.x; i < n; i += kAqThreads) {
+    const float a = alpha[i];
+    const float r = rintf(__fdiv_rn(a, scale));  // round_pass value is exactly the rounded value
+    aq[i] = __fmul_rn(fminf(fmaxf(r, qn), qp), scale);
+    cmx += a == mx ? 1.0 : 0.0;
+    cmn += a == mn ? 1.0 : 0.0;
+  }
+  cmx = block_reduce_d(cmx, smd);
+  cmn = block_reduce_d(cmn, smd);
+  if (threadIdx.x == 0) { aux[0] = scale; aux[1] = mx; aux[2] = mn; aux[3] = (float)cmx; aux[4] = (float)cmn; }
+}
+
+// autograd of the above w.r.t. alpha: STE through round, inclusive clamp mask, scale through max/min with
+// ties sharing the gradient evenly (torch's full-reduction max/min backward)
+__global__ void __launch_bounds__(kAqThreads) alpha_quant_bwd_kernel(const float *__restrict__ alpha,
+                                                                     const float *__restrict__ gaq, int n, float qn,
+                                                                     float qp, const float *__restrict__ aux,
+                                                                     float *__restrict__ galpha) {
+  __shared__ double smd[32];
+  const float scale = aux[0], mx = aux[1], mn = aux[2], cmx = aux[3], cmn = aux[4];
+  double gs = 0.0;
+  for (int i = threadIdx.x; i < n; i += kAqThreads) {
+    const float a = alpha[i], g = gaq[i];
+    const float r = rintf(__fdiv_rn(a, scale));
+    const bool inside = r >= qn && r <= qp;
+    const float c = fminf(fmaxf(r, qn), qp);
+    const float gt = inside ? g * scale : 0.0f;
+    gs += (double)g * c - (double)gt * ((double)a / ((double)scale * scale));
+    galpha[i] = gt / scale;
+  }
+  gs = block_reduce_d(gs, smd);
+  const float grange = (float)(gs / (double)(qp - qn));
+  for (int i = threadIdx.x; i < n; i += kAqThreads) {
+    const float a = alpha[i];
+    float v = galpha[i];
+    if (a == mx) v += grange / cmx;
+    if (a == mn) v -= grange / cmn;
+    galpha[i] = v;
+  }
+}
+
 }  // namespace
+
+int launch_alpha_quant(const float *alpha, int64_t n, int qn, int qp, const float *gaq, float *out, float *aux,
+                       cudaStream_t st) {
+  CIMQ_REQUIRE(n > 0 && n < (1ll << 30), "alpha_quant: bad element count");
+  if (gaq == nullptr)
+    alpha_quant_fwd_kernel<<<1, kAqThreads, 0, st>>>(alpha, (int)n, (float)qn, (float)qp, out, aux);
+  else
+    alpha_quant_bwd_kernel<<<1, kAqThreads, 0, st>>>(alpha, gaq, (int)n, (float)qn, (float)qp, aux, out);
+  CIMQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int launch_adc_table(const Geo &g, const float *s, const float *alpha_q, const int8_t *mask, void *table,
                      int32_t *status, cudaStream_t st) {

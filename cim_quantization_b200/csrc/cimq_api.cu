@@ -82,6 +82,18 @@ int cimq_lsq_backward(const float *grad_xq, const float *x, int64_t n, const flo
   return launch_lsq_backward(grad_xq, x, n, s, qn, qp, g, grad_x, grad_alpha, workspace, as_stream(stream));
 }
 
+int cimq_alpha_quantize(const float *alpha, int64_t n, int32_t qn, int32_t qp, float *alpha_q, float *aux,
+                        void *stream) {
+  CIMQ_REQUIRE(alpha && alpha_q && aux, "alpha_quantize: NULL argument");
+  return launch_alpha_quant(alpha, n, qn, qp, nullptr, alpha_q, aux, as_stream(stream));
+}
+
+int cimq_alpha_quantize_backward(const float *alpha, const float *grad_alpha_q, int64_t n, int32_t qn, int32_t qp,
+                                 const float *aux, float *grad_alpha, void *stream) {
+  CIMQ_REQUIRE(alpha && grad_alpha_q && aux && grad_alpha, "alpha_quantize_backward: NULL argument");
+  return launch_alpha_quant(alpha, n, qn, qp, grad_alpha_q, grad_alpha, const_cast<float *>(aux), as_stream(stream));
+}
+
 int cimq_adc_table(const cimq_layer_t *layer, const float *s, const float *alpha_q, const int8_t *binary_mask,
                    void *table, int32_t *status, void *stream) {
   Geo g;

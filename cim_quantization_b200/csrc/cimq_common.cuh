@@ -102,6 +102,8 @@ int64_t lsq_backward_ws_bytes(int64_t n);
 
 int launch_adc_table(const Geo &g, const float *s, const float *alpha_q, const int8_t *mask, void *table,
                      int32_t *status, cudaStream_t st);
+int launch_alpha_quant(const float *alpha, int64_t n, int qn, int qp, const float *gaq, float *out, float *aux,
+                       cudaStream_t st);
 int launch_weight_prepare(const Geo &g, const int8_t *wcodes, float *wdigits, void *wtiles, cudaStream_t st);
 int64_t wtiles_bytes(const Geo &g);
 bool tc_forward_supported(const Geo &g);

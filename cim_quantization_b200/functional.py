@@ -190,6 +190,29 @@ def lsq_fake_quant(x, alpha, g: float, qn: int, qp: int, rescale: bool = True):
     return _LsqFakeQuant.apply(x, alpha, g, qn, qp, rescale)
 
 
+class _AlphaQuant(Function):
+    """``nbits_alpha``-bit range quantiser of alpha_cim with torch-autograd-equivalent backward
+    (lsq.py:566-571), one kernel each way instead of ~25 elementwise launches."""
+
+    @staticmethod
+    def forward(ctx, alpha, qn, qp):
+        _require_cuda(alpha)
+        a = alpha.detach().contiguous()
+        aq, aux = _lib.alpha_quantize(a, qn, qp)
+        ctx.save_for_backward(a, aux)
+        ctx.q = (qn, qp)
+        return aq
+
+    @staticmethod
+    def backward(ctx, grad_aq):
+        a, aux = ctx.saved_tensors
+        return _lib.alpha_quantize_backward(a, grad_aq.contiguous().float(), ctx.q[0], ctx.q[1], aux), None, None
+
+
+def alpha_quantize(alpha, nbits_alpha: int):
+    return _AlphaQuant.apply(alpha, 1, 2 ** nbits_alpha - 1)
+
+
 def alpha_cim_initial_value(spec: LayerSpec, xcodes, wcodes, s, qp_adc: float = 1.0):
     """Data-dependent initial ``alpha_cim`` (lsq.py:557-563): ``2*mean|psum*s_w*s_a| / sqrt(Qp_adc)``
     over (batch, pixel), zeros replaced by ``s_w*s_a``.  The |psum| sums are exact integers."""

@@ -72,11 +72,7 @@ class Conv2dLSQCiM(_Conv2dQCiM):
 
     def _alpha_q(self):
         """``nbits_alpha``-bit range quantiser of alpha_cim, inside autograd (lsq.py:566-571)."""
-        qp_alpha = 2 ** self.nbits_alpha - 1
-        qn_alpha = 1
-        alpha = self.alpha_cim
-        alpha_scale = (alpha.max() - alpha.min()) / (qp_alpha - qn_alpha)
-        return round_pass(alpha / alpha_scale).clamp(qn_alpha, qp_alpha) * alpha_scale
+        return CF.alpha_quantize(self.alpha_cim, self.nbits_alpha)
 
     def forward(self, x):
         if not x.is_cuda:

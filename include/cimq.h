@@ -113,6 +113,16 @@ int64_t cimq_lsq_backward_workspace_bytes(int64_t n);
 int cimq_lsq_backward(const float *grad_xq, const float *x, int64_t n, const float *s, int32_t qn, int32_t qp,
                       float g, float *grad_x, float *grad_alpha, void *workspace, void *stream);
 
+/* nbits_alpha range quantiser of alpha_cim (lsq.py:566-571):
+ *   scale = (max(alpha) - min(alpha)) / (qp - qn);  alpha_q = clamp(rint(alpha / scale), qn, qp) * scale
+ * aux (5 floats: scale, max, min, #max, #min) is kept for the backward, which reproduces torch autograd:
+ * straight-through round, inclusive clamp mask, and the scale's gradient flowing into the max / min elements
+ * (shared evenly between ties). */
+int cimq_alpha_quantize(const float *alpha, int64_t n, int32_t qn, int32_t qp, float *alpha_q, float *aux,
+                        void *stream);
+int cimq_alpha_quantize_backward(const float *alpha, const float *grad_alpha_q, int64_t n, int32_t qn, int32_t qp,
+                                 const float *aux, float *grad_alpha, void *stream);
+
 /* ---- per-step tables ----------------------------------------------------------------------- */
 
 /* ADC decision thresholds and amplitudes for every (crossbar, w-slice, a-slice, channel).

@@ -139,6 +139,23 @@ def test_lsq_backward(n):
     assert abs(float(ga.item()) - ga_ref) <= TOL * g * float(terms.sum())
 
 
+def test_alpha_quantizer_matches_oracle():
+    """Fused alpha_cim range quantiser (lsq.py:566-571) and its autograd-equivalent backward."""
+    L = _lib()
+    rng = np.random.default_rng(5)
+    cfg = O.CimConfig(in_channels=64, out_channels=64, kernel=3, padding=1, xbar=128)
+    for shape in ((1, 5, 3, 3, 1, 64), (1, 1, 8, 8, 1, 16), (1, 2, 2, 2, 1, 7)):
+        alpha = rng.uniform(0.01, 0.4, size=shape).astype(np.float32)
+        alpha.flat[3] = alpha.max()  # a tie at the maximum shares the range gradient
+        g = rng.standard_normal(shape).astype(np.float32)
+        aq_ref, aux = O.quantize_alpha(cfg, alpha)
+        ga_ref = O.quantize_alpha_backward(alpha, g, aux)
+        aq, auxd = L.alpha_quantize(_cuda(alpha), 1, 255)
+        np.testing.assert_array_equal(aq.cpu().numpy(), aq_ref)
+        ga = L.alpha_quantize_backward(_cuda(alpha), _cuda(g), 1, 255, auxd)
+        assert rel_err(ga.cpu().numpy(), ga_ref) < TOL
+
+
 def test_step_sizes_match_grad_scale():
     L = _lib()
     rng = np.random.default_rng(0)

@@ -61,7 +61,7 @@ def main():
         step()
     torch.cuda.synchronize()
     runner, graphed = step, False
-    if not a.no_graph and world == 1:
+    if not a.no_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -99,9 +99,12 @@ def main():
                                                         "batch_per_gpu": a.batch, "global_batch": a.batch * world,
                                                         "cuda_graph": graphed, "optimizer": "SGD m0.9 wd1e-4"},
                           "gpu_launches_per_step": launches, "grad_allreduce_bytes": reducer.nbytes}))
+    sys.stdout.flush()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # the step graph holds NCCL work: tearing the communicator down afterwards can hang, and nothing is left
+        # to do, so leave without the collective teardown
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":
