@@ -102,3 +102,24 @@ def test_dropin_install_resolves_reference_import():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/utils/wrapper"), reason="reference tree not available")
+def test_reference_model_surgery_accepts_dropin_class():
+    """The reference's own ReplaceModuleTool (utils/wrapper/replace_module.py:70-115) builds our Conv2dLSQCiM
+    from its model zoo exactly as main_lsq.py:53-56 does (construction only: no GPU here)."""
+    import importlib.util
+    import cim_quantization_b200 as cq
+    spec = importlib.util.spec_from_file_location("ref_replace_module", "/root/reference/utils/wrapper/replace_module.py")
+    rm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rm)
+    spec2 = importlib.util.spec_from_file_location("ref_resnet", "/root/reference/models/cifar10/resnet.py")
+    zoo = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(zoo)
+    model = zoo.resnet20(pretrained=False)
+    rm.ReplaceModuleTool(model, {'Conv2d': [cq.Conv2dLSQCiM]}, True, nbits_w=3, nbits_a=3, nbits_alpha=8, wbitslice=1,
+                         abitslice=1, xbar=128, adcbits=1.5, signed_xbar=False, stochastic_quant=False).replace()
+    convs = [m for m in model.modules() if isinstance(m, cq.Conv2dLSQCiM)]
+    assert len(convs) == 19 and (convs[0].nbits_w, convs[0].nbits_a) == (8, 8) and convs[1].nbits_w == 3
+    assert sum(p.numel() for p in model.parameters()) == 293536
+    assert sum(p.numel() for n, p in model.named_parameters() if 'alpha' in n) == 23814
