@@ -77,6 +77,8 @@ bool make_plan(const Geo &g, TcParams &P, size_t &smem) {
 
 }  // namespace
 
+long long *g_tc_debug = nullptr;  // set by cimq_debug_set_timers (development aid, not part of the product path)
+
 int tc_channel_tile_for(const Geo &g) {
   // channels per CTA: multiple of 16, at most 64, NSW*CT <= 256 (UMMA N) and 2*NSW*CT <= 512 (TMEM); an
   // epilogue thread keeps CT/2 * (accumulator + partial sum + 2 floats per state word) in registers
@@ -119,6 +121,7 @@ int launch_conv_tc_forward(const Geo &g, const uint8_t *xcodes, const void *wtil
   P.s = s;
   P.out = out;
   P.state = state;
+  P.debug = g_tc_debug;
   const int ntiles = P.mtiles * P.nct;
   const int grid = ntiles < 148 ? ntiles : 148;
   const int ch = P.CT / 2;

@@ -66,7 +66,15 @@ struct TcParams {
   const float *s;
   float *out;
   uint32_t *state;
+  long long *debug;  // optional (tools/prof_fwd.py --timers): per-role cycle counters of CTA 0
 };
+// Per-role cycle counters (tools/prof_fwd.py --timers) exist only in builds made with `make TIMERS=1`;
+// the shipped library pays no registers for them.
+#ifndef CIMQ_TIMERS
+#define CIMQ_TIMERS 0
+#endif
+constexpr bool kTimers = CIMQ_TIMERS != 0;
+#define CIMQ_T0() (dbg ? clock64() : 0ll)
 
 // shared-memory carve-up (all offsets from the dynamic smem base)
 struct Smem {
@@ -179,6 +187,51 @@ __device__ __forceinline__ void produce_fast(const TcParams &P, const Smem &sm, 
         }
     }
   }
+  // ---- 2b. (3x3 kernels) taps of the two channels cut by the chunk edges: gather them into a 16-byte block
+  //          (head taps, then tail taps) and OR it into w[] at byte nfull*9 -- a switch on the (uniform) number of
+  //          complete channels makes the word positions compile-time
+  bool partial_done = false;
+  if constexpr (KT == 3) {
+    unsigned long long ph = 0ull, pt = 0ull;
+    const uint8_t *cbh = pb + (size_t)cl.nfull * slot_bytes;
+    const uint8_t *cbt = pb + (size_t)(cl.nfull + (cl.nhead > 0 ? 1 : 0)) * slot_bytes;
+#pragma unroll
+    for (int e = 0; e < KK - 1; ++e) {
+      if (e < cl.nhead) {
+        const int tap = cl.head_tap0 + e;
+        ph |= (unsigned long long)cbh[(tap / KT) * pitch + tap % KT] << (8 * e);
+      }
+      if (e < cl.ntail) pt |= (unsigned long long)cbt[(e / KT) * pitch + e % KT] << (8 * e);
+    }
+    const int hs = 8 * cl.nhead;  // 0..64
+    const unsigned long long lo64 = ph | (hs < 64 ? pt << hs : 0ull);
+    const unsigned long long hi64 = hs == 0 ? 0ull : (hs < 64 ? pt >> (64 - hs) : pt);
+    const uint32_t p0 = (uint32_t)lo64, p1 = (uint32_t)(lo64 >> 32), p2 = (uint32_t)hi64, p3 = (uint32_t)(hi64 >> 32);
+#define CIMQ_MERGE_CASE(N)                                                                    \
+  case N: {                                                                                   \
+    constexpr int START = N * 9, IDX = START >> 2, SH = (START & 3) * 8;                       \
+    if constexpr (SH == 0) {                                                                  \
+      w[IDX] |= p0;                                                                           \
+      if constexpr (IDX + 1 < 32) w[IDX + 1] |= p1;                                           \
+      if constexpr (IDX + 2 < 32) w[IDX + 2] |= p2;                                           \
+      if constexpr (IDX + 3 < 32) w[IDX + 3] |= p3;                                           \
+    } else {                                                                                  \
+      w[IDX] |= p0 << SH;                                                                     \
+      if constexpr (IDX + 1 < 32) w[IDX + 1] |= __funnelshift_l(p0, p1, SH);                  \
+      if constexpr (IDX + 2 < 32) w[IDX + 2] |= __funnelshift_l(p1, p2, SH);                  \
+      if constexpr (IDX + 3 < 32) w[IDX + 3] |= __funnelshift_l(p2, p3, SH);                  \
+      if constexpr (IDX + 4 < 32) w[IDX + 4] |= p3 >> (32 - SH);                              \
+    }                                                                                         \
+  } break;
+    switch (cl.nfull) {
+      CIMQ_MERGE_CASE(0) CIMQ_MERGE_CASE(1) CIMQ_MERGE_CASE(2) CIMQ_MERGE_CASE(3) CIMQ_MERGE_CASE(4)
+      CIMQ_MERGE_CASE(5) CIMQ_MERGE_CASE(6) CIMQ_MERGE_CASE(7) CIMQ_MERGE_CASE(8) CIMQ_MERGE_CASE(9)
+      CIMQ_MERGE_CASE(10) CIMQ_MERGE_CASE(11) CIMQ_MERGE_CASE(12) CIMQ_MERGE_CASE(13) CIMQ_MERGE_CASE(14)
+      default: break;
+    }
+#undef CIMQ_MERGE_CASE
+    partial_done = true;
+  }
   // ---- 3. digit planes (LSB first, slicing_act lsq.py:466-480) -> A operands, 16 bytes per store
   const uint32_t amask4 = (uint32_t)g.amask * 0x01010101u;
   const int ngroups = ((cl.rows + 31) & ~31) >> 4;
@@ -195,8 +248,8 @@ __device__ __forceinline__ void produce_fast(const TcParams &P, const Smem &sm, 
       }
     }
   }
-  // ---- 4. taps of the channels cut by the chunk edges: few elements, byte stores after the vector stores
-  {
+  // ---- 4. (other kernel sizes) taps of the channels cut by the chunk edges: byte stores after the vector stores
+  if (!partial_done) {
     int pos = cl.nfull * KK;
     for (int part = 0; part < 2; ++part) {
       const int cnt = part == 0 ? cl.nhead : cl.ntail;
@@ -248,9 +301,10 @@ __device__ __forceinline__ void produce_generic(const TcParams &P, int i, uint8_
 
 // ---------------------------------------------------------------------------------------------------
 // the kernel.  NSW/NSA: weight / activation digit planes; CH: output channels per epilogue thread (CT/2);
-// MB: multi-bit ADC (clamp) instead of the binary / ternary threshold ADC
+// MB: multi-bit ADC (clamp) instead of the binary / ternary threshold ADC; WS: also write the ADC state the
+// backward pass reads (training) -- a compile-time switch, so the inference kernel carries none of it
 // ---------------------------------------------------------------------------------------------------
-template <int NSW, int NSA, int CH, bool MB>
+template <int NSW, int NSA, int CH, bool MB, bool WS>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) {
   constexpr int CT = 2 * CH;
   constexpr int NROWS = NSW * CT;  // UMMA N
@@ -286,6 +340,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
     // =========================== producers ===========================
     reg_dealloc<kRegsProducer>();
     const int r = threadIdx.x;  // tile row = output pixel
+    const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long d_wait = 0, d_prod = 0, d_tile = 0;
     uint32_t it = 0;
     int tpar = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tpar ^= 1) {
@@ -321,7 +377,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
       for (int i = 0; i < g.NX; ++i, ++it) {
         const int sidx = it % P.stages;
         const uint32_t use = it / P.stages;
+        long long t0 = CIMQ_T0();
         mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
+        long long t1 = CIMQ_T0();
+        d_wait += t1 - t0;
         uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
         if (threadIdx.x == 0) {
           mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
@@ -338,12 +397,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
         }
         fence_proxy_async();
         mbar_arrive(sm.full0 + 8 * sidx);
+        d_prod += CIMQ_T0() - t1;
       }
     }
+    if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_prod; P.debug[2] = d_tile; }
   } else if (warp >= kMmaWarp) {
     // =========================== MMA issuer ===========================
     reg_dealloc<kRegsMma>();
     if (warp == kMmaWarp && lane == 0) {
+      const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0;
+      long long d_full = 0, d_tempty = 0, t_begin = CIMQ_T0();
       const uint32_t idesc = idesc_i8_u8s8(kTcTileM, NROWS);
       const uint32_t sbo = 8u * (uint32_t)P.Kp;
       uint32_t it = 0, acc_it = 0;
@@ -353,13 +416,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
           const uint32_t use = it / P.stages;
           const int rows = min(rows_full, g.F - i * g.xbar);
           const int ksteps = (rows + 31) >> 5;
+          long long t0 = CIMQ_T0();
           mbar_wait(sm.full0 + 8 * sidx, use & 1);
+          d_full += CIMQ_T0() - t0;
           tc_fence_after();
           const uint32_t a0 = smem_u32(sm.stage_base + (size_t)sidx * P.stage_bytes);
           const uint32_t b0 = a0 + NSA * P.a_bytes;
           for (int j = 0; j < NSA; ++j, ++acc_it) {
             const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
+            long long t2 = CIMQ_T0();
             mbar_wait(sm.tempty0 + 8 * buf, (buse & 1) ^ 1);
+            d_tempty += CIMQ_T0() - t2;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * NROWS;
             for (int ks = 0; ks < ksteps; ++ks) {
@@ -372,6 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
           umma_commit(sm.empty0 + 8 * sidx);  // all MMAs reading this stage complete -> producers
         }
       }
+      if (dbg) { P.debug[4] = d_full; P.debug[5] = d_tempty; P.debug[6] = clock64() - t_begin; }
     }
   } else {
     // =========================== epilogue ===========================
@@ -383,7 +451,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
     const int r = quarter * 32 + lane;
     const float sa = P.s[0], sw = P.s[1];
     const int swords = g.state_words;
-    const bool want_state = P.state != nullptr;
+    constexpr bool want_state = WS;
+    const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && warp == kProducerWarps && lane == 0;
+    long long d_tfull = 0, d_comp = 0, d_tab = 0, d_st = 0;
     // per-warpgroup table slice [pair][tp|tg|amp][CH], double buffered by chunk parity
     constexpr int SLICE_WORDS = PAIRS * 3 * CH;
     uint32_t *tbuf = sm.ttab + (size_t)half * 2 * (P.ttab_bytes / 4);
@@ -399,6 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
         // stage this chunk's thresholds / amplitudes for our channels (the previous use of this buffer was
         // two chunks ago; the barrier below orders it)
         uint32_t *tb = tbuf + (size_t)(chunk_it & 1) * (P.ttab_bytes / 4);
+        long long ta = CIMQ_T0();
         {
           const uint32_t *src = P.ttab + ((size_t)(ct * g.NX + i) * PAIRS * 3) * CT + half * CH;
           for (int idx = wgt; idx < SLICE_WORDS / 4; idx += 128) {
@@ -408,6 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
           }
         }
         named_barrier_sync(2 + half, 128);
+        d_tab += CIMQ_T0() - ta;
         // ADC state, accumulated on the FMA pipe: every 32-bit state word is two fp32 accumulators (bits
         // [0,HB) and [HB,32)) that start at 2^23, so their low mantissa bits are an exact integer, and
         // receive decision * 2^bit.  State bit of (type t, act slice j, weight slice k) = t*PAIRS + j*NSW + k:
@@ -422,7 +494,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
 #pragma unroll
         for (int j = 0; j < NSA; ++j, ++acc_it) {
           const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
+          long long tw = CIMQ_T0();
           mbar_wait(sm.tfull0 + 8 * buf, buse & 1);
+          long long tc0 = CIMQ_T0();
+          d_tfull += tc0 - tw;
           tc_fence_after();
           // first bit of this activation slice in the +1 / -1 / clip groups, its accumulator and weight there
           constexpr int kTypes = MB ? 1 : 3;
@@ -436,53 +511,63 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
             abase[t] = (float)(1u << ((b0 & 31) - (hi ? HB : 0)));
           }
           float wk = 1.0f;  // 2^k
+          const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NROWS + half * CH;
+          // The accumulator is read VW columns at a time; as soon as a group is converted to fp32 its registers
+          // are free and the next group (same weight slice, or the next one) is fetched while this one is quantised.
+          constexpr int VW = CH < 16 ? CH : 16, NG = CH / VW;
+          int v[VW];
+          tmem_ld<VW>(tcol, v);
 #pragma unroll 1
           for (int k = 0; k < NSW; ++k, wk *= 2.0f) {
-            int v[CH];
-            tmem_ld<CH>(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NROWS + k * CT + half * CH, v);
             const uint32_t *trow = tb + (k * NSA + j) * 3 * CH;
-            tmem_ld_wait();
-            if constexpr (MB) {
-              const float kBit = abase[0] * wk;
+            const float kPos = abase[0] * wk, kNeg = abase[MB ? 0 : 1] * wk, kClp = abase[MB ? 0 : 2] * wk;
 #pragma unroll
-              for (int c4 = 0; c4 < CH / 4; ++c4) {
-                const float4 amp4 = *reinterpret_cast<const float4 *>(trow + 2 * CH + 4 * c4);
-                const float ampv[4] = {amp4.x, amp4.y, amp4.z, amp4.w};
+            for (int gq = 0; gq < NG; ++gq) {
+              tmem_ld_wait();
+              // int32 partial sums -> fp32 without the conversion unit (exact for |p| < 2^22)
+              float pfv[VW];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const int cc = 4 * c4 + u;
-                  const float ph = psum_as_stored(v[cc]);
-                  const float cf = fminf(fmaxf(ph, (float)g.qn), (float)g.qp);
-                  acc[cc] += __fmul_rn(__fmul_rn(cf, sw), sa) * ampv[u];
-                  if (ph > (float)g.qp || ph < (float)g.qn) stf[cc][aidx[0]] += kBit;
-                }
+              for (int cc = 0; cc < VW; ++cc) {
+                if constexpr (MB) pfv[cc] = psum_as_stored(v[cc]);
+                else pfv[cc] = __int_as_float(v[cc] + 0x4B400000) - 12582912.0f;
               }
-            } else {
-              const float kPos = abase[0] * wk, kNeg = abase[1] * wk, kClp = abase[2] * wk;
+              if (gq + 1 < NG) tmem_ld<VW>(tcol + k * CT + (gq + 1) * VW, v);
+              else if (k + 1 < NSW) tmem_ld<VW>(tcol + (k + 1) * CT, v);
 #pragma unroll
-              for (int c4 = 0; c4 < CH / 4; ++c4) {
-                const float4 tp4 = *reinterpret_cast<const float4 *>(trow + 4 * c4);
-                const float4 amp4 = *reinterpret_cast<const float4 *>(trow + 2 * CH + 4 * c4);
-                const float tpv[4] = {tp4.x, tp4.y, tp4.z, tp4.w};
+              for (int c4 = 0; c4 < VW / 4; ++c4) {
+                const int cb = gq * VW + 4 * c4;
+                const float4 amp4 = *reinterpret_cast<const float4 *>(trow + 2 * CH + cb);
                 const float ampv[4] = {amp4.x, amp4.y, amp4.z, amp4.w};
-                float tgv[4] = {0.f, 0.f, 0.f, 0.f};
-                if (want_state) {
-                  const float4 tg4 = *reinterpret_cast<const float4 *>(trow + CH + 4 * c4);
-                  tgv[0] = tg4.x; tgv[1] = tg4.y; tgv[2] = tg4.z; tgv[3] = tg4.w;
-                }
+                if constexpr (MB) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const int cc = 4 * c4 + u;
-                  // int32 partial sum -> fp32 without the conversion unit (exact for |p| < 2^22)
-                  const float pf = __int_as_float(v[cc] + 0x4B400000) - 12582912.0f;
-                  const float tpos = __saturatef(pf - tpv[u]);    // 1 if p >= tp
-                  const float tneg = __saturatef(-pf - tpv[u]);   // 1 if p <= -tp
-                  acc[cc] = fmaf(tpos - tneg, ampv[u], acc[cc]);  // ternary / sign code times alpha*2^shift
+                  for (int u = 0; u < 4; ++u) {
+                    const int cc = cb + u;
+                    const float ph = pfv[4 * c4 + u];
+                    const float cf = fminf(fmaxf(ph, (float)g.qn), (float)g.qp);
+                    acc[cc] += __fmul_rn(__fmul_rn(cf, sw), sa) * ampv[u];
+                    if (ph > (float)g.qp || ph < (float)g.qn) stf[cc][aidx[0]] += kPos;
+                  }
+                } else {
+                  const float4 tp4 = *reinterpret_cast<const float4 *>(trow + cb);
+                  const float tpv[4] = {tp4.x, tp4.y, tp4.z, tp4.w};
+                  float tgv[4] = {0.f, 0.f, 0.f, 0.f};
                   if (want_state) {
-                    const float tclp = __saturatef(fabsf(pf) - tgv[u]);  // 1 if |p| >= tg (STE clip, lsq.py:310)
-                    stf[cc][aidx[0]] = fmaf(tpos, kPos, stf[cc][aidx[0]]);
-                    stf[cc][aidx[1]] = fmaf(tneg, kNeg, stf[cc][aidx[1]]);
-                    stf[cc][aidx[2]] = fmaf(tclp, kClp, stf[cc][aidx[2]]);
+                    const float4 tg4 = *reinterpret_cast<const float4 *>(trow + CH + cb);
+                    tgv[0] = tg4.x; tgv[1] = tg4.y; tgv[2] = tg4.z; tgv[3] = tg4.w;
+                  }
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const int cc = cb + u;
+                    const float pf = pfv[4 * c4 + u];
+                    const float tpos = __saturatef(pf - tpv[u]);    // 1 if p >= tp
+                    const float tneg = __saturatef(-pf - tpv[u]);   // 1 if p <= -tp
+                    acc[cc] = fmaf(tpos - tneg, ampv[u], acc[cc]);  // ternary / sign code times alpha*2^shift
+                    if (want_state) {
+                      const float tclp = __saturatef(fabsf(pf) - tgv[u]);  // 1 if |p| >= tg (STE clip, lsq.py:310)
+                      stf[cc][aidx[0]] = fmaf(tpos, kPos, stf[cc][aidx[0]]);
+                      stf[cc][aidx[1]] = fmaf(tneg, kNeg, stf[cc][aidx[1]]);
+                      stf[cc][aidx[2]] = fmaf(tclp, kClp, stf[cc][aidx[2]]);
+                    }
                   }
                 }
               }
@@ -491,7 +576,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(sm.tempty0 + 8 * buf);  // this warp has drained the accumulator
+          d_comp += CIMQ_T0() - tc0;
         }
+        long long ts = CIMQ_T0();
         uint32_t stw[CH][SWORDS_MAX];
 #pragma unroll
         for (int cc = 0; cc < CH; ++cc)
@@ -500,13 +587,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
             stw[cc][w] = (__float_as_uint(stf[cc][2 * w]) & 0x7fffffu) |
                          ((__float_as_uint(stf[cc][2 * w + 1]) & 0x7fffffu) << HB);
         if (want_state && m < g.M) {
+          uint32_t *sp = P.state + ((size_t)i * g.Cout + c_first) * swords * g.M + m;  // [i][c][word][m]
 #pragma unroll
           for (int cc = 0; cc < CH; ++cc)
 #pragma unroll
             for (int w = 0; w < SWORDS_MAX; ++w)
-              if (w < swords)
-                P.state[(((size_t)i * g.Cout + c_first + cc) * swords + w) * g.M + m] = stw[cc][w];
+              if (w < swords) {
+                *sp = stw[cc][w];
+                sp += g.M;
+              }
         }
+        d_st += CIMQ_T0() - ts;
       }
       if (m < g.M) {
         const int b = m / g.L, l = m % g.L;
@@ -514,6 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
         for (int cc = 0; cc < CH; ++cc) P.out[((size_t)b * g.Cout + c_first + cc) * g.L + l] = acc[cc];
       }
     }
+    if (dbg) { P.debug[8] = d_tfull; P.debug[9] = d_comp; P.debug[10] = d_tab; P.debug[11] = d_st; }
   }
 
   tc_fence_before();
@@ -526,15 +618,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
 
 template <int NSW, int NSA, int CH>
 int launch_instance(const TcParams &P, size_t smem, int grid, cudaStream_t st) {
-  if (P.g.adc_mode == CIMQ_ADC_MULTIBIT) {
-    CIMQ_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NSW, NSA, CH, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_kernel<NSW, NSA, CH, true><<<grid, kThreads, smem, st>>>(P);
-  } else {
-    CIMQ_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NSW, NSA, CH, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_kernel<NSW, NSA, CH, false><<<grid, kThreads, smem, st>>>(P);
-  }
+  const bool mb = P.g.adc_mode == CIMQ_ADC_MULTIBIT, ws = P.state != nullptr;
+#define CIMQ_TC_LAUNCH(MB_, WS_)                                                                      \
+  do {                                                                                                \
+    CIMQ_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<NSW, NSA, CH, MB_, WS_>,                         \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    conv_tc_kernel<NSW, NSA, CH, MB_, WS_><<<grid, kThreads, smem, st>>>(P);                          \
+  } while (0)
+  if (mb && ws) CIMQ_TC_LAUNCH(true, true);
+  else if (mb) CIMQ_TC_LAUNCH(true, false);
+  else if (ws) CIMQ_TC_LAUNCH(false, true);
+  else CIMQ_TC_LAUNCH(false, false);
+#undef CIMQ_TC_LAUNCH
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

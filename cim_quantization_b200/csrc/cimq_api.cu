@@ -28,6 +28,10 @@ int cimq_version(void) { return CIMQ_VERSION; }
 
 const char *cimq_last_error(void) { return g_error; }
 
+/* development aid (not declared in cimq.h): device buffer of 16 int64 that CTA 0 of the tcgen05 forward kernel
+ * fills with per-role cycle counters; NULL disables */
+int cimq_debug_set_timers(long long *buf) { g_tc_debug = buf; return 0; }
+
 int cimq_layer_info(const cimq_layer_t *layer, cimq_info_t *info) {
   Geo g;
   if (make_geo(layer, &g)) return 1;

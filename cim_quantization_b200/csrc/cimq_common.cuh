@@ -109,6 +109,7 @@ int64_t wtiles_bytes(const Geo &g);
 bool tc_forward_supported(const Geo &g);
 int tc_channel_tile_for(const Geo &g);          // output channels per CTA of the tcgen05 kernel (0: unsupported)
 int launch_im2col_lut(const Geo &g, void *lut, cudaStream_t st);
+extern long long *g_tc_debug;
 bool tc_backward_supported(const Geo &g);
 int64_t wtiles_bwd_bytes(const Geo &g);
 int launch_weight_tiles_bwd(const Geo &g, const int8_t *wcodes, void *tiles, cudaStream_t st);

@@ -12,6 +12,7 @@ p.add_argument("--iters", type=int, default=3)
 p.add_argument("--bwd", action="store_true")
 p.add_argument("--quant", action="store_true")
 p.add_argument("--no-state", action="store_true")
+p.add_argument("--timers", action="store_true")
 a = p.parse_args()
 adc = int(a.adcbits) if a.adcbits == int(a.adcbits) else a.adcbits
 B, C, HW = a.batch, 64, 32
@@ -31,6 +32,11 @@ if adc in (1, 1.5):
 table = L.adc_table(spec, s, aq, mask)
 wdig, wtiles = L.weight_prepare(spec, wc)
 go = torch.randn(B, C, HW * HW, device="cuda", generator=g)
+dbg = None
+if a.timers:
+    import ctypes
+    dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+    L.load().cimq_debug_set_timers(ctypes.c_void_p(dbg.data_ptr()))
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for it in range(a.iters + 1):
     if it == 1:
@@ -42,4 +48,10 @@ for it in range(a.iters + 1):
         L.lsq_quantize(x, s[0:1], 0, 7)
         L.lsq_backward(go.view_as(x), x, s[0:1], 0, 7, 1e-3)
 ev[1].record(); torch.cuda.synchronize()
+if dbg is not None:
+    d = dbg.cpu().tolist()
+    names = {0: "producer wait empty", 1: "producer produce", 4: "mma wait full", 5: "mma wait tmem-empty", 6: "mma total",
+             8: "epilogue wait tmem-full", 9: "epilogue compute", 10: "epilogue table+barrier", 11: "epilogue state store"}
+    for k, n in names.items():
+        print(f"  timer {n:28s} {d[k] / 1e3:10.1f} kcycles")
 print("avg ms per iter:", ev[0].elapsed_time(ev[1]) / a.iters, "codes nonzero frac", float((xc != 0).float().mean()))
