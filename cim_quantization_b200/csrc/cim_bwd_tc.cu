@@ -255,13 +255,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
       for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
         for (int i = 0; i < g.NX; ++i, ++acc_it) {
           const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
-          mbar_wait(cv.tempty0 + 8 * buf, (buse & 1) ^ 1);
+          mbar_wait<400>(cv.tempty0 + 8 * buf, (buse & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * Nf;
           for (int k = 0; k < NSW; ++k, ++it) {
             const int sidx = it % P.stages;
             const uint32_t use = it / P.stages;
-            mbar_wait(cv.full0 + 8 * sidx, use & 1);
+            mbar_wait<400>(cv.full0 + 8 * sidx, use & 1);
             tc_fence_after();
             const uint32_t a0 = smem_u32(cv.stage_base + (size_t)sidx * P.stage_bytes);
             const uint32_t b0 = a0 + 3 * P.a_bytes;
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           for (int j = 0; j < NSA; ++j, ++it) {
             const int sidx = it % P.stages;
             const uint32_t use = it / P.stages;
-            mbar_wait(cv.full0 + 8 * sidx, use & 1);
+            mbar_wait<400>(cv.full0 + 8 * sidx, use & 1);
             tc_fence_after();
             const uint32_t a0 = smem_u32(cv.stage_base + (size_t)sidx * P.stage_bytes);
             const uint32_t b0 = a0 + P.a_bytes;

@@ -40,7 +40,7 @@ bool make_plan(const Geo &g, TcParams &P, size_t &smem) {
   P.tmem_cols = cols;
   P.ttab_bytes = (uint32_t)((g.pairs * 3 * (P.CT / 2) * 4 + 15) & ~15);
   // staged (fast) producer
-  P.fast = 0; P.owt = 0; P.rpt = 0; P.pitch_log2 = 0; P.col0 = 0; P.raw_bytes = 0;
+  P.fast = 0; P.owt = 0; P.rpt = 0; P.rk = 0; P.prow = 0; P.shared_rows = 0; P.prefetch = 0; P.pitch_log2 = 0; P.col0 = 0; P.raw_bytes = 0;
   if ((g.K == 3 || g.K == 5) && g.W % 4 == 0 && g.OW <= kTcTileM && kTcTileM % g.OW == 0 && P.Kp <= 128 &&
       (kTcTileM / g.OW) * g.K <= 128 && g.pad < g.K) {
     const int col0 = (4 - g.pad % 4) % 4;
@@ -53,9 +53,15 @@ bool make_plan(const Geo &g, TcParams &P, size_t &smem) {
       const int n = cl.nfull + (cl.nhead > 0) + (cl.ntail > 0);
       nslots = n > nslots ? n : nslots;
     }
-    const size_t raw = ((size_t)nslots * (kTcTileM / g.OW) * g.K * (1u << pl) + 15) & ~(size_t)15;
-    if (nslots <= kMaxSlots && raw <= 48 * 1024 && pl <= 9) {
-      P.fast = 1; P.owt = g.OW; P.rpt = kTcTileM / g.OW; P.pitch_log2 = pl; P.col0 = col0;
+    // a tile that is 128 consecutive pixels of one image reads consecutive input rows: output rows share them
+    const int rpt = kTcTileM / g.OW;
+    const bool shared_rows = g.L % kTcTileM == 0;
+    const int rk = shared_rows ? (rpt - 1) * g.stride + g.K : rpt * g.K;
+    const size_t raw = ((size_t)nslots * rk * (1u << pl) + 15) & ~(size_t)15;
+    if (nslots <= kMaxSlots && raw <= 48 * 1024 && pl <= 9 && rk <= 128) {
+      P.fast = 1; P.owt = g.OW; P.rpt = rpt; P.pitch_log2 = pl; P.col0 = col0;
+      P.rk = rk; P.prow = shared_rows ? g.stride : g.K; P.shared_rows = shared_rows ? 1 : 0;
+      P.prefetch = (raw / 4 + kProducerThreads - 1) / kProducerThreads <= (size_t)kPrefetchWords;
       P.raw_bytes = (uint32_t)raw;
     }
   }

@@ -54,6 +54,11 @@ struct TcParams {
   int fast;          // 1: staged producer, 0: generic per-element gather
   int owt;           // output pixels per staged row segment (= OW, divides 128)
   int rpt;           // output rows per tile (128 / OW)
+  int rk;            // staged input rows per channel slot: (rpt-1)*stride+K when the rows of a tile are
+                     // consecutive rows of one image (shared between output rows), else rpt*K
+  int prow;          // staged row of output row `orow`, tap row 0: orow * prow
+  int shared_rows;   // 1: a tile reads consecutive input rows of one image (rk, prow as above)
+  int prefetch;      // 1: the rows of the next stage are loaded into registers while this one is assembled
   int pitch_log2;    // staged row pitch in bytes (power of two)
   int col0;          // staged column of input column -pad (alignment shift)
   uint32_t raw_bytes;    // one staging buffer
@@ -115,54 +120,103 @@ __device__ __forceinline__ uint32_t put_byte(uint32_t w, uint32_t b) {
 // ---------------------------------------------------------------------------------------------------
 // fast producer: one stage = digit planes of 128 im2col rows for crossbar chunk i
 // ---------------------------------------------------------------------------------------------------
+constexpr int kPrefetchWords = 16;  // staged words a producer thread may hold in registers for the next stage
+
+// which input rows / columns a producer thread stages (fixed for the kernel)
+struct StageThread {
+  int xw;        // word column inside a staged row
+  int row0;      // first staged row (slot-major row list) of this thread
+  int rstep;     // rows advanced per pass of all producer threads
+  bool xok;      // the word lies inside the image horizontally
+};
+__device__ __forceinline__ StageThread stage_thread(const TcParams &P) {
+  StageThread t;
+  const int wpr_log2 = P.pitch_log2 - 2;  // words per staged row (<= 128)
+  t.xw = threadIdx.x & ((1 << wpr_log2) - 1);
+  t.row0 = threadIdx.x >> wpr_log2;
+  t.rstep = kProducerThreads >> wpr_log2;
+  const int ix = 4 * t.xw - P.col0 - P.g.pad;  // input column of this thread's word
+  t.xok = ix >= 0 && ix < P.g.W;
+  return t;
+}
+
+// staged rows of a tile: rowoff[staged row] = offset of staged column 0 of that input row in channel 0 of its
+// image, or kNoRow (outside the image / past the last pixel)
+__device__ __forceinline__ void stage_set_rowoff(const TcParams &P, int mt, int *rowoff) {
+  const Geo &g = P.g;
+  const int r = threadIdx.x;
+  if (r < P.rk) {
+    int off = kNoRow;
+    if (P.shared_rows) {  // consecutive output rows of one image: input rows oy0*stride - pad + r
+      const int m0 = mt * kTcTileM;
+      if (m0 < g.M) {
+        const int b = m0 / g.L, oy0 = (m0 % g.L) / g.OW;
+        const int iy = oy0 * g.stride - g.pad + r;
+        if (iy >= 0 && iy < g.H) off = (b * g.Cin * g.H + iy) * g.W - g.pad - P.col0;
+      }
+    } else {
+      const int orow = r / g.K, ky = r % g.K;
+      const int m_row = mt * kTcTileM + orow * P.owt;
+      if (m_row < g.M) {
+        const int b = m_row / g.L, oy = (m_row % g.L) / g.OW;
+        const int iy = oy * g.stride - g.pad + ky;
+        if (iy >= 0 && iy < g.H) off = (b * g.Cin * g.H + iy) * g.W - g.pad - P.col0;
+      }
+    }
+    rowoff[r] = off;
+  }
+}
+
+// Load up to NW words of chunk i's staged rows, starting at pass `pass0` of the thread's row walk.  Slot s < nfull
+// holds channel cf0+s, then the head channel cf0-1, then the tail channel cf0+nfull; slots are contiguous
+// (slot_bytes = rk * pitch), so word q of the slot-major row list lives at raw32[q].
+template <int NW>
+__device__ __forceinline__ void stage_load(const TcParams &P, const StageThread &t, const ChunkLayout &cl,
+                                           const int *rowoff, int pass0, uint32_t (&v)[NW]) {
+  const Geo &g = P.g;
+  const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
+  const int total_rows = nslots * P.rk, HW = g.H * g.W;
+  int rl = t.row0 + pass0 * t.rstep;
+  int sl = rl / P.rk, row = rl - sl * P.rk;
+#pragma unroll
+  for (int u = 0; u < NW; ++u) {
+    v[u] = 0u;
+    if (rl < total_rows) {
+      int ch = cl.cf0 + sl;
+      if (sl >= cl.nfull) ch = (sl == cl.nfull && cl.nhead > 0) ? cl.cf0 - 1 : cl.cf0 + cl.nfull;
+      const int off = rowoff[row];
+      if (t.xok && off != kNoRow)
+        v[u] = __ldg(reinterpret_cast<const uint32_t *>(P.xcodes + (size_t)ch * HW + off + 4 * t.xw));
+    }
+    rl += t.rstep;
+    row += t.rstep;
+    while (row >= P.rk) { row -= P.rk; ++sl; }
+  }
+}
+template <int NW>
+__device__ __forceinline__ void stage_store(const TcParams &P, const StageThread &t, const ChunkLayout &cl,
+                                            int pass0, const uint32_t (&v)[NW], uint8_t *raw) {
+  const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
+  const int total_words = (nslots * P.rk) << (P.pitch_log2 - 2);
+  uint32_t *raw32 = reinterpret_cast<uint32_t *>(raw);
+#pragma unroll
+  for (int u = 0; u < NW; ++u) {
+    const int q = threadIdx.x + (pass0 + u) * kProducerThreads;
+    if (q < total_words) raw32[q] = v[u];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fast producer, assembly: digit planes of this thread's im2col row of chunk `cl` from the staged rows
+// ---------------------------------------------------------------------------------------------------
 template <int NSA, int KT>
-__device__ __forceinline__ void produce_fast(const TcParams &P, const Smem &sm, int i, uint8_t *st_ptr,
-                                             uint8_t *raw, const int *rowoff, int r, int pix_base) {
+__device__ __forceinline__ void produce_fast(const TcParams &P, const ChunkLayout &cl, uint8_t *st_ptr,
+                                             const uint8_t *raw, int r, int pix_base) {
   constexpr int KK = KT * KT;
   constexpr int NFMAX = 126 / KK < kMaxSlots - 2 ? 126 / KK : kMaxSlots - 2;  // complete channels in 128 bytes
   const Geo &g = P.g;
-  const ChunkLayout cl = chunk_layout(g, i);
   const int pitch = 1 << P.pitch_log2;
-  const int slot_bytes = P.rpt * KT * pitch;
-  const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
-  const int HW = g.H * g.W;
-  // ---- 1. stage rows: slot s < nfull -> channel cf0+s, then head channel cf0-1, then tail channel cf0+nfull
-  //         A thread owns one 4-byte column of the staged rows and walks the (slot, row) list in steps of
-  //         `rstep` rows; eight independent global loads are issued before the first store (latency).
-  {
-    const int wpr_log2 = P.pitch_log2 - 2;          // words per staged row (<= 128)
-    const int xw = threadIdx.x & ((1 << wpr_log2) - 1);
-    const int rstep = kProducerThreads >> wpr_log2;  // rows covered per pass
-    const int rk = P.rpt * KT;                       // staged rows per slot
-    const int total_rows = nslots * rk;
-    const int ix = 4 * xw - P.col0 - g.pad;          // input column of this thread's word
-    const bool xok = ix >= 0 && ix < g.W;
-    int row = threadIdx.x >> wpr_log2, sl = 0;
-    while (row >= rk) { row -= rk; ++sl; }
-    for (int r0 = threadIdx.x >> wpr_log2; r0 < total_rows; r0 += 8 * rstep) {
-      uint32_t v[8];
-      int dsto[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        v[u] = 0u;
-        dsto[u] = -1;
-        if (r0 + u * rstep < total_rows) {
-          int ch = cl.cf0 + sl;
-          if (sl >= cl.nfull) ch = (sl == cl.nfull && cl.nhead > 0) ? cl.cf0 - 1 : cl.cf0 + cl.nfull;
-          const int off = rowoff[row];  // offset of staged column 0 of this row in channel 0, or kNoRow
-          if (xok && off != kNoRow)
-            v[u] = __ldg(reinterpret_cast<const uint32_t *>(P.xcodes + (size_t)ch * HW + off + 4 * xw));
-          dsto[u] = sl * slot_bytes + (row << P.pitch_log2) + 4 * xw;
-        }
-        row += rstep;
-        while (row >= rk) { row -= rk; ++sl; }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (dsto[u] >= 0) *reinterpret_cast<uint32_t *>(raw + dsto[u]) = v[u];
-    }
-  }
-  named_barrier_sync(1, kProducerThreads);
+  const int slot_bytes = P.rk * pitch;
   // ---- 2. assemble this thread's im2col row: complete channels at compile-time byte positions
   uint32_t w[32];
 #pragma unroll
@@ -343,38 +397,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
     const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long d_wait = 0, d_prod = 0, d_tile = 0;
     uint32_t it = 0;
-    int tpar = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tpar ^= 1) {
-      const int mt = tile / P.nct, ct = tile % P.nct;
-      const int m = mt * kTcTileM + r;
-      int base = 0, pix_base = 0;
-      uint32_t vm = 0;  // generic path: bit t set = tap t of this pixel is inside the image
-      int *rowoff = sm.rowoff + tpar * 128;
-      if (P.fast) {
-        // staged rows of this tile: row index (orow, ky) -> offset of staged column 0 in channel 0 of its image
-        if (r < P.rpt * g.K) {
-          const int orow = r / g.K, ky = r % g.K;
-          const int m_row = mt * kTcTileM + orow * P.owt;
-          int off = kNoRow;
-          if (m_row < g.M) {
-            const int b = m_row / g.L, oy = (m_row % g.L) / g.OW;
-            const int iy = oy * g.stride - g.pad + ky;
-            if (iy >= 0 && iy < g.H) off = (b * g.Cin * g.H + iy) * g.W - g.pad - P.col0;
-          }
-          rowoff[r] = off;
-        }
-        const int orow = r / P.owt, oxl = r % P.owt;
-        pix_base = ((orow * g.K) << P.pitch_log2) + oxl * g.stride + P.col0;
+    if (P.fast) {
+      // ---- staged producer.  Stage `it` is (tile, chunk i); its input rows sit in raw[it & 1].
+      const StageThread stt = stage_thread(P);
+      const int pix_base = (((r / P.owt) * P.prow) << P.pitch_log2) + (r % P.owt) * g.stride + P.col0;
+      int tile = blockIdx.x, i = 0, tpar = 0;
+      uint32_t v[kPrefetchWords];
+      if (tile < ntiles) {
+        stage_set_rowoff(P, tile / P.nct, sm.rowoff);
         named_barrier_sync(1, kProducerThreads);
-      } else if (m < g.M) {
-        const int b = m / g.L, l = m % g.L, oy = l / g.OW, ox = l % g.OW;
-        const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
-        base = (b * g.Cin * g.H + iy0) * g.W + ix0;
-        for (int ky = 0; ky < g.K; ++ky)
-          for (int kx = 0; kx < g.K; ++kx)
-            if (iy0 + ky >= 0 && iy0 + ky < g.H && ix0 + kx >= 0 && ix0 + kx < g.W) vm |= 1u << (ky * g.K + kx);
+        if (P.prefetch) {
+          const ChunkLayout cl0 = chunk_layout(g, 0);
+          stage_load<kPrefetchWords>(P, stt, cl0, sm.rowoff, 0, v);
+          stage_store<kPrefetchWords>(P, stt, cl0, 0, v, sm.raw);
+          named_barrier_sync(1, kProducerThreads);
+        }
       }
-      for (int i = 0; i < g.NX; ++i, ++it) {
+      while (tile < ntiles) {
+        const int ct = tile % P.nct;
+        const ChunkLayout cl = chunk_layout(g, i);
+        uint8_t *raw = sm.raw + (size_t)(it & 1) * P.raw_bytes;
+        // the stage after this one
+        int ni = i + 1, ntile = tile, ntpar = tpar;
+        if (ni == g.NX) { ni = 0; ntile = tile + gridDim.x; ntpar ^= 1; }
+        const bool more = ntile < ntiles;
+        ChunkLayout ncl = cl;
+        if (more) {
+          ncl = chunk_layout(g, ni);
+          if (ni == 0) {  // new tile: publish its row table first (its buffer was last read a whole tile ago)
+            stage_set_rowoff(P, ntile / P.nct, sm.rowoff + ntpar * 128);
+            named_barrier_sync(1, kProducerThreads);
+          }
+          // its input rows start their trip from L2 / HBM now and land in registers while this stage is built
+          if (P.prefetch) stage_load<kPrefetchWords>(P, stt, ncl, sm.rowoff + ntpar * 128, 0, v);
+        }
+        if (!P.prefetch) {  // too many rows for the registers: stage this chunk now, eight loads in flight
+          const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
+          const int passes = ((nslots * P.rk) + stt.rstep - 1) / stt.rstep;
+          for (int p0 = 0; p0 < passes; p0 += 8) {
+            uint32_t v8[8];
+            stage_load<8>(P, stt, cl, sm.rowoff + tpar * 128, p0, v8);
+            stage_store<8>(P, stt, cl, p0, v8, raw);
+          }
+          named_barrier_sync(1, kProducerThreads);
+        }
         const int sidx = it % P.stages;
         const uint32_t use = it / P.stages;
         long long t0 = CIMQ_T0();
@@ -387,17 +453,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
           bulk_copy_g2s(smem_u32(st_ptr + (size_t)NSA * P.a_bytes), P.wtiles + (size_t)(ct * g.NX + i) * P.b_bytes,
                         P.b_bytes, sm.full0 + 8 * sidx);
         }
-        if (P.fast) {
-          uint8_t *raw = sm.raw + (size_t)(it & 1) * P.raw_bytes;
-          if (g.K == 3) produce_fast<NSA, 3>(P, sm, i, st_ptr, raw, rowoff, r, pix_base);
-          else if (g.K == 1) produce_fast<NSA, 1>(P, sm, i, st_ptr, raw, rowoff, r, pix_base);
-          else produce_fast<NSA, 5>(P, sm, i, st_ptr, raw, rowoff, r, pix_base);
-        } else {
-          produce_generic<NSA>(P, i, st_ptr, r, base, vm);
-        }
+        if (g.K == 3) produce_fast<NSA, 3>(P, cl, st_ptr, raw, r, pix_base);
+        else produce_fast<NSA, 5>(P, cl, st_ptr, raw, r, pix_base);
         fence_proxy_async();
         mbar_arrive(sm.full0 + 8 * sidx);
+        if (P.prefetch) {
+          if (more) stage_store<kPrefetchWords>(P, stt, ncl, 0, v, sm.raw + (size_t)((it + 1) & 1) * P.raw_bytes);
+          // next stage's rows visible to all producers; everyone is done reading this stage's rows
+          named_barrier_sync(1, kProducerThreads);
+        }
         d_prod += CIMQ_T0() - t1;
+        i = ni; tile = ntile; tpar = ntpar; ++it;
+      }
+    } else {
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int mt = tile / P.nct, ct = tile % P.nct;
+        const int m = mt * kTcTileM + r;
+        int base = 0;
+        uint32_t vm = 0;  // bit t set = tap t of this pixel is inside the image
+        if (m < g.M) {
+          const int b = m / g.L, l = m % g.L, oy = l / g.OW, ox = l % g.OW;
+          const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
+          base = (b * g.Cin * g.H + iy0) * g.W + ix0;
+          for (int ky = 0; ky < g.K; ++ky)
+            for (int kx = 0; kx < g.K; ++kx)
+              if (iy0 + ky >= 0 && iy0 + ky < g.H && ix0 + kx >= 0 && ix0 + kx < g.W) vm |= 1u << (ky * g.K + kx);
+        }
+        for (int i = 0; i < g.NX; ++i, ++it) {
+          const int sidx = it % P.stages;
+          const uint32_t use = it / P.stages;
+          mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
+          uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
+          if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
+            bulk_copy_g2s(smem_u32(st_ptr + (size_t)NSA * P.a_bytes),
+                          P.wtiles + (size_t)(ct * g.NX + i) * P.b_bytes, P.b_bytes, sm.full0 + 8 * sidx);
+          }
+          produce_generic<NSA>(P, i, st_ptr, r, base, vm);
+          fence_proxy_async();
+          mbar_arrive(sm.full0 + 8 * sidx);
+        }
       }
     }
     if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_prod; P.debug[2] = d_tile; }
@@ -417,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
           const int rows = min(rows_full, g.F - i * g.xbar);
           const int ksteps = (rows + 31) >> 5;
           long long t0 = CIMQ_T0();
-          mbar_wait(sm.full0 + 8 * sidx, use & 1);
+          mbar_wait<400>(sm.full0 + 8 * sidx, use & 1);
           d_full += CIMQ_T0() - t0;
           tc_fence_after();
           const uint32_t a0 = smem_u32(sm.stage_base + (size_t)sidx * P.stage_bytes);
@@ -425,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
           for (int j = 0; j < NSA; ++j, ++acc_it) {
             const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
             long long t2 = CIMQ_T0();
-            mbar_wait(sm.tempty0 + 8 * buf, (buse & 1) ^ 1);
+            mbar_wait<400>(sm.tempty0 + 8 * buf, (buse & 1) ^ 1);
             d_tempty += CIMQ_T0() - t2;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * NROWS;

@@ -22,6 +22,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// kSleepNs > 0: the caller expects long waits (the MMA issuer waits a whole producer stage) and sleeps that long
+// between polls from the first miss on, so its polling does not take issue slots from the warps sharing its
+// scheduler; 0: short waits, poll a few times before backing off.
+template <int kSleepNs = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done, spins = 0;
   do {
@@ -34,7 +38,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (!done) {
       // back off: a waiting role must not eat the issue slots of the role it waits for
-      if (++spins > 2) __nanosleep(spins < 32 ? 40 : 200);
+      ++spins;
+      if constexpr (kSleepNs > 0) __nanosleep(kSleepNs);
+      else if (spins > 2) __nanosleep(spins < 32 ? 40 : 200);
       if (spins > kSpinLimit) __trap();
     }
   } while (!done);
