@@ -54,6 +54,12 @@ def parse_args():
     return p.parse_args()
 
 
+def _traffic_bytes(traffic, key):
+    """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    e = traffic.get(key)
+    return float(e["total_MB"]) * 1e6 if isinstance(e, dict) and "total_MB" in e else None
+
+
 def layer_ops(batch, channels, hw, nbits):
     """Algorithmic integer/float ops of one step on one GPU."""
     mkn = batch * hw * hw * (channels * 9) * channels
@@ -324,6 +330,7 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     fwd_ops, bwd_ops = layer_ops(B, C, HW, a.nbits)
+    wgrad_ops = dgrad_ops = bwd_ops / 2  # 2*NSA*MKN and 2*NSW*MKN with NSW == NSA
     ops_step = fwd_ops + bwd_ops
     value = ops_step * world * a.steps / (ms * 1e-3) / 1e12
 
@@ -355,6 +362,14 @@ def run_ours(a):
                                                         save_state=False), it, torch)
             t_b = event_time_ms(lambda: L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask,
                                                         need_alpha=aq is not None), it, torch)
+            # the three independent parts of the backward call, each timed alone (NULL outputs skip a part)
+            t_bw = event_time_ms(lambda: L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask, need_alpha=False,
+                                                         need_input=False), it, torch)
+            t_bx = event_time_ms(lambda: L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask, need_alpha=False,
+                                                         need_weight=False), it, torch)
+            t_ba = (event_time_ms(lambda: L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask, need_alpha=True,
+                                                          need_input=False, need_weight=False), it, torch)
+                    if aq is not None else 0.0)
         n = x.numel()
         int8_peak = 2.0 * bf16_peak  # no measured int8 peak: 2x the measured dense bf16 rate
         kernels = {
@@ -365,6 +380,11 @@ def run_ours(a):
             "conv_forward_infer": {"ms": t_fi, "TOPS": fwd_ops / t_fi / 1e9,
                                    "frac_int8_tc": fwd_ops / t_fi / 1e9 / int8_peak},
             "conv_backward": {"ms": t_b, "TFLOP/s": bwd_ops / t_b / 1e9, "frac_bf16_tc": bwd_ops / t_b / 1e9 / bf16_peak},
+            "conv_backward.wgrad(tcgen05=%d)" % info.tc_backward: {
+                "ms": t_bw, "TFLOP/s": wgrad_ops / t_bw / 1e9, "frac_bf16_tc": wgrad_ops / t_bw / 1e9 / bf16_peak},
+            "conv_backward.dgrad+col2im": {
+                "ms": t_bx, "TFLOP/s": dgrad_ops / t_bx / 1e9, "frac_bf16_tc": dgrad_ops / t_bx / 1e9 / bf16_peak},
+            "conv_backward.alpha_grad": {"ms": t_ba},
         }
         # dominant kernel family of the step (by device time); DRAM traffic per launch from the committed ncu
         # capture of the same kernels (profiles/ncu_traffic.json), when present
@@ -373,17 +393,26 @@ def run_ours(a):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except Exception:
             pass
-        if t_b >= t_f:
-            roof = {"kernel": "conv_backward (bwd_weight_tc + bwd_input_tc + col2im + alpha-grad)", "bound": "tensor",
-                    "achieved": bwd_ops / t_b / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
-                    "frac": bwd_ops / t_b / 1e9 / bf16_peak, "traffic": traffic.get("conv_backward"),
+        # the single dominant kernel of the step by device time
+        cand = [
+            (t_f, {"kernel": "conv_tc_kernel (CiM conv forward, tcgen05 kind::i8 + ADC epilogue)", "bound": "tensor",
+                   "achieved": fwd_ops / t_f / 1e9, "peak": int8_peak, "unit": "TOPS",
+                   "frac": fwd_ops / t_f / 1e9 / int8_peak, "traffic": _traffic_bytes(traffic, "conv_forward"),
+                   "peak_source": peak_src + " x2 for int8 (no measured int8 peak)",
+                   "note": "algorithmic ops 2*NSW*NSA*MKN, one contraction per slice pair"}),
+            (t_bw, {"kernel": "bwd_weight_tc_kernel (+ finish; CiM conv wgrad, tcgen05 kind::f16 bf16x3)", "bound": "tensor",
+                    "achieved": wgrad_ops / t_bw / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
+                    "frac": wgrad_ops / t_bw / 1e9 / bf16_peak, "traffic": _traffic_bytes(traffic, "conv_wgrad"),
                     "peak_source": peak_src,
-                    "note": "algorithmic flops 2*(NSW+NSA)*MKN; the kernels issue 3x that in bf16 (hi/mid/lo split)"}
-        else:
-            roof = {"kernel": "conv_forward (conv_tc_kernel, tcgen05 kind::i8)", "bound": "tensor",
-                    "achieved": fwd_ops / t_f / 1e9, "peak": int8_peak, "unit": "TOPS",
-                    "frac": fwd_ops / t_f / 1e9 / int8_peak, "traffic": traffic.get("conv_forward"),
-                    "peak_source": peak_src + " x2 for int8 (no measured int8 peak)"}
+                    "note": "algorithmic flops 2*NSA*MKN; the kernel issues 3x that in bf16 (hi/mid/lo split of grad)"}),
+            (t_bx, {"kernel": "bwd_input_tc_kernel + col2im (CiM conv dgrad, tcgen05 kind::f16 bf16x3)", "bound": "tensor",
+                    "achieved": dgrad_ops / t_bx / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
+                    "frac": dgrad_ops / t_bx / 1e9 / bf16_peak, "traffic": _traffic_bytes(traffic, "conv_dgrad"),
+                    "peak_source": peak_src,
+                    "note": "algorithmic flops 2*NSW*MKN; the kernel issues 3x that in bf16 (hi/mid/lo split of grad)"}),
+        ]
+        roof = max(cand, key=lambda c: c[0])[1]
+        roof["ms_per_launch"] = max(c[0] for c in cand)
 
         # ---- end to end through the module surface with HOST buffers (pinned), copies inside the timed region
         gw_host = torch.empty_like(layer.weight, device="cpu").pin_memory()

@@ -244,12 +244,12 @@ def conv_forward(spec: LayerSpec, xcodes, wcodes, wtiles, table, s, binary_mask,
 
 
 def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, wtiles, state, s, binary_mask, need_alpha: bool,
-                  need_input: bool = True, flags: int = 0):
+                  need_input: bool = True, flags: int = 0, need_weight: bool = True):
     info = layer_info(spec)
     dev = grad_out.device
     gxq = (torch.empty((spec.batch, spec.in_channels, spec.in_hw, spec.in_hw), dtype=torch.float32, device=dev)
            if need_input else None)
-    gwq = torch.empty((spec.out_channels, info.F), dtype=torch.float32, device=dev)
+    gwq = torch.empty((spec.out_channels, info.F), dtype=torch.float32, device=dev) if need_weight else None
     galpha = (torch.empty((1, info.NX, info.NSW, info.NSA, 1, spec.out_channels), dtype=torch.float32, device=dev)
               if need_alpha else None)
     ws = torch.empty(info.bwd_workspace_bytes, dtype=torch.uint8, device=dev)
@@ -257,7 +257,7 @@ def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, wtiles, state, s, 
     _check(load().cimq_conv_backward(C.byref(layer), _ptr(grad_out), _ptr(xcodes), _ptr(wdigits), _ptr(wtiles),
                                      _ptr(state), _ptr(s), _ptr(binary_mask), _ptr(gxq), _ptr(gwq), _ptr(galpha), _ptr(ws),
                                      flags, _stream()))
-    _count(2 + (2 if need_input else 0) + (2 if galpha is not None else 0))
+    _count((2 if need_weight else 0) + (2 if need_input else 0) + (2 if galpha is not None else 0))
     return gxq, gwq, galpha
 
 
