@@ -8,8 +8,9 @@ UtkarshSaxena1/CiM_Quantization (``models/_modules/lsq.py``).
   PyTorch fallback -- importing the compute path without the built library fails.
 """
 from . import _lib  # noqa: F401
+from ._lib import set_deterministic  # noqa: F401
 from .functional import cim_conv2d, get_cim_output_signed, lsq_fake_quant  # noqa: F401
 from .modules import ActLSQ, Conv2dLSQ, Conv2dLSQCiM, LinearLSQ  # noqa: F401
 
 __all__ = ['ActLSQ', 'Conv2dLSQ', 'Conv2dLSQCiM', 'LinearLSQ', 'cim_conv2d', 'get_cim_output_signed',
-           'lsq_fake_quant']
+           'lsq_fake_quant', 'set_deterministic']

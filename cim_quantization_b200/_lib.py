@@ -17,6 +17,22 @@ LIB_PATH = os.path.join(_HERE, "libcimq.so")
 
 ADC_MULTIBIT, ADC_BINARY, ADC_TERNARY = 0, 1, 2
 FLAG_FORCE_SIMT = 1
+FLAG_DETERMINISTIC = 2  # backward: fixed-order fold of grad_x instead of fp32 reductions in the dgrad epilogue
+_deterministic = False
+
+
+def set_deterministic(enabled: bool) -> None:
+    """Make every conv_backward bit-reproducible run to run (also implied by
+    torch.use_deterministic_algorithms(True)); costs the separate col2im pass."""
+    global _deterministic
+    _deterministic = bool(enabled)
+
+
+def _backward_flags(flags: int) -> int:
+    if _deterministic or torch.are_deterministic_algorithms_enabled():
+        flags |= FLAG_DETERMINISTIC
+    return flags
+
 
 
 class CimqLayer(C.Structure):
@@ -256,7 +272,7 @@ def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, wtiles, state, s, 
     layer = spec.c_layer()
     _check(load().cimq_conv_backward(C.byref(layer), _ptr(grad_out), _ptr(xcodes), _ptr(wdigits), _ptr(wtiles),
                                      _ptr(state), _ptr(s), _ptr(binary_mask), _ptr(gxq), _ptr(gwq), _ptr(galpha), _ptr(ws),
-                                     flags, _stream()))
+                                     _backward_flags(flags), _stream()))
     _count((2 if need_weight else 0) + (2 if need_input else 0) + (2 if galpha is not None else 0))
     return gxq, gwq, galpha
 

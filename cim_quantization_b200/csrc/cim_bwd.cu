@@ -435,9 +435,15 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
   }
   if (gxq != nullptr && use_tc) {
     const WtLayout wl = wt_layout(g);
-    if (launch_bwd_input_tc(g, go, state, reinterpret_cast<const uint8_t *>(wtiles) + wl.bwd_off, s, mask, gxuT, st))
-      return 1;
-    if (launch_col2im(g, gxuT, gxq, st)) return 1;
+    const uint8_t *wtb = reinterpret_cast<const uint8_t *>(wtiles) + wl.bwd_off;
+    if (!(flags & CIMQ_FLAG_DETERMINISTIC) && bwd_input_tc_can_fold(g)) {
+      // fused fold: the dgrad epilogue reduces into grad_x (fp32 atomics in L2; summation order varies run to run)
+      CIMQ_CUDA_OK(cudaMemsetAsync(gxq, 0, (size_t)g.B * g.Cin * g.H * g.W * sizeof(float), st));
+      if (launch_bwd_input_tc(g, go, state, wtb, s, mask, gxq, 1, st)) return 1;
+    } else {
+      if (launch_bwd_input_tc(g, go, state, wtb, s, mask, gxuT, 0, st)) return 1;
+      if (launch_col2im(g, gxuT, gxq, st)) return 1;
+    }
   } else if (gxq != nullptr) {
     size_t smem = (size_t)g.NSW * g.Cout * 32 * sizeof(float);
     CIMQ_REQUIRE(smem <= 200 * 1024, "conv_backward: NSW*Cout too large for the SIMT kernel");

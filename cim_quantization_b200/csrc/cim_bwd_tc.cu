@@ -50,6 +50,7 @@ struct BwdParams {
   // wgrad staged activation rows (same geometry as the forward producer, stride 1 only)
   int fastx, ow_log2, rpt, pitch_log2, col0;
   uint32_t raw_bytes;
+  int fold;  // dgrad: 1 = the epilogue folds (col2im) straight into grad_x with fp32 reductions; 0 = writes gxu[b][f][l]
   const float *go;
   const uint32_t *state;
   const uint8_t *xcodes;
@@ -163,6 +164,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
     const int j = threadIdx.x % g.NSA;
     cv.wtab[threadIdx.x] = (float)P.mask[threadIdx.x] * exp2f(-(float)(g.abs_ * j));
   }
+  if (P.fold) {  // unfold row f = (ci, ky, kx) (nn.Unfold order, lsq.py:141) -> offset inside the image, tap index
+    int *ftab = reinterpret_cast<int *>(cv.raw);
+    for (int f = threadIdx.x; f < g.F; f += kThreads) {
+      const int ci = f / g.KK, tap = f % g.KK, ky = tap / g.K, kx = tap % g.K;
+      ftab[f] = (((ci * g.H + ky) * g.W + kx) << 5) | tap;
+    }
+  }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(cv.tmem_slot), P.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -185,17 +193,24 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
       const bool live = m < g.M;
       const int b = live ? (int)(m / g.L) : 0, l = live ? (int)(m % g.L) : 0;
       const float *gop = P.go + ((int64_t)b * g.Cout + h * cpt) * g.L + l;
+      // rows past the last pixel read pixel 0 (valid addresses, no predicates on the loads) and are zeroed
+      // through the slice weights below
       const uint32_t *stp = P.state + (int64_t)CBits::CW0 * g.M + (live ? m : 0);
+      const float livef = live ? 1.0f : 0.0f;
+      const size_t sstride = (size_t)CBits::SWORDS * g.M;  // state words between consecutive channels
       uint32_t sw_n[8][CBits::CWN];
       float gv_n[8];
       auto prefetch = [&](int i, int cg) {
+        // one 64-bit multiply per group of eight channels, then pointer increments
+        const uint32_t *sp = stp + (size_t)(i * g.Cout + h * cpt + cg) * sstride;
+        const float *gp = gop + (size_t)cg * g.L;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int co = h * cpt + cg + e;
 #pragma unroll
-          for (int w = 0; w < CBits::CWN; ++w)
-            sw_n[e][w] = live ? __ldg(stp + ((int64_t)(i * g.Cout + co) * CBits::SWORDS + w) * g.M) : 0xffffffffu;
-          gv_n[e] = live ? __ldg(gop + (int64_t)(cg + e) * g.L) : 0.0f;
+          for (int w = 0; w < CBits::CWN; ++w) sw_n[e][w] = __ldg(sp + (size_t)w * g.M);
+          gv_n[e] = __ldg(gp);
+          sp += sstride;
+          gp += g.L;
         }
       };
       prefetch(0, 0);
@@ -212,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
           }
           float wx[NSA];
 #pragma unroll
-          for (int j = 0; j < NSA; ++j) wx[j] = cv.wtab[k * NSA + j];
+          for (int j = 0; j < NSA; ++j) wx[j] = cv.wtab[k * NSA + j] * livef;
           const int start = CBits::CB + k;  // clip bit of (k, j) = CB + j*NSW + k
           for (int cgi = 0; cgi < G; ++cgi) {
             uint32_t sw[8][CBits::CWN];
@@ -282,10 +297,22 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const float scale = P.s[1] / (float)NSA;  // w_sl * s_w (lsq.py:252), mean over act slices (lsq.py:376)
+    const int *ftab = reinterpret_cast<const int *>(cv.raw);  // fold: per unfold row {offset in the image << 5 | tap}
     uint32_t acc_it = 0;
     for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
       const int64_t m = (int64_t)mt * kTcTileM + r;
       const int eb = m < g.M ? (int)(m / g.L) : 0, el = m < g.M ? (int)(m % g.L) : 0;
+      // fold: taps of this pixel that land inside the image, and the address of tap (0, 0) of channel 0
+      uint32_t vm = 0;
+      float *gxp = P.out;
+      if (P.fold && m < g.M) {
+        const int oy = el / g.OW, ox = el % g.OW;
+        const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
+        for (int ky = 0; ky < g.K; ++ky)
+          for (int kx = 0; kx < g.K; ++kx)
+            if (iy0 + ky >= 0 && iy0 + ky < g.H && ix0 + kx >= 0 && ix0 + kx < g.W) vm |= 1u << (ky * g.K + kx);
+        gxp = P.out + ((int64_t)eb * g.Cin * g.H + iy0) * g.W + ix0;
+      }
       for (int i = 0; i < g.NX; ++i, ++acc_it) {
         const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
         const int lo = i * g.xbar;
@@ -296,7 +323,17 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
           int v[32];
           tmem_ld<32>(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * Nf + c0, v);
           tmem_ld_wait();
-          if (m < g.M) {  // gxu[b][f][l]: image-major so that col2im's nine reads per output stay within one image
+          if (P.fold) {
+            // nn.Fold (lsq.py:378-383) fused: every unfolded gradient is added to its input pixel.  Lanes are
+            // consecutive output pixels, so one warp-wide reduction covers consecutive addresses; grad_x
+            // (zeroed by the caller) stays in L2 while it is accumulated.
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc)
+              if (c0 + cc < rows) {
+                const int e = ftab[lo + c0 + cc];
+                if ((vm >> (e & 31)) & 1u) atomicAdd(gxp + (e >> 5), __int_as_float(v[cc]) * scale);
+              }
+          } else if (m < g.M) {  // gxu[b][f][l]: image-major so that col2im's reads per output stay within one image
             float *dst = P.out + ((int64_t)eb * g.F + lo + c0) * g.L + el;
 #pragma unroll
             for (int cc = 0; cc < 32; ++cc)
@@ -755,8 +792,13 @@ int64_t bwd_tc_partial_bytes(const Geo &g) {
   return (int64_t)ctas * g.F * g.Cout * 4;
 }
 
+bool bwd_input_tc_can_fold(const Geo &g) {
+  // the fold table packs {offset, tap}: 5 bits of tap (K <= 5), offsets below 2^26, table in shared memory
+  return g.K <= 5 && (int64_t)g.Cin * g.H * g.W < (1 << 26) && g.F <= 4096;
+}
+
 int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, const void *wtb, const float *s,
-                        const int8_t *mask, float *gxuT, cudaStream_t st) {
+                        const int8_t *mask, float *out, int fold, cudaStream_t st) {
   BwdParams P;
   memset(&P, 0, sizeof(P));
   P.g = g;
@@ -766,15 +808,17 @@ int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, co
   P.a_bytes = (uint32_t)(kTcTileM * g.Cout * 2);
   P.b_bytes = (uint32_t)(P.Nf * g.Cout * 2);
   P.stage_bytes = 3 * P.a_bytes + P.b_bytes;
-  int stages = (int)((kSmemBudget - kBarrierBytes) / P.stage_bytes);
+  P.fold = fold;
+  P.raw_bytes = fold ? (uint32_t)((g.F * 4 + 15) & ~15) : 0u;
+  int stages = (int)((kSmemBudget - kBarrierBytes - P.raw_bytes) / P.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   CIMQ_REQUIRE(stages >= 1, "dgrad tile does not fit shared memory");
   P.stages = stages;
   uint32_t cols = 32;
   while (cols < 2u * P.Nf) cols <<= 1;
   P.tmem_cols = cols;
-  P.go = go; P.state = state; P.wtb = reinterpret_cast<const uint8_t *>(wtb); P.s = s; P.mask = mask; P.out = gxuT;
-  const size_t smem = (size_t)stages * P.stage_bytes + kBarrierBytes + 1024;
+  P.go = go; P.state = state; P.wtb = reinterpret_cast<const uint8_t *>(wtb); P.s = s; P.mask = mask; P.out = out;
+  const size_t smem = (size_t)stages * P.stage_bytes + kBarrierBytes + P.raw_bytes + 1024;
   const int grid = P.mtiles < 148 ? P.mtiles : 148;
 #define CIMQ_LAUNCH_DGRAD(W, A, T, ...)                                                                         \
   do {                                                                                                          \

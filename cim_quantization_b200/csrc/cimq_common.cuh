@@ -114,8 +114,11 @@ bool tc_backward_supported(const Geo &g);
 int64_t wtiles_bwd_bytes(const Geo &g);
 int launch_weight_tiles_bwd(const Geo &g, const int8_t *wcodes, void *tiles, cudaStream_t st);
 int64_t bwd_tc_partial_bytes(const Geo &g);
+bool bwd_input_tc_can_fold(const Geo &g);
+// fold = 1: `out` is grad_x [B,Cin,H,W], zero-filled, and the kernel folds into it; fold = 0: `out` is the
+// unfolded gradient gxu[b][f][l] for launch_col2im
 int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, const void *wtb, const float *s,
-                        const int8_t *mask, float *gxuT, cudaStream_t st);
+                        const int8_t *mask, float *out, int fold, cudaStream_t st);
 int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, const uint32_t *state,
                          const float *s, const int8_t *mask, float *partial, float *gw, cudaStream_t st);
 

@@ -50,7 +50,9 @@ enum {
 
 /* flags for cimq_conv_forward / backward */
 enum {
-  CIMQ_FLAG_FORCE_SIMT = 1 /* use the CUDA-core kernels even where a tcgen05 kernel exists (tests) */
+  CIMQ_FLAG_FORCE_SIMT = 1,   /* use the CUDA-core kernels even where a tcgen05 kernel exists (tests) */
+  CIMQ_FLAG_DETERMINISTIC = 2 /* backward: fold grad_x with a separate fixed-order pass instead of fp32
+                                 reductions in the dgrad epilogue (bit-reproducible run to run, slower) */
 };
 
 /* Geometry + quantisation of one Conv2dLSQCiM layer (_quan_base.py:174-237, lsq.py:512-531).

@@ -454,3 +454,31 @@ def test_full_size_tc_equals_simt(xbar, adc):
                                    flags=L.FLAG_FORCE_SIMT)
     assert torch.equal(st_tc, st_si)
     assert rel_err(out_tc.cpu().numpy(), out_si.cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("name", ["tern_c16o16_x128_s2", "tern_c32o32_x64", "tern_c16o64_x128"])
+def test_backward_deterministic_fold(name):
+    """CIMQ_FLAG_DETERMINISTIC: the separate fixed-order fold gives the golden grad_x and is bit-identical run to
+    run; the default (fp32 reductions in the dgrad epilogue) agrees with it to rounding."""
+    L = _lib()
+    cfg, d, hw, batch = load_golden(name)
+    spec = _spec(cfg, hw, batch)
+    info = L.layer_info(spec)
+    if not info.tc_backward:
+        pytest.skip("layer not covered by the tcgen05 backward kernels")
+    s = _cuda(np.array([d["s_a"].reshape(()), d["s_w"].reshape(())], dtype=np.float32))
+    xc, wc = _cuda(d["x_codes"], torch.uint8), _cuda(d["w_codes"], torch.int8).reshape(cfg.out_channels, -1)
+    aq = _cuda(d["alpha_q"]) if cfg.has_alpha_cim else None
+    mask = _mask(cfg)
+    table = L.adc_table(spec, s, aq, mask)
+    wdigits, wtiles = L.weight_prepare(spec, wc)
+    _, state = L.conv_forward(spec, xc, wc, wtiles, table, s, mask, save_state=True)
+    oh = cfg.out_hw(hw)
+    go = _cuda(d["grad_y"].reshape(batch, cfg.out_channels, oh * oh))
+    runs = [L.conv_backward(spec, go, xc, wdigits, wtiles, state, s, mask, need_alpha=False,
+                            flags=L.FLAG_DETERMINISTIC)[0].cpu().numpy() for _ in range(2)]
+    np.testing.assert_array_equal(runs[0], runs[1])
+    assert rel_err(runs[0], d["fn_grad_xq"]) < TOL
+    fused = L.conv_backward(spec, go, xc, wdigits, wtiles, state, s, mask, need_alpha=False)[0].cpu().numpy()
+    assert rel_err(fused, d["fn_grad_xq"]) < TOL
+    assert rel_err(fused, runs[0]) < 1e-6
