@@ -62,3 +62,46 @@ def shard_batch(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
         raise ValueError(f"global batch {x.shape[0]} is not divisible by world size {world}")
     n = x.shape[0] // world
     return x[rank * n:(rank + 1) * n]
+
+
+# ---- one-off all-reduce of the data-dependent initialisation statistics -----------------
+# The reference initialises step sizes from each rank's own first batch *after* DDP has broadcast the
+# parameters, so replicas start from different step sizes (H11).  With more than one rank the modules reduce
+# the three statistics below over all ranks, so every replica starts from the value a single process would
+# compute on the global batch (equal shards).  Single-process behaviour is untouched.
+_sync_lazy_init = True
+
+
+def set_sync_lazy_init(enabled: bool) -> None:
+    """False restores the reference's per-rank initialisation."""
+    global _sync_lazy_init
+    _sync_lazy_init = bool(enabled)
+
+
+def _world(group=None) -> int:
+    if _sync_lazy_init and dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group)
+    return 1
+
+
+def global_mean_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In place: mean over ranks of a per-rank mean (equal shard sizes)."""
+    w = _world(group)
+    if w > 1:
+        dist.all_reduce(t, group=group)
+        t.div_(w)
+    return t
+
+
+def global_min_(t: torch.Tensor, group=None) -> torch.Tensor:
+    if _world(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return t
+
+
+def global_sum_(t: torch.Tensor, group=None):
+    """In place sum over ranks; returns (tensor, number of ranks that contributed)."""
+    w = _world(group)
+    if w > 1:
+        dist.all_reduce(t, group=group)
+    return t, w

@@ -213,12 +213,16 @@ def alpha_quantize(alpha, nbits_alpha: int):
     return _AlphaQuant.apply(alpha, 1, 2 ** nbits_alpha - 1)
 
 
-def alpha_cim_initial_value(spec: LayerSpec, xcodes, wcodes, s, qp_adc: float = 1.0):
+def alpha_cim_initial_value(spec: LayerSpec, xcodes, wcodes, s, qp_adc: float = 1.0, reduce_sums=None):
     """Data-dependent initial ``alpha_cim`` (lsq.py:557-563): ``2*mean|psum*s_w*s_a| / sqrt(Qp_adc)``
-    over (batch, pixel), zeros replaced by ``s_w*s_a``.  The |psum| sums are exact integers."""
+    over (batch, pixel), zeros replaced by ``s_w*s_a``.  The |psum| sums are exact integers.
+    ``reduce_sums(t) -> (t, ranks)`` may sum them over data-parallel ranks (distributed.global_sum_)."""
     info = _lib.layer_info(spec)
     sums = _lib.conv_psum_abs_sums(spec, xcodes, wcodes)  # int64 [1,NX,NSW,NSA,1,Cout]
+    ranks = 1
+    if reduce_sums is not None:
+        sums, ranks = reduce_sums(sums)
     sa, sw = s[0].double(), s[1].double()
-    t = 2.0 * (sums.double() / float(spec.batch * info.L)) * sw * sa / math.sqrt(qp_adc)
+    t = 2.0 * (sums.double() / float(ranks * spec.batch * info.L)) * sw * sa / math.sqrt(qp_adc)
     t = torch.where(t == 0, sw * sa, t)
     return t.float()

@@ -10,6 +10,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _lib
+from .. import distributed as CD
 from .. import functional as CF
 from ._quan_base import _ActQ, _Conv2dQ, _Conv2dQCiM, _LinearQ, grad_scale, round_pass
 
@@ -48,9 +49,10 @@ class Conv2dLSQCiM(_Conv2dQCiM):
         """First training batch: data-dependent step sizes (lsq.py:532-542)."""
         qp_a = 2 ** self.nbits_a - 1
         qp_w = 2 ** (self.nbits_w - 1) - 1
-        if x.min() < -1e-5:
+        # with several ranks the statistics are reduced over the global batch (SURVEY H11); no-ops otherwise
+        if CD.global_min_(x.min()) < -1e-5:
             self.signed_act.data.fill_(1)
-        self.alpha_act.data.copy_(2 * x.abs().mean() / math.sqrt(qp_a))
+        self.alpha_act.data.copy_(2 * CD.global_mean_(x.abs().mean()) / math.sqrt(qp_a))
         self.alpha_weight.data.copy_(2 * self.weight.abs().mean() / math.sqrt(qp_w))
         self.init_state.fill_(1)
         self._init_done = True
@@ -66,7 +68,8 @@ class Conv2dLSQCiM(_Conv2dQCiM):
         s = _lib.step_sizes(self.alpha_act.data, self.alpha_weight.data, ga, gw)
         xcodes = _lib.lsq_quantize(x.contiguous(), s[0:1], 0, qp_a)
         wcodes = _lib.lsq_quantize(self.weight.data.contiguous(), s[1:2], qn_w, qp_w)
-        self.alpha_cim.data.copy_(CF.alpha_cim_initial_value(spec, xcodes, wcodes, s, qp_adc=1.0))
+        self.alpha_cim.data.copy_(CF.alpha_cim_initial_value(spec, xcodes, wcodes, s, qp_adc=1.0,
+                                                             reduce_sums=CD.global_sum_))
         self.init_state_cim.fill_(1)
         self._init_cim_done = True
 

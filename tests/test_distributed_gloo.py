@@ -31,7 +31,21 @@ def _worker(rank, world, port, ret):
         ok = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(m.parameters()))
         x = torch.arange(8 * 3).view(8, 3)
         sh = shard_batch(x, rank, world)
-        ret[rank] = (same, ok, sh[0, 0].item(), red.nbytes)
+        # lazy-init statistics reduced over the global batch: every rank gets the value one process
+        # would compute on the concatenation of the shards
+        from cim_quantization_b200 import distributed as CD
+        full = torch.linspace(-1.0, 3.0, 16)
+        mine = shard_batch(full, rank, world)
+        gmean = CD.global_mean_(mine.abs().mean())
+        gmin = CD.global_min_(mine.min())
+        gsum, ranks = CD.global_sum_(mine.to(torch.int64).abs().sum())
+        stats_ok = (torch.allclose(gmean, full.abs().mean()) and gmin.item() == full.min().item()
+                    and gsum.item() == full.to(torch.int64).abs().sum().item() and ranks == world)
+        CD.set_sync_lazy_init(False)
+        local = CD.global_mean_(mine.abs().mean())
+        stats_ok = stats_ok and torch.allclose(local, mine.abs().mean())
+        CD.set_sync_lazy_init(True)
+        ret[rank] = (same, ok, sh[0, 0].item(), red.nbytes, stats_ok)
     finally:
         dist.destroy_process_group()
 
@@ -42,7 +56,8 @@ def test_flat_allreduce_two_ranks():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     for rank in range(world):
-        same, ok, first, nbytes = ret[rank]
+        same, ok, first, nbytes, stats_ok = ret[rank]
+        assert stats_ok, "lazy-init statistics are not the global-batch values"
         assert same, "parameters differ across ranks after broadcast"
         assert ok, "all-reduced gradient is not the DDP average"
         assert first == rank * 12
