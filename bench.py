@@ -103,6 +103,55 @@ def cpu_step_factory(a, batch):
     return step
 
 
+def reference_root():
+    """baseline/_ref: the unmodified reference tree copied next to the repo by tools/make_baseline_ref.sh
+    (git-ignored; it travels to the GPU box).  /root/reference itself is never read by bench.py."""
+    cand = os.path.join(ROOT, "baseline", "_ref")
+    return cand if os.path.isfile(os.path.join(cand, "models", "_modules", "lsq.py")) else None
+
+
+def ref_cpu_step_factory(a, batch):
+    """The reference's own Conv2dLSQCiM (models/_modules/lsq.py, unmodified) forward+backward on the host
+    cores, behind the two-line CPU shim of SURVEY 8c (the reference hard-codes torch.cuda allocations).
+    Only ever called in a `--impl reference` process: the shim patches torch.Tensor.cuda."""
+    import torch
+    torch.cuda.FloatTensor = lambda *t: torch.FloatTensor(*t)  # lsq.py:64,169,215,336
+    torch.Tensor.cuda = lambda self, *t, **k: self              # lsq.py:169
+    sys.path.insert(0, reference_root())
+    import models._modules as ref_nn
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    adc = int(a.adcbits) if a.adcbits == int(a.adcbits) else a.adcbits
+    m = ref_nn.Conv2dLSQCiM(a.channels, a.channels, (3, 3), (1, 1), (1, 1), (1, 1), 1, False, nbits_w=a.nbits,
+                            nbits_a=a.nbits, nbits_alpha=8, wbitslice=1, abitslice=1, xbar=a.xbar, adcbits=adc,
+                            signed_xbar=False, stochastic_quant=False)
+    with torch.no_grad():
+        m.weight.copy_(torch.randn(m.weight.shape, generator=g) * math.sqrt(2.0 / (a.channels * 9)))
+    x = torch.relu(torch.randn(batch, a.channels, a.hw, a.hw, generator=g))
+    gy = torch.randn(batch, a.channels, a.hw, a.hw, generator=g)
+    m.train()
+    m(x)  # lazy inits (lsq.py:532-563) outside the timed steps
+
+    def step():
+        xi = x.clone().requires_grad_(True)
+        for p_ in m.parameters():
+            p_.grad = None
+        m(xi).backward(gy)
+        return xi.grad
+
+    return step
+
+
+def cpu_step(a, batch):
+    """(step function, kind): the unmodified reference when baseline/_ref is there, else the numpy port."""
+    if reference_root() is not None:
+        try:
+            return ref_cpu_step_factory(a, batch), "reference"
+        except Exception as e:  # e.g. a torch build the reference cannot import under: fall back, and say so
+            print(f"bench: reference import failed ({e!r}); timing the oracle port", file=sys.stderr)
+    return cpu_step_factory(a, batch), "port"
+
+
 def time_cpu(a, batch, reps):
     step = cpu_step_factory(a, batch)
     step()  # warm-up (BLAS threads, page faults)
@@ -122,7 +171,7 @@ def run_reference(a):
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     b = a.cpu_sample_batch
-    step = cpu_step_factory(a, b)
+    step, kind = cpu_step(a, b)
     for _ in range(min(a.warmup, 1)):
         step()
     t0 = time.perf_counter()
@@ -131,12 +180,14 @@ def run_reference(a):
     dt = time.perf_counter() - t0
     fwd, bwd = layer_ops(b, a.channels, a.hw, a.nbits)
     value = (fwd + bwd) * a.steps / dt / 1e12
-    sample = f"{b} images per step of the same layer (numpy port of the reference algorithm, all host threads)"
+    what = ("the reference's own Conv2dLSQCiM module on CPU (baseline/_ref, unmodified, CUDA-allocation shim)"
+            if kind == "reference" else "numpy port of the reference algorithm (oracle/)")
+    sample = f"{b} images per step of the same layer, {what}, all host threads"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
             "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": dt / a.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (holding integers)",
             "data": "synthetic", "config": workload_config(a),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -439,11 +490,18 @@ def run_ours(a):
 
         cpu = None
         if not a.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            v, sec = time_cpu(a, a.cpu_sample_batch, 3)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{a.cpu_sample_batch} images of the same layer per step, median of 3 "
-                             f"({sec:.2f} s/step), numpy port of the reference algorithm"}
+            # a separate process: the reference needs torch.Tensor.cuda patched out, which must not leak in here
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3",
+                                    "--warmup", "1", "--xbar", str(a.xbar), "--adcbits", str(a.adcbits), "--nbits",
+                                    str(a.nbits), "--channels", str(a.channels), "--hw", str(a.hw),
+                                    "--cpu-sample-batch", str(a.cpu_sample_batch)],
+                                   capture_output=True, text=True, timeout=600,
+                                   env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE")})
+                cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception as e:
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                       "sample": f"CPU baseline failed: {e!r}"}
         clocks = clk.summary()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",

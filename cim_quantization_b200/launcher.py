@@ -1,0 +1,193 @@
+"""Launcher shim: runs the reference's own entry point
+``examples/classifier_cifar10/main_lsq.py`` UNCHANGED on this package's kernels.
+
+    python -m cim_quantization_b200.launcher --reference-root baseline/_ref --train-batches 8 --val-batches 2
+
+What the shim supplies, and nothing else:
+* ``models._modules`` -> this package (``dropin.install()``), so ``replace_map={'Conv2d': [my_nn.Conv2dLSQCiM]}``
+  (main_lsq.py:53-56) builds our modules.  ``--impl reference`` skips this step and runs the reference's own
+  PyTorch-CUDA modules instead (the number a user of the reference sees today).
+* stand-ins for the four third-party imports of ``examples/__init__.py:14-30`` that this image lacks
+  (``plotly``, ``pytorchcv``, ``tensorboardX``, ``warmup_scheduler``) -- none of them is on the hot path.
+* a synthetic CIFAR-10 (``torchvision.datasets.CIFAR10`` downloads, ``examples/__init__.py:600``; there is no
+  network) and a prototxt equal to the shipped ``resnet_w3a3.prototxt`` except ``pretrained: false``, no
+  ``resume``, and the epoch / batch / worker counts given on the command line.
+* a wall-clock + CUDA-synchronised timer around the reference's ``train()`` so the run reports img/s.
+
+The reference tree is looked up at ``--reference-root`` (default: ``$CIMQ_REFERENCE_ROOT``, ``baseline/_ref`` next
+to this package, ``/root/reference``).  Nothing of it is imported by the product path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import runpy
+import sys
+import tempfile
+import time
+import types
+
+
+def _find_reference(root: str | None) -> str:
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in [root, os.environ.get("CIMQ_REFERENCE_ROOT"), os.path.join(here, "baseline", "_ref"), "/root/reference"]:
+        if cand and os.path.isfile(os.path.join(cand, "examples", "classifier_cifar10", "main_lsq.py")):
+            return os.path.abspath(cand)
+    raise FileNotFoundError("reference tree not found (tools/make_baseline_ref.sh copies it to baseline/_ref)")
+
+
+def install_stubs() -> None:
+    """Inert stand-ins for the optional third-party modules examples/__init__.py imports at the top."""
+    def mod(name, **attrs):
+        if name in sys.modules:
+            return sys.modules[name]
+        try:
+            __import__(name)
+            return sys.modules[name]
+        except Exception:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+            return m
+
+    class SummaryWriter:  # tensorboardX.SummaryWriter: the log directory must exist (prototxt dump, checkpoints)
+        def __init__(self, logdir=None, *a, **k):
+            if logdir:
+                os.makedirs(logdir, exist_ok=True)
+
+        def __getattr__(self, name):
+            return lambda *a, **k: None
+
+    class GradualWarmupScheduler:  # only constructed when the prototxt has a `warmup` block
+        def __init__(self, *a, **k):
+            raise NotImplementedError("warmup_scheduler is not installed")
+
+    def ptcv_get_model(*a, **k):
+        raise NotImplementedError("pytorchcv is not installed")
+
+    plotly = mod("plotly")
+    go = mod("plotly.graph_objects")
+    if not hasattr(plotly, "graph_objects"):
+        plotly.graph_objects = go
+    ptcv = mod("pytorchcv")
+    mp_ = mod("pytorchcv.model_provider", get_model=ptcv_get_model)
+    if not hasattr(ptcv, "model_provider"):
+        ptcv.model_provider = mp_
+    mod("tensorboardX", SummaryWriter=SummaryWriter)
+    mod("warmup_scheduler", GradualWarmupScheduler=GradualWarmupScheduler)
+
+
+def install_synthetic_cifar10(train_images: int, val_images: int, seed: int = 0) -> None:
+    """torchvision.datasets.CIFAR10 -> deterministic random 32x32 RGB images with the same interface."""
+    import numpy as np
+    import torchvision
+    from PIL import Image
+
+    class SyntheticCIFAR10:
+        classes = [str(i) for i in range(10)]
+
+        def __init__(self, root=None, train=True, transform=None, target_transform=None, download=False):
+            n = train_images if train else val_images
+            rng = np.random.RandomState(seed + (0 if train else 1))
+            self.data = rng.randint(0, 256, size=(n, 32, 32, 3), dtype=np.uint8)
+            self.targets = rng.randint(0, 10, size=(n,)).tolist()
+            self.transform, self.target_transform = transform, target_transform
+
+        def __len__(self):
+            return len(self.targets)
+
+        def __getitem__(self, i):
+            img, t = Image.fromarray(self.data[i]), self.targets[i]
+            if self.transform is not None:
+                img = self.transform(img)
+            if self.target_transform is not None:
+                t = self.target_transform(t)
+            return img, t
+
+    torchvision.datasets.CIFAR10 = SyntheticCIFAR10
+
+
+def write_prototxt(ref_root: str, path: str, epochs: int, batch_size: int, workers: int, overrides: dict) -> None:
+    """The shipped prototxt with the offline-only fields changed (text-level edit, parsed by the reference)."""
+    src = os.path.join(ref_root, "examples", "classifier_cifar10", "prototxt", "resnet_w3a3.prototxt")
+    keep = []
+    fixed = {"pretrained": "false", "epochs": str(epochs), "batch_size": str(batch_size), "workers": str(workers),
+             "print_freq": "4", "log_name": '"launcher"'}
+    fixed.update({k: str(v) for k, v in overrides.items()})
+    seen = set()
+    for line in open(src):
+        key = line.split(":")[0].strip()
+        if key == "resume":
+            continue  # a checkpoint path on the author's machine
+        if key in fixed:
+            keep.append(f"{key}: {fixed[key]}\n")
+            seen.add(key)
+        else:
+            keep.append(line)
+    for k, v in fixed.items():
+        if k not in seen:
+            keep.insert(0, f"{k}: {v}\n")
+    with open(path, "w") as f:
+        f.writelines(keep)
+
+
+def run(argv=None) -> dict:
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--reference-root", default=None)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--epochs", type=int, default=1)
+    ap.add_argument("--batch-size", type=int, default=256)
+    ap.add_argument("--train-batches", type=int, default=8, help="synthetic training set = this many batches")
+    ap.add_argument("--val-batches", type=int, default=2)
+    ap.add_argument("--workers", type=int, default=2)
+    ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE", help="extra prototxt overrides")
+    a = ap.parse_args(argv)
+
+    import torch
+    ref_root = _find_reference(a.reference_root)
+    install_stubs()
+    install_synthetic_cifar10(a.train_batches * a.batch_size, a.val_batches * a.batch_size)
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
+    if a.impl == "ours":
+        from . import dropin
+        dropin.install()  # before `import examples`: `import models._modules as my_nn` must resolve to this package
+    import examples  # the reference's harness (examples/__init__.py)
+
+    examples.get_freer_gpu = lambda: 0  # nvidia-smi text parsing (examples/__init__.py:117-130) is brittle
+    stats = {"epochs": []}
+    ref_train = examples.train
+
+    def timed_train(train_loader, model, criterion, optimizer, epoch, args, writer):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = ref_train(train_loader, model, criterion, optimizer, epoch, args, writer)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        n = len(train_loader.dataset)
+        stats["epochs"].append({"epoch": epoch, "seconds": dt, "images": n, "img_per_s": n / dt})
+        return out
+
+    examples.train = timed_train
+    work = tempfile.mkdtemp(prefix="cimq_launcher_")
+    hp = os.path.join(work, "resnet_w3a3_offline.prototxt")
+    overrides = dict(kv.split("=", 1) for kv in a.set)
+    write_prototxt(ref_root, hp, a.epochs, a.batch_size, a.workers, overrides)
+    cwd, argv0 = os.getcwd(), sys.argv
+    os.chdir(work)  # the reference writes ./logger/... and copies its sources there
+    sys.argv = ["main_lsq.py", "--hp", hp]
+    try:
+        runpy.run_path(os.path.join(ref_root, "examples", "classifier_cifar10", "main_lsq.py"), run_name="__main__")
+    finally:
+        os.chdir(cwd)
+        sys.argv = argv0
+    conv_cls = sys.modules["models._modules"].Conv2dLSQCiM
+    stats.update({"impl": a.impl, "conv_class": conv_cls.__module__ + "." + conv_cls.__name__, "batch_size": a.batch_size,
+                  "reference_root": ref_root})
+    print("LAUNCHER_RESULT " + json.dumps(stats))
+    return stats
+
+
+if __name__ == "__main__":
+    run()
