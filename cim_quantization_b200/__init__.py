@@ -10,7 +10,7 @@ UtkarshSaxena1/CiM_Quantization (``models/_modules/lsq.py``).
 from . import _lib  # noqa: F401
 from ._lib import set_deterministic  # noqa: F401
 from .functional import cim_conv2d, get_cim_output_signed, lsq_fake_quant  # noqa: F401
-from .modules import ActLSQ, Conv2dLSQ, Conv2dLSQCiM, LinearLSQ  # noqa: F401
+from .modules import ActLSQ, Conv2dLSQ, Conv2dLSQCiM, LinearLSQ, LinearLSQCiM  # noqa: F401
 
-__all__ = ['ActLSQ', 'Conv2dLSQ', 'Conv2dLSQCiM', 'LinearLSQ', 'cim_conv2d', 'get_cim_output_signed',
+__all__ = ['ActLSQ', 'Conv2dLSQ', 'Conv2dLSQCiM', 'LinearLSQ', 'LinearLSQCiM', 'cim_conv2d', 'get_cim_output_signed',
            'lsq_fake_quant', 'set_deterministic']

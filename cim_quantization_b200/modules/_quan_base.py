@@ -13,7 +13,8 @@ import torch
 import torch.nn as nn
 from torch.nn.parameter import Parameter
 
-__all__ = ['Qmodes', 'Qmodes_cim', '_Conv2dQ', '_LinearQ', '_ActQ', '_Conv2dQCiM', 'round_pass', 'grad_scale']
+__all__ = ['Qmodes', 'Qmodes_cim', '_Conv2dQ', '_LinearQ', '_ActQ', '_Conv2dQCiM', '_LinearQCiM', 'round_pass',
+           'grad_scale']
 
 
 class Qmodes(Enum):
@@ -41,13 +42,45 @@ def round_pass(x):
 def _default_kwargs_q(kwargs_q, layer):
     """Defaults the reference injects (``get_default_kwargs_q``, _quan_base.py:106-137)."""
     default = {'nbits': 4}
-    if isinstance(layer, _Conv2dQCiM):
+    if isinstance(layer, (_Conv2dQCiM, _LinearQCiM)):
         default['cimmode'] = Qmodes_cim.bit_wise
-    if isinstance(layer, (_Conv2dQ, _Conv2dQCiM)):
+    if isinstance(layer, (_Conv2dQ, _Conv2dQCiM, _LinearQCiM)):
         default['mode'] = Qmodes.layer_wise
     for k, v in default.items():
         kwargs_q.setdefault(k, v)
     return kwargs_q
+
+
+def _init_cim_state(layer, kwargs_q, flattened_dim, out_channels):
+    """Attributes, parameters and buffers of a CiM layer (_quan_base.py:199-237)."""
+    layer.kwargs_q = _default_kwargs_q(kwargs_q, layer)
+    for key in ('nbits_w', 'nbits_a', 'nbits_alpha', 'wbitslice', 'abitslice', 'xbar', 'stochastic_quant',
+                'adcbits'):
+        setattr(layer, key, kwargs_q[key])
+    if layer.nbits_w < 0:
+        layer.register_parameter('alpha', None)
+        layer.register_parameter('alpha_cim', None)
+        return
+    layer.q_mode = kwargs_q['mode']
+    layer.num_xbars = int(math.ceil(flattened_dim / layer.xbar))
+    layer.num_bit_slice_weight = int(layer.nbits_w / layer.wbitslice)
+    layer.num_bit_slice_act = int(layer.nbits_a / layer.abitslice)
+    nsw, nsa = layer.num_bit_slice_weight, layer.num_bit_slice_act
+    mask = torch.empty(nsw, nsa, dtype=torch.int8)
+    for i in range(nsa):
+        for j in range(nsw):
+            mask[j, i] = _wrap_int8(((2 ** layer.abitslice) ** i) * ((2 ** layer.wbitslice) ** j))
+    layer.binary_mask = mask.view(1, 1, nsw, nsa, 1, 1)
+    if layer.adcbits == 1.5 or layer.adcbits == 1:
+        layer.alpha_cim = Parameter(torch.ones(1, layer.num_xbars, nsw, nsa, 1, out_channels))
+    else:  # adcbits == 0 or > 1.5: no partial-sum scale factor
+        layer.alpha_cim = None
+    layer.alpha_weight = Parameter(torch.ones(1))
+    layer.alpha_act = Parameter(torch.ones(1))
+    layer.register_buffer('init_state', torch.zeros(1))
+    layer.register_buffer('signed_act', torch.zeros(1))
+    layer.register_buffer('init_state_cim', torch.zeros(1))
+    layer._flags_stale = True  # host mirror of the three buffers (avoids a device sync per forward)
 
 
 class _QBase:
@@ -101,36 +134,25 @@ class _Conv2dQCiM(nn.Conv2d, _QBase):
                  bias=True, **kwargs_q):
         super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
                          dilation=dilation, groups=groups, bias=bias)
-        self.kwargs_q = _default_kwargs_q(kwargs_q, self)
-        for key in ('nbits_w', 'nbits_a', 'nbits_alpha', 'wbitslice', 'abitslice', 'xbar', 'stochastic_quant',
-                    'adcbits'):
-            setattr(self, key, kwargs_q[key])
-        if self.nbits_w < 0:
-            self.register_parameter('alpha', None)
-            self.register_parameter('alpha_cim', None)
-            return
-        self.q_mode = kwargs_q['mode']
         ks = self.kernel_size  # nn.Conv2d normalises ints to tuples; the reference indexes the ctor arg
-        flattened_dim = in_channels * ks[0] * ks[1]
-        self.num_xbars = int(math.ceil(flattened_dim / self.xbar))
-        self.num_bit_slice_weight = int(self.nbits_w / self.wbitslice)
-        self.num_bit_slice_act = int(self.nbits_a / self.abitslice)
-        nsw, nsa = self.num_bit_slice_weight, self.num_bit_slice_act
-        mask = torch.empty(nsw, nsa, dtype=torch.int8)
-        for i in range(nsa):
-            for j in range(nsw):
-                mask[j, i] = _wrap_int8(((2 ** self.abitslice) ** i) * ((2 ** self.wbitslice) ** j))
-        self.binary_mask = mask.view(1, 1, nsw, nsa, 1, 1)
-        if self.adcbits == 1.5 or self.adcbits == 1:
-            self.alpha_cim = Parameter(torch.ones(1, self.num_xbars, nsw, nsa, 1, self.out_channels))
-        else:  # adcbits == 0 or > 1.5: no partial-sum scale factor
-            self.alpha_cim = None
-        self.alpha_weight = Parameter(torch.ones(1))
-        self.alpha_act = Parameter(torch.ones(1))
-        self.register_buffer('init_state', torch.zeros(1))
-        self.register_buffer('signed_act', torch.zeros(1))
-        self.register_buffer('init_state_cim', torch.zeros(1))
-        self._flags_stale = True  # host mirror of the three buffers (avoids a device sync per forward)
+        _init_cim_state(self, kwargs_q, in_channels * ks[0] * ks[1], out_channels)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._flags_stale = True
+
+    def extra_repr(self):
+        return '{}, {}'.format(super().extra_repr(), self.kwargs_q)
+
+
+class _LinearQCiM(nn.Linear, _QBase):
+    """CiM linear base: the parameter / buffer set of ``_Conv2dQCiM`` on an ``nn.Linear`` (a crossbar sees a
+    fully connected layer as a 1x1 convolution over one pixel).  Not in the reference, which quantises only
+    convolutions with the crossbar model; the state-dict names follow ``_Conv2dQCiM``."""
+
+    def __init__(self, in_features, out_features, bias=True, **kwargs_q):
+        super().__init__(in_features=in_features, out_features=out_features, bias=bias)
+        _init_cim_state(self, kwargs_q, in_features, out_features)
 
     def _load_from_state_dict(self, *args, **kwargs):
         super()._load_from_state_dict(*args, **kwargs)

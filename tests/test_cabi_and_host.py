@@ -123,3 +123,29 @@ def test_reference_model_surgery_accepts_dropin_class():
     assert len(convs) == 19 and (convs[0].nbits_w, convs[0].nbits_a) == (8, 8) and convs[1].nbits_w == 3
     assert sum(p.numel() for p in model.parameters()) == 293536
     assert sum(p.numel() for n, p in model.named_parameters() if 'alpha' in n) == 23814
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/utils/wrapper"), reason="reference tree not available")
+def test_reference_model_surgery_accepts_cim_linear():
+    """replace_map={'Conv2d': [...], 'Linear': [LinearLSQCiM]}: the reference's ReplaceModuleTool also swaps the
+    classifier (utils/wrapper/replace_module.py:34-64 needs an nn.Linear subclass taking the same keywords)."""
+    import importlib.util
+    import torch
+    import cim_quantization_b200 as cq
+    spec = importlib.util.spec_from_file_location("ref_replace_module2", "/root/reference/utils/wrapper/replace_module.py")
+    rm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rm)
+    spec2 = importlib.util.spec_from_file_location("ref_resnet2", "/root/reference/models/cifar10/resnet.py")
+    zoo = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(zoo)
+    model = zoo.resnet20(pretrained=False)
+    fc_w = model.linear.weight.detach().clone()
+    rm.ReplaceModuleTool(model, {'Conv2d': [cq.Conv2dLSQCiM], 'Linear': [cq.LinearLSQCiM]}, True, nbits_w=3, nbits_a=3,
+                         nbits_alpha=8, wbitslice=1, abitslice=1, xbar=128, adcbits=1.5, signed_xbar=False,
+                         stochastic_quant=False).replace()
+    assert isinstance(model.linear, cq.LinearLSQCiM) and isinstance(model.linear, torch.nn.Linear)
+    assert torch.equal(model.linear.weight.detach(), fc_w)
+    assert tuple(model.linear.alpha_cim.shape) == (1, 1, 3, 3, 1, 10) and model.linear.num_xbars == 1
+    assert set(dict(model.linear.named_buffers())) == {"init_state", "signed_act", "init_state_cim"}
+    with pytest.raises(RuntimeError):
+        model.linear(torch.zeros(2, 64))  # no CPU fallback

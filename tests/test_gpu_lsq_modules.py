@@ -88,3 +88,53 @@ def test_conv2d_lsq_matches_reference_formula():
     assert rel_err(conv.weight.grad.cpu().numpy(), wr.grad.cpu().numpy()) < TOL
     for got, ref in ((act.alpha.grad, aa.grad), (conv.alpha.grad, aw.grad)):
         assert abs(got.item() - ref.item()) <= 1e-4 * abs(ref.item()) + 1e-6
+
+
+def test_linear_cim_equals_1x1_conv_and_oracle():
+    """LinearLSQCiM is Conv2dLSQCiM with a 1x1 kernel over one pixel: identical to it bit for bit,
+    and to the oracle's restatement of lsq.py:522-588 at 1e-5.  in=96 over xbar 64 -> a 32-row remainder crossbar."""
+    import numpy as np
+    import cim_quantization_b200 as cq
+    from oracle import cim_oracle as O
+    from tests._util import rel_err
+    torch.manual_seed(3)
+    B, fin, fout = 64, 96, 32
+    kw = dict(nbits_w=3, nbits_a=3, nbits_alpha=8, wbitslice=1, abitslice=1, xbar=64, adcbits=1.5)
+    lin = cq.LinearLSQCiM(fin, fout, bias=True, signed_xbar=False, **kw).cuda().train()
+    conv = cq.Conv2dLSQCiM(fin, fout, 1, 1, 0, 1, 1, False, **kw).cuda().train()  # (the reference's conv bias add
+    # broadcasts over the last axis, lsq.py:582-583: not comparable on a 1x1 map)
+    with torch.no_grad():
+        conv.weight.copy_(lin.weight.view(fout, fin, 1, 1))
+    assert isinstance(lin, torch.nn.Linear)
+    assert {k: tuple(v.shape) for k, v in lin.state_dict().items()} == {
+        "weight": (fout, fin), "bias": (fout,), "alpha_cim": (1, 2, 3, 3, 1, fout), "alpha_weight": (1,),
+        "alpha_act": (1,), "init_state": (1,), "signed_act": (1,), "init_state_cim": (1,)}
+    x = torch.relu(torch.randn(B, fin, device="cuda"))
+    gy = torch.randn(B, fout, device="cuda")
+    xl = x.clone().requires_grad_(True)
+    xc = x.clone().requires_grad_(True)
+    yl = lin(xl)
+    yl.backward(gy)
+    yc = conv(xc[:, :, None, None])
+    yc.backward(gy[:, :, None, None])
+    assert torch.equal(yl, yc.flatten(1) + lin.bias)
+    assert torch.equal(xl.grad, xc.grad)
+    assert torch.equal(lin.weight.grad, conv.weight.grad.view(fout, fin))
+    assert torch.allclose(lin.bias.grad, gy.sum(0), rtol=1e-6, atol=1e-6)
+    for n in ("alpha_cim", "alpha_act", "alpha_weight"):
+        assert torch.equal(getattr(lin, n).grad, getattr(conv, n).grad), n
+    # second step (initialised) against the oracle
+    cfg = O.CimConfig(in_channels=fin, out_channels=fout, kernel=1, stride=1, padding=0, **{k: v for k, v in kw.items()
+                                                                                        if k != "nbits_alpha"})
+    for p_ in lin.parameters():
+        p_.grad = None
+    xl = x.clone().requires_grad_(True)
+    y = lin(xl)
+    y.backward(gy)
+    r = O.module_forward_backward(cfg, x.cpu().numpy()[:, :, None, None], lin.weight.detach().cpu().numpy()[:, :, None, None],
+                                  lin.alpha_act.detach().cpu().numpy(), lin.alpha_weight.detach().cpu().numpy(),
+                                  lin.alpha_cim.detach().cpu().numpy(), gy.cpu().numpy()[:, :, None, None])
+    assert rel_err((y - lin.bias).detach().cpu().numpy(), r["y"].reshape(B, fout)) < 1e-5
+    assert rel_err(xl.grad.cpu().numpy(), r["grad_x"].reshape(B, fin)) < 1e-5
+    assert rel_err(lin.weight.grad.cpu().numpy(), r["grad_weight"].reshape(fout, fin)) < 1e-5
+    assert rel_err(lin.alpha_cim.grad.cpu().numpy(), r["grad_alpha_cim"]) < 1e-5
