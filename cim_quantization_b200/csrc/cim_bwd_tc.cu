@@ -50,6 +50,8 @@ struct BwdParams {
   // wgrad staged activation rows (same geometry as the forward producer, stride 1 only)
   int fastx, ow_log2, rpt, pitch_log2, col0;
   uint32_t raw_bytes;
+  int cached;   // dgrad: 1 = producers keep grad_out of the tile and the state words of the chunk in registers
+  uint32_t pw_off;  // dgrad: byte offset of the pass-weight table inside the raw region
   int fold;  // dgrad: 1 = the epilogue folds (col2im) straight into grad_x with fp32 reductions; 0 = writes gxu[b][f][l]
   const float *go;
   const uint32_t *state;
@@ -164,6 +166,26 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
     const int j = threadIdx.x % g.NSA;
     cv.wtab[threadIdx.x] = (float)P.mask[threadIdx.x] * exp2f(-(float)(g.abs_ * j));
   }
+  // pass weight of weight slice k by table lookup: index = the NSA clip bits of (k, j = 0..NSA-1), which sit NSW
+  // apart in the state word (bit of (k, j) = CB + j*NSW + k), left in place (sparse index, PWN entries per slice)
+  constexpr int PWBITS = (NSA - 1) * NSW + 1, PWN = 1 << (PWBITS <= 7 ? PWBITS : 0);
+  constexpr bool kPwLut = PWBITS <= 7;
+  constexpr uint32_t PWMASK = []() {
+    uint32_t mk = 0;
+    for (int j = 0; j < NSA; ++j)
+      if (j * NSW < 32) mk |= 1u << (j * NSW);
+    return mk;
+  }();
+  if (kPwLut && P.cached) {
+    float *pwl = reinterpret_cast<float *>(cv.raw + P.pw_off);
+    for (int t = threadIdx.x; t < NSW * PWN; t += kThreads) {
+      const int k = t / PWN, pat = t % PWN;
+      float acc = 0.0f;
+      for (int j = 0; j < NSA; ++j)  // same terms, same order as pass_weight()
+        acc += ((pat >> (j * NSW)) & 1) ? 0.0f : (float)P.mask[k * NSA + j] * exp2f(-(float)(g.abs_ * j));
+      pwl[t] = acc;
+    }
+  }
   if (P.fold) {  // unfold row f = (ci, ky, kx) (nn.Unfold order, lsq.py:141) -> offset inside the image, tap index
     int *ftab = reinterpret_cast<int *>(cv.raw);
     for (int f = threadIdx.x; f < g.F; f += kThreads) {
@@ -188,7 +210,104 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
     const int cpt = Kc >> 1;          // channels per thread
     const int G = cpt >> 3;           // groups of 8 channels
     uint32_t it = 0;
-    for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
+    bool done = false;
+    if constexpr (CBits::CWN == 1) {
+      if (P.cached) {
+        // ---- register-resident operands (Cout <= 64): grad_out of the tile (reused by all NX*NSW stages) and the
+        // state words of the chunk (reused by its NSW stages) live in registers; each group of eight is refilled
+        // for the next chunk / tile right after its last use, so the loads fly during the remaining groups and the
+        // following stage.  Rows past the last pixel read pixel 0: their A' rows only feed accumulator rows that
+        // the epilogue never stores.
+        const float *pwl = reinterpret_cast<const float *>(cv.raw + P.pw_off);
+        const size_t sstride = (size_t)CBits::SWORDS * g.M;
+        float gvr[32];
+        uint32_t swr[32];
+        auto tile_ptrs = [&](int mt, const float *&gop, const uint32_t *&stp) {
+          const int64_t m = (int64_t)mt * kTcTileM + r;
+          const bool live = m < g.M;
+          const int b = live ? (int)(m / g.L) : 0, l = live ? (int)(m % g.L) : 0;
+          gop = P.go + ((int64_t)b * g.Cout + h * cpt) * g.L + l;
+          stp = P.state + (int64_t)CBits::CW0 * g.M + (live ? m : 0) + (size_t)(h * cpt) * sstride;
+        };
+        const float *gop = nullptr, *gop_n = nullptr;
+        const uint32_t *stp = nullptr, *stp_n = nullptr;
+        if ((int)blockIdx.x < P.mtiles) {
+          tile_ptrs(blockIdx.x, gop, stp);
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c < cpt) {
+              gvr[c] = __ldg(gop + (size_t)c * g.L);
+              swr[c] = __ldg(stp + (size_t)c * sstride);
+            }
+        }
+        for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
+          const int nmt = mt + gridDim.x;
+          const bool more_tiles = nmt < P.mtiles;
+          if (more_tiles) tile_ptrs(nmt, gop_n, stp_n);
+          for (int i = 0; i < g.NX; ++i) {
+            for (int k = 0; k < NSW; ++k, ++it) {
+              const int sidx = it % P.stages;
+              const uint32_t use = it / P.stages;
+              mbar_wait(cv.empty0 + 8 * sidx, (use & 1) ^ 1);
+              uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
+              if (threadIdx.x == 0) {
+                mbar_arrive_expect_tx(cv.full0 + 8 * sidx, P.b_bytes);
+                bulk_copy_g2s(smem_u32(st_ptr + 3 * (size_t)P.a_bytes), P.wtb + (size_t)(i * NSW + k) * P.b_bytes,
+                              P.b_bytes, cv.full0 + 8 * sidx);
+              }
+              float wx[NSA];
+#pragma unroll
+              for (int j = 0; j < NSA; ++j) wx[j] = cv.wtab[k * NSA + j];
+              const float *pwk = pwl + k * PWN;
+              const bool last_k = k + 1 == NSW;
+              // after the last slice of a chunk the state registers take the next chunk (or the next tile's first)
+              const uint32_t *sp_next = nullptr;
+              if (last_k) {
+                if (i + 1 < g.NX) sp_next = stp + (size_t)(i + 1) * g.Cout * sstride;
+                else if (more_tiles) sp_next = stp_n;
+              }
+              const float *gp_next = (last_k && i + 1 == g.NX && more_tiles) ? gop_n : nullptr;
+#pragma unroll
+              for (int cgi = 0; cgi < 4; ++cgi) {
+                if (cgi < G) {
+                  float v[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const uint32_t sw1[1] = {swr[8 * cgi + e]};
+                    float pw;
+                    if constexpr (kPwLut) pw = pwk[(sw1[0] >> (CBits::CB + k)) & PWMASK];
+                    else pw = pass_weight<NSA, 1>(sw1, CBits::CB + k, NSW, wx);
+                    v[e] = gvr[8 * cgi + e] * pw;
+                  }
+                  if (sp_next != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) swr[8 * cgi + e] = __ldg(sp_next + (size_t)(8 * cgi + e) * sstride);
+                  }
+                  if (gp_next != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) gvr[8 * cgi + e] = __ldg(gp_next + (size_t)(8 * cgi + e) * g.L);
+                  }
+                  uint32_t hi[4], mid[4], lo[4];
+#pragma unroll
+                  for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo[e2]);
+                  const uint32_t off = tc_tile_offset16(r, h * cpt + cgi * 8, kTcLBO, sbo);
+                  *reinterpret_cast<uint4 *>(st_ptr + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  *reinterpret_cast<uint4 *>(st_ptr + P.a_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+                  *reinterpret_cast<uint4 *>(st_ptr + 2 * (size_t)P.a_bytes + off) =
+                      make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+              }
+              fence_proxy_async();
+              mbar_arrive(cv.full0 + 8 * sidx);
+            }
+          }
+          gop = gop_n;
+          stp = stp_n;
+        }
+        done = true;
+      }
+    }
+    for (int mt = blockIdx.x; mt < P.mtiles && !done; mt += gridDim.x) {
       const int64_t m = (int64_t)mt * kTcTileM + r;
       const bool live = m < g.M;
       const int b = live ? (int)(m / g.L) : 0, l = live ? (int)(m % g.L) : 0;
@@ -810,6 +929,10 @@ int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, co
   P.stage_bytes = 3 * P.a_bytes + P.b_bytes;
   P.fold = fold;
   P.raw_bytes = fold ? (uint32_t)((g.F * 4 + 15) & ~15) : 0u;
+  // register-resident operands: 32 channels per producer thread at most, clip bits in one state word
+  P.cached = g.Cout <= 64 ? 1 : 0;
+  P.pw_off = P.raw_bytes;
+  if (P.cached && (g.NSA - 1) * g.NSW + 1 <= 7) P.raw_bytes += (uint32_t)(g.NSW * (1 << ((g.NSA - 1) * g.NSW + 1)) * 4);
   int stages = (int)((kSmemBudget - kBarrierBytes - P.raw_bytes) / P.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   CIMQ_REQUIRE(stages >= 1, "dgrad tile does not fit shared memory");
