@@ -37,8 +37,15 @@ constexpr int kMaxStages = 4;
 constexpr int kMaxPairs = 64;
 constexpr size_t kSmemBudget = 227 * 1024 - 1024;
 constexpr size_t kBarrierBytes = 3072;  // barriers, tmem slot, slice-weight table, pixel / row tables, LUT
+// dgrad register split per warpgroup (setmaxnreg): 2 x 168 + 104 + 40 = 480 <= 512
+constexpr int kDgRegsProducer = 168, kDgRegsEpilogue = 104, kDgRegsMma = 40;
 constexpr int kWgProducerThreads = 384;  // wgrad: warps 0-11 build operands (8-11 also run the final epilogue)
 constexpr int kNoRow = -2147483647 - 1;
+#ifndef CIMQ_TIMERS
+#define CIMQ_TIMERS 0
+#endif
+constexpr bool kTimers = CIMQ_TIMERS != 0;
+#define CIMQ_TB() (dbg ? clock64() : 0ll)
 
 struct BwdParams {
   Geo g;
@@ -50,6 +57,7 @@ struct BwdParams {
   // wgrad staged activation rows (same geometry as the forward producer, stride 1 only)
   int fastx, ow_log2, rpt, pitch_log2, col0;
   uint32_t raw_bytes;
+  long long *debug;  // per-role cycle counters (builds with TIMERS=1 only)
   int cached;   // dgrad: 1 = producers keep grad_out of the tile and the state words of the chunk in registers
   uint32_t pw_off;  // dgrad: byte offset of the pass-weight table inside the raw region
   int fold;  // dgrad: 1 = the epilogue folds (col2im) straight into grad_x with fp32 reductions; 0 = writes gxu[b][f][l]
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
     int *ftab = reinterpret_cast<int *>(cv.raw);
     for (int f = threadIdx.x; f < g.F; f += kThreads) {
       const int ci = f / g.KK, tap = f % g.KK, ky = tap / g.K, kx = tap % g.K;
-      ftab[f] = (((ci * g.H + ky) * g.W + kx) << 5) | tap;
+      ftab[f] = (((ci * g.H + ky) * g.W + kx) << 7) | (kx << 5) | tap;
     }
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(cv.tmem_slot), P.tmem_cols);
@@ -201,6 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
   const int rows_full = g.xbar < g.F ? g.xbar : g.F;
 
   if (warp < kProducerWarps) {
+    reg_alloc<kDgRegsProducer>();  // warpgroups 0-1; taken from the epilogue / MMA warpgroups below
     // ------------------------------------------------------------------ producers
     // thread = (pixel row r, channel half h); per stage (crossbar i, weight slice k) it builds
     // A'[r, co] = go[r, co] * sum_j pass * wx[k][j] for its Kc/2 channels in groups of 8 (one 16-byte
@@ -222,6 +231,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
         const size_t sstride = (size_t)CBits::SWORDS * g.M;
         float gvr[32];
         uint32_t swr[32];
+        const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+        long long d_wait = 0, d_prod = 0;
         auto tile_ptrs = [&](int mt, const float *&gop, const uint32_t *&stp) {
           const int64_t m = (int64_t)mt * kTcTileM + r;
           const bool live = m < g.M;
@@ -248,7 +259,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
             for (int k = 0; k < NSW; ++k, ++it) {
               const int sidx = it % P.stages;
               const uint32_t use = it / P.stages;
+              const long long t0 = CIMQ_TB();
               mbar_wait(cv.empty0 + 8 * sidx, (use & 1) ^ 1);
+              const long long t1 = CIMQ_TB();
+              d_wait += t1 - t0;
               uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
               if (threadIdx.x == 0) {
                 mbar_arrive_expect_tx(cv.full0 + 8 * sidx, P.b_bytes);
@@ -258,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
               float wx[NSA];
 #pragma unroll
               for (int j = 0; j < NSA; ++j) wx[j] = cv.wtab[k * NSA + j];
-              const float *pwk = pwl + k * PWN;
+              const uint32_t pwk = smem_u32(pwl + k * PWN);
               const bool last_k = k + 1 == NSW;
               // after the last slice of a chunk the state registers take the next chunk (or the next tile's first)
               const uint32_t *sp_next = nullptr;
@@ -275,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
                   for (int e = 0; e < 8; ++e) {
                     const uint32_t sw1[1] = {swr[8 * cgi + e]};
                     float pw;
-                    if constexpr (kPwLut) pw = pwk[(sw1[0] >> (CBits::CB + k)) & PWMASK];
+                    if constexpr (kPwLut) pw = lds_const_f32(pwk + 4u * ((sw1[0] >> (CBits::CB + k)) & PWMASK));
                     else pw = pass_weight<NSA, 1>(sw1, CBits::CB + k, NSW, wx);
                     v[e] = gvr[8 * cgi + e] * pw;
                   }
@@ -299,11 +313,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
               }
               fence_proxy_async();
               mbar_arrive(cv.full0 + 8 * sidx);
+              d_prod += CIMQ_TB() - t1;
             }
           }
           gop = gop_n;
           stp = stp_n;
         }
+        if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_prod; }
         done = true;
       }
     }
@@ -380,22 +396,31 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp >= kMmaWarp) {
+    reg_dealloc<kDgRegsMma>();  // warpgroup 3: the MMA issuer and three idle warps
+    if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16_f32(kTcTileM, Nf);
       const int ksteps = Kc >> 4;
       uint32_t it = 0, acc_it = 0;
+      const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0;
+      long long d_full = 0, d_tempty = 0;
+      const long long t_begin = CIMQ_TB();
       for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
         for (int i = 0; i < g.NX; ++i, ++acc_it) {
           const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
+          const long long ta = CIMQ_TB();
           mbar_wait<400>(cv.tempty0 + 8 * buf, (buse & 1) ^ 1);
+          d_tempty += CIMQ_TB() - ta;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * Nf;
           for (int k = 0; k < NSW; ++k, ++it) {
             const int sidx = it % P.stages;
             const uint32_t use = it / P.stages;
+            const long long tb = CIMQ_TB();
             mbar_wait<400>(cv.full0 + 8 * sidx, use & 1);
+            d_full += CIMQ_TB() - tb;
             tc_fence_after();
             const uint32_t a0 = smem_u32(cv.stage_base + (size_t)sidx * P.stage_bytes);
             const uint32_t b0 = a0 + 3 * P.a_bytes;
@@ -410,13 +435,18 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
           umma_commit(cv.tfull0 + 8 * buf);
         }
       }
+      if (dbg) { P.debug[4] = d_full; P.debug[5] = d_tempty; P.debug[6] = clock64() - t_begin; }
+    }
     }
   } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + kEpilogueWarps) {
+    reg_dealloc<kDgRegsEpilogue>();  // warpgroup 2
     // ------------------------------------------------------------------ epilogue
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const float scale = P.s[1] / (float)NSA;  // w_sl * s_w (lsq.py:252), mean over act slices (lsq.py:376)
-    const int *ftab = reinterpret_cast<const int *>(cv.raw);  // fold: per unfold row {offset in the image << 5 | tap}
+    const int *ftab = reinterpret_cast<const int *>(cv.raw);  // fold: per unfold row {offset in the image << 7 | kx << 5 | tap}
+    const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && warp == kEpilogueWarp0 && lane == 0;
+    long long d_tfull = 0, d_comp = 0;
     uint32_t acc_it = 0;
     for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
       const int64_t m = (int64_t)mt * kTcTileM + r;
@@ -436,7 +466,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
         const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
         const int lo = i * g.xbar;
         const int rows = min(rows_full, g.F - lo);
+        const long long te0 = CIMQ_TB();
         mbar_wait(cv.tfull0 + 8 * buf, buse & 1);
+        const long long te1 = CIMQ_TB();
+        d_tfull += te1 - te0;
         tc_fence_after();
         for (int c0 = 0; c0 < rows; c0 += 32) {
           int v[32];
@@ -446,11 +479,16 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
             // nn.Fold (lsq.py:378-383) fused: every unfolded gradient is added to its input pixel.  Lanes are
             // consecutive output pixels, so one warp-wide reduction covers consecutive addresses; grad_x
             // (zeroed by the caller) stays in L2 while it is accumulated.
+            // The table entries are read first, all at once: the reductions below order the compiler's memory
+            // operations, and a table read between two of them would expose its latency 32 times per batch.
+            int te[32];
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) te[cc] = ftab[min(lo + c0 + cc, g.F - 1)];
 #pragma unroll
             for (int cc = 0; cc < 32; ++cc)
               if (c0 + cc < rows) {
-                const int e = ftab[lo + c0 + cc];
-                if ((vm >> (e & 31)) & 1u) atomicAdd(gxp + (e >> 5), __int_as_float(v[cc]) * scale);
+                const int e = te[cc];
+                if ((vm >> (e & 31)) & 1u) atomicAdd(gxp + (e >> 7), __int_as_float(v[cc]) * scale);
               }
           } else if (m < g.M) {  // gxu[b][f][l]: image-major so that col2im's reads per output stay within one image
             float *dst = P.out + ((int64_t)eb * g.F + lo + c0) * g.L + el;
@@ -462,8 +500,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(cv.tempty0 + 8 * buf);
+        d_comp += CIMQ_TB() - te1;
       }
     }
+    if (dbg) { P.debug[8] = d_tfull; P.debug[9] = d_comp; }
   }
 
   tc_fence_before();
@@ -675,7 +715,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           float wv[NSW];
 #pragma unroll
           for (int k = 0; k < NSW; ++k) wv[k] = cv.wtab[k * NSA + j];
-          const float *lutj = cv.lut + j * 16;
+          const uint32_t lutj = smem_u32(cv.lut + j * 16);
           const int pg = tid & 15;
           const int4 pt = ptab[pg];
           const int64_t mg = m0 + pg * 8;
@@ -729,7 +769,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               if constexpr (kLut && CBits::CWN == 1) {
-                v[e] = gv[e] * lutj[(sw[e][0] >> (CBits::CB + j * NSW)) & ((1u << NSW) - 1u)];
+                v[e] = gv[e] * lds_const_f32(lutj + 4u * ((sw[e][0] >> (CBits::CB + j * NSW)) & ((1u << NSW) - 1u)));
               } else {
                 v[e] = gv[e] * pass_weight<NSW, CBits::CWN>(sw[e], CBits::CB + j * NSW, 1, wv);
               }
@@ -912,8 +952,8 @@ int64_t bwd_tc_partial_bytes(const Geo &g) {
 }
 
 bool bwd_input_tc_can_fold(const Geo &g) {
-  // the fold table packs {offset, tap}: 5 bits of tap (K <= 5), offsets below 2^26, table in shared memory
-  return g.K <= 5 && (int64_t)g.Cin * g.H * g.W < (1 << 26) && g.F <= 4096;
+  // the fold table packs {offset, kx, tap}: 5 bits of tap (K <= 5), offsets below 2^24, table in shared memory
+  return g.K <= 5 && (int64_t)g.Cin * g.H * g.W < (1 << 24) && g.F <= 4096;
 }
 
 int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, const void *wtb, const float *s,
@@ -928,6 +968,7 @@ int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, co
   P.b_bytes = (uint32_t)(P.Nf * g.Cout * 2);
   P.stage_bytes = 3 * P.a_bytes + P.b_bytes;
   P.fold = fold;
+  P.debug = g_tc_debug;
   P.raw_bytes = fold ? (uint32_t)((g.F * 4 + 15) & ~15) : 0u;
   // register-resident operands: 32 channels per producer thread at most, clip bits in one state word
   P.cached = g.Cout <= 64 ? 1 : 0;

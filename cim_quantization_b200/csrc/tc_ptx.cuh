@@ -139,6 +139,13 @@ template <int N>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+// Read-only shared-memory table lookup the compiler may move across shared-memory stores (a plain C++ load is
+// pinned behind every earlier STS because it might alias): for tables written once before the main loop.
+__device__ __forceinline__ float lds_const_f32(uint32_t saddr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 

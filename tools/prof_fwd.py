@@ -52,6 +52,10 @@ if dbg is not None:
     d = dbg.cpu().tolist()
     names = {0: "producer wait empty", 1: "producer produce", 4: "mma wait full", 5: "mma wait tmem-empty", 6: "mma total",
              8: "epilogue wait tmem-full", 9: "epilogue compute", 10: "epilogue table+barrier", 11: "epilogue state store"}
+    if a.bwd:  # the dgrad kernel runs after the forward and overwrites these slots with its own counters
+        names = {0: "dgrad producer wait empty", 1: "dgrad producer produce", 4: "dgrad mma wait full",
+                 5: "dgrad mma wait tmem-empty", 6: "dgrad mma total", 8: "dgrad epilogue wait tmem-full",
+                 9: "dgrad epilogue compute"}
     for k, n in names.items():
         print(f"  timer {n:28s} {d[k] / 1e3:10.1f} kcycles")
 print("avg ms per iter:", ev[0].elapsed_time(ev[1]) / a.iters, "codes nonzero frac", float((xc != 0).float().mean()))
