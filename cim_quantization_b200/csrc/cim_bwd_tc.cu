@@ -39,6 +39,8 @@ constexpr size_t kSmemBudget = 227 * 1024 - 1024;
 constexpr size_t kBarrierBytes = 3072;  // barriers, tmem slot, slice-weight table, pixel / row tables, LUT
 // dgrad register split per warpgroup (setmaxnreg): 2 x 168 + 104 + 40 = 480 <= 512
 constexpr int kDgRegsProducer = 168, kDgRegsEpilogue = 104, kDgRegsMma = 40;
+// wgrad: 3 x 152 + 56 = 512
+constexpr int kWgRegsProducer = 152, kWgRegsMma = 56;
 constexpr int kWgProducerThreads = 384;  // wgrad: warps 0-11 build operands (8-11 also run the final epilogue)
 constexpr int kNoRow = -2147483647 - 1;
 #ifndef CIMQ_TIMERS
@@ -562,7 +564,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
 
   if (warp < 12) {
     // ------------------------------------------------------------------ producers (384 threads)
+    reg_alloc<kWgRegsProducer>();  // warpgroups 0-2; the registers come from warpgroup 3 (MMA issuer + idle warps)
     const int tid = threadIdx.x;
+    const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    long long d_stage = 0, d_wait = 0, d_x = 0, d_g = 0;
     const int fr = tid & 127;     // X tile: this thread's crossbar row
     const bool aligned = (g.L % 8) == 0 && (g.OW % 8) == 0;
     const int pitch = 1 << P.pitch_log2;
@@ -570,8 +575,69 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     const int HW = g.H * g.W;
     uint32_t it = 0, chunk_it = 0;
     int tpar = 0;
+    // ---- G' operands kept in registers (Cout <= 72: at most three (channel, 8-pixel group) items per thread, clip
+    // bits in one state word): grad_out of the tile is reused by all chunks and planes, the state words of a chunk
+    // by its NSA planes.  Each item is refilled for the next chunk / tile right after its last use, a whole stage
+    // before it is needed again, so no load latency is exposed in the plane loop.
+    constexpr bool kCacheOk = kLut && CBits::CWN == 1;
+    const bool gcache = kCacheOk && Kc <= 72;
+    const int gpg = tid & 15, gco0 = tid >> 4;
+    float gvc[3][8];
+    uint32_t swc[3][8];
+    auto pix_group = [&](int mt_) {  // {image, output row, first output column, kind} of this thread's pixel group
+      const int64_t m = (int64_t)mt_ * kTcTileM + gpg * 8;
+      int4 e = make_int4(0, 0, 0, -1);
+      if (m < g.M) {
+        const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
+        e = make_int4(b, oy, ox, (aligned && m + 7 < g.M && ox + 7 < g.OW) ? 1 : 0);
+      }
+      return e;
+    };
+    auto load_go = [&](const int4 &pt, int mt_, int co, float (&gv)[8]) {
+      if (pt.w == 1) {
+        const float4 *gp = reinterpret_cast<const float4 *>(P.go + ((int64_t)pt.x * g.Cout + co) * g.L +
+                                                            pt.y * g.OW + pt.z);
+        const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+        gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w;
+        gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int64_t m = (int64_t)mt_ * kTcTileM + gpg * 8 + e;
+          gv[e] = 0.0f;
+          if (m < g.M) gv[e] = __ldg(&P.go[((int64_t)(m / g.L) * g.Cout + co) * g.L + (m % g.L)]);
+        }
+      }
+    };
+    auto load_state = [&](const int4 &pt, int mt_, int i, int co, uint32_t (&sw)[8]) {
+      const int64_t mg = (int64_t)mt_ * kTcTileM + gpg * 8;
+      const uint32_t *sp = P.state + ((int64_t)(i * g.Cout + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
+      if (pt.w == 1) {
+        const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(sp)), s1 = __ldg(reinterpret_cast<const uint4 *>(sp) + 1);
+        sw[0] = s0.x; sw[1] = s0.y; sw[2] = s0.z; sw[3] = s0.w;
+        sw[4] = s1.x; sw[5] = s1.y; sw[6] = s1.z; sw[7] = s1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          sw[e] = 0xffffffffu;  // past the last pixel: everything clipped, contributes nothing
+          if (mg + e < g.M) sw[e] = __ldg(sp + e);
+        }
+      }
+    };
+    int4 gpt = make_int4(0, 0, 0, -1), gpt_n = gpt;
+    if (gcache && (int)blockIdx.x < P.mtiles) {
+      gpt = pix_group(blockIdx.x);
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (gco0 + 24 * q < Kc) {
+          load_go(gpt, blockIdx.x, gco0 + 24 * q, gvc[q]);
+          load_state(gpt, blockIdx.x, i_begin, gco0 + 24 * q, swc[q]);
+        }
+    }
     for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
       const int64_t m0 = (int64_t)mt * kTcTileM;
+      const int mt_n = mt + gridDim.x;
+      if (gcache && mt_n < P.mtiles) gpt_n = pix_group(mt_n);
       // per 8-pixel group: image, output row, first output column; fast = one image row, fully valid, aligned
       if (tid < 16) {
         const int64_t m = m0 + tid * 8;
@@ -604,6 +670,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         if (frow) { const int f = lo + fr; ci = f / g.KK; const int tap = f % g.KK; ky = tap / g.K; kx = tap % g.K; }
         const int c_lo = lo / g.KK;
         uint8_t *raw = cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes;
+        const long long ts0 = CIMQ_TB();
         if (P.fastx) {
           // stage the input rows of the channels this crossbar touches (once per chunk, shared by all planes)
           const int nch = (lo + rows - 1) / g.KK - c_lo + 1;
@@ -638,59 +705,80 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           }
           named_barrier_sync(1, kWgProducerThreads);
         }
+        // ---- the activation codes of this thread's X items (row fr, 8-pixel group pg = tid/128 + 3q), gathered once
+        // per chunk: the NSA digit planes below only shift and mask them
+        uint32_t xlo[6], xhi[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const int pg = (tid >> 7) + 3 * q;
+          xlo[q] = 0u;
+          xhi[q] = 0u;
+          if (pg < 16) {
+          uint32_t lo8 = 0u, hi8 = 0u;
+          if (frow) {
+            if (P.fastx) {
+              const int p0 = pg * 8;
+              const uint8_t *src = raw + (size_t)(ci - c_lo) * slot_bytes +
+                                   ((((p0 >> P.ow_log2) * g.K) + ky) << P.pitch_log2) +
+                                   (p0 & ((1 << P.ow_log2) - 1)) + kx + P.col0;
+              const uint32_t sa = smem_u32(src);
+              const uint32_t *al = reinterpret_cast<const uint32_t *>(src - (sa & 3u));
+              const uint32_t w0 = al[0], w1 = al[1], w2 = al[2];
+              const uint32_t bsh = (sa & 3u) * 8u;
+              lo8 = __funnelshift_r(w0, w1, bsh);
+              hi8 = __funnelshift_r(w1, w2, bsh);
+            } else {
+              const int4 pt = ptab[pg];
+              uint32_t c[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) c[e] = 0u;
+              if (pt.w == 1) {
+                const int iy = pt.y * g.stride - g.pad + ky;
+                if (iy >= 0 && iy < g.H) {
+                  const uint8_t *row = P.xcodes + (((int64_t)pt.x * g.Cin + ci) * g.H + iy) * g.W;
+                  const int ix0 = pt.z * g.stride - g.pad + kx;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const int ix = ix0 + e * g.stride;
+                    if (ix >= 0 && ix < g.W) c[e] = __ldg(row + ix);
+                  }
+                }
+              } else if (pt.w == 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int64_t m = m0 + pg * 8 + e;
+                  if (m < g.M) {
+                    const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
+                    const int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
+                    if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+                      c[e] = P.xcodes[(((int64_t)b * g.Cin + ci) * g.H + iy) * g.W + ix];
+                  }
+                }
+              }
+              lo8 = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+              hi8 = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
+            }
+          }
+            xlo[q] = lo8;
+            xhi[q] = hi8;
+          }
+        }
+        d_stage += CIMQ_TB() - ts0;
         for (int j = 0; j < NSA; ++j, ++it) {
           const int sidx = it % P.stages;
           const uint32_t use = it / P.stages;
+          const long long tw0 = CIMQ_TB();
           mbar_wait(cv.empty0 + 8 * sidx, (use & 1) ^ 1);
+          const long long tw1 = CIMQ_TB();
+          d_wait += tw1 - tw0;
           uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
           // ---- X_j tile [128 crossbar rows x 128 pixels] (bf16 digits); item = (row fr, 8-pixel group pg)
           const int sh = g.abs_ * j;
-          for (int pg = tid >> 7; pg < 16; pg += 3) {
-            uint32_t lo8 = 0u, hi8 = 0u;  // the 8 activation codes of this item, one per byte
-            if (frow) {
-              if (P.fastx) {
-                const int p0 = pg * 8;
-                const uint8_t *src = raw + (size_t)(ci - c_lo) * slot_bytes +
-                                     ((((p0 >> P.ow_log2) * g.K) + ky) << P.pitch_log2) +
-                                     (p0 & ((1 << P.ow_log2) - 1)) + kx + P.col0;
-                const uint32_t sa = smem_u32(src);
-                const uint32_t *al = reinterpret_cast<const uint32_t *>(src - (sa & 3u));
-                const uint32_t w0 = al[0], w1 = al[1], w2 = al[2];
-                const uint32_t bsh = (sa & 3u) * 8u;
-                lo8 = __funnelshift_r(w0, w1, bsh);
-                hi8 = __funnelshift_r(w1, w2, bsh);
-              } else {
-                const int4 pt = ptab[pg];
-                uint32_t c[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) c[e] = 0u;
-                if (pt.w == 1) {
-                  const int iy = pt.y * g.stride - g.pad + ky;
-                  if (iy >= 0 && iy < g.H) {
-                    const uint8_t *row = P.xcodes + (((int64_t)pt.x * g.Cin + ci) * g.H + iy) * g.W;
-                    const int ix0 = pt.z * g.stride - g.pad + kx;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                      const int ix = ix0 + e * g.stride;
-                      if (ix >= 0 && ix < g.W) c[e] = __ldg(row + ix);
-                    }
-                  }
-                } else if (pt.w == 0) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const int64_t m = m0 + pg * 8 + e;
-                    if (m < g.M) {
-                      const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
-                      const int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
-                      if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
-                        c[e] = P.xcodes[(((int64_t)b * g.Cin + ci) * g.H + iy) * g.W + ix];
-                    }
-                  }
-                }
-                lo8 = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
-                hi8 = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
-              }
-            }
+          for (int q = 0; q < 6; ++q) {
+            const int pg = (tid >> 7) + 3 * q;
+            if (pg >= 16) continue;
+            const uint32_t lo8 = xlo[q], hi8 = xhi[q];
             uint32_t d[4];
             if (g.amask == 1) {  // 1-bit digits: bf16(1) = 0x3F80; spread two bytes to 16-bit lanes, one multiply
               const uint32_t tl = (lo8 >> sh) & 0x01010101u, th = (hi8 >> sh) & 0x01010101u;
@@ -711,12 +799,50 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
                 make_uint4(d[0], d[1], d[2], d[3]);
           }
           // ---- G'_j tiles (3 bf16 terms) [Cout x 128 pixels]; item = (channel co, 8-pixel group pg), lanes along pixels
+          const long long tx1 = CIMQ_TB();
+          d_x += tx1 - tw1;
           uint8_t *gb = st_ptr + P.a_bytes;
           float wv[NSW];
 #pragma unroll
           for (int k = 0; k < NSW; ++k) wv[k] = cv.wtab[k * NSA + j];
           const uint32_t lutj = smem_u32(cv.lut + j * 16);
           const int pg = tid & 15;
+          if (gcache) {
+            if constexpr (kCacheOk) {
+              const bool last_j = j + 1 == NSA;
+              const bool next_chunk = i + 1 < i_end, next_tile = !next_chunk && mt_n < P.mtiles;
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                const int co = gco0 + 24 * q;
+                if (co < Kc) {
+                  float v[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    v[e] = gvc[q][e] *
+                           lds_const_f32(lutj + 4u * ((swc[q][e] >> (CBits::CB + j * NSW)) & ((1u << NSW) - 1u)));
+                  if (last_j) {  // last use of this item's state words (and, at the last chunk, of its grad_out)
+                    if (next_chunk) load_state(gpt, mt, i + 1, co, swc[q]);
+                    else if (next_tile) {
+                      load_state(gpt_n, mt_n, i_begin, co, swc[q]);
+                      load_go(gpt_n, mt_n, co, gvc[q]);
+                    }
+                  }
+                  uint32_t hi[4], mid[4], lo3[4];
+#pragma unroll
+                  for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo3[e2]);
+                  const uint32_t off = tc_tile_offset16(co, pg * 8, kWgLBO, b_sbo);
+                  *reinterpret_cast<uint4 *>(gb + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  *reinterpret_cast<uint4 *>(gb + P.b_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+                  *reinterpret_cast<uint4 *>(gb + 2 * (size_t)P.b_bytes + off) =
+                      make_uint4(lo3[0], lo3[1], lo3[2], lo3[3]);
+                }
+              }
+            }
+            fence_proxy_async();
+            mbar_arrive(cv.full0 + 8 * sidx);
+            d_g += CIMQ_TB() - tx1;
+            continue;
+          }
           const int4 pt = ptab[pg];
           const int64_t mg = m0 + pg * 8;
           // loads of the next channel are issued before the current one is processed (latency hiding)
@@ -784,22 +910,31 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           }
           fence_proxy_async();
           mbar_arrive(cv.full0 + 8 * sidx);
+          d_g += CIMQ_TB() - tx1;
         }
       }
+      gpt = gpt_n;
     }
-  } else if (warp == kMmaWarp) {
+    if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_stage; P.debug[2] = d_x; P.debug[3] = d_g; }
+  } else {
+    reg_dealloc<kWgRegsMma>();
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && has_work) {
+    if (warp == kMmaWarp && lane == 0 && has_work) {
       const uint32_t idesc = idesc_bf16_f32(128, Kc);
       uint32_t it = 0;
       bool first_tile = true;
+      const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+      long long d_full = 0;
+      const long long t_begin = CIMQ_TB();
       for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, first_tile = false) {
         for (int i = i_begin; i < i_end; ++i) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(i - i_begin) * Kc;
           for (int j = 0; j < NSA; ++j, ++it) {
             const int sidx = it % P.stages;
             const uint32_t use = it / P.stages;
+            const long long tf0 = CIMQ_TB();
             mbar_wait<400>(cv.full0 + 8 * sidx, use & 1);
+            d_full += CIMQ_TB() - tf0;
             tc_fence_after();
             const uint32_t a0 = smem_u32(cv.stage_base + (size_t)sidx * P.stage_bytes);
             const uint32_t b0 = a0 + P.a_bytes;
@@ -814,6 +949,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         }
       }
       umma_commit(cv.tfull0);  // every accumulation of this CTA is complete
+      if (dbg) { P.debug[4] = d_full; P.debug[6] = clock64() - t_begin; }
     }
   }
   if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + kEpilogueWarps) {
@@ -1004,6 +1140,7 @@ int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, c
   P.Kc = g.Cout;
   P.mtiles = (g.M + kTcTileM - 1) / kTcTileM;
   P.a_bytes = 128u * 128u * 2u;
+  P.debug = g_tc_debug;
   P.b_bytes = (uint32_t)(g.Cout / 8) * 16u * (uint32_t)kWgLBO;  // 8-row groups x 16 k-groups x 144 B
   P.stage_bytes = P.a_bytes + 3 * P.b_bytes;
   // staged activation rows (stride 1, output width a power of two between 8 and 128, 4-byte aligned rows)

@@ -13,6 +13,7 @@ p.add_argument("--bwd", action="store_true")
 p.add_argument("--quant", action="store_true")
 p.add_argument("--no-state", action="store_true")
 p.add_argument("--timers", action="store_true")
+p.add_argument("--timers-wgrad", action="store_true", help="with --timers --bwd: label the counters of the wgrad kernel (it runs last)")
 a = p.parse_args()
 adc = int(a.adcbits) if a.adcbits == int(a.adcbits) else a.adcbits
 B, C, HW = a.batch, 64, 32
@@ -56,6 +57,9 @@ if dbg is not None:
         names = {0: "dgrad producer wait empty", 1: "dgrad producer produce", 4: "dgrad mma wait full",
                  5: "dgrad mma wait tmem-empty", 6: "dgrad mma total", 8: "dgrad epilogue wait tmem-full",
                  9: "dgrad epilogue compute"}
+    if a.bwd and a.timers_wgrad:
+        names = {0: "wgrad producer wait empty", 1: "wgrad producer stage rows", 2: "wgrad producer X tile",
+                 3: "wgrad producer G' tile", 4: "wgrad mma wait full", 6: "wgrad mma total"}
     for k, n in names.items():
         print(f"  timer {n:28s} {d[k] / 1e3:10.1f} kcycles")
 print("avg ms per iter:", ev[0].elapsed_time(ev[1]) / a.iters, "codes nonzero frac", float((xc != 0).float().mean()))
