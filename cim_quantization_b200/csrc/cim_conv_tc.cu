@@ -40,10 +40,13 @@ bool make_plan(const Geo &g, TcParams &P, size_t &smem) {
   P.tmem_cols = cols;
   P.ttab_bytes = (uint32_t)((g.pairs * 3 * (P.CT / 2) * 4 + 15) & ~15);
   // staged (fast) producer
-  P.fast = 0; P.owt = 0; P.rpt = 0; P.rk = 0; P.prow = 0; P.shared_rows = 0; P.prefetch = 0; P.pitch_log2 = 0; P.col0 = 0; P.raw_bytes = 0;
+  P.fast = 0; P.owt = 0; P.rpt = 0; P.rk = 0; P.rk_magic = 0; P.tma_rows = 0; P.prow = 0; P.shared_rows = 0; P.prefetch = 0; P.pitch_log2 = 0; P.col0 = 0; P.raw_bytes = 0;
   if ((g.K == 3 || g.K == 5) && g.W % 4 == 0 && g.OW <= kTcTileM && kTcTileM % g.OW == 0 && P.Kp <= 128 &&
       (kTcTileM / g.OW) * g.K <= 128 && g.pad < g.K) {
-    const int col0 = (4 - g.pad % 4) % 4;
+    // input rows by 16-byte asynchronous copies need 16-byte aligned rows on both sides: W % 16 == 0 and column 0 of the image
+    // staged at byte 16 (col0 = 16 - pad); otherwise 4-byte loads with column -pad on a word boundary
+    const bool tma = g.W % 16 == 0 && g.pad <= 16;
+    const int col0 = tma ? 16 - g.pad : (4 - g.pad % 4) % 4;
     const int needp = (g.OW - 1) * g.stride + g.K + col0;
     int pl = 2;
     while ((1 << pl) < needp) ++pl;
@@ -61,7 +64,9 @@ bool make_plan(const Geo &g, TcParams &P, size_t &smem) {
     if (nslots <= kMaxSlots && raw <= 48 * 1024 && pl <= 9 && rk <= 128) {
       P.fast = 1; P.owt = g.OW; P.rpt = rpt; P.pitch_log2 = pl; P.col0 = col0;
       P.rk = rk; P.prow = shared_rows ? g.stride : g.K; P.shared_rows = shared_rows ? 1 : 0;
-      P.prefetch = (raw / 4 + kProducerThreads - 1) / kProducerThreads <= (size_t)kPrefetchWords;
+      P.rk_magic = (uint32_t)(((1ull << 32) + rk - 1) / rk);
+      P.tma_rows = tma && rk >= 2 ? 1 : 0;
+      P.prefetch = !P.tma_rows && (raw / 4 + kProducerThreads - 1) / kProducerThreads <= (size_t)kPrefetchWords;
       P.raw_bytes = (uint32_t)raw;
     }
   }
@@ -120,6 +125,10 @@ int launch_conv_tc_forward(const Geo &g, const uint8_t *xcodes, const void *wtil
   CIMQ_REQUIRE(make_plan(g, P, smem), "tcgen05 forward plan failed");
   const WtLayout wl = wt_layout(g);
   P.xcodes = xcodes;
+  if (P.tma_rows && (reinterpret_cast<uintptr_t>(xcodes) & 15u) != 0) {  // cp.async needs a 16-byte aligned image
+    P.tma_rows = 0;  // same staging layout, rows by 4-byte loads instead
+    P.prefetch = (P.raw_bytes / 4 + kProducerThreads - 1) / kProducerThreads <= (uint32_t)kPrefetchWords;
+  }
   P.wtiles = reinterpret_cast<const uint8_t *>(wtiles) + wl.fwd_off;
   P.lut = reinterpret_cast<const int2 *>(reinterpret_cast<const uint8_t *>(wtiles) + wl.lut_off);
   P.table = reinterpret_cast<const int4 *>(table);

@@ -58,6 +58,8 @@ struct TcParams {
                      // consecutive rows of one image (shared between output rows), else rpt*K
   int prow;          // staged row of output row `orow`, tap row 0: orow * prow
   int shared_rows;   // 1: a tile reads consecutive input rows of one image (rk, prow as above)
+  uint32_t rk_magic; // ceil(2^32 / rk): q / rk = umulhi(q, rk_magic) for q < 2^16
+  int tma_rows;      // 1: staged rows arrive by 16-byte cp.async copies; needs W % 16 == 0 and a 16-byte aligned image
   int prefetch;      // 1: the rows of the next stage are loaded into registers while this one is assembled
   int pitch_log2;    // staged row pitch in bytes (power of two)
   int col0;          // staged column of input column -pad (alignment shift)
@@ -142,7 +144,7 @@ __device__ __forceinline__ StageThread stage_thread(const TcParams &P) {
 
 // staged rows of a tile: rowoff[staged row] = offset of staged column 0 of that input row in channel 0 of its
 // image, or kNoRow (outside the image / past the last pixel)
-__device__ __forceinline__ void stage_set_rowoff(const TcParams &P, int mt, int *rowoff) {
+__device__ __forceinline__ bool stage_set_rowoff(const TcParams &P, int mt, int *rowoff) {
   const Geo &g = P.g;
   const int r = threadIdx.x;
   if (r < P.rk) {
@@ -152,7 +154,7 @@ __device__ __forceinline__ void stage_set_rowoff(const TcParams &P, int mt, int 
       if (m0 < g.M) {
         const int b = m0 / g.L, oy0 = (m0 % g.L) / g.OW;
         const int iy = oy0 * g.stride - g.pad + r;
-        if (iy >= 0 && iy < g.H) off = (b * g.Cin * g.H + iy) * g.W - g.pad - P.col0;
+        if (iy >= 0 && iy < g.H) off = (b * g.Cin * g.H + iy) * g.W - (P.tma_rows ? 0 : g.pad + P.col0);
       }
     } else {
       const int orow = r / g.K, ky = r % g.K;
@@ -160,11 +162,13 @@ __device__ __forceinline__ void stage_set_rowoff(const TcParams &P, int mt, int 
       if (m_row < g.M) {
         const int b = m_row / g.L, oy = (m_row % g.L) / g.OW;
         const int iy = oy * g.stride - g.pad + ky;
-        if (iy >= 0 && iy < g.H) off = (b * g.Cin * g.H + iy) * g.W - g.pad - P.col0;
+        if (iy >= 0 && iy < g.H) off = (b * g.Cin * g.H + iy) * g.W - (P.tma_rows ? 0 : g.pad + P.col0);
       }
     }
     rowoff[r] = off;
+    return off != kNoRow;
   }
+  return false;
 }
 
 // Load up to NW words of chunk i's staged rows, starting at pass `pass0` of the thread's row walk.  Slot s < nfull
@@ -205,6 +209,32 @@ __device__ __forceinline__ void stage_store(const TcParams &P, const StageThread
     if (q < total_words) raw32[q] = v[u];
   }
 }
+
+// Staged rows by asynchronous 16-byte copies (cp.async): row q of the slot-major list (slot = q / rk) is one input
+// row of W bytes, copied to column pad+col0 (= 16, so both sides are 16-byte aligned) of its staged row; rows
+// outside the image are zero-filled by the same instruction (source size 0).  The padding columns are zeroed once
+// at kernel start and never written again.  No registers are held while the rows are in flight; the issuing
+// thread waits for its own copies (cp.async.wait_group) before the barrier that publishes the buffer.
+__device__ __forceinline__ void stage_issue_async(const TcParams &P, const ChunkLayout &cl, const int *rowoff,
+                                                  uint8_t *raw) {
+  const Geo &g = P.g;
+  const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
+  const int cpr = g.W >> 4;  // 16-byte pieces per row
+  const int total = nslots * P.rk * cpr, HW = g.H * g.W;
+  const int ch_head = cl.nhead > 0 ? cl.cf0 - 1 : cl.cf0 + cl.nfull, ch_tail = cl.cf0 + cl.nfull;
+  for (int q = threadIdx.x; q < total; q += kProducerThreads) {
+    const int rq = q / cpr, c16 = q - rq * cpr;
+    const int sl = (int)__umulhi((uint32_t)rq, P.rk_magic), row = rq - sl * P.rk;
+    const int off = rowoff[row];
+    const bool ok = off != kNoRow;
+    const int ch = sl < cl.nfull ? cl.cf0 + sl : (sl == cl.nfull ? ch_head : ch_tail);
+    const uint8_t *src = P.xcodes + (ok ? (size_t)ch * HW + off + 16 * c16 : (size_t)0);
+    const uint32_t dst = smem_u32(raw + ((size_t)rq << P.pitch_log2) + g.pad + P.col0 + 16 * c16);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------
 // fast producer, assembly: digit planes of this thread's im2col row of chunk `cl` from the staged rows
@@ -406,6 +436,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
       if (tile < ntiles) {
         stage_set_rowoff(P, tile / P.nct, sm.rowoff);
         named_barrier_sync(1, kProducerThreads);
+        if (P.tma_rows) {
+          // padding columns are zero for the whole kernel: clear both buffers once, then only rows are written
+          for (uint32_t q = threadIdx.x * 16u; q < 2u * P.raw_bytes; q += kProducerThreads * 16u)
+            *reinterpret_cast<uint4 *>(sm.raw + q) = make_uint4(0u, 0u, 0u, 0u);
+          named_barrier_sync(1, kProducerThreads);
+          stage_issue_async(P, chunk_layout(g, 0), sm.rowoff, sm.raw);
+          stage_async_wait();
+          named_barrier_sync(1, kProducerThreads);
+        }
         if (P.prefetch) {
           const ChunkLayout cl0 = chunk_layout(g, 0);
           stage_load<kPrefetchWords>(P, stt, cl0, sm.rowoff, 0, v);
@@ -428,10 +467,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
             stage_set_rowoff(P, ntile / P.nct, sm.rowoff + ntpar * 128);
             named_barrier_sync(1, kProducerThreads);
           }
-          // its input rows start their trip from L2 / HBM now and land in registers while this stage is built
-          if (P.prefetch) stage_load<kPrefetchWords>(P, stt, ncl, sm.rowoff + ntpar * 128, 0, v);
+          // its input rows start their trip from L2 / HBM now: by bulk copy straight into the other staging buffer,
+          // or into registers, while this stage is built
+          if (P.tma_rows) stage_issue_async(P, ncl, sm.rowoff + ntpar * 128, sm.raw + (size_t)((it + 1) & 1) * P.raw_bytes);
+          else if (P.prefetch) stage_load<kPrefetchWords>(P, stt, ncl, sm.rowoff + ntpar * 128, 0, v);
         }
-        if (!P.prefetch) {  // too many rows for the registers: stage this chunk now, eight loads in flight
+        if (!P.prefetch && !P.tma_rows) {  // too many rows for the registers: stage this chunk now, eight loads in flight
           const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
           const int passes = ((nslots * P.rk) + stt.rstep - 1) / stt.rstep;
           for (int p0 = 0; p0 < passes; p0 += 8) {
@@ -457,8 +498,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
         else produce_fast<NSA, 5>(P, cl, st_ptr, raw, r, pix_base);
         fence_proxy_async();
         mbar_arrive(sm.full0 + 8 * sidx);
-        if (P.prefetch) {
-          if (more) stage_store<kPrefetchWords>(P, stt, ncl, 0, v, sm.raw + (size_t)((it + 1) & 1) * P.raw_bytes);
+        if (P.prefetch || P.tma_rows) {
+          if (P.prefetch && more)
+            stage_store<kPrefetchWords>(P, stt, ncl, 0, v, sm.raw + (size_t)((it + 1) & 1) * P.raw_bytes);
+          if (P.tma_rows) stage_async_wait();  // my copies of the next stage's rows have landed
           // next stage's rows visible to all producers; everyone is done reading this stage's rows
           named_barrier_sync(1, kProducerThreads);
         }

@@ -97,6 +97,18 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
 __device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// barrier + population count of `pred` over the participating threads
+__device__ __forceinline__ uint32_t named_barrier_popc(uint32_t id, uint32_t nthreads, bool pred) {
+  uint32_t cnt;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %3, 0;\n\t"
+      "bar.red.popc.u32 %0, %1, %2, p;\n\t}"
+      : "=r"(cnt)
+      : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
+      : "memory");
+  return cnt;
+}
 // K-major, no-swizzle shared-memory matrix descriptor (see cim_tc_layout.cuh).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
