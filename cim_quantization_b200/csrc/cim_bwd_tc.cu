@@ -58,6 +58,8 @@ struct BwdParams {
   int nxg, chunk0;  // wgrad: crossbars handled by this launch's blockIdx.y group
   // wgrad staged activation rows (same geometry as the forward producer, stride 1 only)
   int fastx, ow_log2, rpt, pitch_log2, col0;
+  int rk, prow;      // wgrad staging: rows per channel slot, staged row of (output row o, tap row ky) = o*prow + ky
+  int async_rows;    // wgrad staging: rows arrive by 16-byte cp.async copies issued one chunk ahead
   uint32_t raw_bytes;
   long long *debug;  // per-role cycle counters (builds with TIMERS=1 only)
   int cached;   // dgrad: 1 = producers keep grad_out of the tile and the state words of the chunk in registers
@@ -571,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     const int fr = tid & 127;     // X tile: this thread's crossbar row
     const bool aligned = (g.L % 8) == 0 && (g.OW % 8) == 0;
     const int pitch = 1 << P.pitch_log2;
-    const int slot_bytes = P.rpt * g.K * pitch;
+    const int slot_bytes = P.rk * pitch;
     const int HW = g.H * g.W;
     uint32_t it = 0, chunk_it = 0;
     int tpar = 0;
@@ -624,6 +626,45 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         }
       }
     };
+    // staged-row table of tile mt_: offset of the row's first byte source, or kNoRow.  Rows of a slot are
+    // (output row, ky) pairs, or -- when a tile is consecutive rows of one image (P.prow == 1) -- the distinct
+    // input rows oy0 - pad + r.  Async staging copies whole rows (offset of image column 0); the synchronous path
+    // loads words starting at staged column 0 (image column -pad - col0).
+    auto fill_rowoff = [&](int mt_, int *tab) {
+      if (tid >= 128 && tid < 128 + P.rk) {
+        const int rr = tid - 128;
+        const int orow = P.prow == 1 ? 0 : rr / g.K, ky = P.prow == 1 ? rr : rr % g.K;
+        const int64_t m_row = (int64_t)mt_ * kTcTileM + (orow << P.ow_log2);
+        int off = kNoRow;
+        if (m_row < g.M) {
+          const int b = (int)(m_row / g.L), oy = (int)(m_row % g.L) >> P.ow_log2;
+          const int iy = oy - g.pad + ky;  // stride 1
+          if (iy >= 0 && iy < g.H) off = (b * g.Cin * g.H + iy) * g.W - (P.async_rows ? 0 : g.pad + P.col0);
+        }
+        tab[rr] = off;
+      }
+    };
+    // async staging of the channels crossbar i_ touches: 16-byte pieces, zero-fill for rows outside the image
+    auto issue_rows = [&](int i_, const int *tab, uint8_t *dstbuf) {
+      const int lo_ = i_ * g.xbar, rows_ = min(rows_full, g.F - lo_);
+      const int c_lo_ = lo_ / g.KK, nch_ = (lo_ + rows_ - 1) / g.KK - c_lo_ + 1;
+      const int cpr = g.W >> 4, total = nch_ * P.rk * cpr;
+      for (int q = tid; q < total; q += kWgProducerThreads) {
+        const int rq = q / cpr, c16 = q - rq * cpr;
+        const int sl = rq / P.rk, row = rq - sl * P.rk;
+        const int off = tab[row];
+        const bool ok = off != kNoRow;
+        const uint8_t *src = P.xcodes + (ok ? (size_t)(c_lo_ + sl) * HW + off + 16 * c16 : (size_t)0);
+        const uint32_t dst = smem_u32(dstbuf + ((size_t)rq << P.pitch_log2) + g.pad + P.col0 + 16 * c16);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (P.async_rows) {  // padding columns stay zero for the whole kernel
+      for (uint32_t q = tid * 16u; q < 2u * P.raw_bytes; q += kWgProducerThreads * 16u)
+        *reinterpret_cast<uint4 *>(cv.raw + q) = make_uint4(0u, 0u, 0u, 0u);
+    }
     int4 gpt = make_int4(0, 0, 0, -1), gpt_n = gpt;
     if (gcache && (int)blockIdx.x < P.mtiles) {
       gpt = pix_group(blockIdx.x);
@@ -649,18 +690,14 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         cv.pixtab[tpar * 16 + tid] = e;
       }
       int *rowoff = cv.rowoff + tpar * 128;
-      if (P.fastx && tid >= 128 && tid < 128 + P.rpt * g.K) {  // staged row (output row, ky) -> global offset
-        const int rr = tid - 128, orow = rr / g.K, ky = rr % g.K;
-        const int64_t m_row = m0 + (orow << P.ow_log2);
-        int off = kNoRow;
-        if (m_row < g.M) {
-          const int b = (int)(m_row / g.L), oy = (int)(m_row % g.L) >> P.ow_log2;
-          const int iy = oy - g.pad + ky;  // stride 1
-          if (iy >= 0 && iy < g.H) off = (b * g.Cin * g.H + iy) * g.W - g.pad - P.col0;
-        }
-        rowoff[rr] = off;
-      }
+      // async staging fills the table of a tile one chunk before the tile starts (below); the first tile's here
+      if (P.fastx && (!P.async_rows || mt == (int)blockIdx.x)) fill_rowoff(mt, rowoff);
       named_barrier_sync(1, kWgProducerThreads);
+      if (P.async_rows && mt == (int)blockIdx.x) {  // rows of the very first chunk
+        issue_rows(i_begin, rowoff, cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        named_barrier_sync(1, kWgProducerThreads);
+      }
       const int4 *ptab = cv.pixtab + tpar * 16;
       for (int i = i_begin; i < i_end; ++i, ++chunk_it) {
         const int lo = i * g.xbar;
@@ -671,13 +708,23 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         const int c_lo = lo / g.KK;
         uint8_t *raw = cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes;
         const long long ts0 = CIMQ_TB();
-        if (P.fastx) {
+        if (P.async_rows) {
+          // the rows of this chunk are already in raw[chunk_it & 1]; start the next chunk's (or next tile's first)
+          uint8_t *nbuf = cv.raw + (size_t)((chunk_it + 1) & 1) * P.raw_bytes;
+          if (i + 1 < i_end) {
+            issue_rows(i + 1, rowoff, nbuf);
+          } else if (mt_n < P.mtiles) {
+            fill_rowoff(mt_n, cv.rowoff + (tpar ^ 1) * 128);
+            named_barrier_sync(1, kWgProducerThreads);
+            issue_rows(i_begin, cv.rowoff + (tpar ^ 1) * 128, nbuf);
+          }
+        } else if (P.fastx) {
           // stage the input rows of the channels this crossbar touches (once per chunk, shared by all planes)
           const int nch = (lo + rows - 1) / g.KK - c_lo + 1;
           const int wpr_log2 = P.pitch_log2 - 2;
           const int xw = tid & ((1 << wpr_log2) - 1);
           const int rstep = kWgProducerThreads >> wpr_log2;
-          const int rk = P.rpt * g.K;
+          const int rk = P.rk;
           const int total_rows = nch * rk;
           const int ix = 4 * xw - P.col0 - g.pad;
           const bool xok = ix >= 0 && ix < g.W;
@@ -719,7 +766,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
             if (P.fastx) {
               const int p0 = pg * 8;
               const uint8_t *src = raw + (size_t)(ci - c_lo) * slot_bytes +
-                                   ((((p0 >> P.ow_log2) * g.K) + ky) << P.pitch_log2) +
+                                   ((((p0 >> P.ow_log2) * P.prow) + ky) << P.pitch_log2) +
                                    (p0 & ((1 << P.ow_log2) - 1)) + kx + P.col0;
               const uint32_t sa = smem_u32(src);
               const uint32_t *al = reinterpret_cast<const uint32_t *>(src - (sa & 3u));
@@ -911,6 +958,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           fence_proxy_async();
           mbar_arrive(cv.full0 + 8 * sidx);
           d_g += CIMQ_TB() - tx1;
+        }
+        if (P.async_rows) {  // my copies of the next chunk's rows have landed; publish them, retire this chunk's buffer
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          named_barrier_sync(1, kWgProducerThreads);
         }
       }
       gpt = gpt_n;
@@ -1146,18 +1197,26 @@ int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, c
   // staged activation rows (stride 1, output width a power of two between 8 and 128, 4-byte aligned rows)
   P.fastx = 0; P.raw_bytes = 0;
   if (g.stride == 1 && g.W % 4 == 0 && g.OW >= 8 && g.OW <= kTcTileM && (g.OW & (g.OW - 1)) == 0 &&
-      (kTcTileM / g.OW) * g.K <= 128 && g.pad < g.K) {
+      g.pad < g.K) {
     int owl = 0;
     while ((1 << owl) < g.OW) ++owl;
-    const int col0 = (4 - g.pad % 4) % 4;
+    // rows by 16-byte cp.async copies: 16-byte aligned rows on both sides (W % 16 == 0, image column 0 staged at
+    // byte 16); otherwise 4-byte loads with image column -pad on a word boundary
+    const bool async_rows = g.W % 16 == 0 && g.pad <= 16 && (reinterpret_cast<uintptr_t>(xcodes) & 15u) == 0;
+    const int col0 = async_rows ? 16 - g.pad : (4 - g.pad % 4) % 4;
     const int needp = (g.OW - 1) + g.K + col0 + 4;  // + 4: the unaligned 8-byte window reads one word further
     int pl = 2;
     while ((1 << pl) < needp) ++pl;
     const int rows = g.xbar < g.F ? g.xbar : g.F;
     const int nch = (rows + g.KK - 2) / g.KK + 1;  // channels one crossbar can touch
-    const size_t raw = ((size_t)nch * (kTcTileM / g.OW) * g.K * (1u << pl) + 8 + 15) & ~(size_t)15;
-    if (pl <= 9 && 2 * raw + 2 * P.stage_bytes + kBarrierBytes <= kSmemBudget) {
-      P.fastx = 1; P.ow_log2 = owl; P.rpt = kTcTileM / g.OW; P.pitch_log2 = pl; P.col0 = col0;
+    // a tile that is 128 consecutive pixels of one image reads consecutive input rows: output rows share them
+    const int rpt = kTcTileM / g.OW;
+    const bool shared_rows = g.L % kTcTileM == 0;
+    const int rk = shared_rows ? rpt - 1 + g.K : rpt * g.K;
+    const size_t raw = ((size_t)nch * rk * (1u << pl) + 8 + 15) & ~(size_t)15;
+    if (pl <= 9 && rk <= 128 && 2 * raw + 2 * P.stage_bytes + kBarrierBytes <= kSmemBudget) {
+      P.fastx = 1; P.ow_log2 = owl; P.rpt = rpt; P.pitch_log2 = pl; P.col0 = col0;
+      P.rk = rk; P.prow = shared_rows ? 1 : g.K; P.async_rows = async_rows ? 1 : 0;
       P.raw_bytes = (uint32_t)raw;
     }
   }

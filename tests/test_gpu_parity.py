@@ -482,3 +482,32 @@ def test_backward_deterministic_fold(name):
     fused = L.conv_backward(spec, go, xc, wdigits, wtiles, state, s, mask, need_alpha=False)[0].cpu().numpy()
     assert rel_err(fused, d["fn_grad_xq"]) < TOL
     assert rel_err(fused, runs[0]) < 1e-6
+
+
+def test_full_size_backward_tc_equals_simt():
+    """Full microbench shape (3x3 64->64 32x32 B=256 w3a3 xbar128 adc1.5): the tcgen05 dgrad / wgrad kernels
+    (register-resident operands, staged rows, fused fold) against the CUDA-core backward on the same ADC state."""
+    L = _lib()
+    B, C, HW = 256, 64, 32
+    cfg = O.CimConfig(in_channels=C, out_channels=C, kernel=3, stride=1, padding=1, nbits_w=3, nbits_a=3,
+                      wbitslice=1, abitslice=1, xbar=128, adcbits=1.5)
+    spec = _spec(cfg, HW, B)
+    info = L.layer_info(spec)
+    assert info.tc_backward
+    g = torch.Generator(device="cuda").manual_seed(2)
+    xc = (torch.randint(0, 8, (B, C, HW, HW), device="cuda", generator=g, dtype=torch.uint8) *
+          (torch.rand(B, C, HW, HW, device="cuda", generator=g) < 0.5)).to(torch.uint8)
+    wc = torch.randint(-4, 4, (C, C * 9), device="cuda", generator=g, dtype=torch.int8)
+    s = torch.tensor([0.21, 0.037], device="cuda")
+    mask = _mask(cfg)
+    sums = L.conv_psum_abs_sums(spec, xc, wc).double()
+    aq = (2.0 * sums / (B * HW * HW) * float(s[0]) * float(s[1])).float().clamp_min(1e-4)
+    table = L.adc_table(spec, s, aq, mask)
+    wdigits, wtiles = L.weight_prepare(spec, wc)
+    _, state = L.conv_forward(spec, xc, wc, wtiles, table, s, mask, save_state=True)
+    go = torch.randn(B, C, HW * HW, device="cuda", generator=g)
+    ref = L.conv_backward(spec, go, xc, wdigits, wtiles, state, s, mask, need_alpha=True, flags=L.FLAG_FORCE_SIMT)
+    for flags in (0, L.FLAG_DETERMINISTIC):
+        got = L.conv_backward(spec, go, xc, wdigits, wtiles, state, s, mask, need_alpha=True, flags=flags)
+        for a, b, name in zip(got, ref, ("grad_xq", "grad_wq", "grad_alpha_q")):
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < TOL, (name, flags)
