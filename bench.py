@@ -469,24 +469,42 @@ def run_ours(a):
         gw_host = torch.empty_like(layer.weight, device="cpu").pin_memory()
         small_host = torch.empty(flat.numel() - layer.weight.numel(), device="cpu").pin_memory()
 
-        def e2e_step():
-            xin = x_host.to(dev, non_blocking=True).requires_grad_(True)
-            gyin = gy_host.to(dev, non_blocking=True)
-            for p in params:
-                p.grad = None
-            layer(xin).backward(gyin)
-            gw_host.copy_(layer.weight.grad, non_blocking=True)
-            small_host.copy_(torch.cat([p.grad.reshape(-1) for p in params if p is not layer.weight]),
-                             non_blocking=True)
+        # Host batches reach the GPU through the package's HostBatchPipeline (a copy stream, two batches deep): the
+        # H2D copy of step n+1 overlaps the kernels of step n.  Every timed step still copies its own inputs from
+        # pinned host memory and reads its gradients back; the pipeline starts empty inside the timed region.
+        from cim_quantization_b200.harness import HostBatchPipeline
 
-        for _ in range(3):
-            e2e_step()
+        def e2e_run(nsteps):
+            pipe = HostBatchPipeline(dev, depth=2)
+            submitted = 0
+            for n in range(nsteps):
+                while submitted < nsteps and pipe.can_submit():
+                    pipe.submit((x_host, gy_host))
+                    submitted += 1
+                xin, gyin = pipe.get()
+                xin = xin.detach().requires_grad_(True)
+                for p in params:
+                    p.grad = None
+                layer(xin).backward(gyin)
+                pipe.release()
+                gw_host.copy_(layer.weight.grad, non_blocking=True)
+                small_host.copy_(torch.cat([p.grad.reshape(-1) for p in params if p is not layer.weight]),
+                                 non_blocking=True)
+
+        e2e_run(3)
+        torch.cuda.synchronize()
         e2e_iters = max(3, min(a.steps, 10))
-        e2e_ms = event_time_ms(e2e_step, e2e_iters, torch, graph=False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_run(e2e_iters)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = e0.elapsed_time(e1) / e2e_iters
         e2e = {"value": ops_step / (e2e_ms * 1e-3) / 1e12, "unit": UNIT,
                "h2d_bytes_per_step": int(x_host.numel() * 4 + gy_host.numel() * 4),
                "d2h_bytes_per_step": int(gw_host.numel() * 4 + small_host.numel() * 4), "n_gpus": 1,
-               "ms_per_step": e2e_ms}
+               "ms_per_step": e2e_ms, "steps": e2e_iters,
+               "pipeline": "HostBatchPipeline depth 2 (copy stream); starts empty inside the timed region"}
 
         cpu = None
         if not a.no_cpu_baseline:

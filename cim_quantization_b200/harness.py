@@ -103,3 +103,57 @@ def sgd_param_groups(model, weight_decay=1e-4):
     for n, p in model.named_parameters():
         (no_decay if "alpha" in n else decay).append(p)
     return [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}]
+
+
+class HostBatchPipeline:
+    """Feeds batches that live in pinned host memory to the GPU through a side stream, ``depth`` batches ahead
+    of the consumer, so the PCIe copy of step n+1 overlaps the kernels of step n (the CiM step moves 134 MB of
+    fp32 activations / gradients per 1.8 ms of compute at the microbench shape: unpipelined, the copy dominates).
+
+        pipe = HostBatchPipeline(device)
+        for host_batch in loader:            # tuples of pinned CPU tensors
+            pipe.submit(host_batch)          # asynchronous H2D on the copy stream
+            ...
+            dev_batch = pipe.get()           # the oldest submitted batch, ready on the current stream
+            ... forward / backward ...
+            pipe.release()                   # its device buffers may be overwritten by a later submit
+    """
+
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.depth = depth
+        self.stream = torch.cuda.Stream(self.device)
+        self.slots = [None] * depth          # device tensors per slot, allocated on first use
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.freed = [torch.cuda.Event() for _ in range(depth)]
+        self.n_submitted = self.n_got = self.n_released = 0
+
+    def can_submit(self) -> bool:
+        return self.n_submitted - self.n_released < self.depth
+
+    def submit(self, host_tensors) -> None:
+        if not self.can_submit():
+            raise RuntimeError("HostBatchPipeline: all slots in flight; release() one first")
+        k = self.n_submitted % self.depth
+        if self.slots[k] is None:
+            self.slots[k] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_tensors]
+        with torch.cuda.stream(self.stream):
+            if self.n_submitted >= self.depth:
+                self.stream.wait_event(self.freed[k])  # the consumer of the previous batch in this slot is done
+            for d, h in zip(self.slots[k], host_tensors):
+                d.copy_(h, non_blocking=True)
+            self.ready[k].record(self.stream)
+        self.n_submitted += 1
+
+    def get(self):
+        if self.n_got >= self.n_submitted:
+            raise RuntimeError("HostBatchPipeline: nothing submitted")
+        k = self.n_got % self.depth
+        torch.cuda.current_stream(self.device).wait_event(self.ready[k])
+        self.n_got += 1
+        return self.slots[k]
+
+    def release(self) -> None:
+        k = self.n_released % self.depth
+        self.freed[k].record(torch.cuda.current_stream(self.device))
+        self.n_released += 1
