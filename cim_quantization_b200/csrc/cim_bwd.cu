@@ -132,14 +132,27 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_w1_kernel(Geo g, int m_
   }
 }
 
-__global__ void bwd_alpha_finish_kernel(Geo g, int nsplit, float gfac, const int8_t *__restrict__ mask,
-                                        const float *__restrict__ partial, float *__restrict__ galpha) {
+// Block = 32 consecutive table entries x 8 slices of the split range, combined through shared memory in a fixed
+// order (deterministic).
+__global__ void __launch_bounds__(256) bwd_alpha_finish_kernel(Geo g, int nsplit, float gfac,
+                                                               const int8_t *__restrict__ mask,
+                                                               const float *__restrict__ partial,
+                                                               float *__restrict__ galpha) {
+  __shared__ float red[8][32];
   const int64_t n = table_entries(g);
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    float v = 0.0f;
-    for (int sidx = 0; sidx < nsplit; ++sidx) v += partial[(int64_t)sidx * n + e];
-    int q = (int)((e / g.Cout) % g.pairs);
-    galpha[e] = v * gfac * (float)mask[q];  // lsq.py:306, 323-325 / 330-332
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int64_t e = (int64_t)blockIdx.x * 32 + lane;
+  float v = 0.0f;
+  if (e < n)
+    for (int sidx = slice; sidx < nsplit; sidx += 8) v += __ldg(partial + (int64_t)sidx * n + e);
+  red[slice][lane] = v;
+  __syncthreads();
+  if (slice == 0 && e < n) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][lane];
+    const int q = (int)((e / g.Cout) % g.pairs);
+    galpha[e] = t * gfac * (float)mask[q];  // lsq.py:306, 323-325 / 330-332
   }
 }
 
@@ -430,7 +443,7 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
     double numel = (double)g.B * g.NX * g.NSW * g.NSA * g.L * g.Cout;
     float gfac = (float)(1.0 / sqrt(numel));
     int64_t n = table_entries(g);
-    bwd_alpha_finish_kernel<<<(int)((n + 127) / 128), 128, 0, st>>>(g, p.alpha_splits, gfac, mask, apart, galpha);
+    bwd_alpha_finish_kernel<<<(int)((n + 31) / 32), 256, 0, st>>>(g, p.alpha_splits, gfac, mask, apart, galpha);
     CIMQ_CUDA_OK(cudaGetLastError());
   }
   if (gxq != nullptr && use_tc) {

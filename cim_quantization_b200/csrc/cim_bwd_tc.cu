@@ -1044,15 +1044,27 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
   }
 }
 
-__global__ void bwd_weight_tc_finish_kernel(Geo g, int nparts, const float *__restrict__ partial,
-                                            float *__restrict__ gw) {
+// Sum of the per-CTA partials [part][F][Cout] -> grad_w [Cout][F] (weight layout, lsq.py:369).  Block = 32
+// consecutive elements of the partial layout (coalesced 128-byte reads) x 8 slices of the part range; the slices
+// are combined through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) bwd_weight_tc_finish_kernel(Geo g, int nparts,
+                                                                   const float *__restrict__ partial,
+                                                                   float *__restrict__ gw) {
+  __shared__ float red[8][32];
   const int64_t n = (int64_t)g.Cout * g.F;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int f = (int)(idx % g.F), co = (int)(idx / g.F);
-    float v = 0.0f;
-    for (int p = 0; p < nparts; ++p) v += partial[((int64_t)p * g.F + f) * g.Cout + co];
-    gw[idx] = v;  // [Cout, F] == weight layout (lsq.py:369)
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int64_t e = (int64_t)blockIdx.x * 32 + lane;  // e = f * Cout + co
+  float v = 0.0f;
+  if (e < n)
+    for (int p = slice; p < nparts; p += 8) v += __ldg(partial + (int64_t)p * n + e);
+  red[slice][lane] = v;
+  __syncthreads();
+  if (slice == 0 && e < n) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][lane];
+    const int f = (int)(e / g.Cout), co = (int)(e % g.Cout);
+    gw[(int64_t)co * g.F + f] = t;
   }
 }
 
@@ -1245,7 +1257,7 @@ int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, c
 #undef CIMQ_LAUNCH_WGRAD
   CIMQ_CUDA_OK(cudaGetLastError());
   const int64_t n = (int64_t)g.Cout * g.F;
-  bwd_weight_tc_finish_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, ctas, partial, gw);
+  bwd_weight_tc_finish_kernel<<<(int)((n + 31) / 32), 256, 0, st>>>(g, ctas, partial, gw);
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
