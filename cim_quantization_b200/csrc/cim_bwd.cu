@@ -132,6 +132,77 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_w1_kernel(Geo g, int m_
   }
 }
 
+// Vectorised variant: a thread handles four consecutive pixels per load (one 128-bit load of the state word(s) and
+// of grad_out, one address computation per four pixels -- the scalar version is bound by the integer pipe, and a
+// third of its integer work is addressing).  Needs L % 4 == 0 and split boundaries that are multiples of 4.
+template <int NSW, int NSA>
+__global__ void __launch_bounds__(256) bwd_alpha_partial_w4_kernel(Geo g, int m_per_split,
+                                                                   const float *__restrict__ go,
+                                                                   const uint32_t *__restrict__ state,
+                                                                   float *__restrict__ partial) {
+  constexpr int PAIRS = NSW * NSA;
+  constexpr int SWORDS = (3 * PAIRS + 31) / 32;
+  constexpr int NW = (2 * PAIRS + 31) / 32;
+  constexpr int U = PAIRS <= 16 ? 2 : 1;  // independent 4-pixel groups in flight per thread
+  __shared__ float red[8][PAIRS];
+  const int c = blockIdx.x, i = blockIdx.y, ms = blockIdx.z;
+  const int64_t mbeg = (int64_t)ms * m_per_split;
+  const int64_t mend = min((int64_t)g.M, mbeg + m_per_split);
+  const uint32_t *st = state + ((int64_t)i * g.Cout + c) * SWORDS * g.M;
+  float acc[PAIRS];
+#pragma unroll
+  for (int q = 0; q < PAIRS; ++q) acc[q] = 0.0f;
+  int64_t m = mbeg + 4 * threadIdx.x;
+  int b = (int)(m / g.L), l = (int)(m % g.L);
+  const float *gbase = go + (int64_t)c * g.L;
+  const int64_t gimg = (int64_t)g.Cout * g.L;
+  for (; m < mend; m += U * 1024) {
+    float4 gv[U];
+    uint4 w[U][NW];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = m + u * 1024 < mend;
+      gv[u] = ok ? __ldg(reinterpret_cast<const float4 *>(gbase + (int64_t)b * gimg + l))
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < NW; ++t)
+        w[u][t] = ok ? __ldg(reinterpret_cast<const uint4 *>(st + (int64_t)t * g.M + m + u * 1024))
+                     : make_uint4(0u, 0u, 0u, 0u);
+      l += 1024;
+      while (l >= g.L) { l -= g.L; ++b; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float g4[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+#pragma unroll
+        for (int q = 0; q < PAIRS; ++q) {
+          const int sq = (q % NSA) * NSW + q / NSA;
+          const int bp = sq, bn = PAIRS + sq;
+          const uint4 wp = w[u][bp >> 5], wn = w[u][bn >> 5];
+          const uint32_t wpe = e == 0 ? wp.x : e == 1 ? wp.y : e == 2 ? wp.z : wp.w;
+          const uint32_t wne = e == 0 ? wn.x : e == 1 ? wn.y : e == 2 ? wn.z : wn.w;
+          if (wpe & (1u << (bp & 31))) acc[q] += g4[e];
+          if (wne & (1u << (bn & 31))) acc[q] -= g4[e];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PAIRS; ++q) {
+    float v = acc[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < PAIRS) {
+    float v = 0.0f;
+    for (int w8 = 0; w8 < 8; ++w8) v += red[w8][threadIdx.x];
+    partial[(int64_t)ms * table_entries(g) + ((int64_t)i * PAIRS + threadIdx.x) * g.Cout + c] = v;
+  }
+}
+
 // Block = 32 consecutive table entries x 8 slices of the split range, combined through shared memory in a fixed
 // order (deterministic).
 __global__ void __launch_bounds__(256) bwd_alpha_finish_kernel(Geo g, int nsplit, float gfac,
@@ -428,7 +499,16 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
 
   if (galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
     dim3 grid(g.Cout, g.NX, p.alpha_splits);
-    if (g.NSW == 3 && g.NSA == 3)
+    // four pixels per load when the pixel runs allow 128-bit loads (state rows and grad_out rows 16-byte aligned)
+    const bool vec4 = g.L % 4 == 0 && p.alpha_m_per_split % 4 == 0 && g.M % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(go) & 15u) == 0 && (reinterpret_cast<uintptr_t>(state) & 15u) == 0;
+    if (g.NSW == 3 && g.NSA == 3 && vec4)
+      bwd_alpha_partial_w4_kernel<3, 3><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
+    else if (g.NSW == 2 && g.NSA == 2 && vec4)
+      bwd_alpha_partial_w4_kernel<2, 2><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
+    else if (g.NSW == 4 && g.NSA == 4 && vec4)
+      bwd_alpha_partial_w4_kernel<4, 4><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
+    else if (g.NSW == 3 && g.NSA == 3)
       bwd_alpha_partial_w1_kernel<3, 3><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
     else if (g.NSW == 2 && g.NSA == 2)
       bwd_alpha_partial_w1_kernel<2, 2><<<grid, 256, 0, st>>>(g, p.alpha_m_per_split, go, state, apart);
