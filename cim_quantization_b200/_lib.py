@@ -78,6 +78,13 @@ EXPORTS = {
                                      C.c_void_p, C.c_uint32, C.c_void_p]),
     "cimq_conv_psums": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cimq_conv_psum_abs_sums": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cimq_bn_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "cimq_bn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cimq_bn_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -293,3 +300,38 @@ def conv_psum_abs_sums(spec: LayerSpec, xcodes, wcodes):
     layer = spec.c_layer()
     _check(load().cimq_conv_psum_abs_sums(C.byref(layer), _ptr(xcodes), _ptr(wcodes), _ptr(sums), _stream()))
     return sums
+
+
+# ---- batch norm (+ residual) (+ ReLU) ------------------------------------------------------------------------
+def bn_forward(x, residual, weight, bias, running_mean, running_var, training: bool, momentum: float, eps: float,
+               relu: bool):
+    """y, save_mean, save_invstd (None, None in inference)."""
+    b, c = x.shape[0], x.shape[1]
+    hw = x.numel() // (b * c)
+    y = torch.empty_like(x)
+    mean = invstd = ws = None
+    if training:
+        mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(c, dtype=torch.float32, device=x.device)
+        ws = torch.empty(load().cimq_bn_workspace_bytes(b, c), dtype=torch.uint8, device=x.device)
+    _check(load().cimq_bn_forward(_ptr(x), _ptr(residual), _ptr(weight), _ptr(bias), _ptr(running_mean),
+                                  _ptr(running_var), int(training), float(momentum), float(eps), int(relu), b, c, hw,
+                                  _ptr(y), _ptr(mean), _ptr(invstd), _ptr(ws), _stream()))
+    _count(2 if training else 1)
+    return y, mean, invstd
+
+
+def bn_backward(grad_y, x, y, weight, mean, invstd, training: bool, relu: bool, need_residual: bool):
+    """grad_x, grad_residual (or None), grad_weight, grad_bias."""
+    b, c = x.shape[0], x.shape[1]
+    hw = x.numel() // (b * c)
+    gx = torch.empty_like(x)
+    gres = torch.empty_like(x) if need_residual else None
+    gw = torch.empty(c, dtype=torch.float32, device=x.device)
+    gb = torch.empty(c, dtype=torch.float32, device=x.device)
+    ws = torch.empty(load().cimq_bn_workspace_bytes(b, c), dtype=torch.uint8, device=x.device)
+    _check(load().cimq_bn_backward(_ptr(grad_y), _ptr(x), _ptr(y), _ptr(weight), _ptr(mean), _ptr(invstd),
+                                   int(training), int(relu), b, c, hw, _ptr(gx), _ptr(gres), _ptr(gw), _ptr(gb),
+                                   _ptr(ws), _stream()))
+    _count(2)
+    return gx, gres, gw, gb

@@ -1,0 +1,292 @@
+// Batch norm (+ residual add) (+ ReLU), training and inference, forward and backward, fp32 NCHW -- the
+// element-wise step either side of the CiM convolution (the reference model is
+// models/cifar10/resnet.py:60-66, 110-112: conv -> nn.BatchNorm2d -> [+ shortcut] -> F.relu).
+//
+// HBM-bound.  A channel's data is B runs of HW contiguous floats; the work of a channel is split over `splits`
+// blocks (grid = (C, splits)) so that narrow layers (16 channels) still fill 148 SMs -- cuDNN's spatial
+// batch-norm kernels use one block per channel and take 134 / 267 us (forward / backward) on [256,16,32,32],
+// 16.8 MB.  Two launches per direction: per-block partial sums (fp32 in the block, double across blocks, fixed
+// order: deterministic), then the element-wise pass, whose blocks each re-reduce the few partials of their channel.
+#include "cimq_common.cuh"
+
+namespace cimq {
+
+namespace {
+
+constexpr int kBnThreads = 256;
+
+__device__ __forceinline__ float block_sum(float v, float *red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.0f;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < kBnThreads / 32 ? red[threadIdx.x] : 0.0f;
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;  // valid in thread 0
+}
+
+// forward pass 1: partial[c][s] = {sum x, sum x^2} over the images b = s, s+splits, ...
+template <bool VEC>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float *__restrict__ x, int B, int C, int HW,
+                                                              double2 *__restrict__ partial) {
+  __shared__ float red[kBnThreads / 32];
+  const int c = blockIdx.x, s = blockIdx.y, splits = gridDim.y;
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int b = s; b < B; b += splits) {
+    const float *p = x + ((int64_t)b * C + c) * HW;
+    if (VEC) {
+      const float4 *p4 = reinterpret_cast<const float4 *>(p);
+      for (int i = threadIdx.x; i < HW / 4; i += kBnThreads) {
+        const float4 v = __ldg(p4 + i);
+        s1 += (v.x + v.y) + (v.z + v.w);
+        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW; i += kBnThreads) {
+        const float v = __ldg(p + i);
+        s1 += v;
+        s2 += v * v;
+      }
+    }
+  }
+  const float t1 = block_sum(s1, red), t2 = block_sum(s2, red);
+  if (threadIdx.x == 0) partial[(int64_t)c * splits + s] = make_double2((double)t1, (double)t2);
+}
+
+// forward pass 2: statistics of the channel from the partials (training) or the running buffers (inference),
+// y = (x - mean) * invstd * gamma + beta [+ residual] [ReLU]; block (c, 0) publishes mean / invstd and updates the
+// running statistics (momentum, unbiased variance -- torch.nn.BatchNorm2d semantics).
+template <bool VEC>
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
+    const float *__restrict__ x, const float *__restrict__ residual, const float *__restrict__ weight,
+    const float *__restrict__ bias, float *__restrict__ running_mean, float *__restrict__ running_var,
+    const double2 *__restrict__ partial, int training, float momentum, float eps, int relu, int B, int C, int HW,
+    float *__restrict__ y, float *__restrict__ save_mean, float *__restrict__ save_invstd) {
+  __shared__ float sh[2];
+  const int c = blockIdx.x, s = blockIdx.y, splits = gridDim.y;
+  if (threadIdx.x == 0) {
+    float mean, invstd;
+    if (training) {
+      double a = 0.0, q = 0.0;
+      for (int t = 0; t < splits; ++t) {
+        const double2 v = partial[(int64_t)c * splits + t];
+        a += v.x;
+        q += v.y;
+      }
+      const double n = (double)B * HW;
+      const double m = a / n;
+      double var = q / n - m * m;
+      var = var < 0.0 ? 0.0 : var;
+      mean = (float)m;
+      invstd = (float)(1.0 / sqrt(var + (double)eps));
+      if (s == 0) {
+        save_mean[c] = mean;
+        save_invstd[c] = invstd;
+        if (running_mean != nullptr) {
+          running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
+          running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)(var * n / (n > 1.0 ? n - 1.0 : 1.0));
+        }
+      }
+    } else {
+      mean = running_mean[c];
+      invstd = rsqrtf(running_var[c] + eps);
+    }
+    sh[0] = mean;
+    sh[1] = invstd;
+  }
+  __syncthreads();
+  const float mean = sh[0];
+  const float g = (weight != nullptr ? weight[c] : 1.0f) * sh[1], be = bias != nullptr ? bias[c] : 0.0f;
+  for (int b = s; b < B; b += splits) {
+    const int64_t off = ((int64_t)b * C + c) * HW;
+    if (VEC) {
+      const float4 *p4 = reinterpret_cast<const float4 *>(x + off);
+      const float4 *r4 = residual != nullptr ? reinterpret_cast<const float4 *>(residual + off) : nullptr;
+      float4 *y4 = reinterpret_cast<float4 *>(y + off);
+      for (int i = threadIdx.x; i < HW / 4; i += kBnThreads) {
+        const float4 v = __ldg(p4 + i);
+        float4 o = make_float4(fmaf(v.x - mean, g, be), fmaf(v.y - mean, g, be), fmaf(v.z - mean, g, be),
+                               fmaf(v.w - mean, g, be));
+        if (r4 != nullptr) {
+          const float4 r = __ldg(r4 + i);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        y4[i] = o;
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW; i += kBnThreads) {
+        float o = fmaf(__ldg(x + off + i) - mean, g, be);
+        if (residual != nullptr) o += __ldg(residual + off + i);
+        if (relu) o = fmaxf(o, 0.f);
+        y[off + i] = o;
+      }
+    }
+  }
+}
+
+// backward pass 1: partial[c][s] = {sum dy', sum dy' * (x - mean)} with dy' = dy where the ReLU passed
+template <bool VEC>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_stats_kernel(const float *__restrict__ gy,
+                                                                  const float *__restrict__ x,
+                                                                  const float *__restrict__ y,
+                                                                  const float *__restrict__ save_mean, int relu, int B,
+                                                                  int C, int HW, double2 *__restrict__ partial) {
+  __shared__ float red[kBnThreads / 32];
+  const int c = blockIdx.x, s = blockIdx.y, splits = gridDim.y;
+  const float mean = save_mean[c];
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int b = s; b < B; b += splits) {
+    const int64_t off = ((int64_t)b * C + c) * HW;
+    if (VEC) {
+      const float4 *g4 = reinterpret_cast<const float4 *>(gy + off);
+      const float4 *x4 = reinterpret_cast<const float4 *>(x + off);
+      const float4 *y4 = reinterpret_cast<const float4 *>(y + off);
+      for (int i = threadIdx.x; i < HW / 4; i += kBnThreads) {
+        float4 d = __ldg(g4 + i);
+        const float4 v = __ldg(x4 + i);
+        if (relu) {
+          const float4 o = __ldg(y4 + i);
+          d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
+          d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+        }
+        s1 += (d.x + d.y) + (d.z + d.w);
+        s2 += (d.x * (v.x - mean) + d.y * (v.y - mean)) + (d.z * (v.z - mean) + d.w * (v.w - mean));
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW; i += kBnThreads) {
+        float d = __ldg(gy + off + i);
+        if (relu && !(__ldg(y + off + i) > 0.f)) d = 0.f;
+        s1 += d;
+        s2 += d * (__ldg(x + off + i) - mean);
+      }
+    }
+  }
+  const float t1 = block_sum(s1, red), t2 = block_sum(s2, red);
+  if (threadIdx.x == 0) partial[(int64_t)c * splits + s] = make_double2((double)t1, (double)t2);
+}
+
+// backward pass 2: dx = gamma * invstd * (dy' - mean(dy') - xhat * mean(dy' * xhat)), d_residual = dy';
+// block (c, 0) writes grad_weight = sum dy' * xhat and grad_bias = sum dy'.  Inference mode (training == 0):
+// the statistics are constants, dx = gamma * invstd * dy'.
+template <bool VEC>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
+    const float *__restrict__ gy, const float *__restrict__ x, const float *__restrict__ y,
+    const float *__restrict__ weight, const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
+    const double2 *__restrict__ partial, int training, int relu, int B, int C, int HW, float *__restrict__ gx,
+    float *__restrict__ gres, float *__restrict__ gweight, float *__restrict__ gbias) {
+  __shared__ float sh[2];
+  const int c = blockIdx.x, s = blockIdx.y, splits = gridDim.y;
+  const float mean = save_mean[c], invstd = save_invstd[c];
+  if (threadIdx.x == 0) {
+    double a = 0.0, q = 0.0;
+    for (int t = 0; t < splits; ++t) {
+      const double2 v = partial[(int64_t)c * splits + t];
+      a += v.x;
+      q += v.y;
+    }
+    if (s == 0) {
+      if (gbias != nullptr) gbias[c] = (float)a;
+      if (gweight != nullptr) gweight[c] = (float)(q * (double)invstd);
+    }
+    const double n = (double)B * HW;
+    sh[0] = training ? (float)(a / n) : 0.0f;                                        // mean of dy'
+    sh[1] = training ? (float)(q / n * (double)invstd * (double)invstd) : 0.0f;      // mean(dy' * xhat) * invstd
+  }
+  __syncthreads();
+  const float m1 = sh[0], m2 = sh[1];
+  const float k = (weight != nullptr ? weight[c] : 1.0f) * invstd;
+  for (int b = s; b < B; b += splits) {
+    const int64_t off = ((int64_t)b * C + c) * HW;
+    if (VEC) {
+      const float4 *g4 = reinterpret_cast<const float4 *>(gy + off);
+      const float4 *x4 = reinterpret_cast<const float4 *>(x + off);
+      const float4 *y4 = reinterpret_cast<const float4 *>(y + off);
+      float4 *o4 = reinterpret_cast<float4 *>(gx + off);
+      float4 *r4 = gres != nullptr ? reinterpret_cast<float4 *>(gres + off) : nullptr;
+      for (int i = threadIdx.x; i < HW / 4; i += kBnThreads) {
+        float4 d = __ldg(g4 + i);
+        const float4 v = __ldg(x4 + i);
+        if (relu) {
+          const float4 o = __ldg(y4 + i);
+          d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
+          d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+        }
+        if (r4 != nullptr) r4[i] = d;
+        o4[i] = make_float4(k * (d.x - m1 - (v.x - mean) * m2), k * (d.y - m1 - (v.y - mean) * m2),
+                            k * (d.z - m1 - (v.z - mean) * m2), k * (d.w - m1 - (v.w - mean) * m2));
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW; i += kBnThreads) {
+        float d = __ldg(gy + off + i);
+        if (relu && !(__ldg(y + off + i) > 0.f)) d = 0.f;
+        if (gres != nullptr) gres[off + i] = d;
+        gx[off + i] = k * (d - m1 - (__ldg(x + off + i) - mean) * m2);
+      }
+    }
+  }
+}
+
+inline int bn_splits(int B, int C) {
+  int s = (148 * 4 + C - 1) / C;  // about four blocks per SM in total
+  s = s < 1 ? 1 : s;
+  return s > B ? B : s;
+}
+
+inline bool aligned16(const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+int64_t bn_workspace_bytes(int B, int C) { return (int64_t)C * bn_splits(B, C) * (int64_t)sizeof(double2); }
+
+int launch_bn_forward(const float *x, const float *residual, const float *weight, const float *bias,
+                      float *running_mean, float *running_var, int training, float momentum, float eps, int relu,
+                      int B, int C, int HW, float *y, float *save_mean, float *save_invstd, void *workspace,
+                      cudaStream_t st) {
+  CIMQ_REQUIRE(x != nullptr && y != nullptr && B > 0 && C > 0 && HW > 0, "bn_forward: bad argument");
+  CIMQ_REQUIRE(training ? (save_mean && save_invstd && workspace) : (running_mean && running_var),
+               "bn_forward: missing statistics buffers");
+  const dim3 grid(C, bn_splits(B, C));
+  const bool vec = HW % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(residual);
+  double2 *part = reinterpret_cast<double2 *>(workspace);
+  if (training) {
+    if (vec) bn_stats_kernel<true><<<grid, kBnThreads, 0, st>>>(x, B, C, HW, part);
+    else bn_stats_kernel<false><<<grid, kBnThreads, 0, st>>>(x, B, C, HW, part);
+    CIMQ_CUDA_OK(cudaGetLastError());
+  }
+  if (vec)
+    bn_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(x, residual, weight, bias, running_mean, running_var, part,
+                                                       training, momentum, eps, relu, B, C, HW, y, save_mean,
+                                                       save_invstd);
+  else
+    bn_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(x, residual, weight, bias, running_mean, running_var, part,
+                                                        training, momentum, eps, relu, B, C, HW, y, save_mean,
+                                                        save_invstd);
+  CIMQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_bn_backward(const float *gy, const float *x, const float *y, const float *weight, const float *save_mean,
+                       const float *save_invstd, int training, int relu, int B, int C, int HW, float *gx, float *gres,
+                       float *gweight, float *gbias, void *workspace, cudaStream_t st) {
+  CIMQ_REQUIRE(gy && x && save_mean && save_invstd && gx && workspace && (!relu || y), "bn_backward: bad argument");
+  const dim3 grid(C, bn_splits(B, C));
+  const bool vec = HW % 4 == 0 && aligned16(gy) && aligned16(x) && aligned16(y) && aligned16(gx) && aligned16(gres);
+  double2 *part = reinterpret_cast<double2 *>(workspace);
+  if (vec) {
+    bn_bwd_stats_kernel<true><<<grid, kBnThreads, 0, st>>>(gy, x, y, save_mean, relu, B, C, HW, part);
+    bn_bwd_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(gy, x, y, weight, save_mean, save_invstd, part, training,
+                                                           relu, B, C, HW, gx, gres, gweight, gbias);
+  } else {
+    bn_bwd_stats_kernel<false><<<grid, kBnThreads, 0, st>>>(gy, x, y, save_mean, relu, B, C, HW, part);
+    bn_bwd_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(gy, x, y, weight, save_mean, save_invstd, part, training,
+                                                            relu, B, C, HW, gx, gres, gweight, gbias);
+  }
+  CIMQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cimq

@@ -154,4 +154,22 @@ int cimq_conv_psum_abs_sums(const cimq_layer_t *layer, const uint8_t *xcodes, co
                           sums, as_stream(stream));
 }
 
+int64_t cimq_bn_workspace_bytes(int32_t batch, int32_t channels) { return bn_workspace_bytes(batch, channels); }
+
+int cimq_bn_forward(const float *x, const float *residual, const float *weight, const float *bias,
+                    float *running_mean, float *running_var, int32_t training, float momentum, float eps,
+                    int32_t relu, int32_t batch, int32_t channels, int32_t hw, float *y, float *save_mean,
+                    float *save_invstd, void *workspace, void *stream) {
+  return launch_bn_forward(x, residual, weight, bias, running_mean, running_var, training, momentum, eps, relu, batch,
+                           channels, hw, y, save_mean, save_invstd, workspace, as_stream(stream));
+}
+
+int cimq_bn_backward(const float *grad_y, const float *x, const float *y, const float *weight, const float *mean,
+                     const float *invstd, int32_t training, int32_t relu, int32_t batch, int32_t channels, int32_t hw,
+                     float *grad_x, float *grad_residual, float *grad_weight, float *grad_bias, void *workspace,
+                     void *stream) {
+  return launch_bn_backward(grad_y, x, y, weight, mean, invstd, training, relu, batch, channels, hw, grad_x,
+                            grad_residual, grad_weight, grad_bias, workspace, as_stream(stream));
+}
+
 }  // extern "C"

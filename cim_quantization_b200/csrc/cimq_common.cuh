@@ -109,6 +109,14 @@ int64_t wtiles_bytes(const Geo &g);
 bool tc_forward_supported(const Geo &g);
 int tc_channel_tile_for(const Geo &g);          // output channels per CTA of the tcgen05 kernel (0: unsupported)
 int launch_im2col_lut(const Geo &g, void *lut, cudaStream_t st);
+int64_t bn_workspace_bytes(int B, int C);
+int launch_bn_forward(const float *x, const float *residual, const float *weight, const float *bias,
+                      float *running_mean, float *running_var, int training, float momentum, float eps, int relu,
+                      int B, int C, int HW, float *y, float *save_mean, float *save_invstd, void *workspace,
+                      cudaStream_t st);
+int launch_bn_backward(const float *gy, const float *x, const float *y, const float *weight, const float *save_mean,
+                       const float *save_invstd, int training, int relu, int B, int C, int HW, float *gx, float *gres,
+                       float *gweight, float *gbias, void *workspace, cudaStream_t st);
 extern long long *g_tc_debug;
 bool tc_backward_supported(const Geo &g);
 int64_t wtiles_bwd_bytes(const Geo &g);

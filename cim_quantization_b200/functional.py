@@ -226,3 +226,41 @@ def alpha_cim_initial_value(spec: LayerSpec, xcodes, wcodes, s, qp_adc: float = 
     t = 2.0 * (sums.double() / float(ranks * spec.batch * info.L)) * sw * sa / math.sqrt(qp_adc)
     t = torch.where(t == 0, sw * sa, t)
     return t.float()
+
+
+class _BatchNormAct(torch.autograd.Function):
+    """BatchNorm2d (+ residual) (+ ReLU) in two launches per direction (csrc/bn_fused.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, training, momentum, eps, relu):
+        x = x.contiguous()
+        res = residual.contiguous() if residual is not None else None
+        y, mean, invstd = _lib.bn_forward(x, res, weight, bias, running_mean, running_var, training, momentum, eps,
+                                          relu)
+        if not training:
+            mean, invstd = running_mean, torch.rsqrt(running_var + eps)
+        ctx.save_for_backward(x, y if relu else None, weight, mean, invstd)
+        ctx.training, ctx.relu, ctx.has_res = training, relu, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, weight, mean, invstd = ctx.saved_tensors
+        gx, gres, gw, gb = _lib.bn_backward(gy.contiguous(), x, y, weight, mean, invstd, ctx.training, ctx.relu,
+                                            ctx.has_res and ctx.needs_input_grad[1])
+        return (gx, gres, gw if weight is not None else None, gb if ctx.needs_input_grad[3] else None, None, None,
+                None, None, None, None)
+
+
+def batch_norm_act(x, bn: torch.nn.BatchNorm2d, residual=None, relu: bool = False):
+    """``relu?(bn(x) + residual?)`` with ``bn``'s parameters, buffers and train/eval mode."""
+    if not x.is_cuda:
+        raise RuntimeError("batch_norm_act needs CUDA tensors; there is no CPU fallback")
+    training = bn.training or not bn.track_running_stats
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    return _BatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean if bn.track_running_stats else None,
+                               bn.running_var if bn.track_running_stats else None, training, momentum, bn.eps, relu)

@@ -172,6 +172,28 @@ int cimq_conv_psums(const cimq_layer_t *layer, const uint8_t *xcodes, const int8
 int cimq_conv_psum_abs_sums(const cimq_layer_t *layer, const uint8_t *xcodes, const int8_t *wcodes,
                             unsigned long long *sums, void *stream);
 
+/* ---- batch norm (+ residual) (+ ReLU): the element-wise step either side of the CiM convolution ------
+ * The reference model is conv -> nn.BatchNorm2d -> [+ shortcut] -> F.relu (models/cifar10/resnet.py:60-66,
+ * 110-112); SURVEY 8 f-2.  fp32 NCHW, x/y/grad [B,C,HW]; torch.nn.BatchNorm2d semantics: batch statistics with
+ * biased variance in training (running buffers updated with `momentum` and the unbiased variance), running
+ * statistics otherwise.  workspace: cimq_bn_workspace_bytes(B, C) bytes. */
+int64_t cimq_bn_workspace_bytes(int32_t batch, int32_t channels);
+
+/* y = BN(x) [+ residual] [ReLU].  residual / weight / bias may be NULL; running_mean / running_var may be NULL in
+ * training (no running statistics); save_mean / save_invstd [C] receive the batch statistics in training. */
+int cimq_bn_forward(const float *x, const float *residual, const float *weight, const float *bias,
+                    float *running_mean, float *running_var, int32_t training, float momentum, float eps,
+                    int32_t relu, int32_t batch, int32_t channels, int32_t hw, float *y, float *save_mean,
+                    float *save_invstd, void *workspace, void *stream);
+
+/* Gradients of the above: grad_x [B,C,HW], grad_residual (NULL if there was none; = grad_y where the ReLU passed),
+ * grad_weight / grad_bias [C] (may be NULL).  y is the forward output (ReLU mask; may be NULL if relu == 0);
+ * mean / invstd are save_mean / save_invstd of the forward (training) or the running statistics (inference). */
+int cimq_bn_backward(const float *grad_y, const float *x, const float *y, const float *weight, const float *mean,
+                     const float *invstd, int32_t training, int32_t relu, int32_t batch, int32_t channels, int32_t hw,
+                     float *grad_x, float *grad_residual, float *grad_weight, float *grad_bias, void *workspace,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,10 +22,12 @@ def main():
     p.add_argument("--width", type=int, default=1)
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--native-bn", action="store_true", help="ATen batch norm instead of cuDNN's (measured slower here)")
+    p.add_argument("--torch-bn", action="store_true", help="torch / cuDNN batch norm instead of the fused kernels")
     a = p.parse_args()
     if a.native_bn:
         torch.backends.cudnn.enabled = False
     from cim_quantization_b200 import harness, _lib
+    harness.FUSED_BN = not a.torch_bn
     from cim_quantization_b200.distributed import FlatGradAllReducer, broadcast_parameters
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
