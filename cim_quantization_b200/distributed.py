@@ -33,11 +33,11 @@ class FlatGradAllReducer:
     def all_reduce_(self, average: bool = True):
         """In place: p.grad <- mean over ranks of p.grad (DDP semantics).  Parameters without a gradient
         contribute zeros."""
-        for v, p in zip(self.views, self.params):
-            if p.grad is None:
-                v.zero_()
-            else:
-                v.copy_(p.grad)
+        # one multi-tensor copy instead of a launch per parameter (about 80 for ResNet-20)
+        src = [p.grad if p.grad is not None else torch.zeros_like(v) for v, p in zip(self.views, self.params)]
+        todo = [(v, g) for v, g in zip(self.views, src) if g.data_ptr() != v.data_ptr()]  # already a view: in place
+        if todo:
+            torch._foreach_copy_([v for v, _ in todo], [g for _, g in todo])
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self.flat, group=self.group)
             if average:
