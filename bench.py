@@ -326,12 +326,16 @@ def run_ours(a):
     reducer = FlatGradAllReducer(params)
     flat = reducer.flat
 
-    def step():
+    def compute():
         for p in params:
             p.grad = None
         x.grad = None
         y = layer(x)
         y.backward(gy)
+        return y
+
+    def step():
+        y = compute()
         if world > 1:  # one flat all-reduce of all parameter gradients (weights + step sizes), DDP average
             reducer.all_reduce_()
         return y
@@ -345,17 +349,28 @@ def run_ours(a):
 
     runner = step
     graph = None
-    if not a.no_graph and world == 1:  # (N > 1 launches eagerly: NCCL teardown after graph capture is fragile)
-        try:  # replay the whole step as one CUDA graph: no launch gaps, no host work in the timed region
+    if not a.no_graph:
+        try:  # replay the kernels of the step as one CUDA graph: no launch gaps, no host work in the timed region.
+            # With N > 1 the gradient all-reduce stays outside the graph (NCCL work captured in a graph made the
+            # process teardown hang here): graph replay, then the eager flat all-reduce, every step.
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                step()
+                compute()
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                step()
-            runner = graph.replay
+                compute()
+            if world == 1:
+                runner = graph.replay
+            else:
+                captured = [p.grad for p in params]  # the graph rewrites these buffers on every replay
+
+                def runner():
+                    graph.replay()
+                    for p, g_ in zip(params, captured):
+                        p.grad = g_
+                    reducer.all_reduce_()
             runner()
             torch.cuda.synchronize()
         except Exception as e:  # pragma: no cover
