@@ -280,7 +280,11 @@ def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, wtiles, state, s, 
     _check(load().cimq_conv_backward(C.byref(layer), _ptr(grad_out), _ptr(xcodes), _ptr(wdigits), _ptr(wtiles),
                                      _ptr(state), _ptr(s), _ptr(binary_mask), _ptr(gxq), _ptr(gwq), _ptr(galpha), _ptr(ws),
                                      _backward_flags(flags), _stream()))
-    _count((2 if need_weight else 0) + (2 if need_input else 0) + (2 if galpha is not None else 0))
+    bflags = _backward_flags(flags)
+    fused_fold = bool(info.tc_backward) and not (bflags & (FLAG_FORCE_SIMT | FLAG_DETERMINISTIC))
+    # kernels launched: wgrad + finish, dgrad (+ col2im unless the fold is fused into its epilogue), alpha-grad + finish
+    _count((2 if need_weight else 0) + ((1 if fused_fold else 2) if need_input else 0) +
+           (2 if galpha is not None else 0))
     return gxq, gwq, galpha
 
 
