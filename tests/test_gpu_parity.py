@@ -335,6 +335,11 @@ RANDOM_CASES = [
     (32, 64, 8, 2, 1, 4, 128, 3),
     (16, 16, 12, 5, 1, 2, 128, 1),
     (3, 16, 16, 2, 1, 8, 128, 1.5),
+    # Cout = 128: beyond the register-resident operand paths of dgrad (Cout <= 64) and wgrad (Cout <= 72)
+    (32, 128, 16, 3, 1, 3, 128, 1.5),
+    (64, 128, 8, 2, 1, 3, 128, 1),
+    # several 128-pixel tiles per CTA-less grid, W = 32 rows staged by cp.async, remainder crossbar of 64 rows
+    (64, 32, 32, 2, 1, 3, 128, 1.5),
 ]
 
 
