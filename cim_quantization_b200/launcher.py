@@ -142,6 +142,7 @@ def run(argv=None) -> dict:
     ap.add_argument("--val-batches", type=int, default=2)
     ap.add_argument("--workers", type=int, default=2)
     ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE", help="extra prototxt overrides")
+    ap.add_argument("--work-dir", default=None, help="where the reference writes ./logger/... (default: a temp dir)")
     a = ap.parse_args(argv)
 
     import torch
@@ -170,7 +171,8 @@ def run(argv=None) -> dict:
         return out
 
     examples.train = timed_train
-    work = tempfile.mkdtemp(prefix="cimq_launcher_")
+    work = a.work_dir or tempfile.mkdtemp(prefix="cimq_launcher_")
+    os.makedirs(work, exist_ok=True)
     hp = os.path.join(work, "resnet_w3a3_offline.prototxt")
     overrides = dict(kv.split("=", 1) for kv in a.set)
     write_prototxt(ref_root, hp, a.epochs, a.batch_size, a.workers, overrides)
@@ -183,6 +185,11 @@ def run(argv=None) -> dict:
         os.chdir(cwd)
         sys.argv = argv0
     conv_cls = sys.modules["models._modules"].Conv2dLSQCiM
+    ckpts = []
+    for root_, _, files in os.walk(os.path.join(work, "logger")):
+        ckpts += [os.path.join(root_, f) for f in files if f.endswith(".pth.tar")]
+    stats["checkpoints"] = sorted(ckpts, key=os.path.getmtime)  # written by the reference's save_checkpoint
+    stats["work_dir"] = work
     stats.update({"impl": a.impl, "conv_class": conv_cls.__module__ + "." + conv_cls.__name__, "batch_size": a.batch_size,
                   "reference_root": ref_root})
     print("LAUNCHER_RESULT " + json.dumps(stats))

@@ -68,3 +68,32 @@ def test_reference_main_lsq_runs_unchanged_on_our_kernels():
     assert res["conv_class"] == "cim_quantization_b200.modules.lsq.Conv2dLSQCiM"
     assert len(res["epochs"]) == 1 and res["epochs"][0]["images"] == 192
     assert "after modules replacement" in r.stdout  # the reference's own surgery ran (examples/__init__.py:529)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_ref, reason="baseline/_ref not present (tools/make_baseline_ref.sh)")
+def test_reference_checkpoint_round_trip(tmp_path):
+    """SURVEY 8 f-4 (checkpoints): a `.pth.tar` written by the reference's save_checkpoint (examples/__init__.py:509-513)
+    from a model built of our modules is loaded back by its `resume` logic (process_model, :540-548) into a fresh
+    model: the validation pass main_lsq.py runs first reproduces the accuracy and loss of the end of the first run."""
+    import json
+    import re
+    import subprocess
+
+    def run(extra):
+        r = subprocess.run([sys.executable, "-m", "cim_quantization_b200.launcher", "--impl", "ours", "--train-batches", "2",
+                            "--val-batches", "1", "--batch-size", "64", "--workers", "0", "--work-dir", str(tmp_path)]
+                           + extra, cwd=ROOT, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("LAUNCHER_RESULT ")][-1][16:])
+        tests = re.findall(r"Test: \[0/1\].*?Loss (\S+) .*?Acc@1\s+(\S+)", r.stdout)
+        return r.stdout, res, tests
+
+    out1, res1, tests1 = run([])
+    assert res1["checkpoints"], "the reference's save_checkpoint wrote nothing"
+    ckpt = [c for c in res1["checkpoints"] if c.endswith("checkpoint.pth.tar")][-1]
+    out2, res2, tests2 = run(["--set", f'resume="{ckpt}"'])
+    assert "=> loading checkpoint" in out2
+    # run 1: [validation before training, validation after the epoch]; run 2 starts from the saved weights
+    assert len(tests1) == 2 and len(tests2) == 2
+    assert tests2[0] == tests1[1], (tests1, tests2)
