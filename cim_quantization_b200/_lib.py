@@ -73,6 +73,8 @@ EXPORTS = {
     "cimq_weight_prepare": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cimq_conv_forward": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "cimq_conv_forward_stochastic": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "cimq_conv_backward": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_uint32, C.c_void_p]),
@@ -262,6 +264,20 @@ def conv_forward(spec: LayerSpec, xcodes, wcodes, wtiles, table, s, binary_mask,
     layer = spec.c_layer()
     _check(load().cimq_conv_forward(C.byref(layer), _ptr(xcodes), _ptr(wcodes), _ptr(wtiles), _ptr(table), _ptr(s),
                                     _ptr(binary_mask), _ptr(out), _ptr(state), flags, _stream()))
+    _count(1)
+    return out, state
+
+
+def conv_forward_stochastic(spec: LayerSpec, xcodes, wcodes, table, s, alpha_q, seed: int, save_state: bool):
+    """Forward with the stochastic near-ADC-less read-out (lsq.py:205-220); CUDA-core kernel."""
+    info = layer_info(spec)
+    dev = xcodes.device
+    out = torch.empty((spec.batch, spec.out_channels, info.L), dtype=torch.float32, device=dev)
+    state = torch.empty(info.state_bytes // 4, dtype=torch.int32, device=dev) if save_state else None
+    layer = spec.c_layer()
+    _check(load().cimq_conv_forward_stochastic(C.byref(layer), _ptr(xcodes), _ptr(wcodes), _ptr(table), _ptr(s),
+                                               _ptr(alpha_q.contiguous()), _ptr(out), _ptr(state),
+                                               C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), _stream()))
     _count(1)
     return out, state
 

@@ -22,11 +22,42 @@ __device__ __forceinline__ int dp4a_u8s8(uint32_t a, int32_t b, int acc) {
   return d;
 }
 
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so the random stream of a partial sum depends only on
+// (seed, its index, draw number) -- reproducible for a given seed whatever the launch geometry.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// Number of successes of `n` Bernoulli(prob) draws, drawn the way the reference does (lsq.py:215-216):
+// ceil(prob - U) with U uniform in [0, 1), i.e. success iff U < prob.  `stream` selects the sigmoid (0 / 1).
+__device__ __forceinline__ int bernoulli_count(float prob, int n, unsigned long long elem, uint32_t stream, uint2 key) {
+  if (prob >= 1.0f) return n;
+  if (prob <= 0.0f) return 0;
+  int cnt = 0;
+  for (int d = 0; d < n; d += 4) {
+    const uint4 r = philox4x32(make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), (uint32_t)(d >> 2), stream), key);
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (d + t < n) cnt += ((float)(rr[t] >> 8) * 5.9604644775390625e-8f) < prob;  // 24-bit uniform
+  }
+  return cnt;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kPix * kCh) conv_simt_kernel(
     Geo g, int KS, const uint8_t *__restrict__ xcodes, const int8_t *__restrict__ wcodes,
     const int4 *__restrict__ table, const float *__restrict__ s, float *__restrict__ out,
-    uint32_t *__restrict__ state, int32_t *__restrict__ psums, unsigned long long *__restrict__ sums) {
+    uint32_t *__restrict__ state, int32_t *__restrict__ psums, unsigned long long *__restrict__ sums,
+    const float *__restrict__ alpha_q, unsigned long long seed) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint8_t *adig = smem;                                  // [NSA][kPix][KS]
   int8_t *wdig = reinterpret_cast<int8_t *>(smem + (size_t)g.NSA * kPix * KS);  // [NSW][kCh][KS]
@@ -37,7 +68,7 @@ __global__ void __launch_bounds__(kPix * kCh) conv_simt_kernel(
   const bool valid = (m < g.M) && (c < g.Cout);
   const int b = m / g.L, l = m % g.L;
   float sa = 1.f, sw = 1.f;
-  if (MODE == SIMT_FORWARD) { sa = s[0]; sw = s[1]; }
+  if (MODE == SIMT_FORWARD || MODE == SIMT_FORWARD_STOCH) { sa = s[0]; sw = s[1]; }
 
   float acc = 0.0f;
   for (int i = 0; i < g.NX; ++i) {
@@ -104,7 +135,23 @@ __global__ void __launch_bounds__(kPix * kCh) conv_simt_kernel(
           } else {
             int pos = p >= te.x, neg = p <= -te.x;                   // ternary / sign code
             clip = (p >= te.y) || (p <= -te.y);
-            acc += pos ? amp : (neg ? -amp : 0.0f);
+            if (MODE == SIMT_FORWARD_STOCH) {
+              // stochastic near-ADC-less read-out (lsq.py:205-220): two sigmoids of sharpness 0.01 around
+              // +-alpha/2, 50 Bernoulli draws each, code = clamp(round(n1/50 + n2/50 - 1), -1, 1).  Only the
+              // output is stochastic: the backward uses the deterministic state below (lsq.py:310-332).
+              const float a = __ldg(&alpha_q[e]);
+              const float v = __fmul_rn(__fmul_rn(psum_as_stored(p), sw), sa);               // lsq.py:169, 195
+              const float s1 = 1.0f / (1.0f + expf(-__fdiv_rn(v - 0.5f * a, 0.01f)));
+              const float s2 = 1.0f / (1.0f + expf(-__fdiv_rn(v + 0.5f * a, 0.01f)));
+              const unsigned long long elem =
+                  (((((unsigned long long)b * g.NX + i) * g.NSW + k) * g.NSA + j) * g.L + l) * g.Cout + c;
+              const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+              const int n12 = bernoulli_count(s1, 50, elem, 0u, key) + bernoulli_count(s2, 50, elem, 1u, key);
+              // round half to even of (n12 - 50) / 50: +1 above 0.5, -1 below -0.5
+              acc += n12 > 75 ? amp : (n12 < 25 ? -amp : 0.0f);
+            } else {
+              acc += pos ? amp : (neg ? -amp : 0.0f);
+            }
             const int sq = state_pair(g, k, j);
             if (pos) { int bit = sq; st[bit >> 5] |= 1u << (bit & 31); }
             if (neg) { int bit = g.pairs + sq; st[bit >> 5] |= 1u << (bit & 31); }
@@ -113,19 +160,19 @@ __global__ void __launch_bounds__(kPix * kCh) conv_simt_kernel(
         }
       }
     }
-    if (MODE == SIMT_FORWARD && valid && state != nullptr) {
+    if ((MODE == SIMT_FORWARD || MODE == SIMT_FORWARD_STOCH) && valid && state != nullptr) {
       for (int w = 0; w < g.state_words; ++w)
         state[(((int64_t)i * g.Cout + c) * g.state_words + w) * g.M + m] = st[w];
     }
   }
-  if (MODE == SIMT_FORWARD && valid) out[((int64_t)b * g.Cout + c) * g.L + l] = acc;
+  if ((MODE == SIMT_FORWARD || MODE == SIMT_FORWARD_STOCH) && valid) out[((int64_t)b * g.Cout + c) * g.L + l] = acc;
 }
 
 }  // namespace
 
 int launch_conv_simt(const Geo &g, int mode, const uint8_t *xcodes, const int8_t *wcodes, const void *table,
                      const float *s, const int8_t *, float *out, uint32_t *state, int32_t *psums,
-                     unsigned long long *sums, cudaStream_t st) {
+                     unsigned long long *sums, cudaStream_t st, const float *alpha_q, unsigned long long seed) {
   CIMQ_REQUIRE(g.state_words <= kMaxStateWords, "too many slice pairs (%d) for the ADC state", g.pairs);
   int rowsmax = g.xbar < g.F ? g.xbar : g.F;
   int ks4 = (rowsmax + 3) / 4;
@@ -139,11 +186,17 @@ int launch_conv_simt(const Geo &g, int mode, const uint8_t *xcodes, const int8_t
   do {                                                                                                      \
     CIMQ_CUDA_OK(cudaFuncSetAttribute(conv_simt_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)smem));                                                          \
-    conv_simt_kernel<MODE><<<grid, block, smem, st>>>(g, KS, xcodes, wcodes, tab, s, out, state, psums, sums); \
+    conv_simt_kernel<MODE><<<grid, block, smem, st>>>(g, KS, xcodes, wcodes, tab, s, out, state, psums, sums,  \
+                                                      alpha_q, seed);                                           \
   } while (0)
   if (mode == SIMT_FORWARD) {
     CIMQ_REQUIRE(table != nullptr && s != nullptr && out != nullptr, "conv_forward: NULL argument");
     CIMQ_LAUNCH_SIMT(SIMT_FORWARD);
+  } else if (mode == SIMT_FORWARD_STOCH) {
+    CIMQ_REQUIRE(table != nullptr && s != nullptr && out != nullptr && alpha_q != nullptr,
+                 "conv_forward_stochastic: NULL argument");
+    CIMQ_REQUIRE(g.adc_mode == CIMQ_ADC_TERNARY, "the stochastic read-out exists for adcbits 1.5 only (lsq.py:203-220)");
+    CIMQ_LAUNCH_SIMT(SIMT_FORWARD_STOCH);
   } else if (mode == SIMT_PSUMS) {
     CIMQ_REQUIRE(psums != nullptr, "conv_psums: NULL output");
     CIMQ_LAUNCH_SIMT(SIMT_PSUMS);

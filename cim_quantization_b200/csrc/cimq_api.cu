@@ -126,6 +126,16 @@ int cimq_conv_forward(const cimq_layer_t *layer, const uint8_t *xcodes, const in
                           as_stream(stream));
 }
 
+int cimq_conv_forward_stochastic(const cimq_layer_t *layer, const uint8_t *xcodes, const int8_t *wcodes,
+                                 const void *table, const float *s, const float *alpha_q, float *out,
+                                 uint32_t *state, uint64_t seed, void *stream) {
+  Geo g;
+  if (make_geo(layer, &g)) return 1;
+  CIMQ_REQUIRE(xcodes && wcodes && table && s && alpha_q && out, "conv_forward_stochastic: NULL argument");
+  return launch_conv_simt(g, SIMT_FORWARD_STOCH, xcodes, wcodes, table, s, nullptr, out, state, nullptr, nullptr,
+                          as_stream(stream), alpha_q, (unsigned long long)seed);
+}
+
 int cimq_conv_backward(const cimq_layer_t *layer, const float *grad_out, const uint8_t *xcodes,
                        const float *wdigits, const void *wtiles, const uint32_t *state, const float *s,
                        const int8_t *binary_mask, float *grad_xq, float *grad_wq, float *grad_alpha_q,

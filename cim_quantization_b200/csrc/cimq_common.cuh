@@ -137,10 +137,11 @@ struct WtLayout {
 };
 WtLayout wt_layout(const Geo &g);
 
-enum SimtMode { SIMT_FORWARD = 0, SIMT_PSUMS = 1, SIMT_ABS_SUMS = 2 };
+enum SimtMode { SIMT_FORWARD = 0, SIMT_PSUMS = 1, SIMT_ABS_SUMS = 2, SIMT_FORWARD_STOCH = 3 };
 int launch_conv_simt(const Geo &g, int mode, const uint8_t *xcodes, const int8_t *wcodes, const void *table,
-                     const float *s, const int8_t *mask, float *out, uint32_t *state, int32_t *psums,
-                     unsigned long long *sums, cudaStream_t st);
+                     const float *s, const int8_t *binary_mask, float *out, uint32_t *state, int32_t *psums,
+                     unsigned long long *sums, cudaStream_t st, const float *alpha_q = nullptr,
+                     unsigned long long seed = 0);
 int launch_conv_tc_forward(const Geo &g, const uint8_t *xcodes, const void *wtiles, const void *table,
                            const float *s, const int8_t *mask, float *out, uint32_t *state, cudaStream_t st);
 

@@ -59,8 +59,8 @@ class get_cim_output_signed(Function):
     def forward(ctx, x, w, conv_stride, conv_padding, conv_dilation, act_bits, act_bit_slice, weight_bits,
                 weight_bit_slice, adc_bits, arr, binary_mask, alpha_cim, weight_scaling_factor,
                 act_scaling_factor, stochastic, signed_act):
-        if stochastic:
-            raise NotImplementedError("stochastic near-ADC-less sampling (lsq.py:205-220) is not implemented")
+        if stochastic and (adc_bits != 1.5 or alpha_cim is None):
+            stochastic = False  # the reference only samples in the adcbits 1.5 branch (lsq.py:203-205)
         if _pair0(conv_dilation) != 1:
             raise ValueError("dilation != 1 is not supported (the reference's Unfold ignores it, lsq.py:141)")
         _require_cuda(x, w)
@@ -80,7 +80,11 @@ class get_cim_output_signed(Function):
         table = _lib.adc_table(spec, s, alpha_q, mask)
         need_bwd = any(ctx.needs_input_grad)
         wdigits, wtiles = _lib.weight_prepare(spec, wcodes, want_digits=need_bwd and not info.tc_backward)
-        out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd)
+        if stochastic:  # sampled read-out, lsq.py:205-220
+            out, state = _lib.conv_forward_stochastic(spec, xcodes, wcodes, table, s, alpha_q, _stochastic_seed(),
+                                                      save_state=need_bwd)
+        else:
+            out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd)
         ctx.spec, ctx.has_alpha, ctx.w_shape = spec, has_alpha, tuple(w.shape)
         ctx.save_for_backward(xcodes, wdigits, wtiles, state, s, mask)
         return out.transpose(1, 2)  # [B, L, Cout] like lsq.py:233 (a view of the NCHW buffer)
@@ -103,7 +107,7 @@ class _CimConv2dFused(Function):
 
     @staticmethod
     def forward(ctx, x, weight, alpha_act, alpha_weight, alpha_q, binary_mask, stride, padding, nbits_a,
-                abitslice, nbits_w, wbitslice, xbar, adcbits, flags):
+                abitslice, nbits_w, wbitslice, xbar, adcbits, flags, stochastic_seed=None):
         _require_cuda(x, weight, alpha_act, alpha_weight)
         x = x.contiguous()
         weight = weight.contiguous()
@@ -123,8 +127,12 @@ class _CimConv2dFused(Function):
         need_bwd = any(ctx.needs_input_grad)
         simt = bool(flags & _lib.FLAG_FORCE_SIMT)
         wdigits, wtiles = _lib.weight_prepare(spec, wcodes, want_digits=need_bwd and (simt or not info.tc_backward))
-        out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd,
-                                       flags=flags)
+        if stochastic_seed is not None and has_alpha and adcbits == 1.5:  # lsq.py:203-220
+            out, state = _lib.conv_forward_stochastic(spec, xcodes, wcodes, table, s, alpha_q.detach(),
+                                                      stochastic_seed, save_state=need_bwd)
+        else:
+            out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd,
+                                           flags=flags)
         ctx.spec, ctx.has_alpha, ctx.flags = spec, has_alpha, flags
         ctx.consts = (qp_a, qn_w, qp_w, ga, gw)
         ctx.save_for_backward(x, weight, xcodes, wdigits, wtiles, state, s, mask)
@@ -144,14 +152,21 @@ class _CimConv2dFused(Function):
         if need_x:
             gx, g_aa = _lib.lsq_backward(gxq, x, s[0:1], 0, qp_a, ga)
         gwt, g_aw = _lib.lsq_backward(gwq.view_as(weight), weight, s[1:2], qn_w, qp_w, gw)
-        return (gx, gwt, g_aa, g_aw, galpha) + (None,) * 10
+        return (gx, gwt, g_aa, g_aw, galpha) + (None,) * 11
+
+
+def _stochastic_seed() -> int:
+    """A fresh 62-bit seed from torch's CPU generator (so torch.manual_seed makes the sampling reproducible)."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 
 def cim_conv2d(x, weight, alpha_act, alpha_weight, alpha_q, binary_mask, stride, padding, nbits_a, abitslice,
-               nbits_w, wbitslice, xbar, adcbits, flags: int = 0):
-    """Fused CiM convolution of ``Conv2dLSQCiM`` (lsq.py:546-581): returns ``[B, Cout, OH, OW]``."""
+               nbits_w, wbitslice, xbar, adcbits, flags: int = 0, stochastic: bool = False):
+    """Fused CiM convolution of ``Conv2dLSQCiM`` (lsq.py:546-581): returns ``[B, Cout, OH, OW]``.
+    ``stochastic``: the sampled near-ADC-less read-out of lsq.py:205-220 (adcbits 1.5 only; CUDA-core kernel)."""
     return _CimConv2dFused.apply(x, weight, alpha_act, alpha_weight, alpha_q, binary_mask, stride, padding, nbits_a,
-                                 abitslice, nbits_w, wbitslice, xbar, adcbits, flags)
+                                 abitslice, nbits_w, wbitslice, xbar, adcbits, flags,
+                                 _stochastic_seed() if stochastic else None)
 
 
 class _LsqFakeQuant(Function):

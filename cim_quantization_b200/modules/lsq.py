@@ -78,11 +78,9 @@ class _CiMForward:
         if self.training and not init_cim_done and self.alpha_cim is not None:
             self._lazy_init_cim(x, w, stride, padding)
         alpha_q = self._alpha_q() if self.alpha_cim is not None else None
-        if self.stochastic_quant:
-            raise NotImplementedError("stochastic_quant (lsq.py:205-220) is not implemented")
         return CF.cim_conv2d(x, w, self.alpha_act, self.alpha_weight, alpha_q, self.binary_mask, stride, padding,
                              self.nbits_a, self.abitslice, self.nbits_w, self.wbitslice, self.xbar, self.adcbits,
-                             self.kernel_flags)
+                             self.kernel_flags, stochastic=bool(self.stochastic_quant))
 
 
 class Conv2dLSQCiM(_Conv2dQCiM, _CiMForward):

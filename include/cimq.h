@@ -155,6 +155,16 @@ int cimq_conv_forward(const cimq_layer_t *layer, const uint8_t *xcodes, const in
                       const void *table, const float *s, const int8_t *binary_mask, float *out, uint32_t *state,
                       uint32_t flags, void *stream);
 
+/* The same with the stochastic near-ADC-less read-out of lsq.py:205-220 (adcbits 1.5 only): every partial sum is
+ * read through two sigmoids of sharpness 0.01 around +-alpha_q/2, 50 Bernoulli draws each, code =
+ * clamp(round(n1/50 + n2/50 - 1), -1, 1).  alpha_q [NX,NSW,NSA,Cout].  The draws come from a counter-based
+ * generator keyed by (seed, index of the partial sum): reproducible for a seed, not bit-comparable with the
+ * reference's torch RNG (statistical parity).  `state` (for the backward) is the deterministic one, as in the
+ * reference, whose backward does not see the sampled code.  CUDA-core kernel. */
+int cimq_conv_forward_stochastic(const cimq_layer_t *layer, const uint8_t *xcodes, const int8_t *wcodes,
+                                 const void *table, const float *s, const float *alpha_q, float *out,
+                                 uint32_t *state, uint64_t seed, void *stream);
+
 /* get_cim_output_signed.backward (lsq.py:244-386): grad_xq [B,Cin,H,W], grad_wq [Cout,F],
  * grad_alpha_q [NX,NSW,NSA,Cout] (NULL for CIMQ_ADC_MULTIBIT).  wdigits is needed by the CUDA-core kernels,
  * wtiles by the tcgen05 kernels; pass both to let the library choose. */

@@ -462,3 +462,37 @@ def module_forward_backward(cfg: CimConfig, x, weight, alpha_act, alpha_weight, 
     if cfg.has_alpha_cim:
         res["grad_alpha_cim"] = quantize_alpha_backward(alpha_cim, gaq, aux)
     return res
+
+
+def stochastic_code_expectation(cfg: CimConfig, ps_int, s_w, s_a, alpha_q, num_iter: int = 50, sharpness: float = 0.01):
+    """Mean and variance of the sampled ternary code of lsq.py:205-220 for every partial sum.
+
+    The reference draws ``n1 ~ Binomial(50, sigmoid((v - alpha/2)/0.01))`` and ``n2 ~ Binomial(50, sigmoid((v +
+    alpha/2)/0.01))`` (``ceil(p - U)`` is 1 iff ``U < p``) and outputs ``clamp(round(n1/50 + n2/50 - 1), -1, 1)``:
+    +1 iff ``n1 + n2 > 75``, -1 iff ``n1 + n2 < 25`` (round half to even).  The distribution of ``n1 + n2`` is the
+    convolution of the two binomials.  Returns ``(mean, var)`` with the shape of ``ps_int``
+    ``[B,NX,NSW,NSA,L,Cout]``."""
+    from math import comb
+    v = _scaled_psums(ps_int, s_w, s_a)
+    a = np.asarray(alpha_q, dtype=F32).reshape(1, cfg.num_xbars, cfg.nsw, cfg.nsa, 1, cfg.out_channels)
+    with np.errstate(over="ignore"):
+        p1 = 1.0 / (1.0 + np.exp(-((v - F32(0.5) * a) / F32(sharpness)).astype(np.float64)))
+        p2 = 1.0 / (1.0 + np.exp(-((v + F32(0.5) * a) / F32(sharpness)).astype(np.float64)))
+    k = np.arange(num_iter + 1)
+    binom = np.array([comb(num_iter, int(i)) for i in k], dtype=np.float64)
+
+    def pmf(p):  # [..., num_iter+1]
+        p = np.clip(p, 0.0, 1.0)[..., None]
+        return binom * p ** k * (1.0 - p) ** (num_iter - k)
+
+    flat1, flat2 = pmf(p1).reshape(-1, num_iter + 1), pmf(p2).reshape(-1, num_iter + 1)
+    # P(n1 + n2 = t): row-wise convolution
+    conv = np.zeros((flat1.shape[0], 2 * num_iter + 1))
+    for i in range(num_iter + 1):
+        conv[:, i:i + num_iter + 1] += flat1[:, i:i + 1] * flat2
+    hi = int(round(1.5 * num_iter))  # 75
+    lo = int(round(0.5 * num_iter))  # 25
+    p_plus, p_minus = conv[:, hi + 1:].sum(1), conv[:, :lo].sum(1)
+    mean = (p_plus - p_minus).reshape(v.shape)
+    var = (p_plus + p_minus).reshape(v.shape) - mean ** 2
+    return mean, var
