@@ -61,6 +61,7 @@ struct BwdParams {
   int rk, prow;      // wgrad staging: rows per channel slot, staged row of (output row o, tap row ky) = o*prow + ky
   int async_rows;    // wgrad staging: rows arrive by 16-byte cp.async copies issued one chunk ahead
   uint32_t raw_bytes;
+  int sdiv;          // virtual 128-row chunks per crossbar: the ADC state of virtual chunk i is that of crossbar i / sdiv
   long long *debug;  // per-role cycle counters (builds with TIMERS=1 only)
   int cached;   // dgrad: 1 = producers keep grad_out of the tile and the state words of the chunk in registers
   uint32_t pw_off;  // dgrad: byte offset of the pass-weight table inside the raw region
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
               // after the last slice of a chunk the state registers take the next chunk (or the next tile's first)
               const uint32_t *sp_next = nullptr;
               if (last_k) {
-                if (i + 1 < g.NX) sp_next = stp + (size_t)(i + 1) * g.Cout * sstride;
+                if (i + 1 < g.NX) sp_next = stp + (size_t)((i + 1) / P.sdiv) * g.Cout * sstride;
                 else if (more_tiles) sp_next = stp_n;
               }
               const float *gp_next = (last_k && i + 1 == g.NX && more_tiles) ? gop_n : nullptr;
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
       float gv_n[8];
       auto prefetch = [&](int i, int cg) {
         // one 64-bit multiply per group of eight channels, then pointer increments
-        const uint32_t *sp = stp + (size_t)(i * g.Cout + h * cpt + cg) * sstride;
+        const uint32_t *sp = stp + (size_t)((i / P.sdiv) * g.Cout + h * cpt + cg) * sstride;
         const float *gp = gop + (size_t)cg * g.L;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -613,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     };
     auto load_state = [&](const int4 &pt, int mt_, int i, int co, uint32_t (&sw)[8]) {
       const int64_t mg = (int64_t)mt_ * kTcTileM + gpg * 8;
-      const uint32_t *sp = P.state + ((int64_t)(i * g.Cout + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
+      const uint32_t *sp = P.state + ((int64_t)((i / P.sdiv) * g.Cout + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
       if (pt.w == 1) {
         const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(sp)), s1 = __ldg(reinterpret_cast<const uint4 *>(sp) + 1);
         sw[0] = s0.x; sw[1] = s0.y; sw[2] = s0.z; sw[3] = s0.w;
@@ -894,7 +895,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           const int64_t mg = m0 + pg * 8;
           // loads of the next channel are issued before the current one is processed (latency hiding)
           auto load_g = [&](int co, float (&gv)[8], uint32_t (&sw)[8][CBits::CWN]) {
-            const uint32_t *sp = P.state + ((int64_t)(i * g.Cout + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
+            const uint32_t *sp = P.state + ((int64_t)((i / P.sdiv) * g.Cout + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
             if (pt.w == 1) {
               const float4 *gp = reinterpret_cast<const float4 *>(
                   P.go + ((int64_t)pt.x * g.Cout + co) * g.L + pt.y * g.OW + pt.z);
@@ -1118,21 +1119,42 @@ inline bool bwd_slices_supported(const Geo &g) {
     else { KERNEL(8, 8, false, __VA_ARGS__); }                                                   \
   } while (0)
 
+// Crossbars deeper than 128 rows are processed as 128-row "virtual" chunks: neither gradient couples the rows of
+// a crossbar (dgrad: the rows are the N dimension; wgrad: the rows are the M dimension), only the pass mask --
+// the ADC state -- is shared, and virtual chunk i reads the state of crossbar i / sdiv.  Needs xbar % 128 == 0.
+static Geo bwd_virtual_geo(const Geo &g, int *sdiv) {
+  Geo v = g;
+  *sdiv = 1;
+  const int rows = g.xbar < g.F ? g.xbar : g.F;
+  if (rows > 128 && g.xbar % 128 == 0) {
+    *sdiv = g.xbar / 128;
+    v.xbar = 128;
+    v.NX = (g.F + 127) / 128;
+  }
+  return v;
+}
+
 bool tc_backward_supported(const Geo &g) {
   if (!bwd_slices_supported(g)) return false;
   if (g.Cout % 16 != 0 || g.Cout > 128) return false;
   if (g.pairs > kMaxPairs) return false;
   const int rows = g.xbar < g.F ? g.xbar : g.F;
-  if (rows > 128) return false;  // wgrad M tile is one crossbar of <= 128 rows; dgrad N <= 128 keeps 3 stages
+  // wgrad M tile / dgrad N tile is one (virtual) chunk of <= 128 rows
+  if (rows > 128 && g.xbar % 128 != 0) return false;
   if ((int64_t)g.B * g.Cin * g.H * g.W >= (1ll << 31)) return false;
   return true;
 }
 
-int64_t wtiles_bwd_bytes(const Geo &g) {
-  return tc_backward_supported(g) ? (int64_t)g.NX * g.NSW * tc_nf(g) * g.Cout * 2 : 0;
+int64_t wtiles_bwd_bytes(const Geo &g0) {
+  if (!tc_backward_supported(g0)) return 0;
+  int sdiv;
+  const Geo g = bwd_virtual_geo(g0, &sdiv);
+  return (int64_t)g.NX * g.NSW * tc_nf(g) * g.Cout * 2;
 }
 
-int launch_weight_tiles_bwd(const Geo &g, const int8_t *wcodes, void *tiles, cudaStream_t st) {
+int launch_weight_tiles_bwd(const Geo &g0, const int8_t *wcodes, void *tiles, cudaStream_t st) {
+  int sdiv;
+  const Geo g = bwd_virtual_geo(g0, &sdiv);
   const int64_t n = (int64_t)g.NX * g.NSW * tc_nf(g) * g.Cout;
   weight_tiles_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, tc_nf(g), wcodes,
                                                                  reinterpret_cast<uint16_t *>(tiles));
@@ -1140,7 +1162,9 @@ int launch_weight_tiles_bwd(const Geo &g, const int8_t *wcodes, void *tiles, cud
   return 0;
 }
 
-int64_t bwd_tc_partial_bytes(const Geo &g) {
+int64_t bwd_tc_partial_bytes(const Geo &g0) {
+  int sdiv;
+  const Geo g = bwd_virtual_geo(g0, &sdiv);
   const int mtiles = (g.M + kTcTileM - 1) / kTcTileM;
   const int nxg = wgrad_chunks_per_group(g);
   const int groups = (g.NX + nxg - 1) / nxg;
@@ -1155,10 +1179,11 @@ bool bwd_input_tc_can_fold(const Geo &g) {
   return g.K <= 5 && (int64_t)g.Cin * g.H * g.W < (1 << 24) && g.F <= 4096;
 }
 
-int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, const void *wtb, const float *s,
+int launch_bwd_input_tc(const Geo &g0, const float *go, const uint32_t *state, const void *wtb, const float *s,
                         const int8_t *mask, float *out, int fold, cudaStream_t st) {
   BwdParams P;
   memset(&P, 0, sizeof(P));
+  const Geo g = bwd_virtual_geo(g0, &P.sdiv);
   P.g = g;
   P.Kc = g.Cout;
   P.Nf = tc_nf(g);
@@ -1195,10 +1220,11 @@ int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, co
   return 0;
 }
 
-int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, const uint32_t *state,
+int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, const uint32_t *state,
                          const float *s, const int8_t *mask, float *partial, float *gw, cudaStream_t st) {
   BwdParams P;
   memset(&P, 0, sizeof(P));
+  const Geo g = bwd_virtual_geo(g0, &P.sdiv);
   P.g = g;
   P.Kc = g.Cout;
   P.mtiles = (g.M + kTcTileM - 1) / kTcTileM;

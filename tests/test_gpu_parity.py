@@ -490,13 +490,15 @@ def test_backward_deterministic_fold(name):
     assert rel_err(fused, runs[0]) < 1e-6
 
 
-def test_full_size_backward_tc_equals_simt():
-    """Full microbench shape (3x3 64->64 32x32 B=256 w3a3 xbar128 adc1.5): the tcgen05 dgrad / wgrad kernels
-    (register-resident operands, staged rows, fused fold) against the CUDA-core backward on the same ADC state."""
+@pytest.mark.parametrize("xbar", [128, 256])
+def test_full_size_backward_tc_equals_simt(xbar):
+    """Full microbench shape (3x3 64->64 32x32 B=256 w3a3 adc1.5): the tcgen05 dgrad / wgrad kernels
+    (register-resident operands, staged rows, fused fold; xbar 256 as 128-row virtual chunks sharing the ADC state)
+    against the CUDA-core backward on the same ADC state."""
     L = _lib()
     B, C, HW = 256, 64, 32
     cfg = O.CimConfig(in_channels=C, out_channels=C, kernel=3, stride=1, padding=1, nbits_w=3, nbits_a=3,
-                      wbitslice=1, abitslice=1, xbar=128, adcbits=1.5)
+                      wbitslice=1, abitslice=1, xbar=xbar, adcbits=1.5)
     spec = _spec(cfg, HW, B)
     info = L.layer_info(spec)
     assert info.tc_backward
