@@ -612,9 +612,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         }
       }
     };
-    auto load_state = [&](const int4 &pt, int mt_, int i, int co, uint32_t (&sw)[8]) {
+    auto load_state = [&](const int4 &pt, int mt_, int i, int co, uint32_t (&sw)[8]) {  // i: crossbar (state) index
       const int64_t mg = (int64_t)mt_ * kTcTileM + gpg * 8;
-      const uint32_t *sp = P.state + ((int64_t)((i / P.sdiv) * g.Cout + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
+      const uint32_t *sp = P.state + ((int64_t)(i * g.Cout + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
       if (pt.w == 1) {
         const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(sp)), s1 = __ldg(reinterpret_cast<const uint4 *>(sp) + 1);
         sw[0] = s0.x; sw[1] = s0.y; sw[2] = s0.z; sw[3] = s0.w;
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
       for (int q = 0; q < 3; ++q)
         if (gco0 + 24 * q < Kc) {
           load_go(gpt, blockIdx.x, gco0 + 24 * q, gvc[q]);
-          load_state(gpt, blockIdx.x, i_begin, gco0 + 24 * q, swc[q]);
+          load_state(gpt, blockIdx.x, i_begin / P.sdiv, gco0 + 24 * q, swc[q]);
         }
     }
     for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
@@ -707,6 +707,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         int ci = 0, ky = 0, kx = 0;
         if (frow) { const int f = lo + fr; ci = f / g.KK; const int tap = f % g.KK; ky = tap / g.K; kx = tap % g.K; }
         const int c_lo = lo / g.KK;
+        const int st_next = (i + 1) / P.sdiv, st_first = i_begin / P.sdiv;  // state (crossbar) index of the next chunk
         uint8_t *raw = cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes;
         const long long ts0 = CIMQ_TB();
         if (P.async_rows) {
@@ -869,9 +870,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
                     v[e] = gvc[q][e] *
                            lds_const_f32(lutj + 4u * ((swc[q][e] >> (CBits::CB + j * NSW)) & ((1u << NSW) - 1u)));
                   if (last_j) {  // last use of this item's state words (and, at the last chunk, of its grad_out)
-                    if (next_chunk) load_state(gpt, mt, i + 1, co, swc[q]);
+                    if (next_chunk) load_state(gpt, mt, st_next, co, swc[q]);
                     else if (next_tile) {
-                      load_state(gpt_n, mt_n, i_begin, co, swc[q]);
+                      load_state(gpt_n, mt_n, st_first, co, swc[q]);
                       load_go(gpt_n, mt_n, co, gvc[q]);
                     }
                   }
