@@ -61,6 +61,7 @@ struct BwdParams {
   int rk, prow;      // wgrad staging: rows per channel slot, staged row of (output row o, tap row ky) = o*prow + ky
   int async_rows;    // wgrad staging: rows arrive by 16-byte cp.async copies issued one chunk ahead
   uint32_t raw_bytes;
+  int co0;           // first output channel of this launch (layers with Cout > 128 run as blocks of 128 channels)
   int sdiv;          // virtual 128-row chunks per crossbar: the ADC state of virtual chunk i is that of crossbar i / sdiv
   long long *debug;  // per-role cycle counters (builds with TIMERS=1 only)
   int cached;   // dgrad: 1 = producers keep grad_out of the tile and the state words of the chunk in registers
@@ -242,8 +243,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
           const int64_t m = (int64_t)mt * kTcTileM + r;
           const bool live = m < g.M;
           const int b = live ? (int)(m / g.L) : 0, l = live ? (int)(m % g.L) : 0;
-          gop = P.go + ((int64_t)b * g.Cout + h * cpt) * g.L + l;
-          stp = P.state + (int64_t)CBits::CW0 * g.M + (live ? m : 0) + (size_t)(h * cpt) * sstride;
+          gop = P.go + ((int64_t)b * g.Cout + P.co0 + h * cpt) * g.L + l;
+          stp = P.state + (int64_t)CBits::CW0 * g.M + (live ? m : 0) + (size_t)(P.co0 + h * cpt) * sstride;
         };
         const float *gop = nullptr, *gop_n = nullptr;
         const uint32_t *stp = nullptr, *stp_n = nullptr;
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
       const int64_t m = (int64_t)mt * kTcTileM + r;
       const bool live = m < g.M;
       const int b = live ? (int)(m / g.L) : 0, l = live ? (int)(m % g.L) : 0;
-      const float *gop = P.go + ((int64_t)b * g.Cout + h * cpt) * g.L + l;
+      const float *gop = P.go + ((int64_t)b * g.Cout + P.co0 + h * cpt) * g.L + l;
       // rows past the last pixel read pixel 0 (valid addresses, no predicates on the loads) and are zeroed
       // through the slice weights below
       const uint32_t *stp = P.state + (int64_t)CBits::CW0 * g.M + (live ? m : 0);
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
       float gv_n[8];
       auto prefetch = [&](int i, int cg) {
         // one 64-bit multiply per group of eight channels, then pointer increments
-        const uint32_t *sp = stp + (size_t)((i / P.sdiv) * g.Cout + h * cpt + cg) * sstride;
+        const uint32_t *sp = stp + (size_t)((i / P.sdiv) * g.Cout + P.co0 + h * cpt + cg) * sstride;
         const float *gp = gop + (size_t)cg * g.L;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -499,7 +500,11 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
             float *dst = P.out + ((int64_t)eb * g.F + lo + c0) * g.L + el;
 #pragma unroll
             for (int cc = 0; cc < 32; ++cc)
-              if (c0 + cc < rows) dst[(int64_t)cc * g.L] = __int_as_float(v[cc]) * scale;
+              if (c0 + cc < rows) {
+                // later channel blocks (Cout > 128) add to what the first one wrote: same thread, launch order
+                const float t = __int_as_float(v[cc]) * scale;
+                dst[(int64_t)cc * g.L] = P.co0 > 0 ? dst[(int64_t)cc * g.L] + t : t;
+              }
           }
         }
         tc_fence_before();
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     };
     auto load_go = [&](const int4 &pt, int mt_, int co, float (&gv)[8]) {
       if (pt.w == 1) {
-        const float4 *gp = reinterpret_cast<const float4 *>(P.go + ((int64_t)pt.x * g.Cout + co) * g.L +
+        const float4 *gp = reinterpret_cast<const float4 *>(P.go + ((int64_t)pt.x * g.Cout + P.co0 + co) * g.L +
                                                             pt.y * g.OW + pt.z);
         const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
         gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w;
@@ -608,13 +613,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         for (int e = 0; e < 8; ++e) {
           const int64_t m = (int64_t)mt_ * kTcTileM + gpg * 8 + e;
           gv[e] = 0.0f;
-          if (m < g.M) gv[e] = __ldg(&P.go[((int64_t)(m / g.L) * g.Cout + co) * g.L + (m % g.L)]);
+          if (m < g.M) gv[e] = __ldg(&P.go[((int64_t)(m / g.L) * g.Cout + P.co0 + co) * g.L + (m % g.L)]);
         }
       }
     };
     auto load_state = [&](const int4 &pt, int mt_, int i, int co, uint32_t (&sw)[8]) {  // i: crossbar (state) index
       const int64_t mg = (int64_t)mt_ * kTcTileM + gpg * 8;
-      const uint32_t *sp = P.state + ((int64_t)(i * g.Cout + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
+      const uint32_t *sp = P.state + ((int64_t)(i * g.Cout + P.co0 + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
       if (pt.w == 1) {
         const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(sp)), s1 = __ldg(reinterpret_cast<const uint4 *>(sp) + 1);
         sw[0] = s0.x; sw[1] = s0.y; sw[2] = s0.z; sw[3] = s0.w;
@@ -896,10 +901,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           const int64_t mg = m0 + pg * 8;
           // loads of the next channel are issued before the current one is processed (latency hiding)
           auto load_g = [&](int co, float (&gv)[8], uint32_t (&sw)[8][CBits::CWN]) {
-            const uint32_t *sp = P.state + ((int64_t)((i / P.sdiv) * g.Cout + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
+            const uint32_t *sp = P.state + ((int64_t)((i / P.sdiv) * g.Cout + P.co0 + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
             if (pt.w == 1) {
               const float4 *gp = reinterpret_cast<const float4 *>(
-                  P.go + ((int64_t)pt.x * g.Cout + co) * g.L + pt.y * g.OW + pt.z);
+                  P.go + ((int64_t)pt.x * g.Cout + P.co0 + co) * g.L + pt.y * g.OW + pt.z);
               const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
               gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w;
               gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
@@ -919,7 +924,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
                 for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = 0xffffffffu;
                 if (m < g.M) {
                   const int b = (int)(m / g.L), l = (int)(m % g.L);
-                  gv[e] = __ldg(&P.go[((int64_t)b * g.Cout + co) * g.L + l]);
+                  gv[e] = __ldg(&P.go[((int64_t)b * g.Cout + P.co0 + co) * g.L + l]);
 #pragma unroll
                   for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = __ldg(sp + (int64_t)w * g.M + e);
                 }
@@ -1028,7 +1033,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           for (int cc = 0; cc < 16; ++cc) v[cc] = 0;
         }
         if (frow < rows) {
-          float4 *dst = reinterpret_cast<float4 *>(part + (int64_t)(lo + frow) * g.Cout + c0);
+          float4 *dst = reinterpret_cast<float4 *>(part + (int64_t)(lo + frow) * g.Cout + P.co0 + c0);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4)
             dst[q4] = make_float4(__int_as_float(v[4 * q4]) * scale, __int_as_float(v[4 * q4 + 1]) * scale,
@@ -1070,18 +1075,22 @@ __global__ void __launch_bounds__(256) bwd_weight_tc_finish_kernel(Geo g, int np
   }
 }
 
-// bf16 weight digit tiles for dgrad: tile (i, k) = [Nf rows (crossbar row) x Cout] K-major no-swizzle
-__global__ void weight_tiles_bwd_kernel(Geo g, int Nf, const int8_t *__restrict__ wcodes,
+// bf16 weight digit tiles for dgrad: tile (channel block cb, i, k) = [Nf rows (crossbar row) x Kc channels]
+// K-major no-swizzle, Kc = min(Cout, 128)
+__global__ void weight_tiles_bwd_kernel(Geo g, int Nf, int Kc, const int8_t *__restrict__ wcodes,
                                         uint16_t *__restrict__ tiles) {
-  const int64_t tile_elems = (int64_t)Nf * g.Cout;
-  const int64_t n = (int64_t)g.NX * g.NSW * tile_elems;
-  const uint32_t sbo = (uint32_t)g.Cout * 16u;
+  const int64_t tile_elems = (int64_t)Nf * Kc;
+  const int64_t tiles_per_block = (int64_t)g.NX * g.NSW;
+  const int64_t n = (int64_t)(g.Cout / Kc) * tiles_per_block * tile_elems;
+  const uint32_t sbo = (uint32_t)Kc * 16u;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t tile = idx / tile_elems;
     const int within = (int)(idx % tile_elems);
-    const int fr = within / g.Cout, co = within % g.Cout;
-    const int i = (int)(tile / g.NSW), k = (int)(tile % g.NSW);
+    const int fr = within / Kc, cl = within % Kc;
+    const int cb = (int)(tile / tiles_per_block), ik = (int)(tile % tiles_per_block);
+    const int i = ik / g.NSW, k = ik % g.NSW;
+    const int co = cb * Kc + cl;
     const int f = i * g.xbar + fr;
     const int hi = min((i + 1) * g.xbar, g.F);
     int digit = 0;
@@ -1091,13 +1100,15 @@ __global__ void weight_tiles_bwd_kernel(Geo g, int Nf, const int8_t *__restrict_
       digit = (mag >> (g.wbs * k)) & g.wmask;
       if (code < 0) digit = -digit;
     }
-    tiles[tile * tile_elems + tc_tile_offset16(fr, co, kTcLBO, sbo) / 2] =
+    tiles[tile * tile_elems + tc_tile_offset16(fr, cl, kTcLBO, sbo) / 2] =
         __bfloat16_as_ushort(__int2bfloat16_rn(digit));
   }
 }
 
+inline int bwd_channel_block(const Geo &g) { return g.Cout > 128 ? 128 : g.Cout; }
+
 inline int wgrad_chunks_per_group(const Geo &g) {
-  int n = 512 / g.Cout;
+  int n = 512 / bwd_channel_block(g);
   return n < g.NX ? n : g.NX;
 }
 
@@ -1137,7 +1148,7 @@ static Geo bwd_virtual_geo(const Geo &g, int *sdiv) {
 
 bool tc_backward_supported(const Geo &g) {
   if (!bwd_slices_supported(g)) return false;
-  if (g.Cout % 16 != 0 || g.Cout > 128) return false;
+  if (g.Cout % 16 != 0 || (g.Cout > 128 && (g.Cout % 128 != 0 || g.Cout > 512))) return false;
   if (g.pairs > kMaxPairs) return false;
   const int rows = g.xbar < g.F ? g.xbar : g.F;
   // wgrad M tile / dgrad N tile is one (virtual) chunk of <= 128 rows
@@ -1157,7 +1168,7 @@ int launch_weight_tiles_bwd(const Geo &g0, const int8_t *wcodes, void *tiles, cu
   int sdiv;
   const Geo g = bwd_virtual_geo(g0, &sdiv);
   const int64_t n = (int64_t)g.NX * g.NSW * tc_nf(g) * g.Cout;
-  weight_tiles_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, tc_nf(g), wcodes,
+  weight_tiles_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, tc_nf(g), bwd_channel_block(g), wcodes,
                                                                  reinterpret_cast<uint16_t *>(tiles));
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1186,17 +1197,17 @@ int launch_bwd_input_tc(const Geo &g0, const float *go, const uint32_t *state, c
   memset(&P, 0, sizeof(P));
   const Geo g = bwd_virtual_geo(g0, &P.sdiv);
   P.g = g;
-  P.Kc = g.Cout;
+  P.Kc = bwd_channel_block(g);
   P.Nf = tc_nf(g);
   P.mtiles = (g.M + kTcTileM - 1) / kTcTileM;
-  P.a_bytes = (uint32_t)(kTcTileM * g.Cout * 2);
-  P.b_bytes = (uint32_t)(P.Nf * g.Cout * 2);
+  P.a_bytes = (uint32_t)(kTcTileM * P.Kc * 2);
+  P.b_bytes = (uint32_t)(P.Nf * P.Kc * 2);
   P.stage_bytes = 3 * P.a_bytes + P.b_bytes;
   P.fold = fold;
   P.debug = g_tc_debug;
   P.raw_bytes = fold ? (uint32_t)((g.F * 4 + 15) & ~15) : 0u;
   // register-resident operands: 32 channels per producer thread at most, clip bits in one state word
-  P.cached = g.Cout <= 64 ? 1 : 0;
+  P.cached = P.Kc <= 64 ? 1 : 0;
   P.pw_off = P.raw_bytes;
   if (P.cached && (g.NSA - 1) * g.NSW + 1 <= 7) P.raw_bytes += (uint32_t)(g.NSW * (1 << ((g.NSA - 1) * g.NSW + 1)) * 4);
   int stages = (int)((kSmemBudget - kBarrierBytes - P.raw_bytes) / P.stage_bytes);
@@ -1215,7 +1226,10 @@ int launch_bwd_input_tc(const Geo &g0, const float *go, const uint32_t *state, c
                                       (int)smem));                                                              \
     bwd_input_tc_kernel<W, A, T><<<grid, kThreads, smem, st>>>(P);                                              \
   } while (0)
-  CIMQ_BWD_DISPATCH(CIMQ_LAUNCH_DGRAD, 0);
+  for (P.co0 = 0; P.co0 < g.Cout; P.co0 += P.Kc) {  // one launch per block of <= 128 output channels
+    P.wtb = reinterpret_cast<const uint8_t *>(wtb) + (size_t)(P.co0 / P.Kc) * g.NX * g.NSW * P.b_bytes;
+    CIMQ_BWD_DISPATCH(CIMQ_LAUNCH_DGRAD, 0);
+  }
 #undef CIMQ_LAUNCH_DGRAD
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1227,11 +1241,11 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
   memset(&P, 0, sizeof(P));
   const Geo g = bwd_virtual_geo(g0, &P.sdiv);
   P.g = g;
-  P.Kc = g.Cout;
+  P.Kc = bwd_channel_block(g);
   P.mtiles = (g.M + kTcTileM - 1) / kTcTileM;
   P.a_bytes = 128u * 128u * 2u;
   P.debug = g_tc_debug;
-  P.b_bytes = (uint32_t)(g.Cout / 8) * 16u * (uint32_t)kWgLBO;  // 8-row groups x 16 k-groups x 144 B
+  P.b_bytes = (uint32_t)(P.Kc / 8) * 16u * (uint32_t)kWgLBO;  // 8-row groups x 16 k-groups x 144 B
   P.stage_bytes = P.a_bytes + 3 * P.b_bytes;
   // staged activation rows (stride 1, output width a power of two between 8 and 128, 4-byte aligned rows)
   P.fastx = 0; P.raw_bytes = 0;
@@ -1266,7 +1280,7 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
   P.nxg = wgrad_chunks_per_group(g);
   const int groups = (g.NX + P.nxg - 1) / P.nxg;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(P.nxg * g.Cout)) cols <<= 1;
+  while (cols < (uint32_t)(P.nxg * P.Kc)) cols <<= 1;
   P.tmem_cols = cols;
   int ctas = 148 / groups;
   if (ctas > P.mtiles) ctas = P.mtiles;
@@ -1280,7 +1294,9 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
                                       (int)smem));                                                               \
     bwd_weight_tc_kernel<W, A, T><<<grid, kThreads, smem, st>>>(P);                                              \
   } while (0)
-  CIMQ_BWD_DISPATCH(CIMQ_LAUNCH_WGRAD, 0);
+  for (P.co0 = 0; P.co0 < g.Cout; P.co0 += P.Kc) {  // one launch per block of <= 128 output channels
+    CIMQ_BWD_DISPATCH(CIMQ_LAUNCH_WGRAD, 0);
+  }
 #undef CIMQ_LAUNCH_WGRAD
   CIMQ_CUDA_OK(cudaGetLastError());
   const int64_t n = (int64_t)g.Cout * g.F;

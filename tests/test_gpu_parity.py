@@ -338,6 +338,8 @@ RANDOM_CASES = [
     # Cout = 128: beyond the register-resident operand paths of dgrad (Cout <= 64) and wgrad (Cout <= 72)
     (32, 128, 16, 3, 1, 3, 128, 1.5),
     (64, 128, 8, 2, 1, 3, 128, 1),
+    # Cout = 256: the backward runs as two blocks of 128 output channels
+    (32, 256, 8, 2, 1, 3, 128, 1.5),
     # several 128-pixel tiles per CTA-less grid, W = 32 rows staged by cp.async, remainder crossbar of 64 rows
     (64, 32, 32, 2, 1, 3, 128, 1.5),
 ]
@@ -375,7 +377,7 @@ def test_random_layer_against_oracle(case):
     table = L.adc_table(spec, s, aqd, mask)
     wdigits, wtiles = L.weight_prepare(spec, wcd)
     np.testing.assert_array_equal(L.conv_psums(spec, xcd, wcd).cpu().numpy(), ps_int)
-    for flags in ([L.FLAG_FORCE_SIMT, 0] if info.tc_forward else [L.FLAG_FORCE_SIMT]):
+    for flags in ([L.FLAG_FORCE_SIMT, 0, L.FLAG_DETERMINISTIC] if info.tc_forward else [L.FLAG_FORCE_SIMT]):
         out, state = L.conv_forward(spec, xcd, wcd, wtiles, table, s, mask, save_state=True, flags=flags)
         codes, clip = unpack_state(state, cfg, info, batch)
         np.testing.assert_array_equal(clip, ref_clip)
