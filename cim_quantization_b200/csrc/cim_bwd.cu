@@ -1,4 +1,6 @@
-// Backward of the CiM convolution (get_cim_output_signed.backward, lsq.py:244-386) on CUDA cores.
+// Backward of the CiM convolution (get_cim_output_signed.backward, lsq.py:244-386): the alpha-grad kernels, the
+// fold (col2im), the CUDA-core dgrad / wgrad for shapes outside the tcgen05 envelope, and the dispatch to the
+// tcgen05 kernels of cim_bwd_tc.cu.
 //
 // The reference broadcasts grad_out to the 6-D partial-sum shape, zeroes clipped entries and runs
 // 2*NX*NSA*NSW small GEMMs.  Here the STE clip mask comes from the ADC state the forward stored
