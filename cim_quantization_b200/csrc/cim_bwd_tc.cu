@@ -61,6 +61,7 @@ struct BwdParams {
   int rk, prow;      // wgrad staging: rows per channel slot, staged row of (output row o, tap row ky) = o*prow + ky
   int async_rows;    // wgrad staging: rows arrive by 16-byte cp.async copies issued one chunk ahead
   uint32_t raw_bytes;
+  int gfast;         // wgrad: every 8-pixel group is an aligned run of one image row (or past the end)
   int co0;           // first output channel of this launch (layers with Cout > 128 run as blocks of 128 channels)
   int sdiv;          // virtual 128-row chunks per crossbar: the ADC state of virtual chunk i is that of crossbar i / sdiv
   long long *debug;  // per-role cycle counters (builds with TIMERS=1 only)
@@ -527,6 +528,43 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
 // =====================================================================================================
 // wgrad
 // =====================================================================================================
+// The 8 activation codes (one per byte) of crossbar row (ci, ky, kx) at the 8 consecutive output pixels starting at
+// m8, for geometries the staged-row path does not cover.  pt = {image, output row, first output column, kind} of
+// the group: kind 1 = one aligned run of an image row, 0 = straddles rows / images / the end, -1 = past the end.
+struct GatherGeo {  // the few geometry fields the gather needs, by value (a reference would pin Geo to the stack)
+  int stride, pad, H, W, Cin, L, OW;
+  int64_t M;
+};
+__device__ __noinline__ uint2 gather_codes_generic(GatherGeo g, const uint8_t *__restrict__ xcodes, int4 pt, int ci,
+                                                   int ky, int kx, int64_t m8) {
+  uint32_t c[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) c[e] = 0u;
+  if (pt.w == 1) {
+    const int iy = pt.y * g.stride - g.pad + ky;
+    if (iy >= 0 && iy < g.H) {
+      const uint8_t *row = xcodes + (((int64_t)pt.x * g.Cin + ci) * g.H + iy) * g.W;
+      const int ix0 = pt.z * g.stride - g.pad + kx;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ix = ix0 + e * g.stride;
+        if (ix >= 0 && ix < g.W) c[e] = __ldg(row + ix);
+      }
+    }
+  } else if (pt.w == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int64_t m = m8 + e;
+      if (m < g.M) {
+        const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
+        const int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
+        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) c[e] = xcodes[(((int64_t)b * g.Cin + ci) * g.H + iy) * g.W + ix];
+      }
+    }
+  }
+  return make_uint2(c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24), c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24));
+}
+
 constexpr int kWgLBO = 144;  // padded K-stride of the G' tiles: producer lanes run along K (bank-conflict free)
 
 template <int NSW, int NSA, bool TERN>
@@ -588,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     // by its NSA planes.  Each item is refilled for the next chunk / tile right after its last use, a whole stage
     // before it is needed again, so no load latency is exposed in the plane loop.
     constexpr bool kCacheOk = kLut && CBits::CWN == 1;
-    const bool gcache = kCacheOk && Kc <= 72;
+    const bool gcache = kCacheOk && Kc <= 72 && P.gfast;
     const int gpg = tid & 15, gco0 = tid >> 4;
     float gvc[3][8];
     uint32_t swc[3][8];
@@ -601,36 +639,25 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
       }
       return e;
     };
+    // The register-resident path is only taken when every 8-pixel group is one aligned run of an image row or lies
+    // entirely past the last pixel (P.gfast, decided on the host): no per-element fallback is compiled into it.
+    // Groups past the end read valid addresses (image 0 / the last valid group): their activation codes are zero
+    // (rows outside the image), so whatever finite values they contribute are multiplied by zero.
     auto load_go = [&](const int4 &pt, int mt_, int co, float (&gv)[8]) {
-      if (pt.w == 1) {
-        const float4 *gp = reinterpret_cast<const float4 *>(P.go + ((int64_t)pt.x * g.Cout + P.co0 + co) * g.L +
-                                                            pt.y * g.OW + pt.z);
-        const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
-        gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w;
-        gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int64_t m = (int64_t)mt_ * kTcTileM + gpg * 8 + e;
-          gv[e] = 0.0f;
-          if (m < g.M) gv[e] = __ldg(&P.go[((int64_t)(m / g.L) * g.Cout + P.co0 + co) * g.L + (m % g.L)]);
-        }
-      }
+      (void)mt_;
+      const float4 *gp = reinterpret_cast<const float4 *>(P.go + ((int64_t)pt.x * g.Cout + P.co0 + co) * g.L +
+                                                          pt.y * g.OW + pt.z);
+      const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+      gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w;
+      gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
     };
     auto load_state = [&](const int4 &pt, int mt_, int i, int co, uint32_t (&sw)[8]) {  // i: crossbar (state) index
-      const int64_t mg = (int64_t)mt_ * kTcTileM + gpg * 8;
+      (void)pt;
+      const int64_t mg = min((int64_t)mt_ * kTcTileM + gpg * 8, (int64_t)g.M - 8);
       const uint32_t *sp = P.state + ((int64_t)(i * g.Cout + P.co0 + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
-      if (pt.w == 1) {
-        const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(sp)), s1 = __ldg(reinterpret_cast<const uint4 *>(sp) + 1);
-        sw[0] = s0.x; sw[1] = s0.y; sw[2] = s0.z; sw[3] = s0.w;
-        sw[4] = s1.x; sw[5] = s1.y; sw[6] = s1.z; sw[7] = s1.w;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          sw[e] = 0xffffffffu;  // past the last pixel: everything clipped, contributes nothing
-          if (mg + e < g.M) sw[e] = __ldg(sp + e);
-        }
-      }
+      const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(sp)), s1 = __ldg(reinterpret_cast<const uint4 *>(sp) + 1);
+      sw[0] = s0.x; sw[1] = s0.y; sw[2] = s0.z; sw[3] = s0.w;
+      sw[4] = s1.x; sw[5] = s1.y; sw[6] = s1.z; sw[7] = s1.w;
     };
     // staged-row table of tile mt_: offset of the row's first byte source, or kNoRow.  Rows of a slot are
     // (output row, ky) pairs, or -- when a tile is consecutive rows of one image (P.prow == 1) -- the distinct
@@ -781,36 +808,11 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
               const uint32_t bsh = (sa & 3u) * 8u;
               lo8 = __funnelshift_r(w0, w1, bsh);
               hi8 = __funnelshift_r(w1, w2, bsh);
-            } else {
-              const int4 pt = ptab[pg];
-              uint32_t c[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) c[e] = 0u;
-              if (pt.w == 1) {
-                const int iy = pt.y * g.stride - g.pad + ky;
-                if (iy >= 0 && iy < g.H) {
-                  const uint8_t *row = P.xcodes + (((int64_t)pt.x * g.Cin + ci) * g.H + iy) * g.W;
-                  const int ix0 = pt.z * g.stride - g.pad + kx;
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const int ix = ix0 + e * g.stride;
-                    if (ix >= 0 && ix < g.W) c[e] = __ldg(row + ix);
-                  }
-                }
-              } else if (pt.w == 0) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const int64_t m = m0 + pg * 8 + e;
-                  if (m < g.M) {
-                    const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
-                    const int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
-                    if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
-                      c[e] = P.xcodes[(((int64_t)b * g.Cin + ci) * g.H + iy) * g.W + ix];
-                  }
-                }
-              }
-              lo8 = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
-              hi8 = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
+            } else {  // geometries without staged rows: out of line, it would be inlined six times here
+              const uint2 c8 = gather_codes_generic(GatherGeo{g.stride, g.pad, g.H, g.W, g.Cin, g.L, g.OW, g.M}, P.xcodes,
+                                                    ptab[pg], ci, ky, kx, m0 + pg * 8);
+              lo8 = c8.x;
+              hi8 = c8.y;
             }
           }
             xlo[q] = lo8;
@@ -1277,6 +1279,8 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
   if (stages > kMaxStages) stages = kMaxStages;
   CIMQ_REQUIRE(stages >= 1, "wgrad tile does not fit shared memory");
   P.stages = stages;
+  P.gfast = (g.L % 8 == 0 && g.OW % 8 == 0 && g.M % 8 == 0 && g.M >= 8 &&
+             (reinterpret_cast<uintptr_t>(go) & 15u) == 0 && (reinterpret_cast<uintptr_t>(state) & 15u) == 0) ? 1 : 0;
   P.nxg = wgrad_chunks_per_group(g);
   const int groups = (g.NX + P.nxg - 1) / P.nxg;
   uint32_t cols = 32;
