@@ -149,3 +149,17 @@ def test_reference_model_surgery_accepts_cim_linear():
     assert set(dict(model.linear.named_buffers())) == {"init_state", "signed_act", "init_state_cim"}
     with pytest.raises(RuntimeError):
         model.linear(torch.zeros(2, 64))  # no CPU fallback
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/cimq.h is the C ABI: it must compile as C99 (no C++ or torch types in the signatures)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text('#include "cimq.h"\nint main(void){ cimq_layer_t l; cimq_info_t i; (void)l; (void)i; return 0; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
