@@ -40,10 +40,14 @@ def _make_spec(x_shape, w_shape, stride, padding, nbits_a, abitslice, nbits_w, w
                      nbits_w=int(nbits_w), wbitslice=int(wbitslice), xbar=int(xbar), adcbits=adcbits)
 
 
-def _require_cuda(*tensors):
+def _require_cuda(*tensors, f32: bool = True):
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("cim_quantization_b200 runs on CUDA tensors only; there is no CPU fallback")
+        if f32 and t.dtype != torch.float32:  # the kernels read raw fp32; the reference is fp32 end to end as well
+            raise TypeError(f"cim_quantization_b200 expects float32 tensors, got {t.dtype}")
 
 
 class get_cim_output_signed(Function):
@@ -63,7 +67,7 @@ class get_cim_output_signed(Function):
             stochastic = False  # the reference only samples in the adcbits 1.5 branch (lsq.py:203-205)
         if _pair0(conv_dilation) != 1:
             raise ValueError("dilation != 1 is not supported (the reference's Unfold ignores it, lsq.py:141)")
-        _require_cuda(x, w)
+        _require_cuda(x, w, f32=False)  # converted with .float() below
         spec = _make_spec(x.shape, w.shape, conv_stride, conv_padding, act_bits, act_bit_slice, weight_bits,
                           weight_bit_slice, arr, adc_bits)
         info = _lib.layer_info(spec)
@@ -269,8 +273,7 @@ class _BatchNormAct(torch.autograd.Function):
 
 def batch_norm_act(x, bn: torch.nn.BatchNorm2d, residual=None, relu: bool = False):
     """``relu?(bn(x) + residual?)`` with ``bn``'s parameters, buffers and train/eval mode."""
-    if not x.is_cuda:
-        raise RuntimeError("batch_norm_act needs CUDA tensors; there is no CPU fallback")
+    _require_cuda(x, residual)
     training = bn.training or not bn.track_running_stats
     momentum = 0.0 if bn.momentum is None else bn.momentum
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
