@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libcimq.so")
 ADC_MULTIBIT, ADC_BINARY, ADC_TERNARY = 0, 1, 2
 FLAG_FORCE_SIMT = 1
 FLAG_DETERMINISTIC = 2  # backward: fixed-order fold of grad_x instead of fp32 reductions in the dgrad epilogue
+FLAG_V2 = 4  # second-generation kernels + uint8 ADC-state planes (include/cimq.h); set by conv_forward(v2=True)
 _deterministic = False
 
 
@@ -45,9 +46,9 @@ class CimqLayer(C.Structure):
 class CimqInfo(C.Structure):
     """``cimq_info_t``."""
     _fields_ = ([(n, C.c_int32) for n in ("out_hw", "L", "M", "F", "NX", "NSW", "NSA", "pairs", "state_words",
-                                          "tc_forward", "tc_backward", "reserved_")] +
+                                          "tc_forward", "tc_backward", "tc_v2")] +
                 [(n, C.c_int64) for n in ("state_bytes", "table_bytes", "wdigits_bytes", "wtiles_bytes",
-                                          "bwd_workspace_bytes", "psum_count")])
+                                          "bwd_workspace_bytes", "psum_count", "state_v2_bytes")])
 
 
 EXPORTS = {
@@ -70,6 +71,8 @@ EXPORTS = {
                                                C.c_void_p, C.c_void_p]),
     "cimq_adc_table": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    "cimq_adc_table2": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "cimq_weight_prepare": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cimq_conv_forward": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
@@ -234,14 +237,25 @@ def alpha_quantize_backward(alpha, grad_aq, qn: int, qp: int, aux):
     return ga
 
 
-def adc_table(spec: LayerSpec, s, alpha_q, binary_mask, status=None):
+def adc_table(spec: LayerSpec, s, alpha_q, binary_mask, status=None, alpha_scale=None):
+    """ADC thresholds / amplitudes.  ``alpha_scale`` (1-element CUDA tensor: the step of the alpha quantiser,
+    ``aux[0]`` of :func:`alpha_quantize`) additionally builds the constants of the v2 kernels (always built for the
+    multi-bit ADC, which has no alpha)."""
     info = layer_info(spec)
     table = torch.empty(info.table_bytes, dtype=torch.uint8, device=s.device)
     layer = spec.c_layer()
-    _check(load().cimq_adc_table(C.byref(layer), _ptr(s), _ptr(alpha_q), _ptr(binary_mask), _ptr(table),
-                                 _ptr(status), _stream()))
-    _count(1)
+    _check(load().cimq_adc_table2(C.byref(layer), _ptr(s), _ptr(alpha_q), _ptr(alpha_scale), _ptr(binary_mask),
+                                  _ptr(table), _ptr(status), _stream()))
+    _count(2 if (info.tc_v2 and (alpha_scale is not None or alpha_q is None)) else 1)
     return table
+
+
+def v2_usable(spec: LayerSpec, has_alpha: bool, alpha_scale, flags: int = 0) -> bool:
+    """Whether a step of this layer can run on the v2 kernels: covered shape, not forced onto the CUDA-core
+    kernels, and -- for the binary / ternary ADC -- the alpha quantiser's step at hand."""
+    if flags & FLAG_FORCE_SIMT or os.environ.get("CIMQ_DISABLE_V2"):
+        return False
+    return bool(layer_info(spec).tc_v2) and (not has_alpha or alpha_scale is not None)
 
 
 def weight_prepare(spec: LayerSpec, wcodes, want_digits=True, want_tiles=True):
@@ -257,10 +271,17 @@ def weight_prepare(spec: LayerSpec, wcodes, want_digits=True, want_tiles=True):
 
 
 def conv_forward(spec: LayerSpec, xcodes, wcodes, wtiles, table, s, binary_mask, save_state: bool, flags: int = 0):
+    """``flags & FLAG_V2``: v2 kernel; the state then is a uint8 tensor (v2 planes) instead of int32 words, which is
+    how :func:`conv_backward` tells the two formats apart."""
     info = layer_info(spec)
     dev = xcodes.device
     out = torch.empty((spec.batch, spec.out_channels, info.L), dtype=torch.float32, device=dev)
-    state = torch.empty(info.state_bytes // 4, dtype=torch.int32, device=dev) if save_state else None
+    if not save_state:
+        state = None
+    elif flags & FLAG_V2:
+        state = torch.empty(info.state_v2_bytes, dtype=torch.uint8, device=dev)
+    else:
+        state = torch.empty(info.state_bytes // 4, dtype=torch.int32, device=dev)
     layer = spec.c_layer()
     _check(load().cimq_conv_forward(C.byref(layer), _ptr(xcodes), _ptr(wcodes), _ptr(wtiles), _ptr(table), _ptr(s),
                                     _ptr(binary_mask), _ptr(out), _ptr(state), flags, _stream()))
@@ -293,6 +314,8 @@ def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, wtiles, state, s, 
               if need_alpha else None)
     ws = torch.empty(info.bwd_workspace_bytes, dtype=torch.uint8, device=dev)
     layer = spec.c_layer()
+    if state.dtype == torch.uint8:  # v2 state planes
+        flags |= FLAG_V2
     _check(load().cimq_conv_backward(C.byref(layer), _ptr(grad_out), _ptr(xcodes), _ptr(wdigits), _ptr(wtiles),
                                      _ptr(state), _ptr(s), _ptr(binary_mask), _ptr(gxq), _ptr(gwq), _ptr(galpha), _ptr(ws),
                                      _backward_flags(flags), _stream()))

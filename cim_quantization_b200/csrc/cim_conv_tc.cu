@@ -3,6 +3,46 @@
 
 namespace cimq {
 
+namespace tcfwd {
+
+// Staged ("fast") producer geometry: which input rows a 128-pixel tile needs per crossbar chunk and how they are
+// laid out in the staging buffers.  Needs P.Kp; leaves P.fast = 0 when the layer does not qualify (the generic
+// per-element gather is used then).  Shared with the v2 kernel (cim_conv_v2.cu).
+void plan_producer(const Geo &g, TcParams &P) {
+  P.fast = 0; P.owt = 0; P.rpt = 0; P.rk = 0; P.rk_magic = 0; P.tma_rows = 0; P.prow = 0; P.shared_rows = 0; P.prefetch = 0; P.pitch_log2 = 0; P.col0 = 0; P.raw_bytes = 0;
+  if ((g.K == 3 || g.K == 5) && g.W % 4 == 0 && g.OW <= kTcTileM && kTcTileM % g.OW == 0 && P.Kp <= 128 &&
+      (kTcTileM / g.OW) * g.K <= 128 && g.pad < g.K) {
+    // input rows by 16-byte asynchronous copies need 16-byte aligned rows on both sides: W % 16 == 0 and column 0 of the image
+    // staged at byte 16 (col0 = 16 - pad); otherwise 4-byte loads with column -pad on a word boundary
+    const bool tma = g.W % 16 == 0 && g.pad <= 16;
+    const int col0 = tma ? 16 - g.pad : (4 - g.pad % 4) % 4;
+    const int needp = (g.OW - 1) * g.stride + g.K + col0;
+    int pl = 2;
+    while ((1 << pl) < needp) ++pl;
+    int nslots = 0;
+    for (int i = 0; i < g.NX; ++i) {
+      const ChunkLayout cl = chunk_layout(g, i);
+      const int n = cl.nfull + (cl.nhead > 0) + (cl.ntail > 0);
+      nslots = n > nslots ? n : nslots;
+    }
+    // a tile that is 128 consecutive pixels of one image reads consecutive input rows: output rows share them
+    const int rpt = kTcTileM / g.OW;
+    const bool shared_rows = g.L % kTcTileM == 0;
+    const int rk = shared_rows ? (rpt - 1) * g.stride + g.K : rpt * g.K;
+    const size_t raw = ((size_t)nslots * rk * (1u << pl) + 15) & ~(size_t)15;
+    if (nslots <= kMaxSlots && raw <= 48 * 1024 && pl <= 9 && rk <= 128) {
+      P.fast = 1; P.owt = g.OW; P.rpt = rpt; P.pitch_log2 = pl; P.col0 = col0;
+      P.rk = rk; P.prow = shared_rows ? g.stride : g.K; P.shared_rows = shared_rows ? 1 : 0;
+      P.rk_magic = (uint32_t)(((1ull << 32) + rk - 1) / rk);
+      P.tma_rows = tma && rk >= 2 ? 1 : 0;
+      P.prefetch = !P.tma_rows && (raw / 4 + kProducerThreads - 1) / kProducerThreads <= (size_t)kPrefetchWords;
+      P.raw_bytes = (uint32_t)raw;
+    }
+  }
+}
+
+}  // namespace tcfwd
+
 namespace {
 
 using namespace tcfwd;
@@ -39,37 +79,7 @@ bool make_plan(const Geo &g, TcParams &P, size_t &smem) {
   while (cols < need) cols <<= 1;
   P.tmem_cols = cols;
   P.ttab_bytes = (uint32_t)((g.pairs * 3 * (P.CT / 2) * 4 + 15) & ~15);
-  // staged (fast) producer
-  P.fast = 0; P.owt = 0; P.rpt = 0; P.rk = 0; P.rk_magic = 0; P.tma_rows = 0; P.prow = 0; P.shared_rows = 0; P.prefetch = 0; P.pitch_log2 = 0; P.col0 = 0; P.raw_bytes = 0;
-  if ((g.K == 3 || g.K == 5) && g.W % 4 == 0 && g.OW <= kTcTileM && kTcTileM % g.OW == 0 && P.Kp <= 128 &&
-      (kTcTileM / g.OW) * g.K <= 128 && g.pad < g.K) {
-    // input rows by 16-byte asynchronous copies need 16-byte aligned rows on both sides: W % 16 == 0 and column 0 of the image
-    // staged at byte 16 (col0 = 16 - pad); otherwise 4-byte loads with column -pad on a word boundary
-    const bool tma = g.W % 16 == 0 && g.pad <= 16;
-    const int col0 = tma ? 16 - g.pad : (4 - g.pad % 4) % 4;
-    const int needp = (g.OW - 1) * g.stride + g.K + col0;
-    int pl = 2;
-    while ((1 << pl) < needp) ++pl;
-    int nslots = 0;
-    for (int i = 0; i < g.NX; ++i) {
-      const ChunkLayout cl = chunk_layout(g, i);
-      const int n = cl.nfull + (cl.nhead > 0) + (cl.ntail > 0);
-      nslots = n > nslots ? n : nslots;
-    }
-    // a tile that is 128 consecutive pixels of one image reads consecutive input rows: output rows share them
-    const int rpt = kTcTileM / g.OW;
-    const bool shared_rows = g.L % kTcTileM == 0;
-    const int rk = shared_rows ? (rpt - 1) * g.stride + g.K : rpt * g.K;
-    const size_t raw = ((size_t)nslots * rk * (1u << pl) + 15) & ~(size_t)15;
-    if (nslots <= kMaxSlots && raw <= 48 * 1024 && pl <= 9 && rk <= 128) {
-      P.fast = 1; P.owt = g.OW; P.rpt = rpt; P.pitch_log2 = pl; P.col0 = col0;
-      P.rk = rk; P.prow = shared_rows ? g.stride : g.K; P.shared_rows = shared_rows ? 1 : 0;
-      P.rk_magic = (uint32_t)(((1ull << 32) + rk - 1) / rk);
-      P.tma_rows = tma && rk >= 2 ? 1 : 0;
-      P.prefetch = !P.tma_rows && (raw / 4 + kProducerThreads - 1) / kProducerThreads <= (size_t)kPrefetchWords;
-      P.raw_bytes = (uint32_t)raw;
-    }
-  }
+  plan_producer(g, P);
   for (int attempt = 0; attempt < 2; ++attempt) {
     const size_t fixed = 2 * (size_t)P.raw_bytes + 4 * (size_t)P.ttab_bytes + kAuxBytes;
     if (fixed + P.stage_bytes <= kSmemBudget) {

@@ -239,7 +239,15 @@ __device__ __forceinline__ void stage_async_wait() { asm volatile("cp.async.wait
 // ---------------------------------------------------------------------------------------------------
 // fast producer, assembly: digit planes of this thread's im2col row of chunk `cl` from the staged rows
 // ---------------------------------------------------------------------------------------------------
-template <int NSA, int KT>
+// ENC: how a digit becomes an operand byte.  0 = the integer digit (kind::i8); 1 = e4m3 2.0 (0x40) for a set bit of a
+// 1-bit digit plane (kind::f8f6f4 of the v2 kernel; the weight tiles then hold +-0.5 so that products are +-1).
+template <int ENC>
+__device__ __forceinline__ uint32_t digit_plane_word(uint32_t w, int sh, uint32_t amask4) {
+  if constexpr (ENC == 0) return (w >> sh) & amask4;
+  else return ((w >> sh) & 0x01010101u) << 6;
+}
+
+template <int NSA, int KT, int ENC = 0>
 __device__ __forceinline__ void produce_fast(const TcParams &P, const ChunkLayout &cl, uint8_t *st_ptr,
                                              const uint8_t *raw, int r, int pix_base) {
   constexpr int KK = KT * KT;
@@ -327,8 +335,8 @@ __device__ __forceinline__ void produce_fast(const TcParams &P, const ChunkLayou
       for (int j = 0; j < NSA; ++j) {
         const int sh = g.abs_ * j;
         *reinterpret_cast<uint4 *>(st_ptr + (size_t)j * P.a_bytes + off) =
-            make_uint4((w[4 * gi] >> sh) & amask4, (w[4 * gi + 1] >> sh) & amask4, (w[4 * gi + 2] >> sh) & amask4,
-                       (w[4 * gi + 3] >> sh) & amask4);
+            make_uint4(digit_plane_word<ENC>(w[4 * gi], sh, amask4), digit_plane_word<ENC>(w[4 * gi + 1], sh, amask4),
+                       digit_plane_word<ENC>(w[4 * gi + 2], sh, amask4), digit_plane_word<ENC>(w[4 * gi + 3], sh, amask4));
       }
     }
   }
@@ -346,14 +354,15 @@ __device__ __forceinline__ void produce_fast(const TcParams &P, const ChunkLayou
         const uint32_t b = cb[ky * pitch + kx];
         const uint32_t off = tc_tile_offset(r, pos, P.Kp);
 #pragma unroll
-        for (int j = 0; j < NSA; ++j) st_ptr[(size_t)j * P.a_bytes + off] = (uint8_t)((b >> (g.abs_ * j)) & g.amask);
+        for (int j = 0; j < NSA; ++j)
+          st_ptr[(size_t)j * P.a_bytes + off] = (uint8_t)digit_plane_word<ENC>(b, g.abs_ * j, (uint32_t)g.amask);
       }
     }
   }
 }
 
 // generic producer: per-element gather through the position LUT (any geometry)
-template <int NSA>
+template <int NSA, int ENC = 0>
 __device__ __forceinline__ void produce_generic(const TcParams &P, int i, uint8_t *st_ptr, int r, int base,
                                                 uint32_t vm) {
   const Geo &g = P.g;
@@ -378,9 +387,135 @@ __device__ __forceinline__ void produce_generic(const TcParams &P, int i, uint8_
     for (int j = 0; j < NSA; ++j) {
       const int sh = g.abs_ * j;
       *reinterpret_cast<uint4 *>(st_ptr + (size_t)j * P.a_bytes + off) =
-          make_uint4((w[0] >> sh) & amask4, (w[1] >> sh) & amask4, (w[2] >> sh) & amask4, (w[3] >> sh) & amask4);
+          make_uint4(digit_plane_word<ENC>(w[0], sh, amask4), digit_plane_word<ENC>(w[1], sh, amask4),
+                     digit_plane_word<ENC>(w[2], sh, amask4), digit_plane_word<ENC>(w[3], sh, amask4));
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the producer role (4 warps): per (pixel tile, crossbar chunk) one pipeline stage = NSA digit planes of 128 im2col
+// rows + the chunk's weight tile (bulk copy).  Shared by the v1 (kind::i8) and v2 (kind::f8f6f4) kernels.
+// ---------------------------------------------------------------------------------------------------
+template <int NSA, int ENC>
+__device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm, int ntiles) {
+  const Geo &g = P.g;
+  const int r = threadIdx.x;  // tile row = output pixel
+  const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  long long d_wait = 0, d_prod = 0, d_tile = 0;
+  uint32_t it = 0;
+  if (P.fast) {
+    // ---- staged producer.  Stage `it` is (tile, chunk i); its input rows sit in raw[it & 1].
+    const StageThread stt = stage_thread(P);
+    const int pix_base = (((r / P.owt) * P.prow) << P.pitch_log2) + (r % P.owt) * g.stride + P.col0;
+    int tile = blockIdx.x, i = 0, tpar = 0;
+    uint32_t v[kPrefetchWords];
+    if (tile < ntiles) {
+      stage_set_rowoff(P, tile / P.nct, sm.rowoff);
+      named_barrier_sync(1, kProducerThreads);
+      if (P.tma_rows) {
+        // padding columns are zero for the whole kernel: clear both buffers once, then only rows are written
+        for (uint32_t q = threadIdx.x * 16u; q < 2u * P.raw_bytes; q += kProducerThreads * 16u)
+          *reinterpret_cast<uint4 *>(sm.raw + q) = make_uint4(0u, 0u, 0u, 0u);
+        named_barrier_sync(1, kProducerThreads);
+        stage_issue_async(P, chunk_layout(g, 0), sm.rowoff, sm.raw);
+        stage_async_wait();
+        named_barrier_sync(1, kProducerThreads);
+      }
+      if (P.prefetch) {
+        const ChunkLayout cl0 = chunk_layout(g, 0);
+        stage_load<kPrefetchWords>(P, stt, cl0, sm.rowoff, 0, v);
+        stage_store<kPrefetchWords>(P, stt, cl0, 0, v, sm.raw);
+        named_barrier_sync(1, kProducerThreads);
+      }
+    }
+    while (tile < ntiles) {
+      const int ct = tile % P.nct;
+      const ChunkLayout cl = chunk_layout(g, i);
+      uint8_t *raw = sm.raw + (size_t)(it & 1) * P.raw_bytes;
+      // the stage after this one
+      int ni = i + 1, ntile = tile, ntpar = tpar;
+      if (ni == g.NX) { ni = 0; ntile = tile + gridDim.x; ntpar ^= 1; }
+      const bool more = ntile < ntiles;
+      ChunkLayout ncl = cl;
+      if (more) {
+        ncl = chunk_layout(g, ni);
+        if (ni == 0) {  // new tile: publish its row table first (its buffer was last read a whole tile ago)
+          stage_set_rowoff(P, ntile / P.nct, sm.rowoff + ntpar * 128);
+          named_barrier_sync(1, kProducerThreads);
+        }
+        // its input rows start their trip from L2 / HBM now: by bulk copy straight into the other staging buffer,
+        // or into registers, while this stage is built
+        if (P.tma_rows) stage_issue_async(P, ncl, sm.rowoff + ntpar * 128, sm.raw + (size_t)((it + 1) & 1) * P.raw_bytes);
+        else if (P.prefetch) stage_load<kPrefetchWords>(P, stt, ncl, sm.rowoff + ntpar * 128, 0, v);
+      }
+      if (!P.prefetch && !P.tma_rows) {  // too many rows for the registers: stage this chunk now, eight loads in flight
+        const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
+        const int passes = ((nslots * P.rk) + stt.rstep - 1) / stt.rstep;
+        for (int p0 = 0; p0 < passes; p0 += 8) {
+          uint32_t v8[8];
+          stage_load<8>(P, stt, cl, sm.rowoff + tpar * 128, p0, v8);
+          stage_store<8>(P, stt, cl, p0, v8, raw);
+        }
+        named_barrier_sync(1, kProducerThreads);
+      }
+      const int sidx = it % P.stages;
+      const uint32_t use = it / P.stages;
+      long long t0 = CIMQ_T0();
+      mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
+      long long t1 = CIMQ_T0();
+      d_wait += t1 - t0;
+      uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
+      if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
+        bulk_copy_g2s(smem_u32(st_ptr + (size_t)NSA * P.a_bytes), P.wtiles + (size_t)(ct * g.NX + i) * P.b_bytes,
+                      P.b_bytes, sm.full0 + 8 * sidx);
+      }
+      if (g.K == 3) produce_fast<NSA, 3, ENC>(P, cl, st_ptr, raw, r, pix_base);
+      else produce_fast<NSA, 5, ENC>(P, cl, st_ptr, raw, r, pix_base);
+      fence_proxy_async();
+      mbar_arrive(sm.full0 + 8 * sidx);
+      if (P.prefetch || P.tma_rows) {
+        if (P.prefetch && more)
+          stage_store<kPrefetchWords>(P, stt, ncl, 0, v, sm.raw + (size_t)((it + 1) & 1) * P.raw_bytes);
+        if (P.tma_rows) stage_async_wait();  // my copies of the next stage's rows have landed
+        // next stage's rows visible to all producers; everyone is done reading this stage's rows
+        named_barrier_sync(1, kProducerThreads);
+      }
+      d_prod += CIMQ_T0() - t1;
+      i = ni; tile = ntile; tpar = ntpar; ++it;
+    }
+  } else {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int mt = tile / P.nct, ct = tile % P.nct;
+      const int m = mt * kTcTileM + r;
+      int base = 0;
+      uint32_t vm = 0;  // bit t set = tap t of this pixel is inside the image
+      if (m < g.M) {
+        const int b = m / g.L, l = m % g.L, oy = l / g.OW, ox = l % g.OW;
+        const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
+        base = (b * g.Cin * g.H + iy0) * g.W + ix0;
+        for (int ky = 0; ky < g.K; ++ky)
+          for (int kx = 0; kx < g.K; ++kx)
+            if (iy0 + ky >= 0 && iy0 + ky < g.H && ix0 + kx >= 0 && ix0 + kx < g.W) vm |= 1u << (ky * g.K + kx);
+      }
+      for (int i = 0; i < g.NX; ++i, ++it) {
+        const int sidx = it % P.stages;
+        const uint32_t use = it / P.stages;
+        mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
+        uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
+        if (threadIdx.x == 0) {
+          mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
+          bulk_copy_g2s(smem_u32(st_ptr + (size_t)NSA * P.a_bytes),
+                        P.wtiles + (size_t)(ct * g.NX + i) * P.b_bytes, P.b_bytes, sm.full0 + 8 * sidx);
+        }
+        produce_generic<NSA, ENC>(P, i, st_ptr, r, base, vm);
+        fence_proxy_async();
+        mbar_arrive(sm.full0 + 8 * sidx);
+      }
+    }
+  }
+  if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_prod; P.debug[2] = d_tile; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -423,122 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
   if (warp < kProducerWarps) {
     // =========================== producers ===========================
     reg_dealloc<kRegsProducer>();
-    const int r = threadIdx.x;  // tile row = output pixel
-    const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-    long long d_wait = 0, d_prod = 0, d_tile = 0;
-    uint32_t it = 0;
-    if (P.fast) {
-      // ---- staged producer.  Stage `it` is (tile, chunk i); its input rows sit in raw[it & 1].
-      const StageThread stt = stage_thread(P);
-      const int pix_base = (((r / P.owt) * P.prow) << P.pitch_log2) + (r % P.owt) * g.stride + P.col0;
-      int tile = blockIdx.x, i = 0, tpar = 0;
-      uint32_t v[kPrefetchWords];
-      if (tile < ntiles) {
-        stage_set_rowoff(P, tile / P.nct, sm.rowoff);
-        named_barrier_sync(1, kProducerThreads);
-        if (P.tma_rows) {
-          // padding columns are zero for the whole kernel: clear both buffers once, then only rows are written
-          for (uint32_t q = threadIdx.x * 16u; q < 2u * P.raw_bytes; q += kProducerThreads * 16u)
-            *reinterpret_cast<uint4 *>(sm.raw + q) = make_uint4(0u, 0u, 0u, 0u);
-          named_barrier_sync(1, kProducerThreads);
-          stage_issue_async(P, chunk_layout(g, 0), sm.rowoff, sm.raw);
-          stage_async_wait();
-          named_barrier_sync(1, kProducerThreads);
-        }
-        if (P.prefetch) {
-          const ChunkLayout cl0 = chunk_layout(g, 0);
-          stage_load<kPrefetchWords>(P, stt, cl0, sm.rowoff, 0, v);
-          stage_store<kPrefetchWords>(P, stt, cl0, 0, v, sm.raw);
-          named_barrier_sync(1, kProducerThreads);
-        }
-      }
-      while (tile < ntiles) {
-        const int ct = tile % P.nct;
-        const ChunkLayout cl = chunk_layout(g, i);
-        uint8_t *raw = sm.raw + (size_t)(it & 1) * P.raw_bytes;
-        // the stage after this one
-        int ni = i + 1, ntile = tile, ntpar = tpar;
-        if (ni == g.NX) { ni = 0; ntile = tile + gridDim.x; ntpar ^= 1; }
-        const bool more = ntile < ntiles;
-        ChunkLayout ncl = cl;
-        if (more) {
-          ncl = chunk_layout(g, ni);
-          if (ni == 0) {  // new tile: publish its row table first (its buffer was last read a whole tile ago)
-            stage_set_rowoff(P, ntile / P.nct, sm.rowoff + ntpar * 128);
-            named_barrier_sync(1, kProducerThreads);
-          }
-          // its input rows start their trip from L2 / HBM now: by bulk copy straight into the other staging buffer,
-          // or into registers, while this stage is built
-          if (P.tma_rows) stage_issue_async(P, ncl, sm.rowoff + ntpar * 128, sm.raw + (size_t)((it + 1) & 1) * P.raw_bytes);
-          else if (P.prefetch) stage_load<kPrefetchWords>(P, stt, ncl, sm.rowoff + ntpar * 128, 0, v);
-        }
-        if (!P.prefetch && !P.tma_rows) {  // too many rows for the registers: stage this chunk now, eight loads in flight
-          const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
-          const int passes = ((nslots * P.rk) + stt.rstep - 1) / stt.rstep;
-          for (int p0 = 0; p0 < passes; p0 += 8) {
-            uint32_t v8[8];
-            stage_load<8>(P, stt, cl, sm.rowoff + tpar * 128, p0, v8);
-            stage_store<8>(P, stt, cl, p0, v8, raw);
-          }
-          named_barrier_sync(1, kProducerThreads);
-        }
-        const int sidx = it % P.stages;
-        const uint32_t use = it / P.stages;
-        long long t0 = CIMQ_T0();
-        mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
-        long long t1 = CIMQ_T0();
-        d_wait += t1 - t0;
-        uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
-        if (threadIdx.x == 0) {
-          mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
-          bulk_copy_g2s(smem_u32(st_ptr + (size_t)NSA * P.a_bytes), P.wtiles + (size_t)(ct * g.NX + i) * P.b_bytes,
-                        P.b_bytes, sm.full0 + 8 * sidx);
-        }
-        if (g.K == 3) produce_fast<NSA, 3>(P, cl, st_ptr, raw, r, pix_base);
-        else produce_fast<NSA, 5>(P, cl, st_ptr, raw, r, pix_base);
-        fence_proxy_async();
-        mbar_arrive(sm.full0 + 8 * sidx);
-        if (P.prefetch || P.tma_rows) {
-          if (P.prefetch && more)
-            stage_store<kPrefetchWords>(P, stt, ncl, 0, v, sm.raw + (size_t)((it + 1) & 1) * P.raw_bytes);
-          if (P.tma_rows) stage_async_wait();  // my copies of the next stage's rows have landed
-          // next stage's rows visible to all producers; everyone is done reading this stage's rows
-          named_barrier_sync(1, kProducerThreads);
-        }
-        d_prod += CIMQ_T0() - t1;
-        i = ni; tile = ntile; tpar = ntpar; ++it;
-      }
-    } else {
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int mt = tile / P.nct, ct = tile % P.nct;
-        const int m = mt * kTcTileM + r;
-        int base = 0;
-        uint32_t vm = 0;  // bit t set = tap t of this pixel is inside the image
-        if (m < g.M) {
-          const int b = m / g.L, l = m % g.L, oy = l / g.OW, ox = l % g.OW;
-          const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
-          base = (b * g.Cin * g.H + iy0) * g.W + ix0;
-          for (int ky = 0; ky < g.K; ++ky)
-            for (int kx = 0; kx < g.K; ++kx)
-              if (iy0 + ky >= 0 && iy0 + ky < g.H && ix0 + kx >= 0 && ix0 + kx < g.W) vm |= 1u << (ky * g.K + kx);
-        }
-        for (int i = 0; i < g.NX; ++i, ++it) {
-          const int sidx = it % P.stages;
-          const uint32_t use = it / P.stages;
-          mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
-          uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
-          if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
-            bulk_copy_g2s(smem_u32(st_ptr + (size_t)NSA * P.a_bytes),
-                          P.wtiles + (size_t)(ct * g.NX + i) * P.b_bytes, P.b_bytes, sm.full0 + 8 * sidx);
-          }
-          produce_generic<NSA>(P, i, st_ptr, r, base, vm);
-          fence_proxy_async();
-          mbar_arrive(sm.full0 + 8 * sidx);
-        }
-      }
-    }
-    if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_prod; P.debug[2] = d_tile; }
+    producer_loop<NSA, 0>(P, sm, ntiles);
   } else if (warp >= kMmaWarp) {
     // =========================== MMA issuer ===========================
     reg_dealloc<kRegsMma>();
@@ -771,6 +791,8 @@ int launch_instance(const TcParams &P, size_t smem, int grid, cudaStream_t st) {
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+void plan_producer(const Geo &g, TcParams &P);  // cim_conv_tc.cu
 
 // one translation unit per slice count (parallel compilation)
 int launch_ns2(const TcParams &P, size_t smem, int grid, int ch, cudaStream_t st);

@@ -1,5 +1,8 @@
 // Per-step preparation kernels (tiny): ADC decision table and weight digit planes.
+#include <cuda_fp16.h>
+
 #include "cim_tc_layout.cuh"
+#include "cim_v2.cuh"
 
 namespace cimq {
 
@@ -61,6 +64,57 @@ __global__ void adc_table_kernel(Geo g, int CT, const float *__restrict__ s, con
   if (bad && status != nullptr) atomicOr(status, 1);
 }
 
+// v2 constants blocks (cim_v2.cuh): thresholds as negated fp16 "threshold - 1", B2 slabs with the integer amplitudes.
+// One CUDA block per (channel tile, crossbar); reads the AoS table written by adc_table_kernel just before.
+__global__ void __launch_bounds__(256) v2_consts_kernel(Geo g, v2::ConstLayout cl, const float *__restrict__ s,
+                                                        const float *__restrict__ alpha_q,
+                                                        const float *__restrict__ alpha_scale,
+                                                        const int8_t *__restrict__ mask,
+                                                        const int4 *__restrict__ table, uint8_t *__restrict__ section,
+                                                        int32_t *__restrict__ status) {
+  const int ct = blockIdx.x / g.NX, i = blockIdx.x % g.NX;
+  uint8_t *blk = section + 256 + (size_t)blockIdx.x * cl.block_bytes;
+  const bool mb = g.adc_mode == CIMQ_ADC_MULTIBIT;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float *hdr = reinterpret_cast<float *>(section);
+    if (mb) { hdr[0] = s[1]; hdr[1] = s[0]; }            // (code * s_w) * s_a, lsq.py:228-230
+    else { hdr[0] = alpha_scale ? alpha_scale[0] : 0.0f; hdr[1] = 1.0f; }
+  }
+  for (uint32_t o = threadIdx.x * 16u; o < cl.block_bytes; o += 256u * 16u)
+    *reinterpret_cast<uint4 *>(blk + o) = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  bool bad = false;
+  const float scale = (!mb && alpha_scale) ? alpha_scale[0] : 0.0f;
+  __half *thr = reinterpret_cast<__half *>(blk);
+  __half *b2 = reinterpret_cast<__half *>(blk + cl.b2_off);
+  for (int idx = threadIdx.x; idx < g.pairs * cl.CT; idx += 256) {
+    const int q = idx / cl.CT, cl_c = idx % cl.CT;  // q = k*NSA + j
+    const int k = q / g.NSA, j = q % g.NSA;
+    const int c = ct * cl.CT + cl_c;
+    const int64_t e = ((int64_t)i * g.pairs + q) * g.Cout + c;
+    float amp = (float)mask[q];
+    if (!mb) {
+      const int4 t = table[e];
+      const int h = cl_c / cl.CH, ch = cl_c % cl.CH;
+      const int tpm = min(t.x - 1, v2::kThrClamp), tgm = min(t.y - 1, v2::kThrClamp);
+      __half *row = thr + ((size_t)(h * g.pairs + q) * 2) * cl.CH + ch;
+      row[0] = __float2half_rn(-(float)tpm);
+      row[cl.CH] = __float2half_rn(-(float)tgm);
+      // alpha_q = n * scale with integer n (lsq.py:566-571): the tensor core accumulates code * n * mask exactly
+      const float aq = alpha_q[e];
+      const float n = rintf(__fdiv_rn(aq, scale));
+      if (!(scale > 0.0f) || __fmul_rn(n, scale) != aq || !(n >= 0.0f) || n >= 2048.0f) bad = true;
+      amp = n * amp;
+    }
+    if (fabsf(amp) > 60000.0f) bad = true;
+    // slab (j, k, g16): row = output channel within the group, K element = the same channel (diagonal)
+    const int g16 = cl_c / 16, cc = cl_c % 16;
+    __half *slab = b2 + (size_t)((j * g.NSW + k) * cl.G + g16) * (v2::kSlabBytes / 2);
+    slab[tc_tile_offset16(cc, cc, kTcLBO, 256) / 2] = __float2half_rn(amp);
+  }
+  if (bad && status != nullptr) atomicOr(status, 2);
+}
+
 __global__ void weight_digits_kernel(Geo g, const int8_t *__restrict__ wcodes, float *__restrict__ wdigits) {
   const int64_t n = (int64_t)g.Cout * g.F;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n;
@@ -73,7 +127,9 @@ __global__ void weight_digits_kernel(Geo g, const int8_t *__restrict__ wcodes, f
 }
 
 // int8 digit tiles for the tcgen05 kernel: tile (ct, i) = NSW*CT rows x Kp bytes, row = k*CT + c_local.
-__global__ void weight_tiles_kernel(Geo g, int CT, int Kp, const int8_t *__restrict__ wcodes,
+// enc 0: the digit as int8; enc 1: e4m3 +-0.5 (0x30 / 0xB0) for the +-1 digits of 1-bit slices (v2 forward, whose
+// activation planes hold 2.0 for a set bit, so that products are +-1).
+__global__ void weight_tiles_kernel(Geo g, int CT, int Kp, int enc, const int8_t *__restrict__ wcodes,
                                     int8_t *__restrict__ wtiles) {
   const int nct = g.Cout / CT;
   const int rows = g.NSW * CT;
@@ -95,6 +151,7 @@ __global__ void weight_tiles_kernel(Geo g, int CT, int Kp, const int8_t *__restr
       digit = (mag >> (g.wbs * k)) & g.wmask;
       if (code < 0) digit = -digit;
     }
+    if (enc == 1) digit = digit > 0 ? 0x30 : (digit < 0 ? (int)(int8_t)0xB0 : 0);
     wtiles[tile * tile_bytes + tc_tile_offset(r, kk, Kp)] = (int8_t)digit;
   }
 }
@@ -194,8 +251,11 @@ int launch_alpha_quant(const float *alpha, int64_t n, int qn, int qp, const floa
   return 0;
 }
 
-int launch_adc_table(const Geo &g, const float *s, const float *alpha_q, const int8_t *mask, void *table,
-                     int32_t *status, cudaStream_t st) {
+int64_t table_v2_offset(const Geo &g) { return (table_tiled_offset(g) + table_entries(g) * 12 + 255) & ~(int64_t)255; }
+int64_t table_total_bytes(const Geo &g) { return table_v2_offset(g) + v2::const_section_bytes(g); }
+
+int launch_adc_table(const Geo &g, const float *s, const float *alpha_q, const float *alpha_scale, const int8_t *mask,
+                     void *table, int32_t *status, cudaStream_t st) {
   CIMQ_REQUIRE(g.adc_mode == CIMQ_ADC_MULTIBIT || alpha_q != nullptr, "adc_table: alpha_q is NULL");
   int64_t n = table_entries(g);
   int blocks = (int)((n + 127) / 128);
@@ -203,6 +263,14 @@ int launch_adc_table(const Geo &g, const float *s, const float *alpha_q, const i
       g, tc_channel_tile_for(g), s, alpha_q, mask, reinterpret_cast<int4 *>(table),
       reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(table) + table_tiled_offset(g)), status);
   CIMQ_CUDA_OK(cudaGetLastError());
+  // v2 constants: needs the integer amplitudes, i.e. the scale of the alpha quantiser (ternary / binary ADC)
+  if (v2::supported(g) && (g.adc_mode == CIMQ_ADC_MULTIBIT || alpha_scale != nullptr)) {
+    const v2::ConstLayout cl = v2::const_layout(g);
+    v2_consts_kernel<<<(g.Cout / cl.CT) * g.NX, 256, 0, st>>>(
+        g, cl, s, alpha_q, alpha_scale, mask, reinterpret_cast<const int4 *>(table),
+        reinterpret_cast<uint8_t *>(table) + table_v2_offset(g), status);
+    CIMQ_CUDA_OK(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -220,7 +288,13 @@ WtLayout wt_layout(const Geo &g) {
   w.lut_bytes = fwd ? (int64_t)g.F * 8 : 0;
   w.bwd_off = align(w.lut_off + w.lut_bytes);
   w.bwd_bytes = wtiles_bwd_bytes(g);
-  w.total = align(w.bwd_off + w.bwd_bytes);
+  w.fwd8_off = align(w.bwd_off + w.bwd_bytes);
+  w.fwd8_bytes = 0;
+  if (fwd && v2_forward_supported(g))
+    w.fwd8_bytes = (int64_t)g.NX * g.NSW * g.Cout * tc_kp(g);  // (Cout/CT) * NX tiles of NSW*CT rows x Kp
+  w.bwd2_off = align(w.fwd8_off + w.fwd8_bytes);
+  w.bwd2_bytes = (w.fwd8_bytes > 0 && w.bwd_bytes > 0) ? w.bwd_bytes : 0;
+  w.total = align(w.bwd2_off + w.bwd2_bytes);
   if (w.fwd_bytes == 0 && w.bwd_bytes == 0) w.total = 0;
   return w;
 }
@@ -237,8 +311,13 @@ int launch_weight_prepare(const Geo &g, const int8_t *wcodes, float *wdigits, vo
   if (wtiles != nullptr && wl.fwd_bytes > 0) {
     const int CT = tc_channel_tile_for(g);
     weight_tiles_kernel<<<(int)((wl.fwd_bytes + 255) / 256), 256, 0, st>>>(
-        g, CT, tc_kp(g), wcodes, reinterpret_cast<int8_t *>(wtiles) + wl.fwd_off);
+        g, CT, tc_kp(g), 0, wcodes, reinterpret_cast<int8_t *>(wtiles) + wl.fwd_off);
     CIMQ_CUDA_OK(cudaGetLastError());
+    if (wl.fwd8_bytes > 0) {
+      weight_tiles_kernel<<<(int)((wl.fwd8_bytes + 255) / 256), 256, 0, st>>>(
+          g, v2::channel_tile(g), tc_kp(g), 1, wcodes, reinterpret_cast<int8_t *>(wtiles) + wl.fwd8_off);
+      CIMQ_CUDA_OK(cudaGetLastError());
+    }
     if (launch_im2col_lut(g, reinterpret_cast<uint8_t *>(wtiles) + wl.lut_off, st)) return 1;
   }
   if (wtiles != nullptr && wl.bwd_bytes > 0) {

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "cimq_common.cuh"
+#include "cim_v2.cuh"
 
 namespace cimq {
 
@@ -48,6 +49,8 @@ int cimq_layer_info(const cimq_layer_t *layer, cimq_info_t *info) {
   info->wtiles_bytes = wtiles_bytes(g);
   info->bwd_workspace_bytes = conv_backward_ws_bytes(g);
   info->psum_count = (int64_t)g.B * g.NX * g.NSW * g.NSA * g.L * g.Cout;
+  info->tc_v2 = (v2_forward_supported(g) && tc_backward_supported(g)) ? 1 : 0;
+  info->state_v2_bytes = info->tc_v2 ? v2::state_bytes(g) : 0;
   return 0;
 }
 
@@ -103,7 +106,15 @@ int cimq_adc_table(const cimq_layer_t *layer, const float *s, const float *alpha
   Geo g;
   if (make_geo(layer, &g)) return 1;
   CIMQ_REQUIRE(s && binary_mask && table, "adc_table: NULL argument");
-  return launch_adc_table(g, s, alpha_q, binary_mask, table, status, as_stream(stream));
+  return launch_adc_table(g, s, alpha_q, nullptr, binary_mask, table, status, as_stream(stream));
+}
+
+int cimq_adc_table2(const cimq_layer_t *layer, const float *s, const float *alpha_q, const float *alpha_scale,
+                    const int8_t *binary_mask, void *table, int32_t *status, void *stream) {
+  Geo g;
+  if (make_geo(layer, &g)) return 1;
+  CIMQ_REQUIRE(s && binary_mask && table, "adc_table2: NULL argument");
+  return launch_adc_table(g, s, alpha_q, alpha_scale, binary_mask, table, status, as_stream(stream));
 }
 
 int cimq_weight_prepare(const cimq_layer_t *layer, const int8_t *wcodes, float *wdigits, void *wtiles,
@@ -115,14 +126,21 @@ int cimq_weight_prepare(const cimq_layer_t *layer, const int8_t *wcodes, float *
 }
 
 int cimq_conv_forward(const cimq_layer_t *layer, const uint8_t *xcodes, const int8_t *wcodes, const void *wtiles,
-                      const void *table, const float *s, const int8_t *binary_mask, float *out, uint32_t *state,
+                      const void *table, const float *s, const int8_t *binary_mask, float *out, void *state,
                       uint32_t flags, void *stream) {
   Geo g;
   if (make_geo(layer, &g)) return 1;
   CIMQ_REQUIRE(xcodes && wcodes && table && s && out, "conv_forward: NULL argument");
+  if (flags & CIMQ_FLAG_V2) {
+    CIMQ_REQUIRE(!(flags & CIMQ_FLAG_FORCE_SIMT) && wtiles != nullptr && v2_forward_supported(g),
+                 "conv_forward: CIMQ_FLAG_V2 on a layer the v2 kernels do not cover (see cimq_info_t.tc_v2)");
+    return launch_conv_v2_forward(g, xcodes, wtiles, table, out, reinterpret_cast<uint8_t *>(state),
+                                  as_stream(stream));
+  }
+  uint32_t *state1 = reinterpret_cast<uint32_t *>(state);
   if (!(flags & CIMQ_FLAG_FORCE_SIMT) && wtiles != nullptr && tc_forward_supported(g))
-    return launch_conv_tc_forward(g, xcodes, wtiles, table, s, binary_mask, out, state, as_stream(stream));
-  return launch_conv_simt(g, SIMT_FORWARD, xcodes, wcodes, table, s, binary_mask, out, state, nullptr, nullptr,
+    return launch_conv_tc_forward(g, xcodes, wtiles, table, s, binary_mask, out, state1, as_stream(stream));
+  return launch_conv_simt(g, SIMT_FORWARD, xcodes, wcodes, table, s, binary_mask, out, state1, nullptr, nullptr,
                           as_stream(stream));
 }
 
@@ -137,12 +155,13 @@ int cimq_conv_forward_stochastic(const cimq_layer_t *layer, const uint8_t *xcode
 }
 
 int cimq_conv_backward(const cimq_layer_t *layer, const float *grad_out, const uint8_t *xcodes,
-                       const float *wdigits, const void *wtiles, const uint32_t *state, const float *s,
+                       const float *wdigits, const void *wtiles, const void *state, const float *s,
                        const int8_t *binary_mask, float *grad_xq, float *grad_wq, float *grad_alpha_q,
                        void *workspace, uint32_t flags, void *stream) {
   Geo g;
   if (make_geo(layer, &g)) return 1;
-  return launch_conv_backward(g, grad_out, xcodes, wdigits, wtiles, state, s, binary_mask, grad_xq, grad_wq,
+  return launch_conv_backward(g, grad_out, xcodes, wdigits, wtiles, reinterpret_cast<const uint32_t *>(state), s,
+                              binary_mask, grad_xq, grad_wq,
                               grad_alpha_q, workspace, flags, as_stream(stream));
 }
 

@@ -100,8 +100,8 @@ int launch_lsq_backward(const float *gq, const float *x, int64_t n, const float 
                         float *gx, float *galpha, void *ws, cudaStream_t st);
 int64_t lsq_backward_ws_bytes(int64_t n);
 
-int launch_adc_table(const Geo &g, const float *s, const float *alpha_q, const int8_t *mask, void *table,
-                     int32_t *status, cudaStream_t st);
+int launch_adc_table(const Geo &g, const float *s, const float *alpha_q, const float *alpha_scale, const int8_t *mask,
+                     void *table, int32_t *status, cudaStream_t st);
 int launch_alpha_quant(const float *alpha, int64_t n, int qn, int qp, const float *gaq, float *out, float *aux,
                        cudaStream_t st);
 int launch_weight_prepare(const Geo &g, const int8_t *wcodes, float *wdigits, void *wtiles, cudaStream_t st);
@@ -133,7 +133,10 @@ int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, c
 // Sections of the prepared-weights buffer ("wtiles"): forward int8 digit tiles, im2col LUT (int2 per crossbar
 // row), backward bf16 digit tiles.  A section the layer does not support has zero bytes.
 struct WtLayout {
-  int64_t fwd_off, fwd_bytes, lut_off, lut_bytes, bwd_off, bwd_bytes, total;
+  int64_t fwd_off, fwd_bytes, lut_off, lut_bytes, bwd_off, bwd_bytes;
+  int64_t fwd8_off, fwd8_bytes;  // v2 forward: e4m3 digit tiles (+-0.5), same tiling as the int8 ones
+  int64_t bwd2_off, bwd2_bytes;  // v2 dgrad: bf16 digit tiles pre-scaled for the count fields of the v2 state
+  int64_t total;
 };
 WtLayout wt_layout(const Geo &g);
 
@@ -154,6 +157,25 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
 // same values tiled for the tcgen05 epilogue: uint32 [Cout/CT][NX][pairs][tp | tg | amp][CT]
 __host__ __device__ inline int64_t table_entries(const Geo &g) { return (int64_t)g.NX * g.pairs * g.Cout; }
 __host__ __device__ inline int64_t table_tiled_offset(const Geo &g) { return (table_entries(g) * 16 + 255) & ~(int64_t)255; }
-__host__ __device__ inline int64_t table_total_bytes(const Geo &g) { return table_tiled_offset(g) + table_entries(g) * 12; }
+// ... followed (256-byte aligned) by the v2 section: header {o0, o1} + constants blocks (cim_v2.cuh)
+int64_t table_v2_offset(const Geo &g);
+int64_t table_total_bytes(const Geo &g);
+
+// Multi-bit ADC STE clip bounds (lsq.py:310-311): clipped where ps >= Qp + 1e-5 or ps <= Qn - 1e-5, compared in
+// fp32.  chi = smallest integer partial sum that is clipped high, clo = largest one clipped low.  For small ranges
+// that is qp+1 / qn-1; where 1e-5 is below half an ulp of the bound (Qp >= 512, Qn <= -256) the bound itself clips.
+inline void multibit_clip_bounds(int qn, int qp, int *chi, int *clo) {
+  const float hi = (float)((double)qp + 1e-5), lo = (float)((double)qn - 1e-5);
+  int c = qp;
+  while ((float)c < hi) ++c;
+  *chi = c;
+  c = qn;
+  while ((float)c > lo) --c;
+  *clo = c;
+}
+
+bool v2_forward_supported(const Geo &g);
+int launch_conv_v2_forward(const Geo &g, const uint8_t *xcodes, const void *wtiles, const void *table, float *out,
+                           uint8_t *state, cudaStream_t st);
 
 }  // namespace cimq

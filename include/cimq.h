@@ -28,6 +28,12 @@
  *                                   sq = j*NSW + k:
  *                                     binary/ternary: bit sq = code +1, bit pairs+sq = code -1, bit 2*pairs+sq = clipped
  *                                     multi-bit     : bit sq = clipped (STE mask off)
+ *   ADC state v2 (CIMQ_FLAG_V2)     uint8, channel fastest, 1-bit slices with NSW = NSA <= 3:
+ *                                     plane D [NX][M][Cout]      sum_k 4^k * #{j: (i,k,j) not clipped}
+ *                                     plane W [NX][M][Cout]      sum_j 4^j * #{k: (i,k,j) not clipped}
+ *                                     plane C [NX][NSA][M][Cout] sum_k 4^k * (code(i,k,j) + 1)   (not for multi-bit)
+ *                                   i.e. exactly the per-slice sums of the STE mask that dgrad / wgrad need
+ *                                   (lsq.py:298-313, 362-376) and the ternary codes grad_alpha needs (lsq.py:321-334).
  */
 #ifndef CIMQ_H_
 #define CIMQ_H_
@@ -39,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CIMQ_VERSION 100
+#define CIMQ_VERSION 200
 
 /* ADC modes: lsq.py:197-230 */
 enum {
@@ -51,8 +57,12 @@ enum {
 /* flags for cimq_conv_forward / backward */
 enum {
   CIMQ_FLAG_FORCE_SIMT = 1,   /* use the CUDA-core kernels even where a tcgen05 kernel exists (tests) */
-  CIMQ_FLAG_DETERMINISTIC = 2 /* backward: fold grad_x with a separate fixed-order pass instead of fp32
-                                 reductions in the dgrad epilogue (bit-reproducible run to run, slower) */
+  CIMQ_FLAG_DETERMINISTIC = 2, /* backward: fold grad_x with a separate fixed-order pass instead of fp32
+                                  reductions in the dgrad epilogue (bit-reproducible run to run, slower) */
+  CIMQ_FLAG_V2 = 4             /* second-generation kernels and ADC-state format ("v2", below).  Only where
+                                  cimq_info_t.tc_v2 is set; the table must come from cimq_adc_table2 with
+                                  alpha_scale (binary / ternary ADC) and the flag must be passed to BOTH
+                                  cimq_conv_forward and cimq_conv_backward of a step */
 };
 
 /* Geometry + quantisation of one Conv2dLSQCiM layer (_quan_base.py:174-237, lsq.py:512-531).
@@ -72,13 +82,14 @@ typedef struct cimq_info {
   int32_t state_words;          /* uint32 words of ADC state per (crossbar, channel, pixel) */
   int32_t tc_forward;           /* 1 if the tcgen05 forward kernel covers this layer */
   int32_t tc_backward;          /* 1 if the tcgen05 dgrad / wgrad kernels cover this layer */
-  int32_t reserved_;
+  int32_t tc_v2;                /* 1 if the v2 kernels (CIMQ_FLAG_V2) cover this layer */
   int64_t state_bytes;          /* NX*Cout*state_words*M*4 */
   int64_t table_bytes;          /* ADC table: NX*pairs*Cout entries {tp, tg, amp, 0} + a tiled copy for tcgen05 */
   int64_t wdigits_bytes;        /* fp32 weight digit planes [NSW, Cout, F] */
   int64_t wtiles_bytes;         /* int8 weight digit tiles in tcgen05 shared-memory order (0 if !tc_forward) */
   int64_t bwd_workspace_bytes;  /* scratch for cimq_conv_backward */
   int64_t psum_count;           /* B*NX*NSW*NSA*L*Cout */
+  int64_t state_v2_bytes;       /* ADC state in the v2 format (0 if !tc_v2) */
 } cimq_info_t;
 
 int cimq_version(void);
@@ -139,6 +150,14 @@ int cimq_alpha_quantize_backward(const float *alpha, const float *grad_alpha_q, 
 int cimq_adc_table(const cimq_layer_t *layer, const float *s, const float *alpha_q, const int8_t *binary_mask,
                    void *table, int32_t *status, void *stream);
 
+/* The same, plus the constants of the v2 kernels.  alpha_scale (device, 1 float; aux[0] of cimq_alpha_quantize) is the
+ * step of the nbits_alpha quantiser of lsq.py:566-571: alpha_q = n * alpha_scale with integer n in [1, 2^nbits_alpha),
+ * which lets the tensor core do the shift-and-add of lsq.py:233 on exact integers
+ * (out = alpha_scale * sum code * n * binary_mask).  status bit 1 is set if some alpha_q is not such a multiple
+ * (n < 2048 is required).  alpha_scale may be NULL for CIMQ_ADC_MULTIBIT. */
+int cimq_adc_table2(const cimq_layer_t *layer, const float *s, const float *alpha_q, const float *alpha_scale,
+                    const int8_t *binary_mask, void *table, int32_t *status, void *stream);
+
 /* Sign-magnitude digit planes of the weight codes (slicing_weights_signed, lsq.py:438-464):
  * wdigits fp32 [NSW, Cout, F] (CUDA-core backward; may be NULL); wtiles (may be NULL): operand tiles in
  * tcgen05 shared-memory order -- int8 digit tiles + im2col LUT for the forward, bf16 digit tiles for dgrad. */
@@ -152,7 +171,7 @@ int cimq_weight_prepare(const cimq_layer_t *layer, const int8_t *wcodes, float *
  * out [B,Cout,L] fp32; state (optional, needed for backward) records code and clip bit of every
  * partial sum. */
 int cimq_conv_forward(const cimq_layer_t *layer, const uint8_t *xcodes, const int8_t *wcodes, const void *wtiles,
-                      const void *table, const float *s, const int8_t *binary_mask, float *out, uint32_t *state,
+                      const void *table, const float *s, const int8_t *binary_mask, float *out, void *state,
                       uint32_t flags, void *stream);
 
 /* The same with the stochastic near-ADC-less read-out of lsq.py:205-220 (adcbits 1.5 only): every partial sum is
@@ -169,7 +188,7 @@ int cimq_conv_forward_stochastic(const cimq_layer_t *layer, const uint8_t *xcode
  * grad_alpha_q [NX,NSW,NSA,Cout] (NULL for CIMQ_ADC_MULTIBIT).  wdigits is needed by the CUDA-core kernels,
  * wtiles by the tcgen05 kernels; pass both to let the library choose. */
 int cimq_conv_backward(const cimq_layer_t *layer, const float *grad_out, const uint8_t *xcodes,
-                       const float *wdigits, const void *wtiles, const uint32_t *state, const float *s,
+                       const float *wdigits, const void *wtiles, const void *state, const float *s,
                        const int8_t *binary_mask, float *grad_xq, float *grad_wq, float *grad_alpha_q,
                        void *workspace, uint32_t flags, void *stream);
 
