@@ -14,9 +14,18 @@ N > 1 (torchrun, one rank per GPU): every rank runs its own batch shard (weak sc
 weight / step-size gradients are all-reduced with NCCL inside the timed step, as data-parallel
 training does.
 
-``--impl reference`` times the CPU restatement of the reference algorithm (oracle/cim_oracle.py, numpy)
-on the host cores with the same metric; it is the only place besides the ``cpu_baseline`` leg where
-bench.py executes anything under oracle/.
+Every line also carries (BASELINE.json's second metric and configs 2 / 4):
+  ``train``          ResNet-20 w3a3 CiM training step (forward, loss, backward, gradient all-reduce, SGD) at GLOBAL
+                     batch 2048 split evenly over the N GPUs (strong scaling): img/s, ms/step, launches/step;
+  ``matrix``         (N = 1) forward / backward device time of the microbench layer for crossbar rows {64,128,256} x
+                     ADC bits {1, 1.5, 2, 3, 4};
+  ``reference_cuda`` (N = 1) the UNMODIFIED reference module (baseline/_ref) on the same GPU at the same shape: what a
+                     user of the reference gets today.
+
+``--impl reference`` times the reference's own ``Conv2dLSQCiM`` (unmodified, from baseline/_ref) on the host cores
+with the same metric -- or, only if that copy is missing, the numpy restatement under oracle/ (the one other place
+besides the ``cpu_baseline`` leg where bench.py executes anything under oracle/).  It runs a bounded sample
+(``config.cpu_sample_batch`` images per step, rate-normalised) and says so in ``config``.
 """
 import argparse
 import json
@@ -51,6 +60,10 @@ def parse_args():
     p.add_argument("--cpu-sample-batch", type=int, default=8)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    p.add_argument("--no-train", action="store_true", help="skip the ResNet-20 training block")
+    p.add_argument("--no-matrix", action="store_true", help="skip the crossbar x ADC matrix and the reference-on-GPU leg")
+    p.add_argument("--train-global-batch", type=int, default=2048)
+    p.add_argument("--train-steps", type=int, default=10)
     return p.parse_args()
 
 
@@ -152,18 +165,6 @@ def cpu_step(a, batch):
     return cpu_step_factory(a, batch), "port"
 
 
-def time_cpu(a, batch, reps):
-    step = cpu_step_factory(a, batch)
-    step()  # warm-up (BLAS threads, page faults)
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        step()
-        ts.append(time.perf_counter() - t0)
-    fwd, bwd = layer_ops(batch, a.channels, a.hw, a.nbits)
-    return (fwd + bwd) / statistics.median(ts) / 1e12, statistics.median(ts)
-
-
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -186,7 +187,11 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
             "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": dt / a.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (holding integers)",
-            "data": "synthetic", "config": workload_config(a),
+            "data": "synthetic",
+            "config": dict(workload_config(a), batch_per_gpu=b, cpu_sample_batch=b,
+                           note=f"bounded sample: {b} images per step instead of {a.batch} (the reference's 6-D "
+                                "temporaries at 256 images need > 30 GB and minutes per step on CPU); TOPS is a rate, "
+                                "so the figure is comparable"),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -280,6 +285,216 @@ def event_time_ms(fn, iters, torch, graph=True):
     stop.record()
     torch.cuda.synchronize()
     return start.elapsed_time(stop) / iters
+
+
+# --------------------------------------------------------------------------------------------------
+# kernel-level pieces (C-ABI calls on resident tensors), shared by the per-kernel block and the matrix
+# --------------------------------------------------------------------------------------------------
+def prepare_layer_tensors(torch, L, layer, x, gy):
+    """Everything the C-ABI conv calls of one layer need, built the way the module builds it (v2 kernels where the
+    layer is covered, CIMQ_FLAG_V2)."""
+    spec = layer._spec(x)
+    info = L.layer_info(spec)
+    nb_a, nb_w = layer.nbits_a, layer.nbits_w
+    qp_a, qn_w, qp_w = 2 ** nb_a - 1, -(2 ** (nb_w - 1)), 2 ** (nb_w - 1) - 1
+    B, C = x.shape[0], layer.out_channels
+    with torch.no_grad():
+        s = L.step_sizes(layer.alpha_act.data, layer.alpha_weight.data, 1.0 / math.sqrt(x.numel() * qp_a),
+                         1.0 / math.sqrt(layer.weight.numel() * qp_w))
+        xd, wd = x.detach(), layer.weight.detach().contiguous()
+        xc = L.lsq_quantize(xd, s[0:1], 0, qp_a)
+        wc = L.lsq_quantize(wd, s[1:2], qn_w, qp_w).view(C, -1)
+        mask = layer.binary_mask.reshape(info.NSW, info.NSA).contiguous()
+        aq = scale = None
+        if layer.alpha_cim is not None:
+            aq, scale = layer._alpha_q()
+            aq, scale = aq.detach().contiguous(), scale.detach()
+        v2 = L.v2_usable(spec, aq is not None, scale)
+        table = L.adc_table(spec, s, aq, mask, alpha_scale=scale if v2 else None)
+        wdig, wtiles = L.weight_prepare(spec, wc, want_digits=not info.tc_backward)
+    return dict(spec=spec, info=info, s=s, xd=xd, xc=xc, wc=wc, mask=mask, aq=aq, table=table, wdig=wdig,
+                wtiles=wtiles, go=gy.reshape(B, C, -1), flags=L.FLAG_V2 if v2 else 0, v2=bool(v2),
+                qp_a=qp_a)
+
+
+def time_conv_kernels(torch, L, t, iters, parts=True):
+    """Device time (ms) of the conv forward (training / inference) and of the backward and its parts."""
+    fw = lambda save: L.conv_forward(t["spec"], t["xc"], t["wc"], t["wtiles"], t["table"], t["s"], t["mask"],
+                                     save_state=save, flags=t["flags"])
+    out, state = fw(True)
+    bw = lambda **kw: L.conv_backward(t["spec"], t["go"], t["xc"], t["wdig"], t["wtiles"], state, t["s"], t["mask"], **kw)
+    has_alpha = t["aq"] is not None
+    r = {"fwd_train": event_time_ms(lambda: fw(True), iters, torch),
+         "fwd_infer": event_time_ms(lambda: fw(False), iters, torch),
+         "bwd": event_time_ms(lambda: bw(need_alpha=has_alpha), iters, torch)}
+    if parts:
+        r["wgrad"] = event_time_ms(lambda: bw(need_alpha=False, need_input=False), iters, torch)
+        r["dgrad"] = event_time_ms(lambda: bw(need_alpha=False, need_weight=False), iters, torch)
+        r["alpha"] = (event_time_ms(lambda: bw(need_alpha=True, need_input=False, need_weight=False), iters, torch)
+                      if has_alpha else 0.0)
+    del out, state
+    return r
+
+
+def config_matrix(torch, cq, L, a, dev, int8_peak, bf16_peak):
+    """BASELINE.json config 2: the microbench layer for crossbar rows {64,128,256} x ADC bits {1,1.5,2,3,4}:
+    forward (training) and backward device time, algorithmic rate and fraction of the tensor roofline."""
+    C, HW, B = a.channels, a.hw, a.batch
+    fwd_ops, bwd_ops = layer_ops(B, C, HW, a.nbits)
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = torch.relu(torch.randn(B, C, HW, HW, device=dev, generator=g))
+    gy = torch.randn(B, C, HW, HW, device=dev, generator=g)
+    rows = []
+    for xbar in (64, 128, 256):
+        for adc in (1, 1.5, 2, 3, 4):
+            torch.manual_seed(11)
+            layer = cq.Conv2dLSQCiM(C, C, (3, 3), (1, 1), (1, 1), (1, 1), 1, False, nbits_w=a.nbits, nbits_a=a.nbits,
+                                    nbits_alpha=8, wbitslice=1, abitslice=1, xbar=xbar, adcbits=adc).to(dev).train()
+            with torch.no_grad():
+                torch.nn.init.kaiming_normal_(layer.weight)
+                layer(x)  # lazy initialisation
+                t = prepare_layer_tensors(torch, L, layer, x, gy)
+                r = time_conv_kernels(torch, L, t, 3, parts=False)
+            step_ms = r["fwd_train"] + r["bwd"]
+            rows.append({"xbar": xbar, "adcbits": adc, "kernels": "v2" if t["v2"] else "v1",
+                         "fwd_ms": round(r["fwd_train"], 4), "bwd_ms": round(r["bwd"], 4),
+                         "fwd_TOPS": round(fwd_ops / r["fwd_train"] / 1e9, 1),
+                         "fwd_frac_int8_tc": round(fwd_ops / r["fwd_train"] / 1e9 / int8_peak, 4),
+                         "bwd_TFLOPs": round(bwd_ops / r["bwd"] / 1e9, 1),
+                         "bwd_frac_bf16_tc": round(bwd_ops / r["bwd"] / 1e9 / bf16_peak, 4),
+                         "fwd_bwd_TOPS": round((fwd_ops + bwd_ops) / step_ms / 1e9, 1)})
+            del layer, t
+            torch.cuda.empty_cache()
+    return rows
+
+
+def reference_cuda_leg(torch, a, dev):
+    """The UNMODIFIED reference module (baseline/_ref/models/_modules/lsq.py) on this GPU at the bench shape: its
+    own torch-CUDA path (6-D temporaries, python slice loops).  None if baseline/_ref is missing."""
+    root = reference_root()
+    if root is None:
+        return None
+    saved = list(sys.path)
+    try:
+        sys.path.insert(0, root)
+        import importlib
+        ref_nn = importlib.import_module("models._modules")
+        adc = int(a.adcbits) if a.adcbits == int(a.adcbits) else a.adcbits
+        C, HW, B = a.channels, a.hw, a.batch
+        torch.manual_seed(5)
+        m = ref_nn.Conv2dLSQCiM(C, C, (3, 3), (1, 1), (1, 1), (1, 1), 1, False, nbits_w=a.nbits, nbits_a=a.nbits,
+                                nbits_alpha=8, wbitslice=1, abitslice=1, xbar=a.xbar, adcbits=adc, signed_xbar=False,
+                                stochastic_quant=False).to(dev).train()
+        x = torch.relu(torch.randn(B, C, HW, HW, device=dev)).requires_grad_(True)
+        gy = torch.randn(B, C, HW, HW, device=dev)
+        m(x.detach())  # lazy inits
+
+        def step():
+            for p_ in m.parameters():
+                p_.grad = None
+            x.grad = None
+            m(x).backward(gy)
+
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 3
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        fwd_ops, bwd_ops = layer_ops(B, C, HW, a.nbits)
+        peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+        del m, x, gy
+        torch.cuda.empty_cache()
+        return {"ms_per_step": ms, "TOPS": (fwd_ops + bwd_ops) / ms / 1e9, "steps": n, "batch": B,
+                "what": "unmodified reference Conv2dLSQCiM (baseline/_ref) forward+backward on the same GPU, eager torch",
+                "peak_mem_GiB": round(peak_gb, 1)}
+    except Exception as e:  # e.g. out of memory at other shapes
+        return {"error": repr(e)[:300]}
+    finally:
+        sys.path[:] = saved
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            sys.modules.pop(k, None)
+
+
+def train_block(torch, dist, a, world, rank, dev):
+    """BASELINE.json config 4: ResNet-20 w3a3 CiM (19 Conv2dLSQCiM, xbar 128, ternary ADC) training step on synthetic
+    CIFAR-shaped data, GLOBAL batch a.train_global_batch split evenly over the ranks: forward, cross-entropy, backward,
+    one flat NCCL all-reduce of all gradients (N > 1), SGD.  Reference loop: examples/__init__.py:390-462, DDP at
+    :693-716.  Device time by CUDA events around K graph replays, max over ranks."""
+    from cim_quantization_b200 import harness, _lib as L
+    from cim_quantization_b200.distributed import FlatGradAllReducer, broadcast_parameters
+    gb = a.train_global_batch
+    if gb % world != 0:
+        return {"error": f"global batch {gb} does not divide over {world} ranks"}
+    bpg = gb // world
+    torch.manual_seed(0)
+    model = harness.convert_to_cim(harness.resnet20(1), nbits_w=3, nbits_a=3, xbar=128, adcbits=1.5).to(dev).train()
+    torch.manual_seed(1 + rank)
+    x = torch.randn(bpg, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (bpg,), device=dev)
+    crit = torch.nn.CrossEntropyLoss()
+    model(x)  # lazy initialisation of all step sizes on the first batch (lsq.py:532-563)
+    if world > 1:
+        broadcast_parameters(model, 0)
+    opt = torch.optim.SGD(harness.sgd_param_groups(model), lr=0.01, momentum=0.9)
+    reducer = FlatGradAllReducer(model.parameters())
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(x), y)
+        loss.backward()
+        if world > 1:
+            reducer.all_reduce_()
+        opt.step()
+        return loss
+
+    L.launch_counter = 0
+    step()
+    launches = L.launch_counter
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    runner, graphed = step, False
+    if not a.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            g.replay()
+            torch.cuda.synchronize()
+            runner, graphed = g.replay, True
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] train graph capture failed ({e!r}); eager steps", file=sys.stderr)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.train_steps):
+        runner()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    nconv = sum(1 for m_ in model.modules() if m_.__class__.__name__ == "Conv2dLSQCiM")
+    return {"metric": "resnet20_w3a3_cim_train_img_per_s", "img_per_s": gb * a.train_steps / (ms * 1e-3), "unit": "img/s",
+            "ms_per_step": ms / a.train_steps, "steps": a.train_steps, "global_batch": gb, "batch_per_gpu": bpg,
+            "n_gpus": world, "scaling": "strong", "cim_convs": nconv, "cuda_graph": graphed,
+            "gpu_launches_per_step": int(launches), "grad_allreduce_bytes": int(reducer.nbytes),
+            "model": "ResNet-20 CIFAR (harness.resnet20; option-A shortcuts), w3a3, first conv w8a8, xbar 128, adcbits 1.5, "
+                     "SGD lr 0.01 momentum 0.9 wd 1e-4, synthetic 32x32 data"}
 
 
 def run_ours(a):
@@ -400,126 +615,145 @@ def run_ours(a):
     ops_step = fwd_ops + bwd_ops
     value = ops_step * world * a.steps / (ms * 1e-3) / 1e12
 
+    # ---- end to end through the module surface with HOST buffers (pinned), copies inside the timed region
+    gw_host = torch.empty_like(layer.weight, device="cpu").pin_memory()
+    small_host = torch.empty(flat.numel() - layer.weight.numel(), device="cpu").pin_memory()
+
+    # Host batches reach the GPU through the package's HostBatchPipeline (a copy stream, two batches deep): the
+    # H2D copy of step n+1 overlaps the kernels of step n.  Every timed step still copies its own inputs from
+    # pinned host memory and reads its gradients back; the pipeline starts empty inside the timed region.
+    from cim_quantization_b200.harness import HostBatchPipeline
+
+    def e2e_run(nsteps):
+        pipe = HostBatchPipeline(dev, depth=2)
+        submitted = 0
+        for n in range(nsteps):
+            while submitted < nsteps and pipe.can_submit():
+                pipe.submit((x_host, gy_host))
+                submitted += 1
+            xin, gyin = pipe.get()
+            xin = xin.detach().requires_grad_(True)
+            for p in params:
+                p.grad = None
+            layer(xin).backward(gyin)
+            pipe.release()
+            if world > 1:
+                reducer.all_reduce_()
+            gw_host.copy_(layer.weight.grad, non_blocking=True)
+            small_host.copy_(torch.cat([p.grad.reshape(-1) for p in params if p is not layer.weight]),
+                             non_blocking=True)
+
+    e2e_run(3)
+    torch.cuda.synchronize()
+    e2e_iters = max(3, min(a.steps, 10))
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_run(e2e_iters)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / e2e_iters
+    if world > 1:  # every rank feeds its own GPU from its own pinned buffers; the job's time is the slowest rank's
+        t_ = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t_.item())
+    e2e = {"value": ops_step * world / (e2e_ms * 1e-3) / 1e12, "unit": UNIT,
+           "h2d_bytes_per_step": int(x_host.numel() * 4 + gy_host.numel() * 4),
+           "d2h_bytes_per_step": int(gw_host.numel() * 4 + small_host.numel() * 4), "n_gpus": world,
+           "ms_per_step": e2e_ms, "steps": e2e_iters,
+           "pipeline": "HostBatchPipeline depth 2 (copy stream); starts empty inside the timed region"}
+
+
+    # ---- ResNet-20 training block (every rank takes part), before the rank-0-only legs
+    train = None
+    if not a.no_train:
+        try:
+            train = train_block(torch, dist, a, world, rank, dev)
+        except Exception as e:  # pragma: no cover
+            train = {"error": repr(e)[:300]}
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank != 0:
+            # the training step graph holds NCCL work: tearing the communicator down afterwards can hang, and nothing is
+            # left for this rank to do, so leave without the collective teardown
+            sys.stdout.flush()
+            os._exit(0)
+
     line = None
     if rank == 0:
         # ---- per-kernel device times (CUDA events, same process, same resident tensors)
-        spec = layer._spec(x)
-        info = L.layer_info(spec)
-        qp_a, qn_w, qp_w = 2 ** a.nbits - 1, -(2 ** (a.nbits - 1)), 2 ** (a.nbits - 1) - 1
+        t = prepare_layer_tensors(torch, L, layer, x, gy)
+        info = t["info"]
+        it = max(3, min(a.steps, 10))
         with torch.no_grad():
-            s = L.step_sizes(layer.alpha_act.data, layer.alpha_weight.data, 1.0 / math.sqrt(x.numel() * qp_a),
-                             1.0 / math.sqrt(layer.weight.numel() * qp_w))
-            xd, wd = x.detach(), layer.weight.detach().contiguous()
-            xc = L.lsq_quantize(xd, s[0:1], 0, qp_a)
-            wc = L.lsq_quantize(wd, s[1:2], qn_w, qp_w)
-            mask = layer.binary_mask.reshape(info.NSW, info.NSA).contiguous()
-            aq = layer._alpha_q().detach().contiguous() if layer.alpha_cim is not None else None
-            table = L.adc_table(spec, s, aq, mask)
-            wdig, wtiles = L.weight_prepare(spec, wc.view(C, -1))
-            out, state = L.conv_forward(spec, xc, wc.view(C, -1), wtiles, table, s, mask, save_state=True)
-            go = gy.view(B, C, -1)
-            gxq = torch.empty_like(xd)
-            it = max(3, min(a.steps, 10))
-            t_q = event_time_ms(lambda: L.lsq_quantize(xd, s[0:1], 0, qp_a), it, torch)
-            t_qb = event_time_ms(lambda: L.lsq_backward(gxq, xd, s[0:1], 0, qp_a, 1e-3), it, torch)
-            t_f = event_time_ms(lambda: L.conv_forward(spec, xc, wc.view(C, -1), wtiles, table, s, mask,
-                                                       save_state=True), it, torch)
-            t_fi = event_time_ms(lambda: L.conv_forward(spec, xc, wc.view(C, -1), wtiles, table, s, mask,
-                                                        save_state=False), it, torch)
-            t_b = event_time_ms(lambda: L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask,
-                                                        need_alpha=aq is not None), it, torch)
-            # the three independent parts of the backward call, each timed alone (NULL outputs skip a part)
-            t_bw = event_time_ms(lambda: L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask, need_alpha=False,
-                                                         need_input=False), it, torch)
-            t_bx = event_time_ms(lambda: L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask, need_alpha=False,
-                                                         need_weight=False), it, torch)
-            t_ba = (event_time_ms(lambda: L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask, need_alpha=True,
-                                                          need_input=False, need_weight=False), it, torch)
-                    if aq is not None else 0.0)
+            xd, gxq = t["xd"], torch.empty_like(t["xd"])
+            t_q = event_time_ms(lambda: L.lsq_quantize(xd, t["s"][0:1], 0, t["qp_a"]), it, torch)
+            t_qb = event_time_ms(lambda: L.lsq_backward(gxq, xd, t["s"][0:1], 0, t["qp_a"], 1e-3), it, torch)
+            kt = time_conv_kernels(torch, L, t, it)
+        t_f, t_fi, t_b, t_bw, t_bx, t_ba = (kt["fwd_train"], kt["fwd_infer"], kt["bwd"], kt["wgrad"], kt["dgrad"],
+                                            kt["alpha"])
+        gen = "v2" if t["v2"] else "v1"
         n = x.numel()
         int8_peak = 2.0 * bf16_peak  # no measured int8 peak: 2x the measured dense bf16 rate
+        psums = float(info.psum_count)
+        # conv-minimal HBM bytes: codes + output + weights (forward); + grad_out + grad_x (backward)
+        alg_fwd = n * 1.0 + B * C * HW * HW * 4.0 + layer.weight.numel() * 4.0
+        alg_dgrad = B * C * HW * HW * 4.0 + n * 4.0 + layer.weight.numel() * 4.0
+        alg_wgrad = B * C * HW * HW * 4.0 + n * 1.0 + layer.weight.numel() * 4.0
         kernels = {
+            "generation": gen,
             "lsq_quantize_x": {"ms": t_q, "GB/s": 5.0 * n / t_q / 1e6, "frac_hbm": 5.0 * n / t_q / 1e6 / hbm_peak},
             "lsq_backward_x": {"ms": t_qb, "GB/s": 12.0 * n / t_qb / 1e6, "frac_hbm": 12.0 * n / t_qb / 1e6 / hbm_peak},
-            "conv_forward_train(tcgen05=%d)" % info.tc_forward: {"ms": t_f, "TOPS": fwd_ops / t_f / 1e9,
-                                                                 "frac_int8_tc": fwd_ops / t_f / 1e9 / int8_peak},
+            "conv_forward_train": {"ms": t_f, "TOPS": fwd_ops / t_f / 1e9, "frac_int8_tc": fwd_ops / t_f / 1e9 / int8_peak},
             "conv_forward_infer": {"ms": t_fi, "TOPS": fwd_ops / t_fi / 1e9,
                                    "frac_int8_tc": fwd_ops / t_fi / 1e9 / int8_peak},
             "conv_backward": {"ms": t_b, "TFLOP/s": bwd_ops / t_b / 1e9, "frac_bf16_tc": bwd_ops / t_b / 1e9 / bf16_peak},
-            "conv_backward.wgrad(tcgen05=%d)" % info.tc_backward: {
-                "ms": t_bw, "TFLOP/s": wgrad_ops / t_bw / 1e9, "frac_bf16_tc": wgrad_ops / t_bw / 1e9 / bf16_peak},
-            "conv_backward.dgrad+col2im": {
-                "ms": t_bx, "TFLOP/s": dgrad_ops / t_bx / 1e9, "frac_bf16_tc": dgrad_ops / t_bx / 1e9 / bf16_peak},
-            "conv_backward.alpha_grad": {"ms": t_ba},
+            "conv_backward.wgrad": {"ms": t_bw, "TFLOP/s": wgrad_ops / t_bw / 1e9,
+                                    "frac_bf16_tc": wgrad_ops / t_bw / 1e9 / bf16_peak},
+            "conv_backward.dgrad+fold": {"ms": t_bx, "TFLOP/s": dgrad_ops / t_bx / 1e9,
+                                         "frac_bf16_tc": dgrad_ops / t_bx / 1e9 / bf16_peak},
+            "conv_backward.alpha_grad": (
+                {"ms": t_ba, "GB/s": (psums / 3.0 + n * 4.0) / t_ba / 1e6,
+                 "frac_hbm": (psums / 3.0 + n * 4.0) / t_ba / 1e6 / hbm_peak,
+                 "bytes": "state plane C (1 byte per 3 partial sums) + grad_out"} if t_ba > 0 else {"ms": 0.0}),
         }
-        # dominant kernel family of the step (by device time); DRAM traffic per launch from the committed ncu
-        # capture of the same kernels (profiles/ncu_traffic.json), when present
+        # DRAM traffic per launch from the committed ncu capture of the same kernels (profiles/ncu_traffic.json)
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except Exception:
             pass
-        # the single dominant kernel of the step by device time
+        fwd_name = ("conv_v2_kernel (CiM conv forward: tcgen05 kind::f8f6f4 -> fp16 TMEM partial sums, packed-half ADC "
+                    "epilogue, kind::f16 A-from-TMEM shift-and-add)" if t["v2"]
+                    else "conv_tc_kernel (CiM conv forward, tcgen05 kind::i8 + ADC epilogue)")
         cand = [
-            (t_f, {"kernel": "conv_tc_kernel (CiM conv forward, tcgen05 kind::i8 + ADC epilogue)", "bound": "tensor",
+            (t_f, {"kernel": fwd_name, "bound": "tensor",
                    "achieved": fwd_ops / t_f / 1e9, "peak": int8_peak, "unit": "TOPS",
                    "frac": fwd_ops / t_f / 1e9 / int8_peak, "traffic": _traffic_bytes(traffic, "conv_forward"),
-                   "peak_source": peak_src + " x2 for int8 (no measured int8 peak)",
+                   "algorithmic_bytes": alg_fwd,
+                   "peak_source": peak_src + " x2 for 8-bit operands (no measured int8 / fp8 peak)",
                    "note": "algorithmic ops 2*NSW*NSA*MKN, one contraction per slice pair"}),
             (t_bw, {"kernel": "bwd_weight_tc_kernel (+ finish; CiM conv wgrad, tcgen05 kind::f16 bf16x3)", "bound": "tensor",
                     "achieved": wgrad_ops / t_bw / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
                     "frac": wgrad_ops / t_bw / 1e9 / bf16_peak, "traffic": _traffic_bytes(traffic, "conv_wgrad"),
-                    "peak_source": peak_src,
+                    "algorithmic_bytes": alg_wgrad, "peak_source": peak_src,
                     "note": "algorithmic flops 2*NSA*MKN; the kernel issues 3x that in bf16 (hi/mid/lo split of grad)"}),
-            (t_bx, {"kernel": "bwd_input_tc_kernel + col2im (CiM conv dgrad, tcgen05 kind::f16 bf16x3)", "bound": "tensor",
+            (t_bx, {"kernel": "bwd_input_tc_kernel (CiM conv dgrad + fused fold, tcgen05 kind::f16 bf16x3)", "bound": "tensor",
                     "achieved": dgrad_ops / t_bx / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
                     "frac": dgrad_ops / t_bx / 1e9 / bf16_peak, "traffic": _traffic_bytes(traffic, "conv_dgrad"),
-                    "peak_source": peak_src,
+                    "algorithmic_bytes": alg_dgrad, "peak_source": peak_src,
                     "note": "algorithmic flops 2*NSW*MKN; the kernel issues 3x that in bf16 (hi/mid/lo split of grad)"}),
         ]
         roof = max(cand, key=lambda c: c[0])[1]
+        if roof.get("traffic"):
+            roof["traffic_over_algorithmic"] = roof["traffic"] / roof["algorithmic_bytes"]
+        # the whole step against the roofline the metric names (int tensor core)
+        roof["step"] = {"ops": ops_step, "ms": ms / a.steps, "TOPS": value / world,
+                        "frac_int8_tc": value / world / int8_peak,
+                        "note": "fwd+bwd algorithmic ops of one GPU / step time / (2 x measured bf16 peak)"}
         roof["ms_per_launch"] = max(c[0] for c in cand)
-
-        # ---- end to end through the module surface with HOST buffers (pinned), copies inside the timed region
-        gw_host = torch.empty_like(layer.weight, device="cpu").pin_memory()
-        small_host = torch.empty(flat.numel() - layer.weight.numel(), device="cpu").pin_memory()
-
-        # Host batches reach the GPU through the package's HostBatchPipeline (a copy stream, two batches deep): the
-        # H2D copy of step n+1 overlaps the kernels of step n.  Every timed step still copies its own inputs from
-        # pinned host memory and reads its gradients back; the pipeline starts empty inside the timed region.
-        from cim_quantization_b200.harness import HostBatchPipeline
-
-        def e2e_run(nsteps):
-            pipe = HostBatchPipeline(dev, depth=2)
-            submitted = 0
-            for n in range(nsteps):
-                while submitted < nsteps and pipe.can_submit():
-                    pipe.submit((x_host, gy_host))
-                    submitted += 1
-                xin, gyin = pipe.get()
-                xin = xin.detach().requires_grad_(True)
-                for p in params:
-                    p.grad = None
-                layer(xin).backward(gyin)
-                pipe.release()
-                gw_host.copy_(layer.weight.grad, non_blocking=True)
-                small_host.copy_(torch.cat([p.grad.reshape(-1) for p in params if p is not layer.weight]),
-                                 non_blocking=True)
-
-        e2e_run(3)
-        torch.cuda.synchronize()
-        e2e_iters = max(3, min(a.steps, 10))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        e2e_run(e2e_iters)
-        e1.record()
-        torch.cuda.synchronize()
-        e2e_ms = e0.elapsed_time(e1) / e2e_iters
-        e2e = {"value": ops_step / (e2e_ms * 1e-3) / 1e12, "unit": UNIT,
-               "h2d_bytes_per_step": int(x_host.numel() * 4 + gy_host.numel() * 4),
-               "d2h_bytes_per_step": int(gw_host.numel() * 4 + small_host.numel() * 4), "n_gpus": 1,
-               "ms_per_step": e2e_ms, "steps": e2e_iters,
-               "pipeline": "HostBatchPipeline depth 2 (copy stream); starts empty inside the timed region"}
 
         cpu = None
         if not a.no_cpu_baseline:
@@ -536,19 +770,30 @@ def run_ours(a):
                 cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                        "sample": f"CPU baseline failed: {e!r}"}
         clocks = clk.summary()
+        matrix = ref_cuda = None
+        if world == 1 and not a.no_matrix:
+            try:
+                matrix = config_matrix(torch, cq, L, a, dev, int8_peak, bf16_peak)
+            except Exception as e:  # pragma: no cover
+                matrix = {"error": repr(e)[:300]}
+            ref_cuda = reference_cuda_leg(torch, a, dev)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8 x s8 -> s32 (forward), f32 (backward)", "data": "synthetic",
+                "vs_baseline": None, "dtype": "8-bit digits (e4m3 / s8) -> fp16 / s32 partial sums (forward), f32 via bf16x3 (backward)", "data": "synthetic",
                 "config": dict(workload_config(a), cuda_graph=graph is not None,
                                tcgen05_forward=bool(info.tc_forward)),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps),
                 "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
-                "ops_per_step": {"forward": fwd_ops, "backward": bwd_ops}}
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+                "ops_per_step": {"forward": fwd_ops, "backward": bwd_ops},
+                "matrix": matrix, "reference_cuda": ref_cuda}
+        line["config"]["kernels"] = gen
     if line is not None:
+        line["train"] = train
         print(json.dumps(line))
+        sys.stdout.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():

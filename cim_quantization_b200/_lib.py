@@ -137,6 +137,29 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_tensor_device(fn):
+    """Run a wrapper inside the CUDA device context of its tensor arguments (they must share one device): kernels
+    are launched on that device's current stream and outputs allocated there, whatever the caller's current device
+    is -- a model moved with ``.cuda(1)`` works without ``torch.cuda.set_device``."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise RuntimeError(f"libcimq: tensor arguments on different devices ({dev} and {a.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
 def adc_mode_of(adcbits) -> tuple[int, int, int]:
     """Map the reference's ``adcbits`` (a float from protobuf) to (mode, qn, qp) -- lsq.py:125-129."""
     if adcbits == 1:
@@ -188,6 +211,7 @@ def layer_info(spec: LayerSpec) -> CimqInfo:
 
 
 # ---- thin wrappers (tensors in, tensors out; all allocation happens here, in torch) ------------------
+@_on_tensor_device
 def step_sizes(alpha_act, alpha_weight, ga: float, gw: float):
     s = torch.empty(2, dtype=torch.float32, device=alpha_act.device)
     _check(load().cimq_step_sizes(_ptr(alpha_act), _ptr(alpha_weight), ga, gw, _ptr(s), _stream()))
@@ -195,6 +219,7 @@ def step_sizes(alpha_act, alpha_weight, ga: float, gw: float):
     return s
 
 
+@_on_tensor_device
 def lsq_quantize(x, s_elem, qn: int, qp: int, from_fakequant: bool = False):
     """x fp32 (contiguous) -> one-byte codes (uint8 if qn >= 0 else int8); s_elem: 1-element CUDA tensor."""
     codes = torch.empty(x.shape, dtype=torch.uint8 if qn >= 0 else torch.int8, device=x.device)
@@ -204,6 +229,7 @@ def lsq_quantize(x, s_elem, qn: int, qp: int, from_fakequant: bool = False):
     return codes
 
 
+@_on_tensor_device
 def lsq_fakequant(x, s_elem, qn: int, qp: int, rescale: bool):
     y = torch.empty_like(x)
     _check(load().cimq_lsq_fakequant(_ptr(x), x.numel(), _ptr(s_elem), qn, qp, int(rescale), _ptr(y), _stream()))
@@ -211,6 +237,7 @@ def lsq_fakequant(x, s_elem, qn: int, qp: int, rescale: bool):
     return y
 
 
+@_on_tensor_device
 def lsq_backward(grad_xq, x, s_elem, qn: int, qp: int, g: float):
     gx = torch.empty_like(x)
     galpha = torch.empty(1, dtype=torch.float32, device=x.device)
@@ -221,6 +248,7 @@ def lsq_backward(grad_xq, x, s_elem, qn: int, qp: int, g: float):
     return gx, galpha
 
 
+@_on_tensor_device
 def alpha_quantize(alpha, qn: int, qp: int):
     aq = torch.empty_like(alpha)
     aux = torch.empty(8, dtype=torch.float32, device=alpha.device)
@@ -229,6 +257,7 @@ def alpha_quantize(alpha, qn: int, qp: int):
     return aq, aux
 
 
+@_on_tensor_device
 def alpha_quantize_backward(alpha, grad_aq, qn: int, qp: int, aux):
     ga = torch.empty_like(alpha)
     _check(load().cimq_alpha_quantize_backward(_ptr(alpha), _ptr(grad_aq), alpha.numel(), qn, qp, _ptr(aux), _ptr(ga),
@@ -237,6 +266,7 @@ def alpha_quantize_backward(alpha, grad_aq, qn: int, qp: int, aux):
     return ga
 
 
+@_on_tensor_device
 def adc_table(spec: LayerSpec, s, alpha_q, binary_mask, status=None, alpha_scale=None):
     """ADC thresholds / amplitudes.  ``alpha_scale`` (1-element CUDA tensor: the step of the alpha quantiser,
     ``aux[0]`` of :func:`alpha_quantize`) additionally builds the constants of the v2 kernels (always built for the
@@ -258,6 +288,7 @@ def v2_usable(spec: LayerSpec, has_alpha: bool, alpha_scale, flags: int = 0) -> 
     return bool(layer_info(spec).tc_v2) and (not has_alpha or alpha_scale is not None)
 
 
+@_on_tensor_device
 def weight_prepare(spec: LayerSpec, wcodes, want_digits=True, want_tiles=True):
     info = layer_info(spec)
     dev = wcodes.device
@@ -270,6 +301,7 @@ def weight_prepare(spec: LayerSpec, wcodes, want_digits=True, want_tiles=True):
     return wdigits, wtiles
 
 
+@_on_tensor_device
 def conv_forward(spec: LayerSpec, xcodes, wcodes, wtiles, table, s, binary_mask, save_state: bool, flags: int = 0):
     """``flags & FLAG_V2``: v2 kernel; the state then is a uint8 tensor (v2 planes) instead of int32 words, which is
     how :func:`conv_backward` tells the two formats apart."""
@@ -289,6 +321,7 @@ def conv_forward(spec: LayerSpec, xcodes, wcodes, wtiles, table, s, binary_mask,
     return out, state
 
 
+@_on_tensor_device
 def conv_forward_stochastic(spec: LayerSpec, xcodes, wcodes, table, s, alpha_q, seed: int, save_state: bool):
     """Forward with the stochastic near-ADC-less read-out (lsq.py:205-220); CUDA-core kernel."""
     info = layer_info(spec)
@@ -303,6 +336,7 @@ def conv_forward_stochastic(spec: LayerSpec, xcodes, wcodes, table, s, alpha_q, 
     return out, state
 
 
+@_on_tensor_device
 def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, wtiles, state, s, binary_mask, need_alpha: bool,
                   need_input: bool = True, flags: int = 0, need_weight: bool = True):
     info = layer_info(spec)
@@ -327,6 +361,7 @@ def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, wtiles, state, s, 
     return gxq, gwq, galpha
 
 
+@_on_tensor_device
 def conv_psums(spec: LayerSpec, xcodes, wcodes):
     info = layer_info(spec)
     ps = torch.empty((spec.batch, info.NX, info.NSW, info.NSA, info.L, spec.out_channels), dtype=torch.int32,
@@ -336,6 +371,7 @@ def conv_psums(spec: LayerSpec, xcodes, wcodes):
     return ps
 
 
+@_on_tensor_device
 def conv_psum_abs_sums(spec: LayerSpec, xcodes, wcodes):
     info = layer_info(spec)
     sums = torch.zeros((1, info.NX, info.NSW, info.NSA, 1, spec.out_channels), dtype=torch.int64,
@@ -346,6 +382,7 @@ def conv_psum_abs_sums(spec: LayerSpec, xcodes, wcodes):
 
 
 # ---- batch norm (+ residual) (+ ReLU) ------------------------------------------------------------------------
+@_on_tensor_device
 def bn_forward(x, residual, weight, bias, running_mean, running_var, training: bool, momentum: float, eps: float,
                relu: bool):
     """y, save_mean, save_invstd (None, None in inference)."""
@@ -364,6 +401,7 @@ def bn_forward(x, residual, weight, bias, running_mean, running_var, training: b
     return y, mean, invstd
 
 
+@_on_tensor_device
 def bn_backward(grad_y, x, y, weight, mean, invstd, training: bool, relu: bool, need_residual: bool):
     """grad_x, grad_residual (or None), grad_weight, grad_bias."""
     b, c = x.shape[0], x.shape[1]

@@ -14,6 +14,7 @@
 //
 // which is the same arithmetic in a different summation order (results agree to fp32 rounding).
 #include "cimq_common.cuh"
+#include "cim_v2.cuh"
 
 namespace cimq {
 
@@ -202,6 +203,76 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_w4_kernel(Geo g, int m_
     float v = 0.0f;
     for (int w8 = 0; w8 < 8; ++w8) v += red[w8][threadIdx.x];
     partial[(int64_t)ms * table_entries(g) + ((int64_t)i * PAIRS + threadIdx.x) * g.Cout + c] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// grad_alpha from the v2 state (cim_v2.cuh): plane C [NX][NSA][M][Cout], byte = sum_k 4^k * (code_k + 1).
+//   sum_m code * go = sum_m (code + 1) * go - sum_m go
+// A field is multiplied in WITHOUT an integer-to-float conversion: the masked bits, read as an fp32 subnormal, are
+// field * 2^(pos - 149) exactly, and go is pre-scaled by 2^100 so that the product is a normal number; the
+// power-of-two factors are undone once at the end.  2 instructions (mask, FMA) per partial sum.
+// Block (i*NSA + j, split): 8 warps; a warp-iteration covers 512 contiguous bytes of the plane
+// (32 / LPP pixels x Cout channels, LPP = Cout / 16 lanes per pixel; lane = (pixel, 16-channel group)).
+// ---------------------------------------------------------------------------------------------
+template <int NSW>
+__global__ void __launch_bounds__(256) bwd_alpha_v2_kernel(Geo g, int m_per_split, const float *__restrict__ go,
+                                                           const uint8_t *__restrict__ cplanes,
+                                                           float *__restrict__ partial) {
+  extern __shared__ float red[];  // [8 warps][NSW * Cout]
+  const int ij = blockIdx.x, i = ij / g.NSA, j = ij % g.NSA, ms = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lpp = g.Cout >> 4, ppw = 32 / lpp;  // lanes per pixel, pixels per warp-iteration
+  const int cg = lane % lpp, pl = lane / lpp;
+  const int64_t mbeg = (int64_t)ms * m_per_split;
+  const int64_t mend = min((int64_t)g.M, mbeg + m_per_split);
+  const uint8_t *plane = cplanes + (int64_t)ij * g.M * g.Cout;
+  float acc[16][NSW], accg[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    accg[c] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NSW; ++k) acc[c][k] = 0.0f;
+  }
+  for (int64_t m = mbeg + warp * ppw + pl; m < mend; m += 8 * ppw) {
+    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(plane + m * g.Cout + 16 * cg));
+    const int b = (int)(m / g.L), l = (int)(m % g.L);
+    const float *gp = go + ((int64_t)b * g.Cout + 16 * cg) * g.L + l;
+    float gs[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) gs[c] = __ldg(gp + (int64_t)c * g.L);
+    const uint32_t wd[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t lo = wd[q], hi = wd[q] >> 16;
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const int c = 4 * q + bb;
+        const uint32_t src = bb < 2 ? lo : hi;
+        accg[c] += gs[c];
+        const float gsc = gs[c] * 1.2676506002282294e30f;  // 2^100
+#pragma unroll
+        for (int k = 0; k < NSW; ++k)
+          acc[c][k] = fmaf(gsc, __uint_as_float(src & (3u << (8 * (bb & 1) + 2 * k))), acc[c][k]);
+      }
+    }
+  }
+  // undo the scaling, subtract sum go, reduce over the lanes that share a channel group, then over warps
+#pragma unroll
+  for (int c = 0; c < 16; ++c)
+#pragma unroll
+    for (int k = 0; k < NSW; ++k) {
+      float v = acc[c][k] * exp2f((float)(49 - 8 * (c & 1) - 2 * k)) - accg[c];
+      for (int o = 16; o >= lpp; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (pl == 0) red[(warp * NSW + k) * g.Cout + 16 * cg + c] = v;
+    }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NSW * g.Cout; t += 256) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) v += red[w8 * NSW * g.Cout + t];
+    const int k = t / g.Cout, c = t % g.Cout;
+    partial[(int64_t)ms * table_entries(g) + ((int64_t)i * g.pairs + k * g.NSA + j) * g.Cout + c] = v;
   }
 }
 
@@ -447,7 +518,7 @@ __global__ void bwd_weight_finish_kernel(Geo g, int nsplit, const float *__restr
 }
 
 struct BwdPlan {
-  int alpha_splits, alpha_m_per_split;
+  int alpha_splits, alpha_m_per_split, alpha_splits_v2;
   int w_splits, w_m_per_split, ftiles;
   int64_t off_gxu, off_wpart, off_apart, total;
 };
@@ -478,7 +549,9 @@ inline BwdPlan make_plan(const Geo &g) {
   int64_t wpart = (int64_t)p.w_splits * g.F * g.Cout * 4;
   if (tc_backward_supported(g) && bwd_tc_partial_bytes(g) > wpart) wpart = bwd_tc_partial_bytes(g);
   p.off_apart = p.off_wpart + align(wpart);
-  p.total = p.off_apart + align((int64_t)p.alpha_splits * table_entries(g) * 4);
+  p.alpha_splits_v2 = (148 * 4 + g.NX * g.NSA - 1) / (g.NX * g.NSA) + 1;
+  const int asmax = p.alpha_splits > p.alpha_splits_v2 ? p.alpha_splits : p.alpha_splits_v2;
+  p.total = p.off_apart + align((int64_t)asmax * table_entries(g) * 4);
   return p;
 }
 
@@ -499,7 +572,29 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
   float *wpart = reinterpret_cast<float *>(base + p.off_wpart);
   float *apart = reinterpret_cast<float *>(base + p.off_apart);
 
-  if (galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
+  const bool v2s = (flags & CIMQ_FLAG_V2) != 0;
+  CIMQ_REQUIRE(!v2s || (use_tc && v2::supported(g) && v2_backward_supported(g)),
+               "conv_backward: CIMQ_FLAG_V2 on a layer the v2 kernels do not cover");
+  const uint8_t *state2 = reinterpret_cast<const uint8_t *>(state);
+  if (v2s && galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
+    const int lpp = g.Cout / 16, pb = 8 * (32 / lpp);  // pixels per block-iteration
+    int splits = (148 * 4 + g.NX * g.NSA - 1) / (g.NX * g.NSA);
+    int mps = (g.M + splits - 1) / splits;
+    mps = (mps + pb - 1) / pb * pb;
+    splits = (g.M + mps - 1) / mps;
+    CIMQ_REQUIRE(splits <= p.alpha_splits_v2, "conv_backward: alpha workspace too small");
+    dim3 grid(g.NX * g.NSA, splits);
+    const size_t smem = (size_t)8 * g.NSW * g.Cout * sizeof(float);
+    const uint8_t *cplanes = state2 + 2 * v2::plane_bytes(g);
+    if (g.NSW == 3) bwd_alpha_v2_kernel<3><<<grid, 256, smem, st>>>(g, mps, go, cplanes, apart);
+    else bwd_alpha_v2_kernel<2><<<grid, 256, smem, st>>>(g, mps, go, cplanes, apart);
+    CIMQ_CUDA_OK(cudaGetLastError());
+    double numel = (double)g.B * g.NX * g.NSW * g.NSA * g.L * g.Cout;
+    float gfac = (float)(1.0 / sqrt(numel));
+    int64_t n = table_entries(g);
+    bwd_alpha_finish_kernel<<<(int)((n + 31) / 32), 256, 0, st>>>(g, splits, gfac, mask, apart, galpha);
+    CIMQ_CUDA_OK(cudaGetLastError());
+  } else if (galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
     dim3 grid(g.Cout, g.NX, p.alpha_splits);
     // four pixels per load when the pixel runs allow 128-bit loads (state rows and grad_out rows 16-byte aligned)
     const bool vec4 = g.L % 4 == 0 && p.alpha_m_per_split % 4 == 0 && g.M % 4 == 0 &&
@@ -531,12 +626,13 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
   if (gxq != nullptr && use_tc) {
     const WtLayout wl = wt_layout(g);
     const uint8_t *wtb = reinterpret_cast<const uint8_t *>(wtiles) + wl.bwd_off;
+    const uint8_t *wtb2 = reinterpret_cast<const uint8_t *>(wtiles) + wl.bwd2_off;
     if (!(flags & CIMQ_FLAG_DETERMINISTIC) && bwd_input_tc_can_fold(g)) {
       // fused fold: the dgrad epilogue reduces into grad_x (fp32 atomics in L2; summation order varies run to run)
       CIMQ_CUDA_OK(cudaMemsetAsync(gxq, 0, (size_t)g.B * g.Cin * g.H * g.W * sizeof(float), st));
-      if (launch_bwd_input_tc(g, go, state, wtb, s, mask, gxq, 1, st)) return 1;
+      if (launch_bwd_input_tc(g, go, state, v2s ? wtb2 : wtb, s, mask, gxq, 1, v2s, st)) return 1;
     } else {
-      if (launch_bwd_input_tc(g, go, state, wtb, s, mask, gxuT, 0, st)) return 1;
+      if (launch_bwd_input_tc(g, go, state, v2s ? wtb2 : wtb, s, mask, gxuT, 0, v2s, st)) return 1;
       if (launch_col2im(g, gxuT, gxq, st)) return 1;
     }
   } else if (gxq != nullptr) {
@@ -549,7 +645,7 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
     if (launch_col2im(g, gxuT, gxq, st)) return 1;
   }
   if (gwq != nullptr && use_tc) {
-    if (launch_bwd_weight_tc(g, go, xcodes, state, s, mask, wpart, gwq, st)) return 1;
+    if (launch_bwd_weight_tc(g, go, xcodes, state, s, mask, wpart, gwq, v2s, st)) return 1;
   } else if (gwq != nullptr) {
     size_t smem = (size_t)32 * g.NSA * 32 * sizeof(float);
     CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include "cim_tc_layout.cuh"
+#include "cim_v2.cuh"
 #include "tc_ptx.cuh"
 
 namespace cimq {
@@ -68,6 +69,8 @@ struct BwdParams {
   int cached;   // dgrad: 1 = producers keep grad_out of the tile and the state words of the chunk in registers
   uint32_t pw_off;  // dgrad: byte offset of the pass-weight table inside the raw region
   int fold;  // dgrad: 1 = the epilogue folds (col2im) straight into grad_x with fp32 reductions; 0 = writes gxu[b][f][l]
+  int v2;    // 1 = `state` holds the v2 byte planes (cim_v2.cuh): D [NX][M][Cout] for dgrad, W for wgrad
+  const uint8_t *state2, *state2w;
   const float *go;
   const uint32_t *state;
   const uint8_t *xcodes;
@@ -227,8 +230,109 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
     const int G = cpt >> 3;           // groups of 8 channels
     uint32_t it = 0;
     bool done = false;
+    if (P.v2) {
+      // ---- v2 state (cim_v2.cuh): one byte per (crossbar, pixel, channel) with the pass counts of the NSW weight
+      // slices as 2-bit fields.  A'_k[m,co] = go * count_k without an integer-to-float conversion: the masked field,
+      // read as an fp32 subnormal, is count * 2^(pos - 149) exactly; go is pre-scaled by 2^100 (once per tile) so the
+      // product is normal, and the power-of-two factors 2^(8*(co&1) + 2k - 49) are undone by the pre-scaled weight
+      // tiles (exact in bf16) and the epilogue's scale.  Register-resident go (reused by NX*NSW stages) and D bytes
+      // (reused by NSW stages), refilled right after their last use.
+      constexpr int CMAX = 32;
+      float gsr[CMAX];
+      uint32_t dlo[CMAX / 4], dhi[CMAX / 4], dnx[CMAX / 4];
+      const int nw = cpt >> 2;  // D words per thread
+      // rows past the last pixel read pixel 0: their A' rows only feed accumulator rows the epilogue never stores
+      auto tile_ptrs2 = [&](int mt, const float *&gop, const uint8_t *&dp) {
+        const int64_t m = (int64_t)mt * kTcTileM + r;
+        const bool live = m < g.M;
+        const int b = live ? (int)(m / g.L) : 0, l = live ? (int)(m % g.L) : 0;
+        gop = P.go + ((int64_t)b * g.Cout + P.co0 + h * cpt) * g.L + l;
+        dp = P.state2 + (live ? m : 0) * (int64_t)g.Cout + P.co0 + h * cpt;
+      };
+      auto load_d = [&](const uint8_t *dp, int i) {
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(dp + (int64_t)i * g.M * g.Cout);
+        if (nw == 8) {
+          const uint4 a = __ldg(reinterpret_cast<const uint4 *>(wp)), b4 = __ldg(reinterpret_cast<const uint4 *>(wp) + 1);
+          dnx[0] = a.x; dnx[1] = a.y; dnx[2] = a.z; dnx[3] = a.w; dnx[4] = b4.x; dnx[5] = b4.y; dnx[6] = b4.z; dnx[7] = b4.w;
+        } else if (nw == 4) {
+          const uint4 a = __ldg(reinterpret_cast<const uint4 *>(wp));
+          dnx[0] = a.x; dnx[1] = a.y; dnx[2] = a.z; dnx[3] = a.w;
+        } else {
+          const uint2 a = __ldg(reinterpret_cast<const uint2 *>(wp));
+          dnx[0] = a.x; dnx[1] = a.y;
+        }
+      };
+      const float *gop = nullptr, *gop_n = nullptr;
+      const uint8_t *dp = nullptr, *dp_n = nullptr;
+#pragma unroll
+      for (int w = 0; w < CMAX / 4; ++w) dnx[w] = 0u;
+      if ((int)blockIdx.x < P.mtiles) {
+        tile_ptrs2(blockIdx.x, gop, dp);
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < cpt) gsr[c] = __ldg(gop + (size_t)c * g.L) * 1.2676506002282294e30f;  // 2^100
+        load_d(dp, 0);
+      }
+      for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
+        const int nmt = mt + gridDim.x;
+        const bool more_tiles = nmt < P.mtiles;
+        if (more_tiles) tile_ptrs2(nmt, gop_n, dp_n);
+        for (int i = 0; i < g.NX; ++i) {
+#pragma unroll
+          for (int w = 0; w < CMAX / 4; ++w) { dlo[w] = dnx[w]; dhi[w] = dnx[w] >> 16; }
+          for (int k = 0; k < NSW; ++k, ++it) {
+            const int sidx = it % P.stages;
+            const uint32_t use = it / P.stages;
+            const bool last_k = k + 1 == NSW;
+            const bool next_tile = last_k && i + 1 == g.NX && more_tiles;
+            // the D bytes of the next chunk (or of the next tile's first chunk) start their trip now
+            if (last_k) {
+              if (i + 1 < g.NX) load_d(dp, i + 1);
+              else if (more_tiles) load_d(dp_n, 0);
+            }
+            mbar_wait(cv.empty0 + 8 * sidx, (use & 1) ^ 1);
+            uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
+            if (threadIdx.x == 0) {
+              mbar_arrive_expect_tx(cv.full0 + 8 * sidx, P.b_bytes);
+              bulk_copy_g2s(smem_u32(st_ptr + 3 * (size_t)P.a_bytes), P.wtb + (size_t)(i * NSW + k) * P.b_bytes,
+                            P.b_bytes, cv.full0 + 8 * sidx);
+            }
+            const uint32_t mk0 = 3u << (2 * k), mk1 = 3u << (8 + 2 * k);
+#pragma unroll
+            for (int cgi = 0; cgi < CMAX / 8; ++cgi) {
+              if (cgi < G) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int c = 8 * cgi + e;
+                  const uint32_t src = (c & 2) ? dhi[c >> 2] : dlo[c >> 2];
+                  v[e] = gsr[c] * __uint_as_float(src & ((c & 1) ? mk1 : mk0));
+                }
+                if (next_tile) {  // last use of these eight grad_out values: refill them for the next tile
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    gsr[8 * cgi + e] = __ldg(gop_n + (size_t)(8 * cgi + e) * g.L) * 1.2676506002282294e30f;
+                }
+                uint32_t hi[4], mid[4], lo[4];
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo[e2]);
+                const uint32_t off = tc_tile_offset16(r, h * cpt + cgi * 8, kTcLBO, sbo);
+                *reinterpret_cast<uint4 *>(st_ptr + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(st_ptr + P.a_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+                *reinterpret_cast<uint4 *>(st_ptr + 2 * (size_t)P.a_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+            }
+            fence_proxy_async();
+            mbar_arrive(cv.full0 + 8 * sidx);
+          }
+        }
+        gop = gop_n;
+        dp = dp_n;
+      }
+      done = true;
+    }
     if constexpr (CBits::CWN == 1) {
-      if (P.cached) {
+      if (P.cached && !done) {
         // ---- register-resident operands (Cout <= 64): grad_out of the tile (reused by all NX*NSW stages) and the
         // state words of the chunk (reused by its NSW stages) live in registers; each group of eight is refilled
         // for the next chunk / tile right after its last use, so the loads fly during the remaining groups and the
@@ -450,7 +554,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
     // ------------------------------------------------------------------ epilogue
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const float scale = P.s[1] / (float)NSA;  // w_sl * s_w (lsq.py:252), mean over act slices (lsq.py:376)
+    // w_sl * s_w (lsq.py:252), mean over act slices (lsq.py:376); v2: times the 2^49 left by the producers' scaling
+    const float scale = P.s[1] / (float)NSA * (P.v2 ? 562949953421312.0f : 1.0f);
     const int *ftab = reinterpret_cast<const int *>(cv.raw);  // fold: per unfold row {offset in the image << 7 | kx << 5 | tap}
     const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && warp == kEpilogueWarp0 && lane == 0;
     long long d_tfull = 0, d_comp = 0;
@@ -567,7 +672,10 @@ __device__ __noinline__ uint2 gather_codes_generic(GatherGeo g, const uint8_t *_
 
 constexpr int kWgLBO = 144;  // padded K-stride of the G' tiles: producer lanes run along K (bank-conflict free)
 
-template <int NSW, int NSA, bool TERN>
+// V2: the pass counts come from plane W of the v2 state (cim_v2.cuh), one byte per (crossbar, pixel, channel), and the
+// producer threads split differently: threads [0, 4*Kc) build the G' tiles (item = 4 channels x 8 pixels), the next 128
+// or 256 threads the X tile -- see the V2 blocks below.
+template <int NSW, int NSA, bool TERN, bool V2>
 __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdParams P) {
   using CBits = ClipBits<NSW, NSA, TERN>;
   constexpr bool kLut = NSW <= 4;  // pass weight of one activation slice by table lookup on its NSW clip bits
@@ -577,7 +685,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Kc = P.Kc;                            // Cout = UMMA N
   const uint32_t a_sbo = 128u * 16u;              // X tile: 8 rows x 128 pixels bf16, LBO 128
-  const uint32_t b_sbo = 16u * (uint32_t)kWgLBO;  // G' tile: 16 k-groups of 144 bytes per 8 rows
+  // G' tile: 16 k-groups of 144 bytes per 8 rows (+ 16 bytes in the v2 variant, whose producer lanes run along the
+  // channels: eight consecutive channel quads then fall into eight different 16-byte bank groups)
+  const uint32_t b_sbo = 16u * (uint32_t)kWgLBO + (V2 ? 16u : 0u);
   const int i_begin = blockIdx.y * P.nxg;
   const int i_end = min(g.NX, i_begin + P.nxg);
 
@@ -614,7 +724,14 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     const int tid = threadIdx.x;
     const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
     long long d_stage = 0, d_wait = 0, d_x = 0, d_g = 0;
-    const int fr = tid & 127;     // X tile: this thread's crossbar row
+    // X tile items (crossbar row fr, 8-pixel group pg = x_pg0 + x_step * q, q < XI) of this thread
+    constexpr int XI = V2 ? 16 : 6;
+    const int n_g = V2 ? 4 * Kc : 0;                     // v2: threads [0, n_g) build G', [n_g, n_g + n_x) build X
+    const int n_x = V2 ? (n_g == 256 ? 128 : 256) : kWgProducerThreads;
+    const int xt = tid - n_g;
+    const bool x_thread = xt >= 0 && xt < n_x;
+    const int x_pg0 = V2 ? (xt >> 7) : (tid >> 7), x_step = V2 ? (n_x >> 7) : 3;
+    const int fr = (V2 ? xt : tid) & 127;     // X tile: this thread's crossbar row
     const bool aligned = (g.L % 8) == 0 && (g.OW % 8) == 0;
     const int pitch = 1 << P.pitch_log2;
     const int slot_bytes = P.rk * pitch;
@@ -708,6 +825,39 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           load_state(gpt, blockIdx.x, i_begin / P.sdiv, gco0 + 24 * q, swc[q]);
         }
     }
+    // ---- v2 G' operands (threads [0, n_g)): item = (channel quad gq2, 8-pixel group gpg2).  grad_out of the tile
+    // (4 channels x 8 pixels, pre-scaled by 2^100) is reused by all chunks and planes, the W bytes of a chunk
+    // (one word = 4 channels per pixel) by its NSA planes; both are refilled right after their last use.  Groups
+    // past the last pixel read the last valid group: their activation digits are zero (staged rows outside the image).
+    const bool g_thread = V2 && tid < n_g;
+    const int nq2 = Kc >> 2;
+    const int gq2 = V2 ? tid % nq2 : 0, gpg2 = V2 ? tid / nq2 : 0;
+    float gs2[4][8];
+    uint32_t wlo2[8], whi2[8], wnx2[8];
+    auto v2_group_m = [&](int mt_) { return min((int64_t)mt_ * kTcTileM + gpg2 * 8, (int64_t)g.M - 8); };
+    auto v2_load_go = [&](int mt_, int c) {
+      const int64_t m = v2_group_m(mt_);
+      const int b = (int)(m / g.L), l = (int)(m % g.L);
+      const float4 *gp = reinterpret_cast<const float4 *>(P.go + ((int64_t)b * g.Cout + P.co0 + 4 * gq2 + c) * g.L + l);
+      const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+      const float sc = 1.2676506002282294e30f;  // 2^100
+      gs2[c][0] = g0.x * sc; gs2[c][1] = g0.y * sc; gs2[c][2] = g0.z * sc; gs2[c][3] = g0.w * sc;
+      gs2[c][4] = g1.x * sc; gs2[c][5] = g1.y * sc; gs2[c][6] = g1.z * sc; gs2[c][7] = g1.w * sc;
+    };
+    auto v2_load_w = [&](int mt_, int i_) {
+      const uint8_t *wp = P.state2w + ((int64_t)i_ * g.M + v2_group_m(mt_)) * g.Cout + P.co0 + 4 * gq2;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wnx2[e] = __ldg(reinterpret_cast<const uint32_t *>(wp + (int64_t)e * g.Cout));
+    };
+    if constexpr (V2) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wnx2[e] = 0u;
+      if (g_thread && (int)blockIdx.x < P.mtiles) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v2_load_go(blockIdx.x, c);
+        v2_load_w(blockIdx.x, i_begin);
+      }
+    }
     for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
       const int64_t m0 = (int64_t)mt * kTcTileM;
       const int mt_n = mt + gridDim.x;
@@ -788,13 +938,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         }
         // ---- the activation codes of this thread's X items (row fr, 8-pixel group pg = tid/128 + 3q), gathered once
         // per chunk: the NSA digit planes below only shift and mask them
-        uint32_t xlo[6], xhi[6];
+        uint32_t xlo[XI], xhi[XI];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          const int pg = (tid >> 7) + 3 * q;
+        for (int q = 0; q < XI; ++q) {
+          const int pg = x_pg0 + x_step * q;
           xlo[q] = 0u;
           xhi[q] = 0u;
-          if (pg < 16) {
+          if (pg < 16 && x_thread) {
           uint32_t lo8 = 0u, hi8 = 0u;
           if (frow) {
             if (P.fastx) {
@@ -820,6 +970,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           }
         }
         d_stage += CIMQ_TB() - ts0;
+        if constexpr (V2) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { wlo2[e] = wnx2[e]; whi2[e] = wnx2[e] >> 16; }
+        }
         for (int j = 0; j < NSA; ++j, ++it) {
           const int sidx = it % P.stages;
           const uint32_t use = it / P.stages;
@@ -830,18 +984,20 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
           // ---- X_j tile [128 crossbar rows x 128 pixels] (bf16 digits); item = (row fr, 8-pixel group pg)
           const int sh = g.abs_ * j;
+          // v2: digit * 2^-j (bf16 exponent field minus j), which undoes the 2^(2j) of the pass-count field of plane W
+          const uint32_t one_bf = V2 ? 0x3F80u - ((uint32_t)j << 7) : 0x3F80u;
 #pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            const int pg = (tid >> 7) + 3 * q;
-            if (pg >= 16) continue;
+          for (int q = 0; q < XI; ++q) {
+            const int pg = x_pg0 + x_step * q;
+            if (pg >= 16 || !x_thread) continue;
             const uint32_t lo8 = xlo[q], hi8 = xhi[q];
             uint32_t d[4];
             if (g.amask == 1) {  // 1-bit digits: bf16(1) = 0x3F80; spread two bytes to 16-bit lanes, one multiply
               const uint32_t tl = (lo8 >> sh) & 0x01010101u, th = (hi8 >> sh) & 0x01010101u;
-              d[0] = __byte_perm(tl, 0u, 0x4140) * 0x3F80u;
-              d[1] = __byte_perm(tl, 0u, 0x4342) * 0x3F80u;
-              d[2] = __byte_perm(th, 0u, 0x4140) * 0x3F80u;
-              d[3] = __byte_perm(th, 0u, 0x4342) * 0x3F80u;
+              d[0] = __byte_perm(tl, 0u, 0x4140) * one_bf;
+              d[1] = __byte_perm(tl, 0u, 0x4342) * one_bf;
+              d[2] = __byte_perm(th, 0u, 0x4140) * one_bf;
+              d[3] = __byte_perm(th, 0u, 0x4342) * one_bf;
             } else {
               const uint32_t am = (uint32_t)g.amask;
 #pragma unroll
@@ -858,6 +1014,38 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           const long long tx1 = CIMQ_TB();
           d_x += tx1 - tw1;
           uint8_t *gb = st_ptr + P.a_bytes;
+          if constexpr (V2) {
+            // G'_j[co, m] = go * (pass count of activation slice j) = (go * 2^100) * (masked field as an fp32 subnormal)
+            //             = go * count * 2^(8*(co&1) + 2j - 49); the factors are undone by X_j (2^-j) and the epilogue
+            if (g_thread) {
+              const bool last_j = j + 1 == NSA;
+              const bool next_chunk = i + 1 < i_end, next_tile = !next_chunk && mt_n < P.mtiles;
+              if (last_j) {  // the W bytes of the next chunk (or of the next tile's first chunk) start their trip now
+                if (next_chunk) v2_load_w(mt, i + 1);
+                else if (next_tile) v2_load_w(mt_n, i_begin);
+              }
+              const uint32_t mk0 = 3u << (2 * j), mk1 = 3u << (8 + 2 * j);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  v[e] = gs2[c][e] * __uint_as_float(((c & 2) ? whi2[e] : wlo2[e]) & ((c & 1) ? mk1 : mk0));
+                if (last_j && next_tile) v2_load_go(mt_n, c);  // last use of this row of grad_out
+                uint32_t hi[4], mid[4], lo3[4];
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo3[e2]);
+                const uint32_t off = tc_tile_offset16(4 * gq2 + c, gpg2 * 8, kWgLBO, b_sbo);
+                *reinterpret_cast<uint4 *>(gb + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(gb + P.b_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+                *reinterpret_cast<uint4 *>(gb + 2 * (size_t)P.b_bytes + off) = make_uint4(lo3[0], lo3[1], lo3[2], lo3[3]);
+              }
+            }
+            fence_proxy_async();
+            mbar_arrive(cv.full0 + 8 * sidx);
+            d_g += CIMQ_TB() - tx1;
+            continue;
+          }
           float wv[NSW];
 #pragma unroll
           for (int k = 0; k < NSW; ++k) wv[k] = cv.wtab[k * NSA + j];
@@ -1036,10 +1224,12 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         }
         if (frow < rows) {
           float4 *dst = reinterpret_cast<float4 *>(part + (int64_t)(lo + frow) * g.Cout + P.co0 + c0);
+          // v2: even / odd channels carry 2^-49 / 2^-41 from the producers' subnormal multiply
+          const float se = V2 ? scale * 562949953421312.0f : scale, so = V2 ? scale * 2199023255552.0f : scale;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4)
-            dst[q4] = make_float4(__int_as_float(v[4 * q4]) * scale, __int_as_float(v[4 * q4 + 1]) * scale,
-                                  __int_as_float(v[4 * q4 + 2]) * scale, __int_as_float(v[4 * q4 + 3]) * scale);
+            dst[q4] = make_float4(__int_as_float(v[4 * q4]) * se, __int_as_float(v[4 * q4 + 1]) * so,
+                                  __int_as_float(v[4 * q4 + 2]) * se, __int_as_float(v[4 * q4 + 3]) * so);
         }
       }
     }
@@ -1079,7 +1269,9 @@ __global__ void __launch_bounds__(256) bwd_weight_tc_finish_kernel(Geo g, int np
 
 // bf16 weight digit tiles for dgrad: tile (channel block cb, i, k) = [Nf rows (crossbar row) x Kc channels]
 // K-major no-swizzle, Kc = min(Cout, 128)
-__global__ void weight_tiles_bwd_kernel(Geo g, int Nf, int Kc, const int8_t *__restrict__ wcodes,
+// v2s != 0: digits scaled by 2^(-k - 8*(co & 1)) (exact in bf16), the inverse of what the v2 dgrad producers leave on
+// the masked operand (pass-count field position of the D byte) beyond the slice weight 2^k.
+__global__ void weight_tiles_bwd_kernel(Geo g, int Nf, int Kc, int v2s, const int8_t *__restrict__ wcodes,
                                         uint16_t *__restrict__ tiles) {
   const int64_t tile_elems = (int64_t)Nf * Kc;
   const int64_t tiles_per_block = (int64_t)g.NX * g.NSW;
@@ -1102,15 +1294,20 @@ __global__ void weight_tiles_bwd_kernel(Geo g, int Nf, int Kc, const int8_t *__r
       digit = (mag >> (g.wbs * k)) & g.wmask;
       if (code < 0) digit = -digit;
     }
-    tiles[tile * tile_elems + tc_tile_offset16(fr, cl, kTcLBO, sbo) / 2] =
-        __bfloat16_as_ushort(__int2bfloat16_rn(digit));
+    float dv = (float)digit;
+    if (v2s) dv = ldexpf(dv, -k - 8 * (co & 1));
+    tiles[tile * tile_elems + tc_tile_offset16(fr, cl, kTcLBO, sbo) / 2] = __bfloat16_as_ushort(__float2bfloat16_rn(dv));
   }
 }
 
-inline int bwd_channel_block(const Geo &g) { return g.Cout > 128 ? 128 : g.Cout; }
+// output channels per launch: layers with more run as blocks (v2: 64, one producer thread holds at most 32 channels)
+inline int bwd_channel_block(const Geo &g, bool v2 = false) {
+  const int cap = v2 ? 64 : 128;
+  return g.Cout > cap ? cap : g.Cout;
+}
 
-inline int wgrad_chunks_per_group(const Geo &g) {
-  int n = 512 / bwd_channel_block(g);
+inline int wgrad_chunks_per_group(const Geo &g, bool v2 = false) {
+  int n = 512 / bwd_channel_block(g, v2);
   return n < g.NX ? n : g.NX;
 }
 
@@ -1132,6 +1329,22 @@ inline bool bwd_slices_supported(const Geo &g) {
     else if (g.NSW == 8 && tern) { KERNEL(8, 8, true, __VA_ARGS__); }                            \
     else { KERNEL(8, 8, false, __VA_ARGS__); }                                                   \
   } while (0)
+
+template <int W, int A, bool T>
+static int launch_wgrad_instance(const BwdParams &P, dim3 grid, size_t smem, cudaStream_t st) {
+  if constexpr (W <= v2::kMaxNS) {
+    if (P.v2) {
+      CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_weight_tc_kernel<W, A, T, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      bwd_weight_tc_kernel<W, A, T, true><<<grid, kThreads, smem, st>>>(P);
+      return 0;
+    }
+  }
+  CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_weight_tc_kernel<W, A, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  bwd_weight_tc_kernel<W, A, T, false><<<grid, kThreads, smem, st>>>(P);
+  return 0;
+}
 
 // Crossbars deeper than 128 rows are processed as 128-row "virtual" chunks: neither gradient couples the rows of
 // a crossbar (dgrad: the rows are the N dimension; wgrad: the rows are the M dimension), only the pass mask --
@@ -1159,6 +1372,14 @@ bool tc_backward_supported(const Geo &g) {
   return true;
 }
 
+bool v2_backward_supported(const Geo &g) {
+  if (!tc_backward_supported(g) || !v2::supported(g)) return false;
+  if (g.Cout > 64 && g.Cout % 64 != 0) return false;
+  // 8-pixel groups of the wgrad operands never straddle images or the end
+  if (g.L % 8 != 0 || g.M % 8 != 0) return false;
+  return true;
+}
+
 int64_t wtiles_bwd_bytes(const Geo &g0) {
   if (!tc_backward_supported(g0)) return 0;
   int sdiv;
@@ -1170,21 +1391,38 @@ int launch_weight_tiles_bwd(const Geo &g0, const int8_t *wcodes, void *tiles, cu
   int sdiv;
   const Geo g = bwd_virtual_geo(g0, &sdiv);
   const int64_t n = (int64_t)g.NX * g.NSW * tc_nf(g) * g.Cout;
-  weight_tiles_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, tc_nf(g), bwd_channel_block(g), wcodes,
+  weight_tiles_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, tc_nf(g), bwd_channel_block(g), 0, wcodes,
                                                                  reinterpret_cast<uint16_t *>(tiles));
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int64_t bwd_tc_partial_bytes(const Geo &g0) {
-  int sdiv;
-  const Geo g = bwd_virtual_geo(g0, &sdiv);
+int launch_weight_tiles_bwd2(const Geo &g, const int8_t *wcodes, void *tiles, cudaStream_t st) {
+  const int64_t n = (int64_t)g.NX * g.NSW * tc_nf(g) * g.Cout;
+  weight_tiles_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, tc_nf(g), bwd_channel_block(g, true), 1, wcodes,
+                                                                 reinterpret_cast<uint16_t *>(tiles));
+  CIMQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int wgrad_ctas(const Geo &g, bool v2, int *nxg_out, int *groups_out) {
   const int mtiles = (g.M + kTcTileM - 1) / kTcTileM;
-  const int nxg = wgrad_chunks_per_group(g);
+  const int nxg = wgrad_chunks_per_group(g, v2);
   const int groups = (g.NX + nxg - 1) / nxg;
   int ctas = 148 / groups;
   if (ctas > mtiles) ctas = mtiles;
   if (ctas < 1) ctas = 1;
+  if (nxg_out) *nxg_out = nxg;
+  if (groups_out) *groups_out = groups;
+  return ctas;
+}
+
+int64_t bwd_tc_partial_bytes(const Geo &g0) {
+  int sdiv;
+  const Geo g = bwd_virtual_geo(g0, &sdiv);
+  int ctas = wgrad_ctas(g, false, nullptr, nullptr);
+  const int c2 = wgrad_ctas(g, true, nullptr, nullptr);
+  if (c2 > ctas) ctas = c2;
   return (int64_t)ctas * g.F * g.Cout * 4;
 }
 
@@ -1194,12 +1432,14 @@ bool bwd_input_tc_can_fold(const Geo &g) {
 }
 
 int launch_bwd_input_tc(const Geo &g0, const float *go, const uint32_t *state, const void *wtb, const float *s,
-                        const int8_t *mask, float *out, int fold, cudaStream_t st) {
+                        const int8_t *mask, float *out, int fold, bool v2, cudaStream_t st) {
   BwdParams P;
   memset(&P, 0, sizeof(P));
   const Geo g = bwd_virtual_geo(g0, &P.sdiv);
   P.g = g;
-  P.Kc = bwd_channel_block(g);
+  P.v2 = v2 ? 1 : 0;
+  P.state2 = reinterpret_cast<const uint8_t *>(state);
+  P.Kc = bwd_channel_block(g, v2);
   P.Nf = tc_nf(g);
   P.mtiles = (g.M + kTcTileM - 1) / kTcTileM;
   P.a_bytes = (uint32_t)(kTcTileM * P.Kc * 2);
@@ -1238,16 +1478,19 @@ int launch_bwd_input_tc(const Geo &g0, const float *go, const uint32_t *state, c
 }
 
 int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, const uint32_t *state,
-                         const float *s, const int8_t *mask, float *partial, float *gw, cudaStream_t st) {
+                         const float *s, const int8_t *mask, float *partial, float *gw, bool v2, cudaStream_t st) {
   BwdParams P;
   memset(&P, 0, sizeof(P));
   const Geo g = bwd_virtual_geo(g0, &P.sdiv);
   P.g = g;
-  P.Kc = bwd_channel_block(g);
+  P.v2 = v2 ? 1 : 0;
+  P.state2 = reinterpret_cast<const uint8_t *>(state);
+  P.state2w = P.state2 + (v2 ? v2::plane_bytes(g0) : 0);
+  P.Kc = bwd_channel_block(g, v2);
   P.mtiles = (g.M + kTcTileM - 1) / kTcTileM;
   P.a_bytes = 128u * 128u * 2u;
   P.debug = g_tc_debug;
-  P.b_bytes = (uint32_t)(P.Kc / 8) * 16u * (uint32_t)kWgLBO;  // 8-row groups x 16 k-groups x 144 B
+  P.b_bytes = (uint32_t)(P.Kc / 8) * (16u * (uint32_t)kWgLBO + (v2 ? 16u : 0u));  // 8-row groups x (16 k-groups x 144 B [+ 16])
   P.stage_bytes = P.a_bytes + 3 * P.b_bytes;
   // staged activation rows (stride 1, output width a power of two between 8 and 128, 4-byte aligned rows)
   P.fastx = 0; P.raw_bytes = 0;
@@ -1281,22 +1524,17 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
   P.stages = stages;
   P.gfast = (g.L % 8 == 0 && g.OW % 8 == 0 && g.M % 8 == 0 && g.M >= 8 &&
              (reinterpret_cast<uintptr_t>(go) & 15u) == 0 && (reinterpret_cast<uintptr_t>(state) & 15u) == 0) ? 1 : 0;
-  P.nxg = wgrad_chunks_per_group(g);
-  const int groups = (g.NX + P.nxg - 1) / P.nxg;
+  int groups = 1;
+  const int ctas = wgrad_ctas(g, v2, &P.nxg, &groups);
   uint32_t cols = 32;
   while (cols < (uint32_t)(P.nxg * P.Kc)) cols <<= 1;
   P.tmem_cols = cols;
-  int ctas = 148 / groups;
-  if (ctas > P.mtiles) ctas = P.mtiles;
-  if (ctas < 1) ctas = 1;
   P.go = go; P.state = state; P.xcodes = xcodes; P.s = s; P.mask = mask; P.out = partial;
   const size_t smem = (size_t)stages * P.stage_bytes + kBarrierBytes + 2 * (size_t)P.raw_bytes + 1024;
   dim3 grid(ctas, groups);
-#define CIMQ_LAUNCH_WGRAD(W, A, T, ...)                                                                          \
-  do {                                                                                                           \
-    CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_weight_tc_kernel<W, A, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (int)smem));                                                               \
-    bwd_weight_tc_kernel<W, A, T><<<grid, kThreads, smem, st>>>(P);                                              \
+#define CIMQ_LAUNCH_WGRAD(W, A, T, ...)                                        \
+  do {                                                                         \
+    if (launch_wgrad_instance<W, A, T>(P, grid, smem, st)) return 1;            \
   } while (0)
   for (P.co0 = 0; P.co0 < g.Cout; P.co0 += P.Kc) {  // one launch per block of <= 128 output channels
     CIMQ_BWD_DISPATCH(CIMQ_LAUNCH_WGRAD, 0);

@@ -131,11 +131,11 @@ struct StageThread {
   int rstep;     // rows advanced per pass of all producer threads
   bool xok;      // the word lies inside the image horizontally
 };
-__device__ __forceinline__ StageThread stage_thread(const TcParams &P) {
+__device__ __forceinline__ StageThread stage_thread(const TcParams &P, int tid) {
   StageThread t;
   const int wpr_log2 = P.pitch_log2 - 2;  // words per staged row (<= 128)
-  t.xw = threadIdx.x & ((1 << wpr_log2) - 1);
-  t.row0 = threadIdx.x >> wpr_log2;
+  t.xw = tid & ((1 << wpr_log2) - 1);
+  t.row0 = tid >> wpr_log2;
   t.rstep = kProducerThreads >> wpr_log2;
   const int ix = 4 * t.xw - P.col0 - P.g.pad;  // input column of this thread's word
   t.xok = ix >= 0 && ix < P.g.W;
@@ -144,9 +144,9 @@ __device__ __forceinline__ StageThread stage_thread(const TcParams &P) {
 
 // staged rows of a tile: rowoff[staged row] = offset of staged column 0 of that input row in channel 0 of its
 // image, or kNoRow (outside the image / past the last pixel)
-__device__ __forceinline__ bool stage_set_rowoff(const TcParams &P, int mt, int *rowoff) {
+__device__ __forceinline__ bool stage_set_rowoff(const TcParams &P, int mt, int *rowoff, int tid) {
   const Geo &g = P.g;
-  const int r = threadIdx.x;
+  const int r = tid;
   if (r < P.rk) {
     int off = kNoRow;
     if (P.shared_rows) {  // consecutive output rows of one image: input rows oy0*stride - pad + r
@@ -199,13 +199,13 @@ __device__ __forceinline__ void stage_load(const TcParams &P, const StageThread 
 }
 template <int NW>
 __device__ __forceinline__ void stage_store(const TcParams &P, const StageThread &t, const ChunkLayout &cl,
-                                            int pass0, const uint32_t (&v)[NW], uint8_t *raw) {
+                                            int pass0, const uint32_t (&v)[NW], uint8_t *raw, int tid) {
   const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
   const int total_words = (nslots * P.rk) << (P.pitch_log2 - 2);
   uint32_t *raw32 = reinterpret_cast<uint32_t *>(raw);
 #pragma unroll
   for (int u = 0; u < NW; ++u) {
-    const int q = threadIdx.x + (pass0 + u) * kProducerThreads;
+    const int q = tid + (pass0 + u) * kProducerThreads;
     if (q < total_words) raw32[q] = v[u];
   }
 }
@@ -216,13 +216,13 @@ __device__ __forceinline__ void stage_store(const TcParams &P, const StageThread
 // at kernel start and never written again.  No registers are held while the rows are in flight; the issuing
 // thread waits for its own copies (cp.async.wait_group) before the barrier that publishes the buffer.
 __device__ __forceinline__ void stage_issue_async(const TcParams &P, const ChunkLayout &cl, const int *rowoff,
-                                                  uint8_t *raw) {
+                                                  uint8_t *raw, int tid) {
   const Geo &g = P.g;
   const int nslots = cl.nfull + (cl.nhead > 0 ? 1 : 0) + (cl.ntail > 0 ? 1 : 0);
   const int cpr = g.W >> 4;  // 16-byte pieces per row
   const int total = nslots * P.rk * cpr, HW = g.H * g.W;
   const int ch_head = cl.nhead > 0 ? cl.cf0 - 1 : cl.cf0 + cl.nfull, ch_tail = cl.cf0 + cl.nfull;
-  for (int q = threadIdx.x; q < total; q += kProducerThreads) {
+  for (int q = tid; q < total; q += kProducerThreads) {
     const int rq = q / cpr, c16 = q - rq * cpr;
     const int sl = (int)__umulhi((uint32_t)rq, P.rk_magic), row = rq - sl * P.rk;
     const int off = rowoff[row];
@@ -398,55 +398,68 @@ __device__ __forceinline__ void produce_generic(const TcParams &P, int i, uint8_
 // rows + the chunk's weight tile (bulk copy).  Shared by the v1 (kind::i8) and v2 (kind::f8f6f4) kernels.
 // ---------------------------------------------------------------------------------------------------
 template <int NSA, int ENC>
-__device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm, int ntiles) {
+__device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm, int ntiles, int tid = threadIdx.x,
+                                              int gidx = 0, int ngroups = 1) {
+  // A producer GROUP is 128 threads (tid = index inside the group) that build whole pipeline stages; with
+  // ngroups > 1 (v2 kernel) group gidx builds stages gidx, gidx + ngroups, ... of the CTA's (tile, chunk) sequence,
+  // with its own staging buffers (sm.raw, sm.rowoff point at the group's) and named barrier (1 + gidx).
   const Geo &g = P.g;
-  const int r = threadIdx.x;  // tile row = output pixel
+  const int r = tid;  // tile row = output pixel
+  const uint32_t bar = 1u + (uint32_t)gidx;
   const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   long long d_wait = 0, d_prod = 0, d_tile = 0;
-  uint32_t it = 0;
+  uint32_t it = (uint32_t)gidx, lit = 0;  // global / group-local stage counters
+  // (tile, i) of stage `it`: advance by n stages
+  auto advance = [&](int &tile_, int &i_, int n) {
+    i_ += n;
+    while (i_ >= g.NX) { i_ -= g.NX; tile_ += gridDim.x; }
+  };
   if (P.fast) {
-    // ---- staged producer.  Stage `it` is (tile, chunk i); its input rows sit in raw[it & 1].
-    const StageThread stt = stage_thread(P);
+    // ---- staged producer.  Stage `it` is (tile, chunk i); its input rows sit in raw[lit & 1].
+    const StageThread stt = stage_thread(P, tid);
     const int pix_base = (((r / P.owt) * P.prow) << P.pitch_log2) + (r % P.owt) * g.stride + P.col0;
     int tile = blockIdx.x, i = 0, tpar = 0;
+    advance(tile, i, gidx);
     uint32_t v[kPrefetchWords];
     if (tile < ntiles) {
-      stage_set_rowoff(P, tile / P.nct, sm.rowoff);
-      named_barrier_sync(1, kProducerThreads);
+      stage_set_rowoff(P, tile / P.nct, sm.rowoff, tid);
+      named_barrier_sync(bar, kProducerThreads);
       if (P.tma_rows) {
         // padding columns are zero for the whole kernel: clear both buffers once, then only rows are written
-        for (uint32_t q = threadIdx.x * 16u; q < 2u * P.raw_bytes; q += kProducerThreads * 16u)
+        for (uint32_t q = tid * 16u; q < 2u * P.raw_bytes; q += kProducerThreads * 16u)
           *reinterpret_cast<uint4 *>(sm.raw + q) = make_uint4(0u, 0u, 0u, 0u);
-        named_barrier_sync(1, kProducerThreads);
-        stage_issue_async(P, chunk_layout(g, 0), sm.rowoff, sm.raw);
+        named_barrier_sync(bar, kProducerThreads);
+        stage_issue_async(P, chunk_layout(g, i), sm.rowoff, sm.raw, tid);
         stage_async_wait();
-        named_barrier_sync(1, kProducerThreads);
+        named_barrier_sync(bar, kProducerThreads);
       }
       if (P.prefetch) {
-        const ChunkLayout cl0 = chunk_layout(g, 0);
+        const ChunkLayout cl0 = chunk_layout(g, i);
         stage_load<kPrefetchWords>(P, stt, cl0, sm.rowoff, 0, v);
-        stage_store<kPrefetchWords>(P, stt, cl0, 0, v, sm.raw);
-        named_barrier_sync(1, kProducerThreads);
+        stage_store<kPrefetchWords>(P, stt, cl0, 0, v, sm.raw, tid);
+        named_barrier_sync(bar, kProducerThreads);
       }
     }
     while (tile < ntiles) {
       const int ct = tile % P.nct;
       const ChunkLayout cl = chunk_layout(g, i);
-      uint8_t *raw = sm.raw + (size_t)(it & 1) * P.raw_bytes;
-      // the stage after this one
-      int ni = i + 1, ntile = tile, ntpar = tpar;
-      if (ni == g.NX) { ni = 0; ntile = tile + gridDim.x; ntpar ^= 1; }
+      uint8_t *raw = sm.raw + (size_t)(lit & 1) * P.raw_bytes;
+      // the group's next stage
+      int ni = i, ntile = tile;
+      advance(ntile, ni, ngroups);
+      const int ntpar = ntile != tile ? tpar ^ 1 : tpar;
       const bool more = ntile < ntiles;
       ChunkLayout ncl = cl;
       if (more) {
         ncl = chunk_layout(g, ni);
-        if (ni == 0) {  // new tile: publish its row table first (its buffer was last read a whole tile ago)
-          stage_set_rowoff(P, ntile / P.nct, sm.rowoff + ntpar * 128);
-          named_barrier_sync(1, kProducerThreads);
+        if (ntile != tile) {  // new tile: publish its row table first (its buffer was last read a whole tile ago)
+          stage_set_rowoff(P, ntile / P.nct, sm.rowoff + ntpar * 128, tid);
+          named_barrier_sync(bar, kProducerThreads);
         }
         // its input rows start their trip from L2 / HBM now: by bulk copy straight into the other staging buffer,
         // or into registers, while this stage is built
-        if (P.tma_rows) stage_issue_async(P, ncl, sm.rowoff + ntpar * 128, sm.raw + (size_t)((it + 1) & 1) * P.raw_bytes);
+        if (P.tma_rows)
+          stage_issue_async(P, ncl, sm.rowoff + ntpar * 128, sm.raw + (size_t)((lit + 1) & 1) * P.raw_bytes, tid);
         else if (P.prefetch) stage_load<kPrefetchWords>(P, stt, ncl, sm.rowoff + ntpar * 128, 0, v);
       }
       if (!P.prefetch && !P.tma_rows) {  // too many rows for the registers: stage this chunk now, eight loads in flight
@@ -455,9 +468,9 @@ __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm,
         for (int p0 = 0; p0 < passes; p0 += 8) {
           uint32_t v8[8];
           stage_load<8>(P, stt, cl, sm.rowoff + tpar * 128, p0, v8);
-          stage_store<8>(P, stt, cl, p0, v8, raw);
+          stage_store<8>(P, stt, cl, p0, v8, raw, tid);
         }
-        named_barrier_sync(1, kProducerThreads);
+        named_barrier_sync(bar, kProducerThreads);
       }
       const int sidx = it % P.stages;
       const uint32_t use = it / P.stages;
@@ -466,7 +479,7 @@ __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm,
       long long t1 = CIMQ_T0();
       d_wait += t1 - t0;
       uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
-      if (threadIdx.x == 0) {
+      if (tid == 0) {
         mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
         bulk_copy_g2s(smem_u32(st_ptr + (size_t)NSA * P.a_bytes), P.wtiles + (size_t)(ct * g.NX + i) * P.b_bytes,
                       P.b_bytes, sm.full0 + 8 * sidx);
@@ -477,42 +490,49 @@ __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm,
       mbar_arrive(sm.full0 + 8 * sidx);
       if (P.prefetch || P.tma_rows) {
         if (P.prefetch && more)
-          stage_store<kPrefetchWords>(P, stt, ncl, 0, v, sm.raw + (size_t)((it + 1) & 1) * P.raw_bytes);
+          stage_store<kPrefetchWords>(P, stt, ncl, 0, v, sm.raw + (size_t)((lit + 1) & 1) * P.raw_bytes, tid);
         if (P.tma_rows) stage_async_wait();  // my copies of the next stage's rows have landed
         // next stage's rows visible to all producers; everyone is done reading this stage's rows
-        named_barrier_sync(1, kProducerThreads);
+        named_barrier_sync(bar, kProducerThreads);
       }
       d_prod += CIMQ_T0() - t1;
-      i = ni; tile = ntile; tpar = ntpar; ++it;
+      i = ni; tile = ntile; tpar = ntpar; it += ngroups; ++lit;
     }
   } else {
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int tile = blockIdx.x, i = 0;
+    advance(tile, i, gidx);
+    int cur_tile = -1, base = 0;
+    uint32_t vm = 0;  // bit t set = tap t of this pixel is inside the image
+    while (tile < ntiles) {
       const int mt = tile / P.nct, ct = tile % P.nct;
-      const int m = mt * kTcTileM + r;
-      int base = 0;
-      uint32_t vm = 0;  // bit t set = tap t of this pixel is inside the image
-      if (m < g.M) {
-        const int b = m / g.L, l = m % g.L, oy = l / g.OW, ox = l % g.OW;
-        const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
-        base = (b * g.Cin * g.H + iy0) * g.W + ix0;
-        for (int ky = 0; ky < g.K; ++ky)
-          for (int kx = 0; kx < g.K; ++kx)
-            if (iy0 + ky >= 0 && iy0 + ky < g.H && ix0 + kx >= 0 && ix0 + kx < g.W) vm |= 1u << (ky * g.K + kx);
-      }
-      for (int i = 0; i < g.NX; ++i, ++it) {
-        const int sidx = it % P.stages;
-        const uint32_t use = it / P.stages;
-        mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
-        uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
-        if (threadIdx.x == 0) {
-          mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
-          bulk_copy_g2s(smem_u32(st_ptr + (size_t)NSA * P.a_bytes),
-                        P.wtiles + (size_t)(ct * g.NX + i) * P.b_bytes, P.b_bytes, sm.full0 + 8 * sidx);
+      if (tile != cur_tile) {
+        cur_tile = tile;
+        const int m = mt * kTcTileM + r;
+        base = 0;
+        vm = 0;
+        if (m < g.M) {
+          const int b = m / g.L, l = m % g.L, oy = l / g.OW, ox = l % g.OW;
+          const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
+          base = (b * g.Cin * g.H + iy0) * g.W + ix0;
+          for (int ky = 0; ky < g.K; ++ky)
+            for (int kx = 0; kx < g.K; ++kx)
+              if (iy0 + ky >= 0 && iy0 + ky < g.H && ix0 + kx >= 0 && ix0 + kx < g.W) vm |= 1u << (ky * g.K + kx);
         }
-        produce_generic<NSA, ENC>(P, i, st_ptr, r, base, vm);
-        fence_proxy_async();
-        mbar_arrive(sm.full0 + 8 * sidx);
       }
+      const int sidx = it % P.stages;
+      const uint32_t use = it / P.stages;
+      mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
+      uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
+      if (tid == 0) {
+        mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
+        bulk_copy_g2s(smem_u32(st_ptr + (size_t)NSA * P.a_bytes), P.wtiles + (size_t)(ct * g.NX + i) * P.b_bytes,
+                      P.b_bytes, sm.full0 + 8 * sidx);
+      }
+      produce_generic<NSA, ENC>(P, i, st_ptr, r, base, vm);
+      fence_proxy_async();
+      mbar_arrive(sm.full0 + 8 * sidx);
+      advance(tile, i, ngroups);
+      it += ngroups;
     }
   }
   if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_prod; P.debug[2] = d_tile; }

@@ -1,21 +1,23 @@
 // Second-generation tcgen05 forward kernel of the CiM convolution (get_cim_output_signed.forward, lsq.py:92-237)
 // for 1-bit slices: ~4 CUDA-core instructions per partial sum instead of ~16.
 //
-//   producers (warps 0-3)    unchanged from v1 (cim_conv_tc_kernel.cuh): im2col digit planes of 128 pixels per
-//                            crossbar chunk, written as e4m3 bytes (2.0 for a set bit), weight digits +-0.5.
-//   MMA issuer (warp 12)     GEMM1: tcgen05.mma.kind::f8f6f4 with **fp16 accumulators** -- partial sums
+//   producers (warps 0-7)    the v1 producer (cim_conv_tc_kernel.cuh): im2col digit planes of 128 pixels per crossbar
+//                            chunk, written as e4m3 bytes (2.0 for a set bit), weight digits +-0.5.  Two groups of
+//                            four warps build alternate stages (a producer thread is latency bound: one warp per
+//                            scheduler assembling its pixel's row byte by byte).
+//   MMA issuer (warp 16)     GEMM1: tcgen05.mma.kind::f8f6f4 with **fp16 accumulators** -- partial sums
 //                            p[128 pixels x NSW*CT] of one activation digit plane, exact integers (|p| <= 128;
 //                            the reference stores them as fp16 too, lsq.py:169), two TMEM buffers.
 //                            GEMM2 (after the epilogue of that plane): tcgen05.mma.kind::f16 with the **A operand
 //                            in TMEM** -- out[128 x CT] += code[128 x (k,c)] * diag(n(i,k,j,c) * 2^(k+j)), one
 //                            N=16,K=16 instruction per (weight slice, 16-channel group), fp32 accumulator that lives
 //                            in TMEM for the whole tile: the shift-and-add of lsq.py:233 costs no CUDA-core work.
-//   epilogue (warps 4-11)    thread = pixel.  tcgen05.ld.pack::16b delivers two fp16 partial sums per register;
+//   epilogue (warps 8-15)    thread = pixel.  tcgen05.ld.pack::16b delivers two fp16 partial sums per register;
 //                            |p| (ALU pipe), code = sat(|p| - (tp-1)) with p's sign OR-ed in (FMA + ALU pipe),
 //                            clip = sat(|p| - (tg-1)); the ternary codes go straight back to tensor memory, in
 //                            place, as GEMM2's A operand (tcgen05.st); the backward's inputs are accumulated as
 //                            small integers in packed-half registers (see cim_v2.cuh) and leave as bytes.
-//   constants (warp 13)      one bulk copy per chunk: thresholds + B2 slabs -> shared memory (double buffered).
+//   constants (warp 17)      one bulk copy per chunk: thresholds + B2 slabs -> shared memory (double buffered).
 #include <cuda_fp16.h>
 #include <string.h>
 
@@ -29,11 +31,14 @@ using namespace ptx;
 using tcfwd::kProducerThreads;
 using tcfwd::kProducerWarps;
 
-constexpr int kThreads = 512;
-constexpr int kMmaWarp = 12, kConstWarp = 13;
-constexpr int kRegsProducer = 104, kRegsMma = 40, kRegsEpilogue = 184;
+constexpr int kProducerGroups = 2;
+constexpr int kEpiWarp0 = kProducerGroups * kProducerWarps;  // 8
+constexpr int kMmaWarp = kEpiWarp0 + 8, kConstWarp = kMmaWarp + 1;
+constexpr int kThreads = (kMmaWarp + 4) * 32;                // 640: five warpgroups
+// registers per warpgroup (setmaxnreg): 2 x 96 (producers) + 2 x 136 (epilogue) + 40 (MMA, constants) = 504 <= 512
+constexpr int kRegsProducer = 96, kRegsMma = 40, kRegsEpilogue = 136;
 constexpr int kMaxStages = 4;
-constexpr size_t kAuxBytes = 2048;
+constexpr size_t kAuxBytes = 4096;
 constexpr size_t kSmemBudget = 227 * 1024 - 1024;
 
 struct V2Params {
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
   sm.stage_base = smem_raw;
   const size_t raw_off = (size_t)T.stages * T.stage_bytes;
   sm.raw = smem_raw + raw_off;
-  const size_t c_off = (raw_off + 2 * (size_t)T.raw_bytes + 127) & ~(size_t)127;  // smem_raw is 1024-byte aligned
+  const size_t c_off = (raw_off + 2 * kProducerGroups * (size_t)T.raw_bytes + 127) & ~(size_t)127;  // smem_raw: 1024-byte aligned
   uint8_t *cbuf = smem_raw + c_off;
   uint8_t *pp = cbuf + 2 * (size_t)P.block_bytes;
   uint64_t *bars = reinterpret_cast<uint64_t *>(pp);
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
   sm.tfull0 = B.tfull0;
   sm.tempty0 = B.tempty0;
   sm.tmem_slot = reinterpret_cast<uint32_t *>(pp + 192);
-  sm.rowoff = reinterpret_cast<int *>(pp + 256);  // 2 x 128 ints
+  sm.rowoff = reinterpret_cast<int *>(pp + 256);  // per producer group 2 x 128 ints
   sm.ttab = nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,10 +200,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
   const int ntiles = T.mtiles * T.nct;
   const int rows_full = g.xbar < g.F ? g.xbar : g.F;
 
-  if (warp < kProducerWarps) {
+  if (warp < kEpiWarp0) {
     // =========================== producers ===========================
     reg_dealloc<kRegsProducer>();
-    tcfwd::producer_loop<NS, 1>(T, sm, ntiles);
+    const int gidx = warp / kProducerWarps;
+    tcfwd::Smem smg = sm;  // the group's staging buffers and row tables
+    smg.raw = sm.raw + (size_t)gidx * 2 * T.raw_bytes;
+    smg.rowoff = sm.rowoff + gidx * 256;
+    tcfwd::producer_loop<NS, 1>(T, smg, ntiles, threadIdx.x & (kProducerThreads - 1), gidx, kProducerGroups);
   } else if (warp >= kMmaWarp) {
     reg_dealloc<kRegsMma>();
     if (warp == kMmaWarp && lane == 0) {
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
   } else {
     // =========================== epilogue ===========================
     reg_alloc<kRegsEpilogue>();
-    const int e = warp - kProducerWarps;
+    const int e = warp - kEpiWarp0;
     const int quarter = warp & 3;
     const int half = e >> 2;
     if (half < EW) {
@@ -411,7 +420,7 @@ static bool make_plan(const Geo &g, V2Params &P, size_t &smem) {
   T.tmem_cols = cols;
   tcfwd::plan_producer(g, T);
   for (int attempt = 0; attempt < 2; ++attempt) {
-    const size_t fixed = 2 * (size_t)T.raw_bytes + 128 + 2 * (size_t)P.block_bytes + kAuxBytes;
+    const size_t fixed = 2 * kProducerGroups * (size_t)T.raw_bytes + 128 + 2 * (size_t)P.block_bytes + kAuxBytes;
     if (fixed + T.stage_bytes <= kSmemBudget) {
       int stages = (int)((kSmemBudget - fixed) / T.stage_bytes);
       if (stages > kMaxStages) stages = kMaxStages;

@@ -293,7 +293,7 @@ WtLayout wt_layout(const Geo &g) {
   if (fwd && v2_forward_supported(g))
     w.fwd8_bytes = (int64_t)g.NX * g.NSW * g.Cout * tc_kp(g);  // (Cout/CT) * NX tiles of NSW*CT rows x Kp
   w.bwd2_off = align(w.fwd8_off + w.fwd8_bytes);
-  w.bwd2_bytes = (w.fwd8_bytes > 0 && w.bwd_bytes > 0) ? w.bwd_bytes : 0;
+  w.bwd2_bytes = (w.fwd8_bytes > 0 && v2_backward_supported(g)) ? w.bwd_bytes : 0;
   w.total = align(w.bwd2_off + w.bwd2_bytes);
   if (w.fwd_bytes == 0 && w.bwd_bytes == 0) w.total = 0;
   return w;
@@ -322,6 +322,9 @@ int launch_weight_prepare(const Geo &g, const int8_t *wcodes, float *wdigits, vo
   }
   if (wtiles != nullptr && wl.bwd_bytes > 0) {
     if (launch_weight_tiles_bwd(g, wcodes, reinterpret_cast<uint8_t *>(wtiles) + wl.bwd_off, st)) return 1;
+  }
+  if (wtiles != nullptr && wl.bwd2_bytes > 0) {
+    if (launch_weight_tiles_bwd2(g, wcodes, reinterpret_cast<uint8_t *>(wtiles) + wl.bwd2_off, st)) return 1;
   }
   return 0;
 }

@@ -49,7 +49,7 @@ int cimq_layer_info(const cimq_layer_t *layer, cimq_info_t *info) {
   info->wtiles_bytes = wtiles_bytes(g);
   info->bwd_workspace_bytes = conv_backward_ws_bytes(g);
   info->psum_count = (int64_t)g.B * g.NX * g.NSW * g.NSA * g.L * g.Cout;
-  info->tc_v2 = (v2_forward_supported(g) && tc_backward_supported(g)) ? 1 : 0;
+  info->tc_v2 = (v2_forward_supported(g) && v2_backward_supported(g)) ? 1 : 0;
   info->state_v2_bytes = info->tc_v2 ? v2::state_bytes(g) : 0;
   return 0;
 }

@@ -125,10 +125,13 @@ int64_t bwd_tc_partial_bytes(const Geo &g);
 bool bwd_input_tc_can_fold(const Geo &g);
 // fold = 1: `out` is grad_x [B,Cin,H,W], zero-filled, and the kernel folds into it; fold = 0: `out` is the
 // unfolded gradient gxu[b][f][l] for launch_col2im
+// v2 = true: `state` is the v2 byte planes (cim_v2.cuh) and `wtb` the pre-scaled dgrad tiles (WtLayout::bwd2)
 int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, const void *wtb, const float *s,
-                        const int8_t *mask, float *out, int fold, cudaStream_t st);
+                        const int8_t *mask, float *out, int fold, bool v2, cudaStream_t st);
 int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, const uint32_t *state,
-                         const float *s, const int8_t *mask, float *partial, float *gw, cudaStream_t st);
+                         const float *s, const int8_t *mask, float *partial, float *gw, bool v2, cudaStream_t st);
+bool v2_backward_supported(const Geo &g);
+int launch_weight_tiles_bwd2(const Geo &g, const int8_t *wcodes, void *tiles, cudaStream_t st);
 
 // Sections of the prepared-weights buffer ("wtiles"): forward int8 digit tiles, im2col LUT (int2 per crossbar
 // row), backward bf16 digit tiles.  A section the layer does not support has zero bytes.

@@ -88,7 +88,10 @@ class get_cim_output_signed(Function):
             out, state = _lib.conv_forward_stochastic(spec, xcodes, wcodes, table, s, alpha_q, _stochastic_seed(),
                                                       save_state=need_bwd)
         else:
-            out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd)
+            # an arbitrary alpha_cim tensor carries no quantiser step, so only the multi-bit ADC can take the v2 kernels
+            flags = _lib.FLAG_V2 if _lib.v2_usable(spec, has_alpha, None) else 0
+            out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd,
+                                           flags=flags)
         ctx.spec, ctx.has_alpha, ctx.w_shape = spec, has_alpha, tuple(w.shape)
         ctx.save_for_backward(xcodes, wdigits, wtiles, state, s, mask)
         return out.transpose(1, 2)  # [B, L, Cout] like lsq.py:233 (a view of the NCHW buffer)
@@ -111,7 +114,7 @@ class _CimConv2dFused(Function):
 
     @staticmethod
     def forward(ctx, x, weight, alpha_act, alpha_weight, alpha_q, binary_mask, stride, padding, nbits_a,
-                abitslice, nbits_w, wbitslice, xbar, adcbits, flags, stochastic_seed=None):
+                abitslice, nbits_w, wbitslice, xbar, adcbits, flags, stochastic_seed=None, alpha_scale=None):
         _require_cuda(x, weight, alpha_act, alpha_weight)
         x = x.contiguous()
         weight = weight.contiguous()
@@ -127,11 +130,16 @@ class _CimConv2dFused(Function):
         wcodes = _lib.lsq_quantize(weight.detach(), s[1:2], qn_w, qp_w)
         mask = _as_mask_2d(binary_mask, info.NSW, info.NSA, x.device)
         has_alpha = alpha_q is not None
-        table = _lib.adc_table(spec, s, alpha_q.detach().contiguous() if has_alpha else None, mask)
+        sampled = stochastic_seed is not None and has_alpha and adcbits == 1.5
+        use_v2 = not sampled and _lib.v2_usable(spec, has_alpha, alpha_scale, flags)
+        table = _lib.adc_table(spec, s, alpha_q.detach().contiguous() if has_alpha else None, mask,
+                               alpha_scale=alpha_scale if use_v2 else None)
+        if use_v2:
+            flags |= _lib.FLAG_V2
         need_bwd = any(ctx.needs_input_grad)
         simt = bool(flags & _lib.FLAG_FORCE_SIMT)
         wdigits, wtiles = _lib.weight_prepare(spec, wcodes, want_digits=need_bwd and (simt or not info.tc_backward))
-        if stochastic_seed is not None and has_alpha and adcbits == 1.5:  # lsq.py:203-220
+        if sampled:  # lsq.py:203-220
             out, state = _lib.conv_forward_stochastic(spec, xcodes, wcodes, table, s, alpha_q.detach(),
                                                       stochastic_seed, save_state=need_bwd)
         else:
@@ -156,7 +164,7 @@ class _CimConv2dFused(Function):
         if need_x:
             gx, g_aa = _lib.lsq_backward(gxq, x, s[0:1], 0, qp_a, ga)
         gwt, g_aw = _lib.lsq_backward(gwq.view_as(weight), weight, s[1:2], qn_w, qp_w, gw)
-        return (gx, gwt, g_aa, g_aw, galpha) + (None,) * 11
+        return (gx, gwt, g_aa, g_aw, galpha) + (None,) * 12
 
 
 def _stochastic_seed() -> int:
@@ -165,12 +173,14 @@ def _stochastic_seed() -> int:
 
 
 def cim_conv2d(x, weight, alpha_act, alpha_weight, alpha_q, binary_mask, stride, padding, nbits_a, abitslice,
-               nbits_w, wbitslice, xbar, adcbits, flags: int = 0, stochastic: bool = False):
+               nbits_w, wbitslice, xbar, adcbits, flags: int = 0, stochastic: bool = False, alpha_scale=None):
     """Fused CiM convolution of ``Conv2dLSQCiM`` (lsq.py:546-581): returns ``[B, Cout, OH, OW]``.
-    ``stochastic``: the sampled near-ADC-less read-out of lsq.py:205-220 (adcbits 1.5 only; CUDA-core kernel)."""
+    ``stochastic``: the sampled near-ADC-less read-out of lsq.py:205-220 (adcbits 1.5 only; CUDA-core kernel).
+    ``alpha_scale``: the step of the alpha quantiser that produced ``alpha_q`` (second output of
+    :func:`alpha_quantize`); with it the layer runs on the v2 kernels where they cover it."""
     return _CimConv2dFused.apply(x, weight, alpha_act, alpha_weight, alpha_q, binary_mask, stride, padding, nbits_a,
                                  abitslice, nbits_w, wbitslice, xbar, adcbits, flags,
-                                 _stochastic_seed() if stochastic else None)
+                                 _stochastic_seed() if stochastic else None, alpha_scale)
 
 
 class _LsqFakeQuant(Function):
@@ -185,8 +195,9 @@ class _LsqFakeQuant(Function):
         y = _lib.lsq_fakequant(x.detach(), s[0:1], qn, qp, rescale)
         ctx.save_for_backward(x, s)
         ctx.consts = (g, qn, qp, rescale)
-        ctx.mark_non_differentiable(s)
-        return y, s[0:1]
+        s1 = s[0:1].clone()  # the tensor that is returned is the one marked (a view of `s` would stay differentiable)
+        ctx.mark_non_differentiable(s1)
+        return y, s1
 
     @staticmethod
     def backward(ctx, grad_y, _grad_s):
@@ -220,15 +231,19 @@ class _AlphaQuant(Function):
         aq, aux = _lib.alpha_quantize(a, qn, qp)
         ctx.save_for_backward(a, aux)
         ctx.q = (qn, qp)
-        return aq
+        scale = aux[0:1].clone()
+        ctx.mark_non_differentiable(scale)
+        return aq, scale
 
     @staticmethod
-    def backward(ctx, grad_aq):
+    def backward(ctx, grad_aq, _grad_scale):
         a, aux = ctx.saved_tensors
         return _lib.alpha_quantize_backward(a, grad_aq.contiguous().float(), ctx.q[0], ctx.q[1], aux), None, None
 
 
 def alpha_quantize(alpha, nbits_alpha: int):
+    """``(alpha_q, scale)``: the quantised alpha_cim (differentiable, lsq.py:566-571) and the quantiser's step
+    ``(max - min) / (Qp - 1)`` as a 1-element tensor (not differentiable; alpha_q = n * scale, n integer)."""
     return _AlphaQuant.apply(alpha, 1, 2 ** nbits_alpha - 1)
 
 

@@ -25,10 +25,16 @@ class _CiMForward:
 
     # -- host mirror of the init buffers -----------------------------------------------------------
     def _flags(self):
-        if self._flags_stale:  # one device read after construction / load_state_dict, then none
+        """(init_state != 0, init_state_cim != 0) without a device read per forward: the host copy is refreshed only
+        when a buffer was written since the last read (tensor version counters catch fill_ / copy_ / load_state_dict /
+        a DDP broadcast; the reference reads both buffers on every forward, lsq.py:532, 557)."""
+        seen = (self.init_state._version, self.init_state_cim._version, self.init_state.data_ptr(),
+                self.init_state_cim.data_ptr())
+        if self._flags_stale or seen != getattr(self, "_flags_seen", None):
             self._init_done = bool(self.init_state.item() != 0)
             self._init_cim_done = bool(self.init_state_cim.item() != 0)
             self._flags_stale = False
+            self._flags_seen = seen
         return self._init_done, self._init_cim_done
 
     @torch.no_grad()
@@ -43,6 +49,11 @@ class _CiMForward:
         self.alpha_weight.data.copy_(2 * w.abs().mean() / math.sqrt(qp_w))
         self.init_state.fill_(1)
         self._init_done = True
+        self._note_flags()
+
+    def _note_flags(self):
+        self._flags_seen = (self.init_state._version, self.init_state_cim._version, self.init_state.data_ptr(),
+                            self.init_state_cim.data_ptr())
 
     @torch.no_grad()
     def _lazy_init_cim(self, x, w, stride, padding):
@@ -60,9 +71,10 @@ class _CiMForward:
                                                              reduce_sums=CD.global_sum_))
         self.init_state_cim.fill_(1)
         self._init_cim_done = True
+        self._note_flags()
 
     def _alpha_q(self):
-        """``nbits_alpha``-bit range quantiser of alpha_cim, inside autograd (lsq.py:566-571)."""
+        """``nbits_alpha``-bit range quantiser of alpha_cim, inside autograd (lsq.py:566-571): (alpha_q, step)."""
         return CF.alpha_quantize(self.alpha_cim, self.nbits_alpha)
 
     def _cim_forward(self, x, w, stride, padding):
@@ -77,10 +89,12 @@ class _CiMForward:
             self.binary_mask = self.binary_mask.to(x.device)
         if self.training and not init_cim_done and self.alpha_cim is not None:
             self._lazy_init_cim(x, w, stride, padding)
-        alpha_q = self._alpha_q() if self.alpha_cim is not None else None
+        alpha_q, alpha_scale = self._alpha_q() if self.alpha_cim is not None else (None, None)
+        if self.nbits_alpha > 11:  # the v2 kernels carry alpha_q / scale as an fp16 integer (< 2048)
+            alpha_scale = None
         return CF.cim_conv2d(x, w, self.alpha_act, self.alpha_weight, alpha_q, self.binary_mask, stride, padding,
                              self.nbits_a, self.abitslice, self.nbits_w, self.wbitslice, self.xbar, self.adcbits,
-                             self.kernel_flags, stochastic=bool(self.stochastic_quant))
+                             self.kernel_flags, stochastic=bool(self.stochastic_quant), alpha_scale=alpha_scale)
 
 
 class Conv2dLSQCiM(_Conv2dQCiM, _CiMForward):

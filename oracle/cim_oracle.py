@@ -293,17 +293,33 @@ def cim_forward(cfg: CimConfig, x_codes, w_codes, s_w, s_a, alpha_q, return_inte
 # --------------------------------------------------------------------------------------
 # backward of the Function (lsq.py:244-386)
 # --------------------------------------------------------------------------------------
-def cim_backward(cfg: CimConfig, grad_out, x_codes, w_codes, s_w, s_a, alpha_q, in_hw):
+def int8_saved_codes(x_codes: np.ndarray) -> np.ndarray:
+    """What ``ctx.x_int = x_int.type(torch.int8)`` (lsq.py:99) keeps of the activation codes: two's-complement
+    wrap-around, i.e. codes 128..255 of an 8-bit layer come back as -128..-1 in the backward."""
+    return ((np.asarray(x_codes, dtype=np.int32) + 128) % 256) - 128
+
+
+def cim_backward(cfg: CimConfig, grad_out, x_codes, w_codes, s_w, s_a, alpha_q, in_hw, signed_act=False,
+                 int8_save=False):
     """``get_cim_output_signed.backward``.
 
     grad_out ``[B, L, Cout]``.  Returns ``(grad_xq [B,Cin,H,W], grad_wq [Cout,Cin,k,k],
     grad_alpha_q [1,NX,NSW,NSA,1,Cout] or None)``.
+
+    ``int8_save`` + ``signed_act`` reproduce the reference's int8 save of the activation codes (lsq.py:99) for
+    layers that slice with ``slicing_act_signed`` (lsq.py:291-292, the 8-bit first conv of a model fed normalised
+    images): a code >= 128 re-enters the backward as ``code - 256`` and is sliced as minus the digits of
+    ``256 - code``, so its contribution to grad_w differs from the forward's digits (hazard H6).  With the unsigned
+    ``slicing_act`` the wrap is invisible (floor-division / remainder recover the same low bits), and codes < 128
+    are unaffected either way.  Default ``False``: the arithmetic the forward used (what the CUDA path computes).
     """
     qn, qp = cfg.adc_range
     s_w = F32(s_w)
     s_a = F32(s_a)
     ps_int = integer_psums(cfg, x_codes, w_codes)
     x_sl, w_sl = sliced_operands(cfg, x_codes, w_codes)
+    if int8_save and signed_act:
+        x_sl, _ = sliced_operands(cfg, int8_saved_codes(x_codes), w_codes)
     w_sl = w_sl * s_w  # lsq.py:252
     x_sl = x_sl * s_a  # lsq.py:295
     if cfg.adcbits in (1, 1.5):

@@ -57,10 +57,21 @@ CASES = {
                                   wbs=1, abs=1, xbar=128, adc=1.5),
     "pw_c32o8_x16": dict(cin=32, cout=8, k=1, stride=1, pad=0, hw=4, batch=2, nbits_w=3, nbits_a=3,
                          wbs=1, abs=1, xbar=16, adc=1.5),
+    # 8-bit first conv on signed images with an activation step so small that codes reach 128..255; the
+    # reference's backward then sees them as int8 (lsq.py:99) sliced by slicing_act_signed (lsq.py:291-292).  The
+    # "h6_" prefix keeps this case out of the generic golden list (tests/_util.golden_names): the CUDA path computes
+    # the un-wrapped gradient on purpose (known deviations) and has its own test.
+    # step sizes as the reference's own init leaves them, NOT snapped to exact recovery: fl(fl(k*s)/s) != k
+    # for some codes, so the reference's digit planes carry its float-recovery artefacts (lsq.py:97-98, 160).  The
+    # "h1_" prefix keeps the case out of the generic list; tests/test_gpu_v2.py quantifies the deviation.
+    "h1_tern_c16o16_x128_unsnapped": dict(cin=16, cout=16, k=3, stride=1, pad=1, hw=8, batch=2, nbits_w=3, nbits_a=3,
+                                          wbs=1, abs=1, xbar=128, adc=1.5, no_snap=True),
+    "h6_first_w8a8_c3o16_x128": dict(cin=3, cout=16, k=3, stride=1, pad=1, hw=8, batch=2, nbits_w=8, nbits_a=8,
+                                     wbs=1, abs=1, xbar=128, adc=1.5, signed_input=True, act_scale_div=12.0),
 }
 
 
-def _exact(s, qn, qp):
+def _exact(s, qn, qp):  # noqa: E302
     k = torch.arange(qn, qp + 1, dtype=torch.float32)
     return bool(((k * s) / s == k).all())
 
@@ -93,8 +104,11 @@ def run_case(name, c, seed):
     ga = 1.0 / math.sqrt(x.numel() * qp_a)
     gw = 1.0 / math.sqrt(m.weight.numel() * qp_w)
     with torch.no_grad():
-        m.alpha_act.copy_(_snap_alpha(m.alpha_act.data, ga, 0, qp_a))
-        m.alpha_weight.copy_(_snap_alpha(m.alpha_weight.data, gw, qn_w, qp_w))
+        if c.get("act_scale_div"):
+            m.alpha_act.div_(c["act_scale_div"])
+        if not c.get("no_snap"):
+            m.alpha_act.copy_(_snap_alpha(m.alpha_act.data, ga, 0, qp_a))
+            m.alpha_weight.copy_(_snap_alpha(m.alpha_weight.data, gw, qn_w, qp_w))
     alpha_cim_init = None
     if m.alpha_cim is not None:
         m.init_state_cim.fill_(0)
@@ -134,9 +148,11 @@ def run_case(name, c, seed):
         grads = ref_lsq.get_cim_output_signed.backward(ctx, go)
     x_codes = (x_q / s_a)
     w_codes = (w_q / s_w)
-    assert (x_codes == x_codes.round()).all() and (w_codes == w_codes.round()).all(), "inexact recovery"
+    inexact = int((x_codes != x_codes.round()).sum()) + int((w_codes != w_codes.round()).sum())
+    assert c.get("no_snap") or inexact == 0, "inexact recovery"
     ps_int = ctx.ps_int.float()
-    assert (ps_int == ps_int.round()).all()
+    assert c.get("no_snap") or (ps_int == ps_int.round()).all()
+    ps_int = ps_int.round()
 
     d = dict(
         cfg=np.array([c["cin"], c["cout"], c["k"], c["stride"], c["pad"], c["hw"], c["batch"], c["nbits_w"],
@@ -157,9 +173,16 @@ def run_case(name, c, seed):
                  alpha_q=alpha_q.numpy(), grad_alpha_cim=m.alpha_cim.grad.numpy(),
                  fn_grad_alpha_q=grads[12].numpy())
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
-    print(f"{name}: y{tuple(y.shape)} ps_int{tuple(ps_int.shape)} |ps|max={int(ps_int.abs().max())}")
+    print(f"{name}: y{tuple(y.shape)} ps_int{tuple(ps_int.shape)} |ps|max={int(ps_int.abs().max())} "
+          f"inexactly recovered codes: {inexact}")
+    return inexact > 0
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate
     for n, (name, c) in enumerate(CASES.items()):
-        run_case(name, c, seed=1234 + n)
+        if not only or name in only:
+            # the un-snapped case walks seeds until the reference's init lands on step sizes with inexact recovery
+            for seed in range(1234 + n, 1234 + n + (64 if c.get("no_snap") else 1)):
+                if run_case(name, c, seed=seed) or not c.get("no_snap"):
+                    break

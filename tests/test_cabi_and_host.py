@@ -26,7 +26,7 @@ def test_header_symbols_exported(lib):
     for name in sorted(declared):
         assert hasattr(dll, name), f"libcimq.so does not export {name}"
     assert declared == set(lib.EXPORTS), "ctypes binding table and header disagree"
-    assert lib.load().cimq_version() == 100
+    assert lib.load().cimq_version() == 200
 
 
 def test_layer_info_microbench(lib):

@@ -76,7 +76,7 @@ V2_CASES = [
 
 
 @pytest.mark.parametrize("case", V2_CASES)
-def test_v2_forward_against_oracle(case):
+def test_v2_forward_backward_against_oracle(case):
     L = _lib()
     cfg, rng, xc, wc, s_a, s_w, aq, scale = _random_case(case)
     cin, cout, hw, batch = case[0], case[1], case[2], case[3]
@@ -97,6 +97,10 @@ def test_v2_forward_against_oracle(case):
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
     table = L.adc_table(spec, s, aqd, mask, status, alpha_scale=sc)
     _, wtiles = L.weight_prepare(spec, wcd, want_digits=False)
+    oh = cfg.out_hw(hw)
+    go = rng.standard_normal((batch, oh * oh, cout)).astype(np.float32)
+    ref_gx, ref_gw, ref_ga = O.cim_backward(cfg, go, xc, wc, s_w, s_a, aq, hw)
+    god = _cuda(np.ascontiguousarray(go.transpose(0, 2, 1)))
     for save in (False, True):
         out, state = L.conv_forward(spec, xcd, wcd, wtiles, table, s, mask, save_state=save, flags=L.FLAG_V2)
         torch.cuda.synchronize()
@@ -109,3 +113,107 @@ def test_v2_forward_against_oracle(case):
             np.testing.assert_array_equal(w, rw)
             if cfg.has_alpha_cim:
                 np.testing.assert_array_equal(c, rc)
+            # backward on the v2 planes (the uint8 state selects CIMQ_FLAG_V2): fused fold and the deterministic path
+            for flags in (0, L.FLAG_DETERMINISTIC):
+                gxq, gwq, galpha = L.conv_backward(spec, god, xcd, None, wtiles, state, s, mask,
+                                                   need_alpha=cfg.has_alpha_cim, flags=flags)
+                assert rel_err(gxq.cpu().numpy(), ref_gx) < TOL
+                assert rel_err(gwq.cpu().numpy().reshape(ref_gw.shape), ref_gw) < TOL
+                if cfg.has_alpha_cim:
+                    assert rel_err(galpha.cpu().numpy(), ref_ga) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_v2_module_matches_reference_goldens(name):
+    """The module surface picks the v2 kernels by itself where they cover the layer: replay the reference's golden
+    vectors (tests/golden/make_golden.py) through Conv2dLSQCiM and compare outputs and all gradients."""
+    from tests.test_gpu_parity import _build_module
+    L = _lib()
+    cfg, d, hw, batch = load_golden(name)
+    if not L.layer_info(_spec(cfg, hw, batch)).tc_v2:
+        pytest.skip("layer not covered by the v2 kernels")
+    m = _build_module(cfg, d, force_simt=False)
+    x = _cuda(d["x"]).requires_grad_(True)
+    y = m(x)
+    y.backward(_cuda(d["grad_y"]))
+    assert rel_err(y.detach().cpu().numpy(), d["y"]) < TOL
+    assert rel_err(x.grad.cpu().numpy(), d["grad_x"]) < TOL
+    assert rel_err(m.weight.grad.cpu().numpy(), d["grad_weight"]) < TOL
+
+
+def test_init_state_reset_reinitialises_alpha_cim():
+    """The reference reads ``init_state_cim`` on every forward (lsq.py:557): zeroing the buffer in place must make the
+    next training forward recompute alpha_cim (the host mirror of the flags follows the buffers' version counters)."""
+    import cim_quantization_b200 as cq
+    torch.manual_seed(0)
+    m = cq.Conv2dLSQCiM(16, 16, (3, 3), (1, 1), (1, 1), (1, 1), 1, False, nbits_w=3, nbits_a=3, nbits_alpha=8,
+                        wbitslice=1, abitslice=1, xbar=128, adcbits=1.5).cuda().train()
+    x = torch.relu(torch.randn(2, 16, 8, 8, device="cuda"))
+    m(x)
+    a0 = m.alpha_cim.detach().clone()
+    assert m.init_state_cim.item() == 1
+    with torch.no_grad():
+        m.alpha_cim.fill_(123.0)
+    m.init_state_cim.fill_(0)
+    m(x)
+    assert m.init_state_cim.item() == 1
+    torch.testing.assert_close(m.alpha_cim.detach(), a0)
+
+
+def test_tensors_on_another_device_than_current():
+    """Kernels run in the device context of their tensors, not the caller's current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    L = _lib()
+    x = torch.randn(1024, device="cuda:1")
+    s = torch.tensor([0.1], device="cuda:1")
+    with torch.cuda.device(0):
+        codes = L.lsq_quantize(x, s, -4, 3)
+    assert codes.device == x.device
+    torch.testing.assert_close(codes.float(), torch.clamp(torch.round(x / s), -4, 3))
+
+
+def _module_on_golden(name):
+    from tests.test_gpu_parity import _build_module
+    cfg, d, hw, batch = load_golden(name)
+    m = _build_module(cfg, d, force_simt=False)
+    x = _cuda(d["x"]).requires_grad_(True)
+    y = m(x)
+    y.backward(_cuda(d["grad_y"]))
+    clean = O.module_forward_backward(cfg, d["x"], d["weight"], d["alpha_act"], d["alpha_weight"], d.get("alpha_cim"),
+                                      d["grad_y"])
+    return cfg, d, m, x, y, clean
+
+
+def test_h6_int8_saved_codes_deviation_is_only_in_grad_weight():
+    """Known deviation: the reference's backward re-reads 8-bit activation codes through an int8 save
+    (lsq.py:99), which turns codes >= 128 of a signed_act layer into negative digits (the oracle reproduces
+    it, tests/test_oracle_golden.py).  The CUDA path uses the digits the forward used.  On a reference-generated case
+    with 13 % of the codes >= 128: output, grad_x and grad_alpha_cim equal the reference's to 1e-5; grad_weight equals
+    the un-wrapped oracle gradient to 1e-5 and differs from the reference's wrapped one by the (large) artefact."""
+    cfg, d, m, x, y, clean = _module_on_golden("h6_first_w8a8_c3o16_x128")
+    assert rel_err(y.detach().cpu().numpy(), d["y"]) < TOL
+    assert rel_err(x.grad.cpu().numpy(), d["grad_x"]) < TOL
+    assert rel_err(m.alpha_cim.grad.cpu().numpy(), d["grad_alpha_cim"]) < TOL
+    gw = m.weight.grad.cpu().numpy()
+    assert rel_err(gw, clean["grad_weight"]) < TOL
+    dev = rel_err(gw, d["grad_weight"])
+    print(f"H6 deviation of grad_weight from the reference (codes >= 128: "
+          f"{float((d['x_codes'] >= 128).mean()):.1%}): {dev:.3f}")
+    assert dev > 0.05  # the artefact is real; if this ever drops to ~0 the reference behaviour is being reproduced
+
+
+def test_h1_unsnapped_step_sizes_deviation_is_only_in_grad_x():
+    """Known deviation: with step sizes whose ``fl(fl(k*s)/s) != k`` for some weight code the
+    reference's backward truncates 0.9999998 digits to 0 (int8 save, lsq.py:160, 249); its grad_x is then off by ~10 %
+    from what its own forward implies.  The CUDA path never divides fake-quant floats: output, grad_weight and
+    grad_alpha_cim equal the reference's to 1e-5, grad_x equals the artefact-free oracle value."""
+    cfg, d, m, x, y, clean = _module_on_golden("h1_tern_c16o16_x128_unsnapped")
+    assert rel_err(y.detach().cpu().numpy(), d["y"]) < TOL
+    assert rel_err(m.weight.grad.cpu().numpy(), d["grad_weight"]) < TOL
+    assert rel_err(m.alpha_cim.grad.cpu().numpy(), d["grad_alpha_cim"]) < TOL
+    gx = x.grad.cpu().numpy()
+    assert rel_err(gx, clean["grad_x"]) < TOL
+    dev = rel_err(gx, d["grad_x"])
+    print(f"H1 deviation of grad_x from the reference on un-snapped step sizes: {dev:.3f}")
+    assert 0.01 < dev < 0.5
