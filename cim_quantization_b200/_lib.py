@@ -73,6 +73,9 @@ EXPORTS = {
                                  C.c_void_p, C.c_void_p]),
     "cimq_adc_table2": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "cimq_layer_prepare": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                     C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cimq_weight_prepare": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cimq_conv_forward": (C.c_int, [C.POINTER(CimqLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
@@ -286,6 +289,29 @@ def v2_usable(spec: LayerSpec, has_alpha: bool, alpha_scale, flags: int = 0) -> 
     if flags & FLAG_FORCE_SIMT or os.environ.get("CIMQ_DISABLE_V2"):
         return False
     return bool(layer_info(spec).tc_v2) and (not has_alpha or alpha_scale is not None)
+
+
+@_on_tensor_device
+def layer_prepare(spec: LayerSpec, weight, alpha_act, alpha_weight, ga: float, gw: float, alpha_cim, aq_qn: int,
+                  aq_qp: int, binary_mask, status=None):
+    """One launch for everything that depends only on the parameters (v2 layers): returns
+    ``(s, wcodes, alpha_q, aux, table, wtiles)``; ``alpha_q`` / ``aux`` are None for the multi-bit ADC."""
+    info = layer_info(spec)
+    dev = weight.device
+    s = torch.empty(2, dtype=torch.float32, device=dev)
+    wcodes = torch.empty((spec.out_channels, info.F), dtype=torch.int8, device=dev)
+    alpha_q = aux = None
+    if alpha_cim is not None:
+        alpha_q = torch.empty_like(alpha_cim)
+        aux = torch.empty(8, dtype=torch.float32, device=dev)
+    table = torch.empty(info.table_bytes, dtype=torch.uint8, device=dev)
+    wtiles = torch.empty(info.wtiles_bytes, dtype=torch.uint8, device=dev)
+    layer = spec.c_layer()
+    _check(load().cimq_layer_prepare(C.byref(layer), _ptr(weight), _ptr(alpha_act), _ptr(alpha_weight), ga, gw,
+                                     _ptr(alpha_cim), aq_qn, aq_qp, _ptr(binary_mask), _ptr(s), _ptr(wcodes),
+                                     _ptr(alpha_q), _ptr(aux), _ptr(table), _ptr(wtiles), _ptr(status), _stream()))
+    _count(1)
+    return s, wcodes, alpha_q, aux, table, wtiles
 
 
 @_on_tensor_device

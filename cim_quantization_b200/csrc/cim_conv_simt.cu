@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(kPix * kCh) conv_simt_kernel(
           if (g.adc_mode == CIMQ_ADC_MULTIBIT) {
             float ph = psum_as_stored(p);
             float cf = fminf(fmaxf(ph, (float)g.qn), (float)g.qp);  // lsq.py:228-229
-            clip = (ph > (float)g.qp) || (ph < (float)g.qn);         // lsq.py:310-311 on integer psums
+            // lsq.py:310-311: ps >= Qp + 1e-5 or ps <= Qn - 1e-5 in fp32 (the bound itself clips where 1e-5 rounds away)
+            clip = (ph >= (float)g.clip_hi) || (ph <= (float)g.clip_lo);
             acc += __fmul_rn(__fmul_rn(cf, sw), sa) * amp;           // lsq.py:230, 233
             if (clip) { int bit = state_pair(g, k, j); st[bit >> 5] |= 1u << (bit & 31); }
           } else {

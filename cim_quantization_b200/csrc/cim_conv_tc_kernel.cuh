@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
                     const float ph = pfv[4 * c4 + u];
                     const float cf = fminf(fmaxf(ph, (float)g.qn), (float)g.qp);
                     acc[cc] += __fmul_rn(__fmul_rn(cf, sw), sa) * ampv[u];
-                    if (ph > (float)g.qp || ph < (float)g.qn) stf[cc][aidx[0]] += kPos;
+                    if (ph >= (float)g.clip_hi || ph <= (float)g.clip_lo) stf[cc][aidx[0]] += kPos;  // lsq.py:310-311
                   }
                 } else {
                   const float4 tp4 = *reinterpret_cast<const float4 *>(trow + cb);

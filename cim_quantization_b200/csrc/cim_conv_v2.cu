@@ -487,10 +487,8 @@ int launch_conv_v2_forward(const Geo &g, const uint8_t *xcodes, const void *wtil
   P.state = state;
   const bool mb = g.adc_mode == CIMQ_ADC_MULTIBIT;
   if (mb) {
-    int chi, clo;
-    multibit_clip_bounds(g.qn, g.qp, &chi, &clo);
     P.mb_qn = (float)g.qn; P.mb_qp = (float)g.qp;
-    P.mb_nchi = -(float)(chi - 1); P.mb_pclo = (float)(clo + 1);
+    P.mb_nchi = -(float)(g.clip_hi - 1); P.mb_pclo = (float)(g.clip_lo + 1);
   }
   const int ntiles = T.mtiles * T.nct;
   const int grid = ntiles < 148 ? ntiles : 148;

@@ -117,6 +117,16 @@ int cimq_adc_table2(const cimq_layer_t *layer, const float *s, const float *alph
   return launch_adc_table(g, s, alpha_q, alpha_scale, binary_mask, table, status, as_stream(stream));
 }
 
+int cimq_layer_prepare(const cimq_layer_t *layer, const float *weight, const float *alpha_act,
+                       const float *alpha_weight, float ga, float gw, const float *alpha_cim, int32_t aq_qn,
+                       int32_t aq_qp, const int8_t *binary_mask, float *s_out, int8_t *wcodes, float *alpha_q,
+                       float *aux, void *table, void *wtiles, int32_t *status, void *stream) {
+  Geo g;
+  if (make_geo(layer, &g)) return 1;
+  return launch_layer_prepare(g, weight, alpha_act, alpha_weight, ga, gw, alpha_cim, aq_qn, aq_qp, binary_mask, s_out,
+                              wcodes, alpha_q, aux, table, wtiles, status, as_stream(stream));
+}
+
 int cimq_weight_prepare(const cimq_layer_t *layer, const int8_t *wcodes, float *wdigits, void *wtiles,
                         void *stream) {
   Geo g;

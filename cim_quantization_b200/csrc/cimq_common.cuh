@@ -31,6 +31,19 @@ void set_error(const char *fmt, ...);
     }                                                                                     \
   } while (0)
 
+// Multi-bit ADC STE clip bounds (lsq.py:310-311): clipped where ps >= Qp + 1e-5 or ps <= Qn - 1e-5, compared in
+// fp32.  chi = smallest integer partial sum that is clipped high, clo = largest one clipped low.  For small ranges
+// that is qp+1 / qn-1; where 1e-5 is below half an ulp of the bound (Qp >= 512, Qn <= -256) the bound itself clips.
+inline void multibit_clip_bounds(int qn, int qp, int *chi, int *clo) {
+  const float hi = (float)((double)qp + 1e-5), lo = (float)((double)qn - 1e-5);
+  int c = qp;
+  while ((float)c < hi) ++c;
+  *chi = c;
+  c = qn;
+  while ((float)c > lo) --c;
+  *clo = c;
+}
+
 // ---- derived layer geometry -------------------------------------------------------------------
 // Plain-old-data copy of the layer with everything the kernels need; passed by value.
 struct Geo {
@@ -41,6 +54,7 @@ struct Geo {
   int amask, wmask;                 // (1<<abs_)-1, (1<<wbs)-1
   int xbar;
   int adc_mode, qn, qp;
+  int clip_hi, clip_lo;             // multi-bit ADC: the STE mask is off where psum >= clip_hi or psum <= clip_lo
   int state_bits, state_words;      // bits of ADC state per (crossbar, channel, pixel)
 };
 
@@ -67,6 +81,7 @@ inline int make_geo(const cimq_layer_t *l, Geo *g) {
   g->pairs = g->NSA * g->NSW;
   g->amask = (1 << g->abs_) - 1; g->wmask = (1 << g->wbs) - 1;
   g->adc_mode = l->adc_mode; g->qn = l->adc_qn; g->qp = l->adc_qp;
+  multibit_clip_bounds(g->qn, g->qp, &g->clip_hi, &g->clip_lo);
   g->state_bits = (g->adc_mode == CIMQ_ADC_MULTIBIT ? 1 : 3) * g->pairs;
   g->state_words = (g->state_bits + 31) / 32;
   return 0;
@@ -164,19 +179,10 @@ __host__ __device__ inline int64_t table_tiled_offset(const Geo &g) { return (ta
 int64_t table_v2_offset(const Geo &g);
 int64_t table_total_bytes(const Geo &g);
 
-// Multi-bit ADC STE clip bounds (lsq.py:310-311): clipped where ps >= Qp + 1e-5 or ps <= Qn - 1e-5, compared in
-// fp32.  chi = smallest integer partial sum that is clipped high, clo = largest one clipped low.  For small ranges
-// that is qp+1 / qn-1; where 1e-5 is below half an ulp of the bound (Qp >= 512, Qn <= -256) the bound itself clips.
-inline void multibit_clip_bounds(int qn, int qp, int *chi, int *clo) {
-  const float hi = (float)((double)qp + 1e-5), lo = (float)((double)qn - 1e-5);
-  int c = qp;
-  while ((float)c < hi) ++c;
-  *chi = c;
-  c = qn;
-  while ((float)c > lo) --c;
-  *clo = c;
-}
-
+int launch_layer_prepare(const Geo &g, const float *weight, const float *alpha_act, const float *alpha_weight, float ga,
+                         float gw, const float *alpha_cim, int aq_qn, int aq_qp, const int8_t *mask, float *s,
+                         int8_t *wcodes, float *alpha_q, float *aux, void *table, void *wtiles, int32_t *status,
+                         cudaStream_t st);
 bool v2_forward_supported(const Geo &g);
 int launch_conv_v2_forward(const Geo &g, const uint8_t *xcodes, const void *wtiles, const void *table, float *out,
                            uint8_t *state, cudaStream_t st);

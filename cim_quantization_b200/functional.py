@@ -167,6 +167,67 @@ class _CimConv2dFused(Function):
         return (gx, gwt, g_aa, g_aw, galpha) + (None,) * 12
 
 
+class _CimConv2dFusedV2(Function):
+    """``Conv2dLSQCiM`` step on the v2 kernels with the parameter-only work in ONE launch: layer_prepare (step sizes,
+    weight codes, alpha quantiser, ADC table / constants, weight tiles), activation quantiser, CiM conv -- three
+    launches forward.  The backward returns the gradients of x, weight, alpha_act, alpha_weight and alpha_cim (the
+    alpha quantiser's backward, lsq.py:566-571, is applied here instead of in a separate autograd node)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, alpha_act, alpha_weight, alpha_cim, binary_mask, stride, padding, nbits_a, abitslice,
+                nbits_w, wbitslice, xbar, adcbits, nbits_alpha, flags):
+        _require_cuda(x, weight, alpha_act, alpha_weight, alpha_cim)
+        x = x.contiguous()
+        weight = weight.contiguous()
+        spec = _make_spec(x.shape, weight.shape, stride, padding, nbits_a, abitslice, nbits_w, wbitslice, xbar,
+                          adcbits)
+        info = _lib.layer_info(spec)
+        qp_a = 2 ** spec.nbits_a - 1
+        qn_w, qp_w = -(2 ** (spec.nbits_w - 1)), 2 ** (spec.nbits_w - 1) - 1
+        ga = 1.0 / math.sqrt(x.numel() * qp_a)  # lsq.py:547
+        gw = 1.0 / math.sqrt(weight.numel() * qp_w)  # lsq.py:553
+        mask = _as_mask_2d(binary_mask, info.NSW, info.NSA, x.device)
+        has_alpha = alpha_cim is not None
+        a_cim = alpha_cim.detach().contiguous() if has_alpha else None
+        s, wcodes, alpha_q, aux, table, wtiles = _lib.layer_prepare(
+            spec, weight.detach(), alpha_act.detach(), alpha_weight.detach(), ga, gw, a_cim, 1, 2 ** nbits_alpha - 1,
+            mask)
+        xcodes = _lib.lsq_quantize(x.detach(), s[0:1], 0, qp_a)
+        need_bwd = any(ctx.needs_input_grad)
+        out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd,
+                                       flags=flags | _lib.FLAG_V2)
+        ctx.spec, ctx.has_alpha, ctx.flags = spec, has_alpha, flags
+        ctx.consts = (qp_a, qn_w, qp_w, ga, gw, nbits_alpha)
+        ctx.save_for_backward(x, weight, xcodes, wtiles, state, s, mask, a_cim, aux)
+        return out.view(spec.batch, spec.out_channels, info.out_hw, info.out_hw)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x, weight, xcodes, wtiles, state, s, mask, a_cim, aux = ctx.saved_tensors
+        spec = ctx.spec
+        qp_a, qn_w, qp_w, ga, gw, nbits_alpha = ctx.consts
+        go = grad_y.contiguous().float().view(spec.batch, spec.out_channels, -1)
+        need_x = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
+        need_alpha = ctx.has_alpha and ctx.needs_input_grad[4]
+        gxq, gwq, galpha_q = _lib.conv_backward(spec, go, xcodes, None, wtiles, state, s, mask, need_alpha=need_alpha,
+                                                need_input=need_x, flags=ctx.flags)
+        gx = g_aa = galpha = None
+        if need_x:
+            gx, g_aa = _lib.lsq_backward(gxq, x, s[0:1], 0, qp_a, ga)
+        gwt, g_aw = _lib.lsq_backward(gwq.view_as(weight), weight, s[1:2], qn_w, qp_w, gw)
+        if need_alpha:
+            galpha = _lib.alpha_quantize_backward(a_cim, galpha_q.view_as(a_cim), 1, 2 ** nbits_alpha - 1, aux)
+        return (gx, gwt, g_aa, g_aw, galpha) + (None,) * 11
+
+
+def cim_conv2d_v2(x, weight, alpha_act, alpha_weight, alpha_cim, binary_mask, stride, padding, nbits_a, abitslice,
+                  nbits_w, wbitslice, xbar, adcbits, nbits_alpha, flags: int = 0):
+    """Fused CiM convolution of ``Conv2dLSQCiM`` (lsq.py:546-581) from the RAW ``alpha_cim`` parameter, for layers the
+    v2 kernels cover (``_lib.layer_info(spec).tc_v2``, ``nbits_alpha <= 11``)."""
+    return _CimConv2dFusedV2.apply(x, weight, alpha_act, alpha_weight, alpha_cim, binary_mask, stride, padding,
+                                   nbits_a, abitslice, nbits_w, wbitslice, xbar, adcbits, nbits_alpha, flags)
+
+
 def _stochastic_seed() -> int:
     """A fresh 62-bit seed from torch's CPU generator (so torch.manual_seed makes the sampling reproducible)."""
     return int(torch.randint(0, 2 ** 62, (1,)).item())

@@ -89,6 +89,15 @@ class _CiMForward:
             self.binary_mask = self.binary_mask.to(x.device)
         if self.training and not init_cim_done and self.alpha_cim is not None:
             self._lazy_init_cim(x, w, stride, padding)
+        # v2 kernels (covered shape, alpha_q / scale an fp16 integer < 2048, deterministic read-out): the raw
+        # alpha_cim goes in and one launch prepares everything that depends only on the parameters
+        spec = CF._make_spec(x.shape, w.shape, stride, padding, self.nbits_a, self.abitslice, self.nbits_w,
+                             self.wbitslice, self.xbar, self.adcbits)
+        if (self.nbits_alpha <= 11 and not self.stochastic_quant and not (self.kernel_flags & _lib.FLAG_FORCE_SIMT)
+                and _lib.v2_usable(spec, self.alpha_cim is not None, True, self.kernel_flags)):
+            return CF.cim_conv2d_v2(x, w, self.alpha_act, self.alpha_weight, self.alpha_cim, self.binary_mask, stride,
+                                    padding, self.nbits_a, self.abitslice, self.nbits_w, self.wbitslice, self.xbar,
+                                    self.adcbits, self.nbits_alpha, self.kernel_flags)
         alpha_q, alpha_scale = self._alpha_q() if self.alpha_cim is not None else (None, None)
         if self.nbits_alpha > 11:  # the v2 kernels carry alpha_q / scale as an fp16 integer (< 2048)
             alpha_scale = None

@@ -158,6 +158,17 @@ int cimq_adc_table(const cimq_layer_t *layer, const float *s, const float *alpha
 int cimq_adc_table2(const cimq_layer_t *layer, const float *s, const float *alpha_q, const float *alpha_scale,
                     const int8_t *binary_mask, void *table, int32_t *status, void *stream);
 
+/* Everything of a training / inference step that depends only on the layer's PARAMETERS, in ONE launch (layers with
+ * cimq_info_t.tc_v2 only): s = {s_a, s_w} (cimq_step_sizes), the weight codes (cimq_lsq_quantize of the fp32
+ * weights [Cout, F]), alpha_q / aux (cimq_alpha_quantize of alpha_cim with range [aq_qn, aq_qp]; skipped for
+ * CIMQ_ADC_MULTIBIT, pass NULL), the ADC table including the v2 constants (cimq_adc_table2) and the v2 sections of
+ * the weight tiles (cimq_weight_prepare).  Bit-identical to calling those entry points one after the other; ten
+ * launches fewer per layer per step.  status as for cimq_adc_table2. */
+int cimq_layer_prepare(const cimq_layer_t *layer, const float *weight, const float *alpha_act,
+                       const float *alpha_weight, float ga, float gw, const float *alpha_cim, int32_t aq_qn,
+                       int32_t aq_qp, const int8_t *binary_mask, float *s_out, int8_t *wcodes, float *alpha_q,
+                       float *aux, void *table, void *wtiles, int32_t *status, void *stream);
+
 /* Sign-magnitude digit planes of the weight codes (slicing_weights_signed, lsq.py:438-464):
  * wdigits fp32 [NSW, Cout, F] (CUDA-core backward; may be NULL); wtiles (may be NULL): operand tiles in
  * tcgen05 shared-memory order -- int8 digit tiles + im2col LUT for the forward, bf16 digit tiles for dgrad. */

@@ -84,3 +84,39 @@ def test_config2_point_against_oracle(xbar, adc):
         if cfg.has_alpha_cim:
             ga = galpha.cpu().numpy()
             assert rel_err(ga, ref_ga) < TOL and rel_err_elem(ga, ref_ga) < 2 * TOL, name
+
+
+def test_multibit_clip_at_the_bound_itself():
+    """lsq.py:310-311 compares in fp32 against Qp + 1e-5 / Qn - 1e-5; for Qn = -256 (adcbits 9) the 1e-5 is below half
+    an ulp, so a partial sum EQUAL to Qn is already clipped (STE mask off).  All-ones activations against all-minus-one
+    weights on a 256-row crossbar produce exactly -256 at the interior pixels."""
+    L = _lib()
+    cin, cout, hw, batch = 32, 16, 6, 1
+    cfg = O.CimConfig(in_channels=cin, out_channels=cout, kernel=3, stride=1, padding=1, nbits_w=3, nbits_a=3,
+                      wbitslice=1, abitslice=1, xbar=256, adcbits=9)
+    xc = np.ones((batch, cin, hw, hw), dtype=np.uint8)
+    wc = -np.ones((cout, cin, 3, 3), dtype=np.int8)
+    s_a, s_w = np.float32(0.173), np.float32(0.0421)
+    ps_int = O.integer_psums(cfg, xc, wc)
+    assert ps_int.min() == -256
+    ref_clip = oracle_clip(cfg, ps_int, s_w, s_a, None)
+    assert ref_clip[ps_int == -256].all() and not ref_clip[ps_int == -255].any()
+    rng = np.random.default_rng(3)
+    go = rng.standard_normal((batch, hw * hw, cout)).astype(np.float32)
+    ref_out = O.cim_forward(cfg, xc, wc, s_w, s_a, None)
+    ref_gx, ref_gw, _ = O.cim_backward(cfg, go, xc, wc, s_w, s_a, None, hw)
+    spec = _spec(cfg, hw, batch)
+    info = L.layer_info(spec)
+    s = _cuda(np.array([s_a, s_w], dtype=np.float32))
+    xcd, wcd, mask = _cuda(xc), _cuda(wc).reshape(cout, -1), _mask(cfg)
+    table = L.adc_table(spec, s, None, mask)
+    wdigits, wtiles = L.weight_prepare(spec, wcd)
+    god = _cuda(np.ascontiguousarray(go.transpose(0, 2, 1)))
+    for flags in ([L.FLAG_FORCE_SIMT, 0] if info.tc_forward else [L.FLAG_FORCE_SIMT]):
+        out, state = L.conv_forward(spec, xcd, wcd, wtiles, table, s, mask, save_state=True, flags=flags)
+        _, clip = unpack_state(state, cfg, info, batch)
+        np.testing.assert_array_equal(clip, ref_clip)
+        assert rel_err(out.cpu().numpy().transpose(0, 2, 1), ref_out) < TOL
+        gxq, gwq, _ = L.conv_backward(spec, god, xcd, wdigits, wtiles, state, s, mask, need_alpha=False, flags=flags)
+        assert rel_err(gxq.cpu().numpy(), ref_gx) < TOL
+        assert rel_err(gwq.cpu().numpy().reshape(ref_gw.shape), ref_gw) < TOL

@@ -217,3 +217,60 @@ def test_h1_unsnapped_step_sizes_deviation_is_only_in_grad_x():
     dev = rel_err(gx, d["grad_x"])
     print(f"H1 deviation of grad_x from the reference on un-snapped step sizes: {dev:.3f}")
     assert 0.01 < dev < 0.5
+
+
+@pytest.mark.parametrize("case", [V2_CASES[0], V2_CASES[2], V2_CASES[4], V2_CASES[6], V2_CASES[8], V2_CASES[9]])
+def test_layer_prepare_equals_separate_entry_points(case):
+    """cimq_layer_prepare (one launch) writes the same bytes as cimq_step_sizes + cimq_lsq_quantize +
+    cimq_alpha_quantize + cimq_adc_table2 + cimq_weight_prepare for everything the v2 kernels read."""
+    L = _lib()
+    cfg, rng, xc, wc, s_a, s_w, aq, scale = _random_case(case)
+    cin, cout, hw, batch, k = case[0], case[1], case[2], case[3], case[8]
+    spec = _spec(cfg, hw, batch)
+    info = L.layer_info(spec)
+    w = (rng.standard_normal((cout, cin * k * k)) * 0.2).astype(np.float32)
+    aa, aw = np.float32(0.173), np.float32(0.0891)
+    ga, gw = 1.0 / np.sqrt(batch * cin * hw * hw * cfg.qp_a), 1.0 / np.sqrt(w.size * cfg.qp_w)
+    alpha = None
+    if cfg.has_alpha_cim:
+        alpha = (rng.uniform(0.05, 2.0, size=(1, info.NX, info.NSW, info.NSA, 1, cout))).astype(np.float32)
+    wd, aad, awd = _cuda(w), _cuda(np.array([aa])), _cuda(np.array([aw]))
+    ald = _cuda(alpha) if alpha is not None else None
+    mask = _mask(cfg)
+    st1 = torch.zeros(1, dtype=torch.int32, device="cuda")
+    s1, wc1, aq1, aux1, tab1, wt1 = L.layer_prepare(spec, wd, aad, awd, ga, gw, ald, 1, 255, mask, st1)
+    # the separate path
+    s2 = L.step_sizes(aad, awd, ga, gw)
+    wc2 = L.lsq_quantize(wd, s2[1:2], cfg.qn_w, cfg.qp_w)
+    aq2 = aux2 = None
+    if alpha is not None:
+        aq2, aux2 = L.alpha_quantize(ald, 1, 255)
+    st2 = torch.zeros(1, dtype=torch.int32, device="cuda")
+    tab2 = L.adc_table(spec, s2, aq2, mask, st2, alpha_scale=aux2[0:1].clone() if aux2 is not None else None)
+    _, wt2 = L.weight_prepare(spec, wc2, want_digits=False)
+    torch.cuda.synchronize()
+    assert st1.item() == 0 and st2.item() == 0
+    np.testing.assert_array_equal(s1.cpu().numpy(), s2.cpu().numpy())
+    np.testing.assert_array_equal(wc1.cpu().numpy(), wc2.cpu().numpy())
+    if alpha is not None:
+        np.testing.assert_array_equal(aq1.cpu().numpy(), aq2.cpu().numpy())
+        np.testing.assert_array_equal(aux1.cpu().numpy()[:5], aux2.cpu().numpy()[:5])
+    # the sections the v2 kernels (and the CUDA-core forward: the AoS table) read; the v1-only sections are not written
+    n_e = info.NX * info.pairs * cout
+    t1, t2 = tab1.cpu().numpy(), tab2.cpu().numpy()
+    np.testing.assert_array_equal(t1[:16 * n_e], t2[:16 * n_e])
+    v2_off = ((16 * n_e + 255) // 256 * 256 + 12 * n_e + 255) // 256 * 256
+    np.testing.assert_array_equal(t1[v2_off:v2_off + 8], t2[v2_off:v2_off + 8])      # header {o0, o1}
+    np.testing.assert_array_equal(t1[v2_off + 256:], t2[v2_off + 256:])              # constants blocks
+    # weight tiles: run the forward + backward on both and compare results bit for bit (covers fwd8, bwd2, lut)
+    xcd = _cuda(xc)
+    go = _cuda(rng.standard_normal((batch, cout, cfg.out_hw(hw) ** 2)).astype(np.float32))
+    res = []
+    for (s_, wc_, tab_, wt_) in ((s1, wc1, tab1, wt1), (s2, wc2, tab2, wt2)):
+        out, state = L.conv_forward(spec, xcd, wc_, wt_, tab_, s_, mask, save_state=True, flags=L.FLAG_V2)
+        gxq, gwq, ga_ = L.conv_backward(spec, go, xcd, None, wt_, state, s_, mask, need_alpha=alpha is not None,
+                                        flags=L.FLAG_DETERMINISTIC)
+        res.append((out, state, gxq, gwq, ga_))
+    for a_, b_ in zip(res[0], res[1]):
+        if a_ is not None:
+            assert torch.equal(a_, b_)
