@@ -216,62 +216,80 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_w4_kernel(Geo g, int m_
 // (32 / LPP pixels x Cout channels, LPP = Cout / 16 lanes per pixel; lane = (pixel, 16-channel group)).
 // ---------------------------------------------------------------------------------------------
 template <int NSW>
-__global__ void __launch_bounds__(256) bwd_alpha_v2_kernel(Geo g, int m_per_split, const float *__restrict__ go,
+__global__ void __launch_bounds__(256) bwd_alpha_v2_kernel(Geo g, int m_per_split, int cblock,
+                                                           const float *__restrict__ go,
                                                            const uint8_t *__restrict__ cplanes,
                                                            float *__restrict__ partial) {
-  extern __shared__ float red[];  // [8 warps][NSW * Cout]
-  const int ij = blockIdx.x, i = ij / g.NSA, j = ij % g.NSA, ms = blockIdx.y;
+  // item = (channel quad, 8-pixel group): 8 state words (one per pixel: 4 channels x NSW two-bit code fields) and
+  // 4 x 8 grad_out values (two 16-byte loads per channel).  lane = quad + nq * (pixel group inside the warp);
+  // 4 x NSW + 4 accumulators per thread.  blockIdx = (i*NSA + j, pixel split, block of <= 128 channels).
+  extern __shared__ float red[];  // [8 warps][NSW * cblock]
+  const int ij = blockIdx.x, i = ij / g.NSA, j = ij % g.NSA, ms = blockIdx.y, c0 = blockIdx.z * cblock;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lpp = g.Cout >> 4, ppw = 32 / lpp;  // lanes per pixel, pixels per warp-iteration
-  const int cg = lane % lpp, pl = lane / lpp;
-  const int64_t mbeg = (int64_t)ms * m_per_split;
-  const int64_t mend = min((int64_t)g.M, mbeg + m_per_split);
-  const uint8_t *plane = cplanes + (int64_t)ij * g.M * g.Cout;
-  float acc[16][NSW], accg[16];
+  const int nq = cblock >> 2, gpw = 32 / nq;  // quads per pixel, pixel groups per warp
+  const int q = lane % nq, pgl = lane / nq;
+  const int mbeg = ms * m_per_split;
+  const int mend = min(g.M, mbeg + m_per_split);
+  const uint8_t *plane = cplanes + (int64_t)ij * g.M * g.Cout + c0 + 4 * q;
+  const float *gbase = go + (int64_t)(c0 + 4 * q) * g.L;
+  const int64_t gimg = (int64_t)g.Cout * g.L;
+  const int step = 8 * gpw * 8;  // pixels per block iteration
+  float acc[4][NSW], accg[4];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
+  for (int c = 0; c < 4; ++c) {
     accg[c] = 0.0f;
 #pragma unroll
     for (int k = 0; k < NSW; ++k) acc[c][k] = 0.0f;
   }
-  for (int64_t m = mbeg + warp * ppw + pl; m < mend; m += 8 * ppw) {
-    const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(plane + m * g.Cout + 16 * cg));
-    const int b = (int)(m / g.L), l = (int)(m % g.L);
-    const float *gp = go + ((int64_t)b * g.Cout + 16 * cg) * g.L + l;
-    float gs[16];
+  int m = mbeg + (warp * gpw + pgl) * 8;
+  int b = m / g.L, l = m % g.L;
+  for (; m < mend; m += step) {
+    uint32_t w[8];
+    float gv[4][8];
+    const uint8_t *wp = plane + (int64_t)m * g.Cout;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) gs[c] = __ldg(gp + (int64_t)c * g.L);
-    const uint32_t wd[4] = {w4.x, w4.y, w4.z, w4.w};
+    for (int e = 0; e < 8; ++e) w[e] = __ldg(reinterpret_cast<const uint32_t *>(wp + (int64_t)e * g.Cout));
+    const float *gp = gbase + b * gimg + l;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t lo = wd[q], hi = wd[q] >> 16;
+    for (int c = 0; c < 4; ++c) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gp + (int64_t)c * g.L));
+      const float4 g1 = __ldg(reinterpret_cast<const float4 *>(gp + (int64_t)c * g.L) + 1);
+      gv[c][0] = g0.x; gv[c][1] = g0.y; gv[c][2] = g0.z; gv[c][3] = g0.w;
+      gv[c][4] = g1.x; gv[c][5] = g1.y; gv[c][6] = g1.z; gv[c][7] = g1.w;
+    }
 #pragma unroll
-      for (int bb = 0; bb < 4; ++bb) {
-        const int c = 4 * q + bb;
-        const uint32_t src = bb < 2 ? lo : hi;
-        accg[c] += gs[c];
-        const float gsc = gs[c] * 1.2676506002282294e30f;  // 2^100
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t lo = w[e], hi = w[e] >> 16;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t src = c < 2 ? lo : hi;
+        accg[c] += gv[c][e];
+        const float gsc = gv[c][e] * 1.2676506002282294e30f;  // 2^100
 #pragma unroll
         for (int k = 0; k < NSW; ++k)
-          acc[c][k] = fmaf(gsc, __uint_as_float(src & (3u << (8 * (bb & 1) + 2 * k))), acc[c][k]);
+          acc[c][k] = fmaf(gsc, __uint_as_float(src & (3u << (8 * (c & 1) + 2 * k))), acc[c][k]);
       }
     }
+    l += step;
+    while (l >= g.L) { l -= g.L; ++b; }
   }
-  // undo the scaling, subtract sum go, reduce over the lanes that share a channel group, then over warps
+  // undo the scaling, subtract sum go, reduce over the lanes that share a quad, then over warps
 #pragma unroll
-  for (int c = 0; c < 16; ++c)
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int k = 0; k < NSW; ++k) {
       float v = acc[c][k] * exp2f((float)(49 - 8 * (c & 1) - 2 * k)) - accg[c];
-      for (int o = 16; o >= lpp; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (pl == 0) red[(warp * NSW + k) * g.Cout + 16 * cg + c] = v;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1)
+        if (o >= nq) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (pgl == 0) red[(warp * NSW + k) * cblock + 4 * q + c] = v;
     }
   __syncthreads();
-  for (int t = threadIdx.x; t < NSW * g.Cout; t += 256) {
+  for (int t = threadIdx.x; t < NSW * cblock; t += 256) {
     float v = 0.0f;
 #pragma unroll
-    for (int w8 = 0; w8 < 8; ++w8) v += red[w8 * NSW * g.Cout + t];
-    const int k = t / g.Cout, c = t % g.Cout;
+    for (int w8 = 0; w8 < 8; ++w8) v += red[w8 * NSW * cblock + t];
+    const int k = t / cblock, c = c0 + t % cblock;
     partial[(int64_t)ms * table_entries(g) + ((int64_t)i * g.pairs + k * g.NSA + j) * g.Cout + c] = v;
   }
 }
@@ -549,7 +567,7 @@ inline BwdPlan make_plan(const Geo &g) {
   int64_t wpart = (int64_t)p.w_splits * g.F * g.Cout * 4;
   if (tc_backward_supported(g) && bwd_tc_partial_bytes(g) > wpart) wpart = bwd_tc_partial_bytes(g);
   p.off_apart = p.off_wpart + align(wpart);
-  p.alpha_splits_v2 = (148 * 4 + g.NX * g.NSA - 1) / (g.NX * g.NSA) + 1;
+  p.alpha_splits_v2 = (148 * 6 + g.NX * g.NSA - 1) / (g.NX * g.NSA) + 1;
   const int asmax = p.alpha_splits > p.alpha_splits_v2 ? p.alpha_splits : p.alpha_splits_v2;
   p.total = p.off_apart + align((int64_t)asmax * table_entries(g) * 4);
   return p;
@@ -577,17 +595,20 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
                "conv_backward: CIMQ_FLAG_V2 on a layer the v2 kernels do not cover");
   const uint8_t *state2 = reinterpret_cast<const uint8_t *>(state);
   if (v2s && galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
-    const int lpp = g.Cout / 16, pb = 8 * (32 / lpp);  // pixels per block-iteration
-    int splits = (148 * 4 + g.NX * g.NSA - 1) / (g.NX * g.NSA);
+    const int cblock = g.Cout > 128 ? (g.Cout % 128 == 0 ? 128 : 64) : g.Cout;  // channels per block (Cout % 16 == 0)
+    const int nq = cblock / 4, pb = 8 * (32 / nq) * 8;  // pixels per block-iteration
+    CIMQ_REQUIRE(32 % nq == 0, "conv_backward: alpha kernel needs 4, 8, 16 or 32 channel quads per block");
+    int splits = (148 * 6 + g.NX * g.NSA - 1) / (g.NX * g.NSA * (g.Cout / cblock));
+    if (splits < 1) splits = 1;
     int mps = (g.M + splits - 1) / splits;
     mps = (mps + pb - 1) / pb * pb;
     splits = (g.M + mps - 1) / mps;
     CIMQ_REQUIRE(splits <= p.alpha_splits_v2, "conv_backward: alpha workspace too small");
-    dim3 grid(g.NX * g.NSA, splits);
-    const size_t smem = (size_t)8 * g.NSW * g.Cout * sizeof(float);
+    dim3 grid(g.NX * g.NSA, splits, g.Cout / cblock);
+    const size_t smem = (size_t)8 * g.NSW * cblock * sizeof(float);
     const uint8_t *cplanes = state2 + 2 * v2::plane_bytes(g);
-    if (g.NSW == 3) bwd_alpha_v2_kernel<3><<<grid, 256, smem, st>>>(g, mps, go, cplanes, apart);
-    else bwd_alpha_v2_kernel<2><<<grid, 256, smem, st>>>(g, mps, go, cplanes, apart);
+    if (g.NSW == 3) bwd_alpha_v2_kernel<3><<<grid, 256, smem, st>>>(g, mps, cblock, go, cplanes, apart);
+    else bwd_alpha_v2_kernel<2><<<grid, 256, smem, st>>>(g, mps, cblock, go, cplanes, apart);
     CIMQ_CUDA_OK(cudaGetLastError());
     double numel = (double)g.B * g.NX * g.NSW * g.NSA * g.L * g.Cout;
     float gfac = (float)(1.0 / sqrt(numel));

@@ -18,6 +18,8 @@
 // Warp roles (16 warps): 0-7 producers, 8-11 epilogue (one per TMEM lane quarter), 12 MMA issuer.
 #include <string.h>
 
+#include <type_traits>
+
 #include "cim_tc_layout.cuh"
 #include "cim_v2.cuh"
 #include "tc_ptx.cuh"
@@ -60,6 +62,8 @@ struct BwdParams {
   // wgrad staged activation rows (same geometry as the forward producer, stride 1 only)
   int fastx, ow_log2, rpt, pitch_log2, col0;
   int rk, prow;      // wgrad staging: rows per channel slot, staged row of (output row o, tap row ky) = o*prow + ky
+  int xshared;       // wgrad staging: 1 = a tile is consecutive rows of ONE image and its output rows share input rows
+                     // (prow == 1); 0 = every output row stages its own K rows (prow == K; also 1 for 1x1 kernels)
   int async_rows;    // wgrad staging: rows arrive by 16-byte cp.async copies issued one chunk ahead
   uint32_t raw_bytes;
   int gfast;         // wgrad: every 8-pixel group is an aligned run of one image row (or past the end)
@@ -672,6 +676,45 @@ __device__ __noinline__ uint2 gather_codes_generic(GatherGeo g, const uint8_t *_
 
 constexpr int kWgLBO = 144;  // padded K-stride of the G' tiles: producer lanes run along K (bank-conflict free)
 
+// ---- wgrad X tile (im2col^T digit planes), v2 fast path: item counts and strides are compile-time per thread role so
+// that every address is base + immediate and no guards remain in the unrolled loops.
+// gather: the 8 activation codes (one per byte) of crossbar row (ci,ky,kx) at pixel groups pg0 + STEP*q, from the staged rows
+template <int CNT, int STEP, int XI>
+__device__ __forceinline__ void x_gather_fast(const uint8_t *src_row, int pg0, int ow_log2, int row_pitch_shift,
+                                              bool frow, uint32_t (&xlo)[XI], uint32_t (&xhi)[XI]) {
+  // src_row = staged byte of (output row 0, output column 0) for this crossbar row; output row r is r << row_pitch_shift
+  // bytes further, output column c is c bytes further
+#pragma unroll
+  for (int q = 0; q < CNT; ++q) {
+    const int p0 = (pg0 + STEP * q) * 8;
+    uint32_t lo8 = 0u, hi8 = 0u;
+    if (frow) {
+      const uint8_t *src = src_row + ((p0 >> ow_log2) << row_pitch_shift) + (p0 & ((1 << ow_log2) - 1));
+      const uint32_t sa = smem_u32(src);
+      const uint32_t *al = reinterpret_cast<const uint32_t *>(src - (sa & 3u));
+      const uint32_t w0 = al[0], w1 = al[1], w2 = al[2];
+      const uint32_t bsh = (sa & 3u) * 8u;
+      lo8 = __funnelshift_r(w0, w1, bsh);
+      hi8 = __funnelshift_r(w1, w2, bsh);
+    }
+    xlo[q] = lo8;
+    xhi[q] = hi8;
+  }
+}
+// store: digit plane `sh` of the gathered codes as bf16 (value cmul << sh for a set bit), one 16-byte row segment per item
+template <int CNT, int STEP, int XI>
+__device__ __forceinline__ void x_store_fast(uint8_t *dst, const uint32_t (&xlo)[XI], const uint32_t (&xhi)[XI], int sh,
+                                             uint32_t cmul) {
+  const uint32_t bit = 0x01010101u << sh;
+#pragma unroll
+  for (int q = 0; q < CNT; ++q) {
+    const uint32_t tl = xlo[q] & bit, th = xhi[q] & bit;  // bytes 0 or 2^sh; cmul = bf16 pattern >> sh
+    *reinterpret_cast<uint4 *>(dst + q * STEP * kTcLBO) =
+        make_uint4(__byte_perm(tl, 0u, 0x4140) * cmul, __byte_perm(tl, 0u, 0x4342) * cmul,
+                   __byte_perm(th, 0u, 0x4140) * cmul, __byte_perm(th, 0u, 0x4342) * cmul);
+  }
+}
+
 // V2: the pass counts come from plane W of the v2 state (cim_v2.cuh), one byte per (crossbar, pixel, channel), and the
 // producer threads split differently: threads [0, 4*Kc) build the G' tiles (item = 4 channels x 8 pixels), the next 128
 // or 256 threads the X tile -- see the V2 blocks below.
@@ -725,13 +768,21 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
     long long d_stage = 0, d_wait = 0, d_x = 0, d_g = 0;
     // X tile items (crossbar row fr, 8-pixel group pg = x_pg0 + x_step * q, q < XI) of this thread
-    constexpr int XI = V2 ? 16 : 6;
-    const int n_g = V2 ? 4 * Kc : 0;                     // v2: threads [0, n_g) build G', [n_g, n_g + n_x) build X
-    const int n_x = V2 ? (n_g == 256 ? 128 : 256) : kWgProducerThreads;
-    const int xt = tid - n_g;
-    const bool x_thread = xt >= 0 && xt < n_x;
-    const int x_pg0 = V2 ? (xt >> 7) : (tid >> 7), x_step = V2 ? (n_x >> 7) : 3;
-    const int fr = (V2 ? xt : tid) & 127;     // X tile: this thread's crossbar row
+    // v2: threads [0, n_g) build G' (one 4-channel x 8-pixel item = 32 elements, ~250 instructions per stage); an X
+    // item costs ~20, so with n_g = 256 the G' threads also take ONE X item each (pixel groups 14, 15) and the other
+    // 128 threads fourteen (groups 0..13); with fewer G' threads the 256 threads after them take eight X items each.
+    constexpr int XI = V2 ? 14 : 6;
+    const int n_g = V2 ? 4 * Kc : 0;
+    int fr, x_pg0, x_step, x_cnt;
+    if (!V2) { fr = tid & 127; x_pg0 = tid >> 7; x_step = 3; x_cnt = 6; }
+    else if (n_g == 256) {
+      if (tid >= 256) { fr = tid - 256; x_pg0 = 0; x_step = 1; x_cnt = 14; }
+      else { fr = tid & 127; x_pg0 = 14 + (tid >> 7); x_step = 1; x_cnt = 1; }
+    } else {
+      const int xt = tid - n_g;
+      fr = xt & 127; x_pg0 = xt >> 7; x_step = 2;
+      x_cnt = (xt >= 0 && xt < 256) ? 8 : 0;
+    }
     const bool aligned = (g.L % 8) == 0 && (g.OW % 8) == 0;
     const int pitch = 1 << P.pitch_log2;
     const int slot_bytes = P.rk * pitch;
@@ -783,7 +834,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     auto fill_rowoff = [&](int mt_, int *tab) {
       if (tid >= 128 && tid < 128 + P.rk) {
         const int rr = tid - 128;
-        const int orow = P.prow == 1 ? 0 : rr / g.K, ky = P.prow == 1 ? rr : rr % g.K;
+        const int orow = P.xshared ? 0 : rr / g.K, ky = P.xshared ? rr : rr % g.K;
         const int64_t m_row = (int64_t)mt_ * kTcTileM + (orow << P.ow_log2);
         int off = kNoRow;
         if (m_row < g.M) {
@@ -939,12 +990,43 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         // ---- the activation codes of this thread's X items (row fr, 8-pixel group pg = tid/128 + 3q), gathered once
         // per chunk: the NSA digit planes below only shift and mask them
         uint32_t xlo[XI], xhi[XI];
+        const bool xfast = V2 && P.fastx;  // (v2 layers have 1-bit digits)
+        if (xfast) {
+          const uint8_t *src_row = raw + (size_t)(ci - c_lo) * slot_bytes + ((size_t)ky << P.pitch_log2) + kx + P.col0;
+          const int rps = P.pitch_log2 + (P.prow == 1 ? 0 : (g.K == 1 ? 0 : -1));  // row pitch shift (see below)
+          (void)rps;
+          // output row r of the tile is staged r * prow rows further down; prow is 1 or K (not a power of two in
+          // general), so the row offset is a multiply
+          const int rowb = P.prow << P.pitch_log2;
+          auto gather = [&](auto cnt, auto stp) {
+#pragma unroll
+            for (int q = 0; q < decltype(cnt)::value; ++q) {
+              const int p0 = (x_pg0 + decltype(stp)::value * q) * 8;
+              uint32_t lo8 = 0u, hi8 = 0u;
+              if (frow) {
+                const uint8_t *src = src_row + (p0 >> P.ow_log2) * rowb + (p0 & ((1 << P.ow_log2) - 1));
+                const uint32_t sa = smem_u32(src);
+                const uint32_t *al = reinterpret_cast<const uint32_t *>(src - (sa & 3u));
+                const uint32_t w0 = al[0], w1 = al[1], w2 = al[2];
+                const uint32_t bsh = (sa & 3u) * 8u;
+                lo8 = __funnelshift_r(w0, w1, bsh);
+                hi8 = __funnelshift_r(w1, w2, bsh);
+              }
+              xlo[q] = lo8;
+              xhi[q] = hi8;
+            }
+          };
+          if (x_cnt == 14) gather(std::integral_constant<int, 14>{}, std::integral_constant<int, 1>{});
+          else if (x_cnt == 8) gather(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
+          else if (x_cnt == 1) gather(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+        }
 #pragma unroll
         for (int q = 0; q < XI; ++q) {
+          if (xfast) break;
           const int pg = x_pg0 + x_step * q;
           xlo[q] = 0u;
           xhi[q] = 0u;
-          if (pg < 16 && x_thread) {
+          if (pg < 16 && q < x_cnt) {
           uint32_t lo8 = 0u, hi8 = 0u;
           if (frow) {
             if (P.fastx) {
@@ -986,10 +1068,18 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           const int sh = g.abs_ * j;
           // v2: digit * 2^-j (bf16 exponent field minus j), which undoes the 2^(2j) of the pass-count field of plane W
           const uint32_t one_bf = V2 ? 0x3F80u - ((uint32_t)j << 7) : 0x3F80u;
+          if (xfast) {
+            uint8_t *dst = st_ptr + tc_tile_offset16(fr, x_pg0 * 8, kTcLBO, a_sbo);
+            const uint32_t cmul = one_bf >> sh;  // (0x7F - j) << (7 - sh): the bf16 pattern of 2^-j divided by the bit weight
+            if (x_cnt == 14) x_store_fast<14, 1, XI>(dst, xlo, xhi, sh, cmul);
+            else if (x_cnt == 8) x_store_fast<8, 2, XI>(dst, xlo, xhi, sh, cmul);
+            else if (x_cnt == 1) x_store_fast<1, 1, XI>(dst, xlo, xhi, sh, cmul);
+          }
 #pragma unroll
           for (int q = 0; q < XI; ++q) {
+            if (xfast) break;
             const int pg = x_pg0 + x_step * q;
-            if (pg >= 16 || !x_thread) continue;
+            if (pg >= 16 || q >= x_cnt) continue;
             const uint32_t lo8 = xlo[q], hi8 = xhi[q];
             uint32_t d[4];
             if (g.amask == 1) {  // 1-bit digits: bf16(1) = 0x3F80; spread two bytes to 16-bit lanes, one multiply
@@ -1514,7 +1604,7 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
     const size_t raw = ((size_t)nch * rk * (1u << pl) + 8 + 15) & ~(size_t)15;
     if (pl <= 9 && rk <= 128 && 2 * raw + 2 * P.stage_bytes + kBarrierBytes <= kSmemBudget) {
       P.fastx = 1; P.ow_log2 = owl; P.rpt = rpt; P.pitch_log2 = pl; P.col0 = col0;
-      P.rk = rk; P.prow = shared_rows ? 1 : g.K; P.async_rows = async_rows ? 1 : 0;
+      P.rk = rk; P.prow = shared_rows ? 1 : g.K; P.xshared = shared_rows ? 1 : 0; P.async_rows = async_rows ? 1 : 0;
       P.raw_bytes = (uint32_t)raw;
     }
   }

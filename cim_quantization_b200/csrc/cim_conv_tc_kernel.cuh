@@ -397,7 +397,9 @@ __device__ __forceinline__ void produce_generic(const TcParams &P, int i, uint8_
 // the producer role (4 warps): per (pixel tile, crossbar chunk) one pipeline stage = NSA digit planes of 128 im2col
 // rows + the chunk's weight tile (bulk copy).  Shared by the v1 (kind::i8) and v2 (kind::f8f6f4) kernels.
 // ---------------------------------------------------------------------------------------------------
-template <int NSA, int ENC>
+// K5: also compile the 5x5 instance of the staged producer (the v2 kernel leaves 5x5 layers to the generic gather:
+// every instance is ~45 KB of code, and the producers' working set should stay inside the instruction cache)
+template <int NSA, int ENC, bool K5 = true>
 __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm, int ntiles, int tid = threadIdx.x,
                                               int gidx = 0, int ngroups = 1) {
   // A producer GROUP is 128 threads (tid = index inside the group) that build whole pipeline stages; with
@@ -484,8 +486,9 @@ __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm,
         bulk_copy_g2s(smem_u32(st_ptr + (size_t)NSA * P.a_bytes), P.wtiles + (size_t)(ct * g.NX + i) * P.b_bytes,
                       P.b_bytes, sm.full0 + 8 * sidx);
       }
-      if (g.K == 3) produce_fast<NSA, 3, ENC>(P, cl, st_ptr, raw, r, pix_base);
-      else produce_fast<NSA, 5, ENC>(P, cl, st_ptr, raw, r, pix_base);
+      if (ENC == 1 && P.debug == reinterpret_cast<long long *>(1)) { /* development: skip the row assembly */ }
+      else if (!K5 || g.K == 3) produce_fast<NSA, 3, ENC>(P, cl, st_ptr, raw, r, pix_base);
+      else if constexpr (K5) produce_fast<NSA, 5, ENC>(P, cl, st_ptr, raw, r, pix_base);
       fence_proxy_async();
       mbar_arrive(sm.full0 + 8 * sidx);
       if (P.prefetch || P.tma_rows) {

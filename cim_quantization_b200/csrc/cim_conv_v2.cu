@@ -5,7 +5,7 @@
 //                            chunk, written as e4m3 bytes (2.0 for a set bit), weight digits +-0.5.  Two groups of
 //                            four warps build alternate stages (a producer thread is latency bound: one warp per
 //                            scheduler assembling its pixel's row byte by byte).
-//   MMA issuer (warp 16)     GEMM1: tcgen05.mma.kind::f8f6f4 with **fp16 accumulators** -- partial sums
+//   MMA issuers (16, 18)      GEMM1: tcgen05.mma.kind::f8f6f4 with **fp16 accumulators** -- partial sums
 //                            p[128 pixels x NSW*CT] of one activation digit plane, exact integers (|p| <= 128;
 //                            the reference stores them as fp16 too, lsq.py:169), two TMEM buffers.
 //                            GEMM2 (after the epilogue of that plane): tcgen05.mma.kind::f16 with the **A operand
@@ -19,6 +19,7 @@
 //                            small integers in packed-half registers (see cim_v2.cuh) and leave as bytes.
 //   constants (warp 17)      one bulk copy per chunk: thresholds + B2 slabs -> shared memory (double buffered).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "cim_conv_tc_kernel.cuh"
@@ -33,10 +34,13 @@ using tcfwd::kProducerWarps;
 
 constexpr int kProducerGroups = 2;
 constexpr int kEpiWarp0 = kProducerGroups * kProducerWarps;  // 8
-constexpr int kMmaWarp = kEpiWarp0 + 8, kConstWarp = kMmaWarp + 1;
+constexpr int kMmaWarp = kEpiWarp0 + 8, kConstWarp = kMmaWarp + 1, kMma2Warp = kMmaWarp + 2;
 constexpr int kThreads = (kMmaWarp + 4) * 32;                // 640: five warpgroups
-// registers per warpgroup (setmaxnreg): 2 x 96 (producers) + 2 x 136 (epilogue) + 40 (MMA, constants) = 504 <= 512
-constexpr int kRegsProducer = 96, kRegsMma = 40, kRegsEpilogue = 136;
+// Registers per warpgroup (setmaxnreg).  The pool setmaxnreg.inc draws from is what the CTA was LAUNCHED with
+// (640 threads x 96 registers, the __launch_bounds__ cap), not the whole register file: the split must satisfy
+// 2 x producers + 2 x epilogue + MMA <= 5 x 96 = 480, or the last warpgroup to ask waits forever.
+constexpr int kRegsProducer = 96, kRegsMma = 40, kRegsEpilogue = 120;
+static_assert(2 * kRegsProducer + 2 * kRegsEpilogue + kRegsMma <= 5 * 96, "setmaxnreg split exceeds the launch allocation");
 constexpr int kMaxStages = 4;
 constexpr size_t kAuxBytes = 4096;
 constexpr size_t kSmemBudget = 227 * 1024 - 1024;
@@ -47,6 +51,9 @@ struct V2Params {
   uint32_t block_bytes, b2_off;
   uint32_t d2_col;     // first TMEM column of the output accumulators
   int d2_bufs;
+  int ngroups;         // producer groups in use (2 needs >= 2 pipeline stages, see make_plan)
+  int dbg;             // development only (env CIMQ_V2_DBG): 1 = skip GEMM2 MMAs, 2 = skip GEMM1 MMAs, 4 = skip the
+                       // epilogue arithmetic, 8 = producers skip the row assembly -- results are then garbage
   const uint8_t *consts;  // [nct][NX] constants blocks
   const float *oscale;    // {o0, o1}: out = (acc * o0) * o1
   float *out;
@@ -153,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
   sm.stage_base = smem_raw;
   const size_t raw_off = (size_t)T.stages * T.stage_bytes;
   sm.raw = smem_raw + raw_off;
-  const size_t c_off = (raw_off + 2 * kProducerGroups * (size_t)T.raw_bytes + 127) & ~(size_t)127;  // smem_raw: 1024-byte aligned
+  const size_t c_off = (raw_off + 2 * (size_t)P.ngroups * T.raw_bytes + 127) & ~(size_t)127;  // smem_raw: 1024-byte aligned
   uint8_t *cbuf = smem_raw + c_off;
   uint8_t *pp = cbuf + 2 * (size_t)P.block_bytes;
   uint64_t *bars = reinterpret_cast<uint64_t *>(pp);
@@ -204,78 +211,83 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
     // =========================== producers ===========================
     reg_dealloc<kRegsProducer>();
     const int gidx = warp / kProducerWarps;
-    tcfwd::Smem smg = sm;  // the group's staging buffers and row tables
-    smg.raw = sm.raw + (size_t)gidx * 2 * T.raw_bytes;
-    smg.rowoff = sm.rowoff + gidx * 256;
-    tcfwd::producer_loop<NS, 1>(T, smg, ntiles, threadIdx.x & (kProducerThreads - 1), gidx, kProducerGroups);
+    if (gidx < P.ngroups) {
+      tcfwd::Smem smg = sm;  // the group's staging buffers and row tables
+      smg.raw = sm.raw + (size_t)gidx * 2 * T.raw_bytes;
+      smg.rowoff = sm.rowoff + gidx * 256;
+      tcfwd::producer_loop<NS, 1, false>(T, smg, ntiles, threadIdx.x & (kProducerThreads - 1), gidx, P.ngroups);
+    }
   } else if (warp >= kMmaWarp) {
     reg_dealloc<kRegsMma>();
     if (warp == kMmaWarp && lane == 0) {
-      // =========================== MMA issuer ===========================
+      // =========================== GEMM1 issuer ===========================
+      // partial sums of one activation digit plane per TMEM buffer; runs ahead of the epilogue by one plane.  Its
+      // commits track only its own MMAs: a stage is released as soon as the GEMM1s that read it are done.
       const uint32_t idesc1 = idesc_e4m3_f16(kTcTileM, N1);
-      const uint32_t idesc2 = idesc_f16_f32(kTcTileM, 16);
       const uint32_t sbo = 8u * (uint32_t)T.Kp;
-      const uint32_t cb_addr = smem_u32(cbuf);
-      uint32_t it = 0, pl = 0, chunk_it = 0, tile_it = 0;
-      // the plane whose GEMM2 is still to be issued
-      bool pend = false;
-      uint32_t q_pl = 0, q_chunk = 0, q_tile = 0;
-      int q_i = 0, q_j = 0;
-      auto issue_gemm2 = [&]() {
-        const uint32_t buf = q_pl & 1, cpar = q_chunk & 1;
-        const uint32_t tb = P.d2_bufs == 2 ? (q_tile & 1) : 0u;
-        const uint32_t tuse = P.d2_bufs == 2 ? (q_tile >> 1) : q_tile;
-        if (q_i == 0 && q_j == 0) {  // first plane of a tile: its output accumulator must have been drained
-          mbar_wait<200>(B.d2empty0 + 8 * tb, (tuse & 1) ^ 1);
-        }
-        if (q_j == 0) mbar_wait<200>(B.cfull0 + 8 * cpar, (q_chunk >> 1) & 1);  // B2 slabs of this chunk
-        mbar_wait<200>(B.a2full0 + 8 * buf, (q_pl >> 1) & 1);                   // codes written by the epilogue
-        tc_fence_after();
-        const uint32_t d2 = tmem_base + P.d2_col + tb * CT;
-        const uint32_t a2 = tmem_base + buf * N1;
-        const uint32_t b2 = cb_addr + cpar * P.block_bytes + P.b2_off + (uint32_t)(q_j * NS * G) * kSlabBytes;
-#pragma unroll
-        for (int k = 0; k < NS; ++k)
-#pragma unroll
-          for (int gi = 0; gi < G; ++gi) {
-            const int h = (16 * gi) / CH;
-            const uint32_t acol = a2 + k * CT + h * CH + (16 * gi - h * CH) / 2;
-            const uint64_t bdesc = make_smem_desc(b2 + (uint32_t)(k * G + gi) * kSlabBytes, kTcLBO, 256u);
-            umma_f16_ts(d2 + 16 * gi, acol, bdesc, idesc2, (q_i | q_j | k) != 0 ? 1u : 0u);
-          }
-        umma_commit(B.tempty0 + 8 * buf);                    // partial-sum buffer free again
-        if (q_j == NS - 1) umma_commit(B.cempty0 + 8 * cpar);  // constants of the chunk no longer read by the MMA
-        if (q_i == g.NX - 1 && q_j == NS - 1) umma_commit(B.d2full0 + 8 * tb);
-      };
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
-        for (int i = 0; i < g.NX; ++i, ++it, ++chunk_it) {
+      uint32_t it = 0, pl = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int i = 0; i < g.NX; ++i, ++it) {
           const int sidx = it % T.stages;
           const uint32_t use = it / T.stages;
           const int rows = min(rows_full, g.F - i * g.xbar);
           const int ksteps = (rows + 31) >> 5;
-          mbar_wait<400>(B.full0 + 8 * sidx, use & 1);
+          mbar_wait(B.full0 + 8 * sidx, use & 1);
           tc_fence_after();
           const uint32_t a0 = smem_u32(sm.stage_base + (size_t)sidx * T.stage_bytes);
           const uint32_t b0 = a0 + NS * T.a_bytes;
           for (int j = 0; j < NS; ++j, ++pl) {
             const uint32_t buf = pl & 1;
-            mbar_wait<200>(B.tempty0 + 8 * buf, ((pl >> 1) & 1) ^ 1);
+            mbar_wait(B.tempty0 + 8 * buf, ((pl >> 1) & 1) ^ 1);  // GEMM2 of the plane two back has read its codes
             tc_fence_after();
             const uint32_t d1 = tmem_base + buf * N1;
-            for (int ks = 0; ks < ksteps; ++ks) {
+            for (int ks = 0; ks < ksteps && !(P.dbg & 2); ++ks) {
               const uint64_t adesc = make_smem_desc(a0 + j * T.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
               const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
               umma_f8(d1, adesc, bdesc, idesc1, ks > 0 ? 1u : 0u);
             }
             umma_commit(B.tfull0 + 8 * buf);
             if (j == NS - 1) umma_commit(B.empty0 + 8 * sidx);  // stage consumed -> producers
-            if (pend) issue_gemm2();
-            pend = true;
-            q_pl = pl; q_chunk = chunk_it; q_tile = tile_it; q_i = i; q_j = j;
           }
         }
       }
-      if (pend) issue_gemm2();
+    } else if (warp == kMma2Warp && lane == 0) {
+      // =========================== GEMM2 issuer ===========================
+      // shift-and-add of one plane as soon as its codes are in tensor memory: a thread of its own, so that waiting
+      // for the epilogue never delays the next GEMM1
+      const uint32_t idesc2 = idesc_f16_f32(kTcTileM, 16);
+      const uint32_t cb_addr = smem_u32(cbuf);
+      uint32_t pl = 0, chunk_it = 0, tile_it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+        const uint32_t tb = P.d2_bufs == 2 ? (tile_it & 1) : 0u;
+        const uint32_t tuse = P.d2_bufs == 2 ? (tile_it >> 1) : tile_it;
+        mbar_wait(B.d2empty0 + 8 * tb, (tuse & 1) ^ 1);  // the tile's output accumulator has been drained
+        const uint32_t d2 = tmem_base + P.d2_col + tb * CT;
+        for (int i = 0; i < g.NX; ++i, ++chunk_it) {
+          const uint32_t cpar = chunk_it & 1;
+          mbar_wait(B.cfull0 + 8 * cpar, (chunk_it >> 1) & 1);  // B2 slabs of this chunk
+          for (int j = 0; j < NS; ++j, ++pl) {
+            const uint32_t buf = pl & 1;
+            mbar_wait(B.a2full0 + 8 * buf, (pl >> 1) & 1);      // codes written by the epilogue
+            tc_fence_after();
+            const uint32_t a2 = tmem_base + buf * N1;
+            const uint32_t b2 = cb_addr + cpar * P.block_bytes + P.b2_off + (uint32_t)(j * NS * G) * kSlabBytes;
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+#pragma unroll
+              for (int gi = 0; gi < G; ++gi) {
+                if (P.dbg & 1) continue;
+                const int h = (16 * gi) / CH;
+                const uint32_t acol = a2 + k * CT + h * CH + (16 * gi - h * CH) / 2;
+                const uint64_t bdesc = make_smem_desc(b2 + (uint32_t)(k * G + gi) * kSlabBytes, kTcLBO, 256u);
+                umma_f16_ts(d2 + 16 * gi, acol, bdesc, idesc2, (i | j | k) != 0 ? 1u : 0u);
+              }
+            umma_commit(B.tempty0 + 8 * buf);                      // partial-sum buffer free again
+            if (j == NS - 1) umma_commit(B.cempty0 + 8 * cpar);    // constants of the chunk no longer read by the MMA
+            if (i == g.NX - 1 && j == NS - 1) umma_commit(B.d2full0 + 8 * tb);
+          }
+        }
+      }
     } else if (warp == kConstWarp && lane == 0) {
       // =========================== constants loader ===========================
       uint32_t chunk_it = 0;
@@ -283,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
         const int ct = tile % T.nct;
         for (int i = 0; i < g.NX; ++i, ++chunk_it) {
           const uint32_t cpar = chunk_it & 1;
-          mbar_wait<200>(B.cempty0 + 8 * cpar, ((chunk_it >> 1) & 1) ^ 1);
+          mbar_wait(B.cempty0 + 8 * cpar, ((chunk_it >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(B.cfull0 + 8 * cpar, P.block_bytes);
           bulk_copy_g2s(smem_u32(cbuf + (size_t)cpar * P.block_bytes),
                         P.consts + (size_t)(ct * g.NX + i) * P.block_bytes, P.block_bytes, B.cfull0 + 8 * cpar);
@@ -320,7 +332,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
           __half2 dfld[R], wfld[R];
 #pragma unroll
           for (int q = 0; q < R; ++q) dfld[q] = wfld[q] = __float2half2_rn(kF0);
-#pragma unroll
+          // j is a REAL loop: the body (NS unrolled weight slices) is ~6 KB of code; unrolled over j as well the
+          // epilogue alone outgrew the instruction cache and a third of its stall samples were instruction fetches
+#pragma unroll 1
           for (int j = 0; j < NS; ++j, ++pl) {
             const uint32_t buf = pl & 1;
             mbar_wait(B.tfull0 + 8 * buf, (pl >> 1) & 1);
@@ -330,15 +344,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
             for (int q = 0; q < R; ++q) cfld[q] = __float2half2_rn(1024.0f + (NS == 3 ? 21.0f : 5.0f));
             const __half2 n4j = __float2half2_rn(-(float)(1 << (2 * j)));
             const uint32_t tcol = lane_base + buf * N1 + half * CH;
+            const uint4 *thr_j = thr + (j * 2) * (CH / 8);
+            // the next weight slice's partial sums are fetched while this one is quantised
+            uint32_t pa[R], pb[R];
+            tmem_ld_pack16<R>(tcol, pa);
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
-              uint32_t p[R];
-              tmem_ld_pack16<R>(tcol + k * CT, p);
+              uint32_t(&p)[R] = (k & 1) ? pb : pa;
+              uint32_t(&pn)[R] = (k & 1) ? pa : pb;
               tmem_ld_wait();
+              if (k + 1 < NS) tmem_ld_pack16<R>(tcol + (k + 1) * CT, pn);
               const __half2 n4k = __float2half2_rn(-(float)(1 << (2 * k))), p4k = __float2half2_rn((float)(1 << (2 * k)));
-              const uint4 *tp = MB ? nullptr : thr + ((k * NS + j) * 2) * (CH / 8);
-              quantise_slice<R, MB, WS>(p, tp, MB ? nullptr : tp + CH / 8, dfld, wfld, cfld, n4k, n4j, p4k, qn2, qp2,
-                                        nchi2, pclo2);
+              const uint4 *tp = MB ? nullptr : thr_j + (k * NS * 2) * (CH / 8);
+              if (!(P.dbg & 4))
+                quantise_slice<R, MB, WS>(p, tp, MB ? nullptr : tp + CH / 8, dfld, wfld, cfld, n4k, n4j, p4k, qn2, qp2,
+                                          nchi2, pclo2);
               tmem_st<R>(tcol + k * CT, p);  // codes: GEMM2's A operand, in place (two per 32-bit column)
             }
             tmem_st_wait();
@@ -419,18 +439,29 @@ static bool make_plan(const Geo &g, V2Params &P, size_t &smem) {
   if (cols > 512) return false;
   T.tmem_cols = cols;
   tcfwd::plan_producer(g, T);
+  if (g.K != 3) { T.fast = 0; T.raw_bytes = 0; }  // only the 3x3 staged producer is compiled into this kernel
+  // Two producer groups build alternate stages.  Every stage slot must then belong to one group or be revisited only
+  // after the other group's use of it was consumed (a group that runs two uses ahead on a slot would pass the parity
+  // wait of the mbarrier spuriously): true for >= 2 stages, not for 1 -- fall back to a single group then, which
+  // also frees two staging buffers.
+  // preference: staged producer with two groups, staged with one, generic gather with two, generic with one
   for (int attempt = 0; attempt < 2; ++attempt) {
-    const size_t fixed = 2 * kProducerGroups * (size_t)T.raw_bytes + 128 + 2 * (size_t)P.block_bytes + kAuxBytes;
-    if (fixed + T.stage_bytes <= kSmemBudget) {
+    if (attempt == 1 && !T.fast) break;  // there was no staged plan to drop
+    const bool fast = attempt == 0 && T.fast;
+    const size_t raw = fast ? T.raw_bytes : 0;
+    for (int groups = kProducerGroups; groups >= 1; --groups) {
+      const size_t fixed = 2 * (size_t)groups * raw + 128 + 2 * (size_t)P.block_bytes + kAuxBytes;
+      if (fixed + (size_t)(groups > 1 ? 2 : 1) * T.stage_bytes > kSmemBudget) continue;
       int stages = (int)((kSmemBudget - fixed) / T.stage_bytes);
       if (stages > kMaxStages) stages = kMaxStages;
       if (stages > g.NX + 1) stages = g.NX + 1;
+      if (groups > 1 && stages < 2) continue;
+      if (!fast) { T.fast = 0; T.raw_bytes = 0; }
       T.stages = stages;
+      P.ngroups = groups;
       smem = (size_t)stages * T.stage_bytes + fixed + 1024;
       return true;
     }
-    T.fast = 0;
-    T.raw_bytes = 0;
   }
   return false;
 }
@@ -493,6 +524,11 @@ int launch_conv_v2_forward(const Geo &g, const uint8_t *xcodes, const void *wtil
   const int ntiles = T.mtiles * T.nct;
   const int grid = ntiles < 148 ? ntiles : 148;
   const bool ws = state != nullptr;
+  if (const char *e = getenv("CIMQ_V2_DBG")) {
+    P.dbg = atoi(e);
+    if (P.dbg & 16) P.ngroups = 1;
+    T.debug = (P.dbg & 8) ? reinterpret_cast<long long *>(1) : nullptr;
+  }
   if (g.NSW == 3) {
     if (P.CH == 32) return launch_instance<3, 32, 2>(P, smem, grid, mb, ws, st);
     if (P.CH == 16 && P.EW == 2) return launch_instance<3, 16, 2>(P, smem, grid, mb, ws, st);

@@ -13,6 +13,11 @@ What the shim supplies, and nothing else:
   network) and a prototxt equal to the shipped ``resnet_w3a3.prototxt`` except ``pretrained: false``, no
   ``resume``, and the epoch / batch / worker counts given on the command line.
 * a wall-clock + CUDA-synchronised timer around the reference's ``train()`` so the run reports img/s.
+* ``--ddp``: the reference's own multi-GPU path (``multi_gpu { multiprocessing_distributed: true }``:
+  ``mp.spawn`` of ``main_worker`` per GPU, ``DistributedDataParallel``, ``DistributedSampler`` --
+  examples/__init__.py:80-104, 693-716, main_lsq.py:24-59).  The spawned interpreters start from scratch, so the
+  same shims are installed in them through a ``sitecustomize`` module on their PYTHONPATH
+  (:func:`install_child_hooks`); every rank writes its timings to ``<work-dir>/launcher_rank<k>.json``.
 
 The reference tree is looked up at ``--reference-root`` (default: ``$CIMQ_REFERENCE_ROOT``, ``baseline/_ref`` next
 to this package, ``/root/reference``).  Nothing of it is imported by the product path.
@@ -132,6 +137,58 @@ def write_prototxt(ref_root: str, path: str, epochs: int, batch_size: int, worke
         f.writelines(keep)
 
 
+CHILD_ENV = "CIMQ_LAUNCHER_CHILD"
+
+
+def _timed_train_patch(examples, stats, sink=None):
+    import torch
+    ref_train = examples.train
+
+    def timed_train(train_loader, model, criterion, optimizer, epoch, args, writer):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = ref_train(train_loader, model, criterion, optimizer, epoch, args, writer)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        sampler = getattr(train_loader, "sampler", None)
+        n = len(sampler) if sampler is not None and hasattr(sampler, "__len__") else len(train_loader.dataset)
+        stats["epochs"].append({"epoch": epoch, "seconds": dt, "images": n, "img_per_s": n / dt,
+                                "model_class": type(model).__name__})
+        if sink is not None:
+            sink(args)
+        return out
+
+    examples.train = timed_train
+
+
+def install_child_hooks() -> None:
+    """Called from the generated ``sitecustomize`` in interpreters spawned by the reference's ``mp.spawn``: the same
+    shims as the parent (stubs, synthetic CIFAR-10, ``models._modules`` -> this package, timed ``train``)."""
+    cfg = os.environ.get(CHILD_ENV)
+    if not cfg:
+        return
+    c = json.loads(cfg)
+    install_stubs()
+    install_synthetic_cifar10(c["train_images"], c["val_images"])
+    if c["ref_root"] not in sys.path:
+        sys.path.insert(0, c["ref_root"])
+    if c["impl"] == "ours":
+        from . import dropin
+        dropin.install()
+    import examples
+    examples.get_freer_gpu = lambda: 0
+    stats = {"epochs": []}
+
+    def sink(args):
+        conv_cls = sys.modules["models._modules"].Conv2dLSQCiM  # in the parent; the ranks report theirs
+        stats["conv_class"] = conv_cls.__module__ + "." + conv_cls.__name__
+        stats["rank"] = int(getattr(args, "gpu", 0) or 0)
+        with open(os.path.join(c["work"], f"launcher_rank{stats['rank']}.json"), "w") as f:
+            json.dump(stats, f)
+
+    _timed_train_patch(examples, stats, sink)
+
+
 def run(argv=None) -> dict:
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--reference-root", default=None)
@@ -143,6 +200,10 @@ def run(argv=None) -> dict:
     ap.add_argument("--workers", type=int, default=2)
     ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE", help="extra prototxt overrides")
     ap.add_argument("--work-dir", default=None, help="where the reference writes ./logger/... (default: a temp dir)")
+    ap.add_argument("--ddp", action="store_true",
+                    help="the reference's own DDP path: multi_gpu { multiprocessing_distributed: true }, one spawned "
+                         "process per visible GPU; --batch-size is then the GLOBAL batch (examples/__init__.py:707)")
+    ap.add_argument("--ddp-port", type=int, default=23456)
     a = ap.parse_args(argv)
 
     import torch
@@ -158,24 +219,26 @@ def run(argv=None) -> dict:
 
     examples.get_freer_gpu = lambda: 0  # nvidia-smi text parsing (examples/__init__.py:117-130) is brittle
     stats = {"epochs": []}
-    ref_train = examples.train
-
-    def timed_train(train_loader, model, criterion, optimizer, epoch, args, writer):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        out = ref_train(train_loader, model, criterion, optimizer, epoch, args, writer)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        n = len(train_loader.dataset)
-        stats["epochs"].append({"epoch": epoch, "seconds": dt, "images": n, "img_per_s": n / dt})
-        return out
-
-    examples.train = timed_train
+    _timed_train_patch(examples, stats)
     work = a.work_dir or tempfile.mkdtemp(prefix="cimq_launcher_")
     os.makedirs(work, exist_ok=True)
     hp = os.path.join(work, "resnet_w3a3_offline.prototxt")
     overrides = dict(kv.split("=", 1) for kv in a.set)
     write_prototxt(ref_root, hp, a.epochs, a.batch_size, a.workers, overrides)
+    if a.ddp:
+        with open(hp, "a") as f:  # the reference's own switch for one process per GPU + DistributedDataParallel
+            f.write('multi_gpu {\n  world_size: 1\n  rank: 0\n  dist_url: "tcp://127.0.0.1:%d"\n  dist_backend: "nccl"\n'
+                    '  multiprocessing_distributed: true\n}\n' % a.ddp_port)
+        hook_dir = os.path.join(work, "_child_hooks")
+        os.makedirs(hook_dir, exist_ok=True)
+        with open(os.path.join(hook_dir, "sitecustomize.py"), "w") as f:
+            f.write("import os\nif os.environ.get(%r):\n    from cim_quantization_b200.launcher import install_child_hooks\n"
+                    "    install_child_hooks()\n" % CHILD_ENV)
+        pkg_parent = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        os.environ["PYTHONPATH"] = os.pathsep.join([hook_dir, pkg_parent, os.environ.get("PYTHONPATH", "")])
+        os.environ[CHILD_ENV] = json.dumps({"ref_root": ref_root, "impl": a.impl, "work": work,
+                                            "train_images": a.train_batches * a.batch_size,
+                                            "val_images": a.val_batches * a.batch_size})
     cwd, argv0 = os.getcwd(), sys.argv
     os.chdir(work)  # the reference writes ./logger/... and copies its sources there
     sys.argv = ["main_lsq.py", "--hp", hp]
@@ -190,6 +253,21 @@ def run(argv=None) -> dict:
         ckpts += [os.path.join(root_, f) for f in files if f.endswith(".pth.tar")]
     stats["checkpoints"] = sorted(ckpts, key=os.path.getmtime)  # written by the reference's save_checkpoint
     stats["work_dir"] = work
+    if a.ddp:
+        os.environ.pop(CHILD_ENV, None)
+        ranks = []
+        for f in sorted(os.listdir(work)):
+            if f.startswith("launcher_rank") and f.endswith(".json"):
+                ranks.append(json.load(open(os.path.join(work, f))))
+        stats["ranks"] = ranks
+        if ranks:  # epoch time = the slowest rank's; images = all ranks' shards
+            ne = min(len(r["epochs"]) for r in ranks)
+            stats["epochs"] = [{"epoch": e, "seconds": max(r["epochs"][e]["seconds"] for r in ranks),
+                                "images": sum(r["epochs"][e]["images"] for r in ranks),
+                                "img_per_s": sum(r["epochs"][e]["images"] for r in ranks) /
+                                max(r["epochs"][e]["seconds"] for r in ranks),
+                                "model_class": ranks[0]["epochs"][e].get("model_class")} for e in range(ne)]
+            stats["world_size"] = len(ranks)
     stats.update({"impl": a.impl, "conv_class": conv_cls.__module__ + "." + conv_cls.__name__, "batch_size": a.batch_size,
                   "reference_root": ref_root})
     print("LAUNCHER_RESULT " + json.dumps(stats))

@@ -97,3 +97,27 @@ def test_reference_checkpoint_round_trip(tmp_path):
     # run 1: [validation before training, validation after the epoch]; run 2 starts from the saved weights
     assert len(tests1) == 2 and len(tests2) == 2
     assert tests2[0] == tests1[1], (tests1, tests2)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_ref, reason="baseline/_ref not present (tools/make_baseline_ref.sh)")
+def test_reference_ddp_runs_on_our_kernels(tmp_path):
+    """The reference's OWN multi-GPU path -- ``multi_gpu { multiprocessing_distributed: true }``: mp.spawn of
+    main_worker per GPU, DistributedDataParallel, DistributedSampler (examples/__init__.py:80-104, 693-716) -- with
+    ``models._modules`` replaced by this package in every spawned rank.  Needs two GPUs (``gpurun --gpus 2``)."""
+    import json
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    r = subprocess.run([sys.executable, "-m", "cim_quantization_b200.launcher", "--impl", "ours", "--ddp",
+                        "--train-batches", "4", "--val-batches", "1", "--batch-size", "128", "--workers", "0",
+                        "--work-dir", str(tmp_path)], cwd=ROOT, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES="0,1"))
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("LAUNCHER_RESULT ")][-1][16:])
+    assert res.get("world_size") == 2 and len(res["ranks"]) == 2
+    for rk in res["ranks"]:
+        assert rk["conv_class"] == "cim_quantization_b200.modules.lsq.Conv2dLSQCiM"
+        assert rk["epochs"][0]["model_class"] == "DistributedDataParallel"
+        assert rk["epochs"][0]["images"] == 256  # DistributedSampler: half of the 512 training images per rank
