@@ -382,8 +382,9 @@ def conv_backward(spec: LayerSpec, grad_out, xcodes, wdigits, wtiles, state, s, 
     bflags = _backward_flags(flags)
     fused_fold = bool(info.tc_backward) and not (bflags & (FLAG_FORCE_SIMT | FLAG_DETERMINISTIC))
     # kernels launched: wgrad + finish, dgrad (+ col2im unless the fold is fused into its epilogue), alpha-grad + finish
+    # (+ the grad_out scale pre-pass of the v2 dgrad / wgrad)
     _count((2 if need_weight else 0) + ((1 if fused_fold else 2) if need_input else 0) +
-           (2 if galpha is not None else 0))
+           (2 if galpha is not None else 0) + (1 if (flags & FLAG_V2) and (need_weight or need_input) else 0))
     return gxq, gwq, galpha
 
 

@@ -538,7 +538,7 @@ __global__ void bwd_weight_finish_kernel(Geo g, int nsplit, const float *__restr
 struct BwdPlan {
   int alpha_splits, alpha_m_per_split, alpha_splits_v2;
   int w_splits, w_m_per_split, ftiles;
-  int64_t off_gxu, off_wpart, off_apart, total;
+  int64_t off_gxu, off_wpart, off_apart, off_scales, total;
 };
 
 inline BwdPlan make_plan(const Geo &g) {
@@ -569,7 +569,8 @@ inline BwdPlan make_plan(const Geo &g) {
   p.off_apart = p.off_wpart + align(wpart);
   p.alpha_splits_v2 = (148 * 6 + g.NX * g.NSA - 1) / (g.NX * g.NSA) + 1;
   const int asmax = p.alpha_splits > p.alpha_splits_v2 ? p.alpha_splits : p.alpha_splits_v2;
-  p.total = p.off_apart + align((int64_t)asmax * table_entries(g) * 4);
+  p.off_scales = p.off_apart + align((int64_t)asmax * table_entries(g) * 4);
+  p.total = p.off_scales + (v2_backward_supported(g) ? align(bwd_v2_scales_bytes(g)) : 0);
   return p;
 }
 
@@ -594,6 +595,10 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
   CIMQ_REQUIRE(!v2s || (use_tc && v2::supported(g) && v2_backward_supported(g)),
                "conv_backward: CIMQ_FLAG_V2 on a layer the v2 kernels do not cover");
   const uint8_t *state2 = reinterpret_cast<const uint8_t *>(state);
+  void *scales = base + p.off_scales;
+  if (v2s && (gxq != nullptr || gwq != nullptr)) {
+    if (launch_go_scales(g, go, scales, st)) return 1;
+  }
   if (v2s && galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
     const int cblock = g.Cout > 128 ? (g.Cout % 128 == 0 ? 128 : 64) : g.Cout;  // channels per block (Cout % 16 == 0)
     const int nq = cblock / 4, pb = 8 * (32 / nq) * 8;  // pixels per block-iteration
@@ -651,9 +656,11 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
     if (!(flags & CIMQ_FLAG_DETERMINISTIC) && bwd_input_tc_can_fold(g)) {
       // fused fold: the dgrad epilogue reduces into grad_x (fp32 atomics in L2; summation order varies run to run)
       CIMQ_CUDA_OK(cudaMemsetAsync(gxq, 0, (size_t)g.B * g.Cin * g.H * g.W * sizeof(float), st));
-      if (launch_bwd_input_tc(g, go, state, v2s ? wtb2 : wtb, s, mask, gxq, 1, v2s, st)) return 1;
+      if (v2s) { if (launch_bwd_input_v2(g, go, state2, wtb2, s, scales, gxq, 1, st)) return 1; }
+      else if (launch_bwd_input_tc(g, go, state, wtb, s, mask, gxq, 1, false, st)) return 1;
     } else {
-      if (launch_bwd_input_tc(g, go, state, v2s ? wtb2 : wtb, s, mask, gxuT, 0, v2s, st)) return 1;
+      if (v2s) { if (launch_bwd_input_v2(g, go, state2, wtb2, s, scales, gxuT, 0, st)) return 1; }
+      else if (launch_bwd_input_tc(g, go, state, wtb, s, mask, gxuT, 0, false, st)) return 1;
       if (launch_col2im(g, gxuT, gxq, st)) return 1;
     }
   } else if (gxq != nullptr) {
@@ -666,7 +673,7 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
     if (launch_col2im(g, gxuT, gxq, st)) return 1;
   }
   if (gwq != nullptr && use_tc) {
-    if (launch_bwd_weight_tc(g, go, xcodes, state, s, mask, wpart, gwq, v2s, st)) return 1;
+    if (launch_bwd_weight_tc(g, go, xcodes, state, s, mask, wpart, gwq, v2s, scales, st)) return 1;
   } else if (gwq != nullptr) {
     size_t smem = (size_t)32 * g.NSA * 32 * sizeof(float);
     CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -75,6 +75,7 @@ struct BwdParams {
   int fold;  // dgrad: 1 = the epilogue folds (col2im) straight into grad_x with fp32 reductions; 0 = writes gxu[b][f][l]
   int v2;    // 1 = `state` holds the v2 byte planes (cim_v2.cuh): D [NX][M][Cout] for dgrad, W for wgrad
   const uint8_t *state2, *state2w;
+  const uint32_t *chmax;  // v2 wgrad: bit pattern of max |grad_out| per output channel (launch_go_scales)
   const float *go;
   const uint32_t *state;
   const uint8_t *xcodes;
@@ -234,107 +235,6 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
     const int G = cpt >> 3;           // groups of 8 channels
     uint32_t it = 0;
     bool done = false;
-    if (P.v2) {
-      // ---- v2 state (cim_v2.cuh): one byte per (crossbar, pixel, channel) with the pass counts of the NSW weight
-      // slices as 2-bit fields.  A'_k[m,co] = go * count_k without an integer-to-float conversion: the masked field,
-      // read as an fp32 subnormal, is count * 2^(pos - 149) exactly; go is pre-scaled by 2^100 (once per tile) so the
-      // product is normal, and the power-of-two factors 2^(8*(co&1) + 2k - 49) are undone by the pre-scaled weight
-      // tiles (exact in bf16) and the epilogue's scale.  Register-resident go (reused by NX*NSW stages) and D bytes
-      // (reused by NSW stages), refilled right after their last use.
-      constexpr int CMAX = 32;
-      float gsr[CMAX];
-      uint32_t dlo[CMAX / 4], dhi[CMAX / 4], dnx[CMAX / 4];
-      const int nw = cpt >> 2;  // D words per thread
-      // rows past the last pixel read pixel 0: their A' rows only feed accumulator rows the epilogue never stores
-      auto tile_ptrs2 = [&](int mt, const float *&gop, const uint8_t *&dp) {
-        const int64_t m = (int64_t)mt * kTcTileM + r;
-        const bool live = m < g.M;
-        const int b = live ? (int)(m / g.L) : 0, l = live ? (int)(m % g.L) : 0;
-        gop = P.go + ((int64_t)b * g.Cout + P.co0 + h * cpt) * g.L + l;
-        dp = P.state2 + (live ? m : 0) * (int64_t)g.Cout + P.co0 + h * cpt;
-      };
-      auto load_d = [&](const uint8_t *dp, int i) {
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(dp + (int64_t)i * g.M * g.Cout);
-        if (nw == 8) {
-          const uint4 a = __ldg(reinterpret_cast<const uint4 *>(wp)), b4 = __ldg(reinterpret_cast<const uint4 *>(wp) + 1);
-          dnx[0] = a.x; dnx[1] = a.y; dnx[2] = a.z; dnx[3] = a.w; dnx[4] = b4.x; dnx[5] = b4.y; dnx[6] = b4.z; dnx[7] = b4.w;
-        } else if (nw == 4) {
-          const uint4 a = __ldg(reinterpret_cast<const uint4 *>(wp));
-          dnx[0] = a.x; dnx[1] = a.y; dnx[2] = a.z; dnx[3] = a.w;
-        } else {
-          const uint2 a = __ldg(reinterpret_cast<const uint2 *>(wp));
-          dnx[0] = a.x; dnx[1] = a.y;
-        }
-      };
-      const float *gop = nullptr, *gop_n = nullptr;
-      const uint8_t *dp = nullptr, *dp_n = nullptr;
-#pragma unroll
-      for (int w = 0; w < CMAX / 4; ++w) dnx[w] = 0u;
-      if ((int)blockIdx.x < P.mtiles) {
-        tile_ptrs2(blockIdx.x, gop, dp);
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c)
-          if (c < cpt) gsr[c] = __ldg(gop + (size_t)c * g.L) * 1.2676506002282294e30f;  // 2^100
-        load_d(dp, 0);
-      }
-      for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
-        const int nmt = mt + gridDim.x;
-        const bool more_tiles = nmt < P.mtiles;
-        if (more_tiles) tile_ptrs2(nmt, gop_n, dp_n);
-        for (int i = 0; i < g.NX; ++i) {
-#pragma unroll
-          for (int w = 0; w < CMAX / 4; ++w) { dlo[w] = dnx[w]; dhi[w] = dnx[w] >> 16; }
-          for (int k = 0; k < NSW; ++k, ++it) {
-            const int sidx = it % P.stages;
-            const uint32_t use = it / P.stages;
-            const bool last_k = k + 1 == NSW;
-            const bool next_tile = last_k && i + 1 == g.NX && more_tiles;
-            // the D bytes of the next chunk (or of the next tile's first chunk) start their trip now
-            if (last_k) {
-              if (i + 1 < g.NX) load_d(dp, i + 1);
-              else if (more_tiles) load_d(dp_n, 0);
-            }
-            mbar_wait(cv.empty0 + 8 * sidx, (use & 1) ^ 1);
-            uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
-            if (threadIdx.x == 0) {
-              mbar_arrive_expect_tx(cv.full0 + 8 * sidx, P.b_bytes);
-              bulk_copy_g2s(smem_u32(st_ptr + 3 * (size_t)P.a_bytes), P.wtb + (size_t)(i * NSW + k) * P.b_bytes,
-                            P.b_bytes, cv.full0 + 8 * sidx);
-            }
-            const uint32_t mk0 = 3u << (2 * k), mk1 = 3u << (8 + 2 * k);
-#pragma unroll
-            for (int cgi = 0; cgi < CMAX / 8; ++cgi) {
-              if (cgi < G) {
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const int c = 8 * cgi + e;
-                  const uint32_t src = (c & 2) ? dhi[c >> 2] : dlo[c >> 2];
-                  v[e] = gsr[c] * __uint_as_float(src & ((c & 1) ? mk1 : mk0));
-                }
-                if (next_tile) {  // last use of these eight grad_out values: refill them for the next tile
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    gsr[8 * cgi + e] = __ldg(gop_n + (size_t)(8 * cgi + e) * g.L) * 1.2676506002282294e30f;
-                }
-                uint32_t hi[4], mid[4], lo[4];
-#pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo[e2]);
-                const uint32_t off = tc_tile_offset16(r, h * cpt + cgi * 8, kTcLBO, sbo);
-                *reinterpret_cast<uint4 *>(st_ptr + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4 *>(st_ptr + P.a_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-                *reinterpret_cast<uint4 *>(st_ptr + 2 * (size_t)P.a_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              }
-            }
-            fence_proxy_async();
-            mbar_arrive(cv.full0 + 8 * sidx);
-          }
-        }
-        gop = gop_n;
-        dp = dp_n;
-      }
-      done = true;
-    }
     if constexpr (CBits::CWN == 1) {
       if (P.cached && !done) {
         // ---- register-resident operands (Cout <= 64): grad_out of the tile (reused by all NX*NSW stages) and the
@@ -558,8 +458,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
     // ------------------------------------------------------------------ epilogue
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    // w_sl * s_w (lsq.py:252), mean over act slices (lsq.py:376); v2: times the 2^49 left by the producers' scaling
-    const float scale = P.s[1] / (float)NSA * (P.v2 ? 562949953421312.0f : 1.0f);
+    // w_sl * s_w (lsq.py:252), mean over act slices (lsq.py:376)
+    const float scale = P.s[1] / (float)NSA;
     const int *ftab = reinterpret_cast<const int *>(cv.raw);  // fold: per unfold row {offset in the image << 7 | kx << 5 | tap}
     const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && warp == kEpilogueWarp0 && lane == 0;
     long long d_tfull = 0, d_comp = 0;
@@ -883,17 +783,22 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     const bool g_thread = V2 && tid < n_g;
     const int nq2 = Kc >> 2;
     const int gq2 = V2 ? tid % nq2 : 0, gpg2 = V2 ? tid / nq2 : 0;
+    // grad_out of the item (4 channels x 8 pixels), scaled per channel to [2^12, 2^13) and split ONCE per tile into two
+    // fp16 pieces (cim_v2.cuh); the W bytes of a chunk (one word = 4 channels per pixel) are re-paired per channel
+    // ([pixel 2q | . | pixel 2q+1 | .]) once per chunk.  Raw grad_out / W words of the next tile / chunk are loaded a
+    // stage ahead.  Groups past the last pixel read the last valid group: their activation digits are zero.
+    constexpr int PB2 = v2::bwd_piece_bits(NSW);
     float gs2[4][8];
-    uint32_t wlo2[8], whi2[8], wnx2[8];
+    uint32_t gp1[4][4], gp2[4][4], wsp[4][4], wnx2[8];
+    float chs[4] = {1.0f, 1.0f, 1.0f, 1.0f};
     auto v2_group_m = [&](int mt_) { return min((int64_t)mt_ * kTcTileM + gpg2 * 8, (int64_t)g.M - 8); };
     auto v2_load_go = [&](int mt_, int c) {
       const int64_t m = v2_group_m(mt_);
       const int b = (int)(m / g.L), l = (int)(m % g.L);
       const float4 *gp = reinterpret_cast<const float4 *>(P.go + ((int64_t)b * g.Cout + P.co0 + 4 * gq2 + c) * g.L + l);
       const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
-      const float sc = 1.2676506002282294e30f;  // 2^100
-      gs2[c][0] = g0.x * sc; gs2[c][1] = g0.y * sc; gs2[c][2] = g0.z * sc; gs2[c][3] = g0.w * sc;
-      gs2[c][4] = g1.x * sc; gs2[c][5] = g1.y * sc; gs2[c][6] = g1.z * sc; gs2[c][7] = g1.w * sc;
+      gs2[c][0] = g0.x; gs2[c][1] = g0.y; gs2[c][2] = g0.z; gs2[c][3] = g0.w;
+      gs2[c][4] = g1.x; gs2[c][5] = g1.y; gs2[c][6] = g1.z; gs2[c][7] = g1.w;
     };
     auto v2_load_w = [&](int mt_, int i_) {
       const uint8_t *wp = P.state2w + ((int64_t)i_ * g.M + v2_group_m(mt_)) * g.Cout + P.co0 + 4 * gq2;
@@ -903,6 +808,14 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     if constexpr (V2) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) wnx2[e] = 0u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gs2[c][e] = 0.0f;
+      if (g_thread) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) chs[c] = v2::bwd_scale_from_maxbits(__ldg(P.chmax + P.co0 + 4 * gq2 + c));
+      }
       if (g_thread && (int)blockIdx.x < P.mtiles) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) v2_load_go(blockIdx.x, c);
@@ -911,6 +824,25 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     }
     for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
       const int64_t m0 = (int64_t)mt * kTcTileM;
+      if constexpr (V2) {
+        if (g_thread) {  // this tile's grad_out (loaded during the previous tile's last stage) -> scaled fp16 pieces
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float v0 = gs2[c][2 * q] * chs[c], v1 = gs2[c][2 * q + 1] * chs[c];
+              constexpr uint32_t kMask = 0xffffffffu << (24 - PB2), kRnd = 1u << (23 - PB2);
+              const float a0 = __uint_as_float((__float_as_uint(v0) + kRnd) & kMask);
+              const float a1 = __uint_as_float((__float_as_uint(v1) + kRnd) & kMask);
+              const float r0 = v0 - a0, r1 = v1 - a1;
+              const float b0 = __uint_as_float((__float_as_uint(r0) + kRnd) & kMask);
+              const float b1 = __uint_as_float((__float_as_uint(r1) + kRnd) & kMask);
+              const __half2 h1 = __floats2half2_rn(a0, a1), h2v = __floats2half2_rn(b0, b1);
+              gp1[c][q] = *reinterpret_cast<const uint32_t *>(&h1);
+              gp2[c][q] = *reinterpret_cast<const uint32_t *>(&h2v);
+            }
+        }
+      }
       const int mt_n = mt + gridDim.x;
       if (gcache && mt_n < P.mtiles) gpt_n = pix_group(mt_n);
       // per 8-pixel group: image, output row, first output column; fast = one image row, fully valid, aligned
@@ -1054,7 +986,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         d_stage += CIMQ_TB() - ts0;
         if constexpr (V2) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { wlo2[e] = wnx2[e]; whi2[e] = wnx2[e] >> 16; }
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) wsp[c][q] = __byte_perm(wnx2[2 * q], wnx2[2 * q + 1], c | ((4 + c) << 8));
         }
         for (int j = 0; j < NSA; ++j, ++it) {
           const int sidx = it % P.stages;
@@ -1066,11 +1000,12 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
           // ---- X_j tile [128 crossbar rows x 128 pixels] (bf16 digits); item = (row fr, 8-pixel group pg)
           const int sh = g.abs_ * j;
-          // v2: digit * 2^-j (bf16 exponent field minus j), which undoes the 2^(2j) of the pass-count field of plane W
-          const uint32_t one_bf = V2 ? 0x3F80u - ((uint32_t)j << 7) : 0x3F80u;
+          // v2: fp16 operands (the G' pieces are fp16); the digit carries the slice weight 2^j (mask[k][j] * 2^(-wbs*k)
+          // = 2^j for 1-bit slices, lsq.py:306, 363-364), the pass COUNT of plane W multiplies grad_out
+          const uint32_t one_bf = V2 ? 0x3C00u + ((uint32_t)j << 10) : 0x3F80u;
           if (xfast) {
             uint8_t *dst = st_ptr + tc_tile_offset16(fr, x_pg0 * 8, kTcLBO, a_sbo);
-            const uint32_t cmul = one_bf >> sh;  // (0x7F - j) << (7 - sh): the bf16 pattern of 2^-j divided by the bit weight
+            const uint32_t cmul = one_bf >> sh;  // the 16-bit pattern of 1.0 divided by the bit weight of the digit
             if (x_cnt == 14) x_store_fast<14, 1, XI>(dst, xlo, xhi, sh, cmul);
             else if (x_cnt == 8) x_store_fast<8, 2, XI>(dst, xlo, xhi, sh, cmul);
             else if (x_cnt == 1) x_store_fast<1, 1, XI>(dst, xlo, xhi, sh, cmul);
@@ -1105,8 +1040,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           d_x += tx1 - tw1;
           uint8_t *gb = st_ptr + P.a_bytes;
           if constexpr (V2) {
-            // G'_j[co, m] = go * (pass count of activation slice j) = (go * 2^100) * (masked field as an fp32 subnormal)
-            //             = go * count * 2^(8*(co&1) + 2j - 49); the factors are undone by X_j (2^-j) and the epilogue
+            // G'_j[co, m] = (go * 2^s_co as two fp16 pieces) * (pass count of activation slice j): exact products
             if (g_thread) {
               const bool last_j = j + 1 == NSA;
               const bool next_chunk = i + 1 < i_end, next_tile = !next_chunk && mt_n < P.mtiles;
@@ -1114,21 +1048,29 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
                 if (next_chunk) v2_load_w(mt, i + 1);
                 else if (next_tile) v2_load_w(mt_n, i_begin);
               }
-              const uint32_t mk0 = 3u << (2 * j), mk1 = 3u << (8 + 2 * j);
+              if (j == 0 && next_tile) {  // next tile's grad_out: three stages ahead of its split
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v2_load_go(mt_n, c);
+              }
+              // count field j of both bytes -> fp16x2 (1024 + cnt * 4^j) -> cnt
+              const uint32_t fmask = 0x00030003u << (2 * j);
+              const __half2 sk = __float2half2_rn(1.0f / (float)(1 << (2 * j)));
+              const __half2 ok = __float2half2_rn(-1024.0f / (float)(1 << (2 * j)));
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                float v[8];
+                uint32_t a1[4], a2[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  v[e] = gs2[c][e] * __uint_as_float(((c & 2) ? whi2[e] : wlo2[e]) & ((c & 1) ? mk1 : mk0));
-                if (last_j && next_tile) v2_load_go(mt_n, c);  // last use of this row of grad_out
-                uint32_t hi[4], mid[4], lo3[4];
-#pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo3[e2]);
+                for (int q = 0; q < 4; ++q) {
+                  const uint32_t fw = (wsp[c][q] & fmask) | 0x64006400u;
+                  const __half2 cnt = __hfma2(*reinterpret_cast<const __half2 *>(&fw), sk, ok);
+                  const __half2 r1 = __hmul2(*reinterpret_cast<const __half2 *>(&gp1[c][q]), cnt);
+                  const __half2 r2 = __hmul2(*reinterpret_cast<const __half2 *>(&gp2[c][q]), cnt);
+                  a1[q] = *reinterpret_cast<const uint32_t *>(&r1);
+                  a2[q] = *reinterpret_cast<const uint32_t *>(&r2);
+                }
                 const uint32_t off = tc_tile_offset16(4 * gq2 + c, gpg2 * 8, kWgLBO, b_sbo);
-                *reinterpret_cast<uint4 *>(gb + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4 *>(gb + P.b_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-                *reinterpret_cast<uint4 *>(gb + 2 * (size_t)P.b_bytes + off) = make_uint4(lo3[0], lo3[1], lo3[2], lo3[3]);
+                *reinterpret_cast<uint4 *>(gb + off) = make_uint4(a1[0], a1[1], a1[2], a1[3]);
+                *reinterpret_cast<uint4 *>(gb + P.b_bytes + off) = make_uint4(a2[0], a2[1], a2[2], a2[3]);
               }
             }
             fence_proxy_async();
@@ -1258,7 +1200,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     reg_dealloc<kWgRegsMma>();
     // ------------------------------------------------------------------ MMA issuer
     if (warp == kMmaWarp && lane == 0 && has_work) {
-      const uint32_t idesc = idesc_bf16_f32(128, Kc);
+      const uint32_t idesc = V2 ? idesc_f16_f32(128, Kc) : idesc_bf16_f32(128, Kc);
+      constexpr int kPieces = V2 ? v2::kBwdPieces : 3;  // terms of the real-valued operand
       uint32_t it = 0;
       bool first_tile = true;
       const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
@@ -1276,7 +1219,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
             tc_fence_after();
             const uint32_t a0 = smem_u32(cv.stage_base + (size_t)sidx * P.stage_bytes);
             const uint32_t b0 = a0 + P.a_bytes;
-            for (int sp = 0; sp < 3; ++sp)
+            for (int sp = 0; sp < kPieces; ++sp)
               for (int ks = 0; ks < 8; ++ks) {  // 128 pixels = 8 x K16
                 const uint64_t adesc = make_smem_desc(a0 + ks * 2 * kTcLBO, kTcLBO, a_sbo);
                 const uint64_t bdesc = make_smem_desc(b0 + sp * P.b_bytes + ks * 2 * kWgLBO, kWgLBO, b_sbo);
@@ -1314,12 +1257,15 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         }
         if (frow < rows) {
           float4 *dst = reinterpret_cast<float4 *>(part + (int64_t)(lo + frow) * g.Cout + P.co0 + c0);
-          // v2: even / odd channels carry 2^-49 / 2^-41 from the producers' subnormal multiply
-          const float se = V2 ? scale * 562949953421312.0f : scale, so = V2 ? scale * 2199023255552.0f : scale;
+          // v2: undo the per-channel power-of-two scale of grad_out
+          float cs[16];
+#pragma unroll
+          for (int cc = 0; cc < 16; ++cc)
+            cs[cc] = V2 ? scale * v2::bwd_scale_inverse(v2::bwd_scale_from_maxbits(__ldg(P.chmax + P.co0 + c0 + cc))) : scale;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4)
-            dst[q4] = make_float4(__int_as_float(v[4 * q4]) * se, __int_as_float(v[4 * q4 + 1]) * so,
-                                  __int_as_float(v[4 * q4 + 2]) * se, __int_as_float(v[4 * q4 + 3]) * so);
+            dst[q4] = make_float4(__int_as_float(v[4 * q4]) * cs[4 * q4], __int_as_float(v[4 * q4 + 1]) * cs[4 * q4 + 1],
+                                  __int_as_float(v[4 * q4 + 2]) * cs[4 * q4 + 2], __int_as_float(v[4 * q4 + 3]) * cs[4 * q4 + 3]);
         }
       }
     }
@@ -1487,14 +1433,6 @@ int launch_weight_tiles_bwd(const Geo &g0, const int8_t *wcodes, void *tiles, cu
   return 0;
 }
 
-int launch_weight_tiles_bwd2(const Geo &g, const int8_t *wcodes, void *tiles, cudaStream_t st) {
-  const int64_t n = (int64_t)g.NX * g.NSW * tc_nf(g) * g.Cout;
-  weight_tiles_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(g, tc_nf(g), bwd_channel_block(g, true), 1, wcodes,
-                                                                 reinterpret_cast<uint16_t *>(tiles));
-  CIMQ_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
 static int wgrad_ctas(const Geo &g, bool v2, int *nxg_out, int *groups_out) {
   const int mtiles = (g.M + kTcTileM - 1) / kTcTileM;
   const int nxg = wgrad_chunks_per_group(g, v2);
@@ -1523,6 +1461,7 @@ bool bwd_input_tc_can_fold(const Geo &g) {
 
 int launch_bwd_input_tc(const Geo &g0, const float *go, const uint32_t *state, const void *wtb, const float *s,
                         const int8_t *mask, float *out, int fold, bool v2, cudaStream_t st) {
+  CIMQ_REQUIRE(!v2, "dgrad: the v2 state is handled by launch_bwd_input_v2");
   BwdParams P;
   memset(&P, 0, sizeof(P));
   const Geo g = bwd_virtual_geo(g0, &P.sdiv);
@@ -1568,7 +1507,8 @@ int launch_bwd_input_tc(const Geo &g0, const float *go, const uint32_t *state, c
 }
 
 int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, const uint32_t *state,
-                         const float *s, const int8_t *mask, float *partial, float *gw, bool v2, cudaStream_t st) {
+                         const float *s, const int8_t *mask, float *partial, float *gw, bool v2, const void *scales,
+                         cudaStream_t st) {
   BwdParams P;
   memset(&P, 0, sizeof(P));
   const Geo g = bwd_virtual_geo(g0, &P.sdiv);
@@ -1581,7 +1521,9 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
   P.a_bytes = 128u * 128u * 2u;
   P.debug = g_tc_debug;
   P.b_bytes = (uint32_t)(P.Kc / 8) * (16u * (uint32_t)kWgLBO + (v2 ? 16u : 0u));  // 8-row groups x (16 k-groups x 144 B [+ 16])
-  P.stage_bytes = P.a_bytes + 3 * P.b_bytes;
+  P.stage_bytes = P.a_bytes + (v2 ? v2::kBwdPieces : 3) * P.b_bytes;
+  CIMQ_REQUIRE(!v2 || scales != nullptr, "wgrad (v2): the grad_out scales are missing");
+  if (v2) P.chmax = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(scales) + (((int64_t)g0.M * 4 + 255) & ~(int64_t)255));
   // staged activation rows (stride 1, output width a power of two between 8 and 128, 4-byte aligned rows)
   P.fastx = 0; P.raw_bytes = 0;
   if (g.stride == 1 && g.W % 4 == 0 && g.OW >= 8 && g.OW <= kTcTileM && (g.OW & (g.OW - 1)) == 0 &&

@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(256) v2_consts_kernel(Geo g, v2::ConstLayout c
       const int h = cl_c / cl.CH, ch = cl_c % cl.CH;
       const int tpm = min(t.x - 1, v2::kThrClamp), tgm = min(t.y - 1, v2::kThrClamp);
       __half *row = thr + ((size_t)(h * g.pairs + q) * 2) * cl.CH + ch;
-      row[0] = __float2half_rn(-(float)tpm);
-      row[cl.CH] = __float2half_rn(-(float)tgm);
+      row[0] = __float2half_rn((float)(-tpm));  // integer negation: threshold 0 stays +0.0
+      row[cl.CH] = __float2half_rn((float)(-tgm));
       // alpha_q = n * scale with integer n (lsq.py:566-571): the tensor core accumulates code * n * mask exactly
       const float aq = alpha_q[e];
       const float n = rintf(__fdiv_rn(aq, scale));

@@ -34,7 +34,7 @@ struct PrepArgs {
   int4 *table;              // AoS table {tp, tg, amp, 0}
   uint8_t *v2sec;           // v2 section of the table buffer (header + constants blocks)
   uint8_t *fwd8;            // e4m3 forward tiles
-  uint16_t *bwd2;           // pre-scaled bf16 dgrad tiles
+  uint16_t *bwd2;           // fp16 dgrad tiles (v2)
   int2 *lut;                // im2col LUT
   int32_t *status;
   int64_t seg[7];           // prefix offsets of the work segments
@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(kThreads) layer_prepare_kernel(const PrepArgs 
         const int ct = c / cl.CT, cl_c = c % cl.CT, h = cl_c / cl.CH, ch = cl_c % cl.CH;
         __half *thr = reinterpret_cast<__half *>(A.v2sec + 256 + (size_t)(ct * g.NX + i) * cl.block_bytes);
         __half *row = thr + ((size_t)(h * g.pairs + q) * 2) * cl.CH + ch;
-        row[0] = __float2half_rn(-(float)min(tp - 1, v2::kThrClamp));
-        row[cl.CH] = __float2half_rn(-(float)min(tg - 1, v2::kThrClamp));
+        row[0] = __float2half_rn((float)(-min(tp - 1, v2::kThrClamp)));  // integer negation: threshold 0 stays +0.0
+        row[cl.CH] = __float2half_rn((float)(-min(tg - 1, v2::kThrClamp)));
       }
       A.table[e] = make_int4(tp, tg, __float_as_int(amp), 0);
     } else if (idx < A.seg[1]) {
@@ -195,23 +195,31 @@ __global__ void __launch_bounds__(kThreads) layer_prepare_kernel(const PrepArgs 
       }
       A.fwd8[tile * tile_bytes + tc_tile_offset(r, kk, A.Kp)] = digit > 0 ? 0x30 : (digit < 0 ? 0xB0 : 0);
     } else if (idx < A.seg[4]) {
-      // ---- pre-scaled bf16 dgrad tile element: tile (channel block, i, k) = [Nf rows x Kc2 channels]
+      // ---- fp16 dgrad tile element: tile (channel block, i, k) = [Nf columns x Kc2 channels], column n = unfold row
+      // dgrad_col_f(i, n), value 2^k * digit (same bytes as weight_tiles_dgrad2_kernel, cim_bwd_v2.cu)
       const int64_t t = idx - A.seg[3];
       const int64_t tile_elems = (int64_t)A.Nf * A.Kc2;
       const int64_t tile = t / tile_elems;
       const int within = (int)(t % tile_elems);
-      const int fr = within / A.Kc2, cl_c = within % A.Kc2;
+      const int col = within / A.Kc2, cl_c = within % A.Kc2;
       const int64_t per_block = (int64_t)g.NX * g.NSW;
       const int cb = (int)(tile / per_block), ik = (int)(tile % per_block);
       const int i = ik / g.NSW, k = ik % g.NSW;
-      const int co = cb * A.Kc2 + cl_c, f = i * g.xbar + fr;
-      const int hi = min((i + 1) * g.xbar, g.F);
-      float dv = 0.0f;
-      if (f < hi)
-        dv = ldexpf((float)weight_digit(g, weight_code(A.weight[(int64_t)co * g.F + f], sw, qn_w, qp_w), k),
-                    -k - 8 * (co & 1));
-      A.bwd2[tile * tile_elems + tc_tile_offset16(fr, cl_c, kTcLBO, (uint32_t)A.Kc2 * 16u) / 2] =
-          __bfloat16_as_ushort(__float2bfloat16_rn(dv));
+      const int co = cb * A.Kc2 + cl_c;
+      const int f = v2::dgrad2_tile_row(g, i, col);
+      int digit = 0;
+      if (f >= 0) digit = weight_digit(g, weight_code(A.weight[(int64_t)co * g.F + f], sw, qn_w, qp_w), k);
+      A.bwd2[tile * tile_elems + tc_tile_offset16(col, cl_c, kTcLBO, (uint32_t)A.Kc2 * 16u) / 2] =
+          __half_as_ushort(__float2half_rn((float)(digit * (1 << k))));
+    } else if (idx >= A.seg[5]) {
+      // ---- padding of the constants blocks (between thresholds and slabs, after the slabs): zero, so that the block is
+      // byte-identical to what cimq_adc_table2 writes
+      const int64_t t = idx - A.seg[5];
+      const uint32_t pad0 = (cl.b2_off - cl.thr_bytes) / 2, pad1 = (cl.block_bytes - cl.b2_off - cl.b2_bytes) / 2;
+      const int64_t blk = t / (pad0 + pad1);
+      const uint32_t e = (uint32_t)(t % (pad0 + pad1));
+      uint16_t *bp = reinterpret_cast<uint16_t *>(A.v2sec + 256 + (size_t)blk * cl.block_bytes);
+      bp[e < pad0 ? cl.thr_bytes / 2 + e : (cl.b2_off + cl.b2_bytes) / 2 + (e - pad0)] = 0;
     } else {
       // ---- im2col LUT of the generic forward producer
       const int p = (int)(idx - A.seg[4]);
@@ -265,7 +273,7 @@ int launch_layer_prepare(const Geo &g, const float *weight, const float *alpha_a
   A.seg[3] = A.seg[2] + wl.fwd8_bytes;
   A.seg[4] = A.seg[3] + wl.bwd2_bytes / 2;
   A.seg[5] = A.seg[4] + g.F;
-  A.seg[6] = A.seg[5];
+  A.seg[6] = A.seg[5] + (int64_t)nct * g.NX * ((A.cl.block_bytes - A.cl.thr_bytes - A.cl.b2_bytes) / 2);
   int blocks = (int)((A.seg[6] + kThreads * 4 - 1) / (kThreads * 4));
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;

@@ -93,5 +93,58 @@ __host__ __device__ inline int64_t state_c_off(const Geo &g, int i, int j) {
   return 2 * plane_bytes(g) + ((int64_t)i * g.NSA + j) * g.M * g.Cout;
 }
 
+
+// ---- backward operands (cim_bwd_v2.cu, the v2 branch of cim_bwd_tc.cu) ------------------------------------------
+// Both backward GEMMs multiply grad_out * (pass count) by exact small integers.  grad_out is scaled by a power of two
+// per pixel row (dgrad) / per output channel (wgrad) so that its largest magnitude lies in [2^12, 2^13), and split
+// ONCE per tile into kBwdPieces fp16 pieces of PB significant bits each (round to nearest; PB = 9 for three digit
+// planes, 11 for two): piece * count (count <= NS) then has at most 11 significant bits, i.e. the per-stage operand
+// piece * count is exact in fp16 and costs one packed multiply per two elements.  The only error of the whole GEMM
+// input is the initial rounding of grad_out to 2*PB bits: relative 2^-19 (PB = 9) or 2^-23 (PB = 11) per element.
+constexpr int kBwdPieces = 2;
+constexpr int kBwdScaleExp = 12;  // scaled row / channel maximum in [2^12, 2^13)
+__host__ __device__ constexpr int bwd_piece_bits(int NS) { return NS >= 3 ? 9 : 11; }
+// power-of-two scale for a row / channel whose largest |grad_out| has the fp32 bit pattern `maxbits`
+__device__ __forceinline__ float bwd_scale_from_maxbits(uint32_t maxbits) {
+  int s = kBwdScaleExp + 127 - (int)((maxbits >> 23) & 0xffu);
+  s = s < -100 ? -100 : (s > 100 ? 100 : s);
+  return __uint_as_float((uint32_t)(s + 127) << 23);
+}
+// 1 / scale for a power of two in [2^-126, 2^126]
+__device__ __forceinline__ float bwd_scale_inverse(float scale) { return __uint_as_float(0x7f000000u - __float_as_uint(scale)); }
+
+// dgrad column (GEMM N) order inside crossbar chunk i: the complete K-tuples -- the K taps (ci, ky, 0..K-1) of one
+// kernel row, consecutive unfold rows -- come first, then the taps cut off by the chunk's lower and upper edge.  The
+// epilogue folds a complete tuple with two warp shuffles and ONE reduction per pixel.
+struct DgradCols {
+  int lo, rows;   // first unfold row, rows of the chunk
+  int t0, ntup;   // first complete tuple (f / K), number of complete tuples
+  int nhead;      // leftover rows before the first complete tuple
+};
+__host__ __device__ inline DgradCols dgrad_cols(const Geo &g, int i) {
+  DgradCols c;
+  c.lo = i * g.xbar;
+  const int hi = (c.lo + g.xbar < g.F) ? c.lo + g.xbar : g.F;
+  c.rows = hi - c.lo;
+  c.t0 = (c.lo + g.K - 1) / g.K;
+  const int t1 = hi / g.K;
+  c.ntup = t1 > c.t0 ? t1 - c.t0 : 0;
+  c.nhead = c.ntup > 0 ? c.t0 * g.K - c.lo : 0;
+  return c;
+}
+// unfold row f at column `pos` (0 <= pos < rows) of the chunk
+__host__ __device__ inline int dgrad_col_f(const Geo &g, const DgradCols &c, int pos) {
+  const int mid = c.ntup * g.K;
+  if (pos < mid) return c.t0 * g.K + pos;
+  pos -= mid;
+  if (pos < c.nhead) return c.lo + pos;
+  return (c.ntup > 0 ? (c.t0 + c.ntup) * g.K : c.lo) + (pos - c.nhead);
+}
+// unfold row held by column n of the v2 dgrad weight tile of chunk i (-1: padding column)
+__host__ __device__ inline int dgrad2_tile_row(const Geo &g, int i, int n) {
+  const DgradCols dc = dgrad_cols(g, i);
+  return n < dc.rows ? dgrad_col_f(g, dc, n) : -1;
+}
+
 }  // namespace v2
 }  // namespace cimq

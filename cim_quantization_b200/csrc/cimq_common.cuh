@@ -143,17 +143,26 @@ bool bwd_input_tc_can_fold(const Geo &g);
 // v2 = true: `state` is the v2 byte planes (cim_v2.cuh) and `wtb` the pre-scaled dgrad tiles (WtLayout::bwd2)
 int launch_bwd_input_tc(const Geo &g, const float *go, const uint32_t *state, const void *wtb, const float *s,
                         const int8_t *mask, float *out, int fold, bool v2, cudaStream_t st);
+// v2 = true also needs `scales` (launch_go_scales)
 int launch_bwd_weight_tc(const Geo &g, const float *go, const uint8_t *xcodes, const uint32_t *state,
-                         const float *s, const int8_t *mask, float *partial, float *gw, bool v2, cudaStream_t st);
+                         const float *s, const int8_t *mask, float *partial, float *gw, bool v2, const void *scales,
+                         cudaStream_t st);
 bool v2_backward_supported(const Geo &g);
+// ---- v2 backward (cim_bwd_v2.cu + the V2 instance of the wgrad kernel in cim_bwd_tc.cu) ----
 int launch_weight_tiles_bwd2(const Geo &g, const int8_t *wcodes, void *tiles, cudaStream_t st);
+// grad_out scale pre-pass: `scales` = float rowscale[M] (power of two per pixel row), then (256-byte aligned)
+// uint32 chmax[Cout] (bit pattern of the largest |grad_out| of the channel); bwd_v2_scales_bytes() bytes
+int64_t bwd_v2_scales_bytes(const Geo &g);
+int launch_go_scales(const Geo &g, const float *go, void *scales, cudaStream_t st);
+int launch_bwd_input_v2(const Geo &g, const float *go, const uint8_t *state, const void *wtb, const float *s,
+                        const void *scales, float *out, int fold, cudaStream_t st);
 
 // Sections of the prepared-weights buffer ("wtiles"): forward int8 digit tiles, im2col LUT (int2 per crossbar
 // row), backward bf16 digit tiles.  A section the layer does not support has zero bytes.
 struct WtLayout {
   int64_t fwd_off, fwd_bytes, lut_off, lut_bytes, bwd_off, bwd_bytes;
   int64_t fwd8_off, fwd8_bytes;  // v2 forward: e4m3 digit tiles (+-0.5), same tiling as the int8 ones
-  int64_t bwd2_off, bwd2_bytes;  // v2 dgrad: bf16 digit tiles pre-scaled for the count fields of the v2 state
+  int64_t bwd2_off, bwd2_bytes;  // v2 dgrad: fp16 digit tiles 2^k * digit, columns in dgrad_col_f order (cim_v2.cuh)
   int64_t total;
 };
 WtLayout wt_layout(const Geo &g);
