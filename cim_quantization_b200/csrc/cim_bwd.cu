@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) bwd_alpha_partial_w4_kernel(Geo g, int m_
 // (32 / LPP pixels x Cout channels, LPP = Cout / 16 lanes per pixel; lane = (pixel, 16-channel group)).
 // ---------------------------------------------------------------------------------------------
 template <int NSW>
-__global__ void __launch_bounds__(256) bwd_alpha_v2_kernel(Geo g, int m_per_split, int cblock,
+__global__ void __launch_bounds__(256, 3) bwd_alpha_v2_kernel(Geo g, int m_per_split, int cblock,
                                                            const float *__restrict__ go,
                                                            const uint8_t *__restrict__ cplanes,
                                                            float *__restrict__ partial) {

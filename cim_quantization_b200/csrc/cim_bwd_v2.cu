@@ -39,7 +39,7 @@ constexpr int kDgRegsProducer = 128, kDgRegsEpilogue = 88, kDgRegsMma = 40;
 static_assert(2 * kDgRegsProducer + 2 * kDgRegsEpilogue + kDgRegsMma <= 5 * 96, "setmaxnreg split exceeds the launch allocation");
 constexpr int kDgMaxStages = 4;
 constexpr size_t kDgSmemBudget = 227 * 1024 - 1024;
-constexpr int kTupStride = 44;  // tuple table entries per chunk (128 / 3 rounded up)
+constexpr int kTupStride = 48;  // tuple table entries per chunk: two runs of 24 (even / odd tuples, one per epilogue warp of a quarter)
 
 struct DgParams {
   Geo g;
@@ -76,8 +76,7 @@ __device__ __forceinline__ void red_add_pred(float *addr, float v, uint32_t pred
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.u32 p, %2, 0;\n\t"
       "@p red.global.add.f32 [%0], %1;\n\t}"
-      ::"l"(addr), "f"(v), "r"(pred)
-      : "memory");
+      ::"l"(addr), "f"(v), "r"(pred));  // (no "memory" clobber: nothing in this kernel reads grad_x back)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -122,7 +121,7 @@ struct DgSmem {
   uint32_t full0, empty0, tfull0, tempty0;
   uint32_t *tmem_slot;
   int *ftab;  // [F]: fold entry of unfold row f: offset inside the image << 7 | kx << 5 | tap
-  int *tup;   // [NX][kTupStride]: complete tuple tt of chunk i: ((ci * H + ky) * W) << 2 | ky
+  int *tup;   // [NX][2][24]: complete tuple tt = 2v + eh of chunk i at [i][eh][v]: ((ci * H + ky) * W) << 2 | ky
 };
 
 // NS: digit planes per operand; CPT: channels per producer thread (Kc / 2)
@@ -165,14 +164,15 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
     sm.ftab[f] = (((ci * g.H + ky) * g.W + kx) << 7) | (kx << 5) | tap;
   }
   for (int e = threadIdx.x; e < g.NX * kTupStride; e += kDgThreads) {
-    const int i = e / kTupStride, tt = e % kTupStride;
+    const int i = e / kTupStride, eh = (e % kTupStride) / 24, v = e % 24;
     const DgradCols dc = dgrad_cols(g, i);
-    int v = 0;
+    const int tt = 2 * v + eh;
+    int val = 3;  // "no such tuple": kernel row 3 never passes the row-validity test
     if (tt < dc.ntup) {
       const int t = dc.t0 + tt, ci = t / g.K, ky = t % g.K;
-      v = (((ci * g.H + ky) * g.W) << 2) | ky;
+      val = (((ci * g.H + ky) * g.W) << 2) | ky;
     }
-    sm.tup[e] = v;
+    sm.tup[e] = val;
   }
   if (warp == kDgMmaWarp) tmem_alloc(smem_u32(sm.tmem_slot), P.tmem_cols);
   tc_fence_before();
@@ -327,6 +327,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
       const int eb = live ? (int)(m / g.L) : 0, el = live ? (int)(m % g.L) : 0;
       const int oy = el / g.OW, ox = el % g.OW;
       const float scale = live ? sw_ns * bwd_scale_inverse(__ldg(P.rowscale + m)) : 0.0f;
+      // scales of the horizontally adjacent pixels (zero where the neighbour is in another image row)
+      const float sc_r = __shfl_down_sync(0xffffffffu, scale, 1) * mr, sc_l = __shfl_up_sync(0xffffffffu, scale, 1) * ml;
       // fold: taps of this pixel that land inside the image, and the address of tap (0, 0) of channel 0
       const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
       uint32_t vm = 0, vy = 0;
@@ -343,11 +345,13 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
         const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
         const DgradCols dc = dgrad_cols(g, i);
         const int ntup = P.fast ? dc.ntup : 0;
-        const int *tup = sm.tup + i * kTupStride;
+        const int *tup = sm.tup + i * kTupStride + eh * 24;
         mbar_wait(sm.tfull0 + 8 * buf, buse & 1);
         tc_fence_after();
         const uint32_t tcol = lane_base + buf * Nf;
-        // ---- complete kernel rows: both warps of the quarter read the batch, each folds every other tuple
+        // ---- complete kernel rows: both warps of the quarter read the batch, each folds every other tuple.  Written
+        // in phases (table entries, tensor-memory loads, all shuffles, all reductions) so that the latencies overlap:
+        // shuffles and reductions are ordered among themselves and would otherwise alternate.
         for (int t0 = 0; t0 < ntup; t0 += 16) {
           // warp eh reads from column 3 * (t0 + eh) on: its tuples t0 + eh + 2u then sit at the static local columns 6u
           // (reads may run past the accumulator into allocated, unused tensor memory: see tmem_cols on the host side)
@@ -356,22 +360,20 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
           tmem_ld<16>(tcol + c0, va);
           if (c0 + 16 < cend) tmem_ld<16>(tcol + c0 + 16, vb);
           if (c0 + 32 < cend) tmem_ld<16>(tcol + c0 + 32, vc);
+          const int4 e0 = *reinterpret_cast<const int4 *>(tup + (t0 >> 1)), e1 = *reinterpret_cast<const int4 *>(tup + (t0 >> 1) + 4);
+          const int ent[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
           tmem_ld_wait();
+          float sum[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int tt = t0 + 2 * u + eh;
-            if (tt < ntup) {  // warp-uniform
-              auto col = [&](int c) { return __int_as_float(c < 16 ? va[c & 15] : (c < 32 ? vb[c & 15] : vc[c & 15])); };
-              // (scaled before the shuffles: every pixel row has its own power-of-two scale)
-              const float d0 = col(6 * u) * scale, d1 = col(6 * u + 1) * scale, d2 = col(6 * u + 2) * scale;
-              // tap kx of pixel ox lands on column ox - 1 + kx: column ox collects tap 0 of its right neighbour,
-              // its own tap 1 and tap 2 of its left neighbour
-              const float fr = __shfl_down_sync(0xffffffffu, d0, 1), fl = __shfl_up_sync(0xffffffffu, d2, 1);
-              const float sum = fmaf(fr, mr, fmaf(fl, ml, d1));
-              const int ent = tup[tt];
-              red_add_pred(gxc + (ent >> 2), sum, (vy >> (ent & 3)) & 1u);
-            }
+            auto col = [&](int c) { return __int_as_float(c < 16 ? va[c & 15] : (c < 32 ? vb[c & 15] : vc[c & 15])); };
+            // tap kx of pixel ox lands on column ox - 1 + kx: column ox collects tap 0 of its right neighbour, its own
+            // tap 1 and tap 2 of its left neighbour, each with the power-of-two scale of the row it comes from
+            const float fr = __shfl_down_sync(0xffffffffu, col(6 * u), 1), fl = __shfl_up_sync(0xffffffffu, col(6 * u + 2), 1);
+            sum[u] = fmaf(fr, sc_r, fmaf(fl, sc_l, col(6 * u + 1) * scale));
           }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) red_add_pred(gxc + (ent[u] >> 2), sum[u], (vy >> (ent[u] & 3)) & 1u);
         }
         // ---- everything else, one unfolded element at a time: columns [3 * ntup, rows), split between the two warps
         const int c_begin = 3 * ntup;
