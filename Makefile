@@ -1,7 +1,7 @@
 # Builds libcimq.so (the C-ABI CUDA library) in-tree for sm_100a.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall -Xptxas -v $(if $(TIMERS),-DCIMQ_TIMERS=1)
+NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall -Xptxas -v $(if $(TIMERS),-DCIMQ_TIMERS=1) $(EXTRA)
 SRC_DIR   := cim_quantization_b200/csrc
 SRCS      := $(wildcard $(SRC_DIR)/*.cu)
 OBJS      := $(SRCS:.cu=.o)

@@ -16,6 +16,7 @@
 //          accumulated over all pixel tiles of the CTA in TMEM, one partial [F x Cout] per CTA
 //
 // Warp roles (16 warps): 0-7 producers, 8-11 epilogue (one per TMEM lane quarter), 12 MMA issuer.
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -72,6 +73,7 @@ struct BwdParams {
   long long *debug;  // per-role cycle counters (builds with TIMERS=1 only)
   int cached;   // dgrad: 1 = producers keep grad_out of the tile and the state words of the chunk in registers
   uint32_t pw_off;  // dgrad: byte offset of the pass-weight table inside the raw region
+  int dbg;   // development only (env CIMQ_V2_DBG, wgrad v2): 1 = no MMAs, 2 = no X stores, 4 = no G' stores, 8 = no X gather
   int fold;  // dgrad: 1 = the epilogue folds (col2im) straight into grad_x with fp32 reductions; 0 = writes gxu[b][f][l]
   int v2;    // 1 = `state` holds the v2 byte planes (cim_v2.cuh): D [NX][M][Cout] for dgrad, W for wgrad
   const uint8_t *state2, *state2w;
@@ -668,9 +670,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
     long long d_stage = 0, d_wait = 0, d_x = 0, d_g = 0;
     // X tile items (crossbar row fr, 8-pixel group pg = x_pg0 + x_step * q, q < XI) of this thread
-    // v2: threads [0, n_g) build G' (one 4-channel x 8-pixel item = 32 elements, ~250 instructions per stage); an X
-    // item costs ~20, so with n_g = 256 the G' threads also take ONE X item each (pixel groups 14, 15) and the other
-    // 128 threads fourteen (groups 0..13); with fewer G' threads the 256 threads after them take eight X items each.
+    // v2: threads [0, n_g) build G' (one 4-channel x 8-pixel item = 32 elements); with n_g = 256 the G' threads also
+    // take ONE X item each (pixel groups 14, 15) and the other 128 threads fourteen (groups 0..13) -- measured: giving
+    // the G' threads three X items each costs 10 %, they are the critical path; with fewer G' threads the 256 threads
+    // after them take eight X items each.
     constexpr int XI = V2 ? 14 : 6;
     const int n_g = V2 ? 4 * Kc : 0;
     int fr, x_pg0, x_step, x_cnt;
@@ -688,6 +691,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     const int slot_bytes = P.rk * pitch;
     const int HW = g.H * g.W;
     uint32_t it = 0, chunk_it = 0;
+    int p_sidx = 0;
+    uint32_t p_phase = 0;
     int tpar = 0;
     // ---- G' operands kept in registers (Cout <= 72: at most three (channel, 8-pixel group) items per thread, clip
     // bits in one state word): grad_out of the tile is reused by all chunks and planes, the state words of a chunk
@@ -750,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
       const int lo_ = i_ * g.xbar, rows_ = min(rows_full, g.F - lo_);
       const int c_lo_ = lo_ / g.KK, nch_ = (lo_ + rows_ - 1) / g.KK - c_lo_ + 1;
       const int cpr = g.W >> 4, total = nch_ * P.rk * cpr;
-      for (int q = tid; q < total; q += kWgProducerThreads) {
+      for (int q = tid; q < total && !(P.dbg & 16); q += kWgProducerThreads) {
         const int rq = q / cpr, c16 = q - rq * cpr;
         const int sl = rq / P.rk, row = rq - sl * P.rk;
         const int off = tab[row];
@@ -793,6 +798,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     float chs[4] = {1.0f, 1.0f, 1.0f, 1.0f};
     auto v2_group_m = [&](int mt_) { return min((int64_t)mt_ * kTcTileM + gpg2 * 8, (int64_t)g.M - 8); };
     auto v2_load_go = [&](int mt_, int c) {
+      if (P.dbg & 32) return;
       const int64_t m = v2_group_m(mt_);
       const int b = (int)(m / g.L), l = (int)(m % g.L);
       const float4 *gp = reinterpret_cast<const float4 *>(P.go + ((int64_t)b * g.Cout + P.co0 + 4 * gq2 + c) * g.L + l);
@@ -801,6 +807,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
       gs2[c][4] = g1.x; gs2[c][5] = g1.y; gs2[c][6] = g1.z; gs2[c][7] = g1.w;
     };
     auto v2_load_w = [&](int mt_, int i_) {
+      if (P.dbg & 32) return;
       const uint8_t *wp = P.state2w + ((int64_t)i_ * g.M + v2_group_m(mt_)) * g.Cout + P.co0 + 4 * gq2;
 #pragma unroll
       for (int e = 0; e < 8; ++e) wnx2[e] = __ldg(reinterpret_cast<const uint32_t *>(wp + (int64_t)e * g.Cout));
@@ -825,7 +832,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
       const int64_t m0 = (int64_t)mt * kTcTileM;
       if constexpr (V2) {
-        if (g_thread) {  // this tile's grad_out (loaded during the previous tile's last stage) -> scaled fp16 pieces
+        if (g_thread && !(P.dbg & 32)) {  // this tile's grad_out (loaded during the previous tile's last stage) -> scaled fp16 pieces
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -923,7 +930,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         // per chunk: the NSA digit planes below only shift and mask them
         uint32_t xlo[XI], xhi[XI];
         const bool xfast = V2 && P.fastx;  // (v2 layers have 1-bit digits)
-        if (xfast) {
+        if (xfast && !(P.dbg & 8)) {
           const uint8_t *src_row = raw + (size_t)(ci - c_lo) * slot_bytes + ((size_t)ky << P.pitch_log2) + kx + P.col0;
           const int rps = P.pitch_log2 + (P.prow == 1 ? 0 : (g.K == 1 ? 0 : -1));  // row pitch shift (see below)
           (void)rps;
@@ -991,8 +998,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
             for (int q = 0; q < 4; ++q) wsp[c][q] = __byte_perm(wnx2[2 * q], wnx2[2 * q + 1], c | ((4 + c) << 8));
         }
         for (int j = 0; j < NSA; ++j, ++it) {
-          const int sidx = it % P.stages;
-          const uint32_t use = it / P.stages;
+          // (stage index and phase as running counters: `it % stages` is a division by a run-time value)
+          const int sidx = p_sidx;
+          const uint32_t use = p_phase;
+          if (++p_sidx == P.stages) { p_sidx = 0; p_phase ^= 1u; }
           const long long tw0 = CIMQ_TB();
           mbar_wait(cv.empty0 + 8 * sidx, (use & 1) ^ 1);
           const long long tw1 = CIMQ_TB();
@@ -1003,7 +1012,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           // v2: fp16 operands (the G' pieces are fp16); the digit carries the slice weight 2^j (mask[k][j] * 2^(-wbs*k)
           // = 2^j for 1-bit slices, lsq.py:306, 363-364), the pass COUNT of plane W multiplies grad_out
           const uint32_t one_bf = V2 ? 0x3C00u + ((uint32_t)j << 10) : 0x3F80u;
-          if (xfast) {
+          if (xfast && !(P.dbg & 2)) {
             uint8_t *dst = st_ptr + tc_tile_offset16(fr, x_pg0 * 8, kTcLBO, a_sbo);
             const uint32_t cmul = one_bf >> sh;  // the 16-bit pattern of 1.0 divided by the bit weight of the digit
             if (x_cnt == 14) x_store_fast<14, 1, XI>(dst, xlo, xhi, sh, cmul);
@@ -1058,6 +1067,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
               const __half2 ok = __float2half2_rn(-1024.0f / (float)(1 << (2 * j)));
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
+                if (P.dbg & 4) break;
                 uint32_t a1[4], a2[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -1203,6 +1213,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
       const uint32_t idesc = V2 ? idesc_f16_f32(128, Kc) : idesc_bf16_f32(128, Kc);
       constexpr int kPieces = V2 ? v2::kBwdPieces : 3;  // terms of the real-valued operand
       uint32_t it = 0;
+      int m_sidx = 0;
+      uint32_t m_phase = 0;
       bool first_tile = true;
       const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
       long long d_full = 0;
@@ -1211,16 +1223,17 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         for (int i = i_begin; i < i_end; ++i) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(i - i_begin) * Kc;
           for (int j = 0; j < NSA; ++j, ++it) {
-            const int sidx = it % P.stages;
-            const uint32_t use = it / P.stages;
+            const int sidx = m_sidx;
+            const uint32_t use = m_phase;
+            if (++m_sidx == P.stages) { m_sidx = 0; m_phase ^= 1u; }
             const long long tf0 = CIMQ_TB();
-            mbar_wait<400>(cv.full0 + 8 * sidx, use & 1);
+            mbar_wait<CIMQ_MMA_SLEEP>(cv.full0 + 8 * sidx, use & 1);
             d_full += CIMQ_TB() - tf0;
             tc_fence_after();
             const uint32_t a0 = smem_u32(cv.stage_base + (size_t)sidx * P.stage_bytes);
             const uint32_t b0 = a0 + P.a_bytes;
             for (int sp = 0; sp < kPieces; ++sp)
-              for (int ks = 0; ks < 8; ++ks) {  // 128 pixels = 8 x K16
+              for (int ks = 0; ks < 8 && !(P.dbg & 1); ++ks) {  // 128 pixels = 8 x K16
                 const uint64_t adesc = make_smem_desc(a0 + ks * 2 * kTcLBO, kTcLBO, a_sbo);
                 const uint64_t bdesc = make_smem_desc(b0 + sp * P.b_bytes + ks * 2 * kWgLBO, kWgLBO, b_sbo);
                 umma_f16(d_tmem, adesc, bdesc, idesc, (first_tile && j == 0 && sp == 0 && ks == 0) ? 0u : 1u);
@@ -1564,6 +1577,7 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
   P.go = go; P.state = state; P.xcodes = xcodes; P.s = s; P.mask = mask; P.out = partial;
   const size_t smem = (size_t)stages * P.stage_bytes + kBarrierBytes + 2 * (size_t)P.raw_bytes + 1024;
   dim3 grid(ctas, groups);
+  if (const char *e = getenv("CIMQ_V2_DBG")) P.dbg = v2 ? atoi(e) : 0;
 #define CIMQ_LAUNCH_WGRAD(W, A, T, ...)                                        \
   do {                                                                         \
     if (launch_wgrad_instance<W, A, T>(P, grid, smem, st)) return 1;            \

@@ -17,7 +17,12 @@
 //         the three taps of a kernel row land on horizontally adjacent pixels = adjacent lanes, so a tuple is combined
 //         with two shuffles and leaves as ONE fp32 reduction per pixel (lanes = consecutive addresses; grad_x stays in
 //         L2 while it is accumulated).  Other geometries: one predicated reduction per unfolded element.
-//   16    MMA issuer (tcgen05.mma.kind::f16, fp32 accumulators, two TMEM buffers).
+//   16    MMA issuer (tcgen05.mma.kind::f16, fp32 accumulators, up to three TMEM buffers); 17: bulk-copy loader of the D bytes.
+// Measured dead ends (B200, microbench layer, kept out of the code): 16-byte vector reductions after a 4x4 lane transpose
+// (same time), staging the folded sums in shared memory and reducing through cp.reduce.async.bulk (+25 %), and a vertical
+// fold in shared memory that halves the number of reductions (+35 %: the extra barrier and one pipeline stage less cost
+// more than the reductions saved).
+#include <stdlib.h>
 #include <string.h>
 
 #include "cim_tc_layout.cuh"
@@ -44,11 +49,16 @@ constexpr int kTupStride = 48;  // tuple table entries per chunk: two runs of 24
 struct DgParams {
   Geo g;
   int Kc, Nf, mtiles, stages;
+  int nbuf;  // accumulator buffers in tensor memory (2..4)
   uint32_t a_bytes, b_bytes, stage_bytes, tmem_cols;
   uint32_t aux_off, ftab_off, tup_off;  // byte offsets inside the dynamic shared memory
   int co0;
   int fold;  // 1: fold into grad_x with fp32 reductions; 0: write gxu[b][f][l] (deterministic path, then col2im)
   int fast;  // fold in registers (3x3, stride 1, pad 1, output width 8 / 16 / 32)
+  int dbulk; // the D bytes of a (tile, chunk) are one contiguous run (Cout == Kc): a loader thread brings them to shared
+             // memory by bulk copy, so that no global load of the producers is in flight at their proxy fences
+  uint32_t dbuf_off;
+  int dbg;   // development only (env CIMQ_V2_DBG): 1 = no MMAs, 2 = epilogue drains nothing, 4 = producers store nothing, 8 = no weight-tile copies, 16 = no grad_out loads / split
   const uint8_t *stateD;
   const float *go, *rowscale, *s;
   const uint8_t *wtb;
@@ -89,25 +99,43 @@ __global__ void __launch_bounds__(256) go_scales_kernel(Geo g, const float *__re
   for (int c = threadIdx.x; c < g.Cout; c += 256) sm_ch[c] = 0u;
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  // channel maxima stay in registers: lane l of a warp keeps the running maximum of channels c = l (mod 32)
+  constexpr int kCB = 16;  // 32-channel blocks (Cout <= 512)
+  uint32_t chreg[kCB];
+#pragma unroll
+  for (int cb = 0; cb < kCB; ++cb) chreg[cb] = 0u;
   for (int m0 = blockIdx.x * 256; m0 < g.M; m0 += gridDim.x * 256) {
     const int m = m0 + threadIdx.x;
     const bool live = m < g.M;
     const int b = live ? m / g.L : 0, l = live ? m % g.L : 0;
     const float *gp = go + (int64_t)b * g.Cout * g.L + l;
     uint32_t rm = 0u;
-    for (int c0 = 0; c0 < g.Cout; c0 += 8) {  // Cout % 16 == 0
-      uint32_t v[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = live ? (__float_as_uint(__ldg(gp + (int64_t)(c0 + e) * g.L)) & 0x7fffffffu) : 0u;
+    for (int cb = 0; cb < kCB; ++cb) {
+      if (cb * 32 < g.Cout) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        rm = max(rm, v[e]);
-        const uint32_t w = __reduce_max_sync(0xffffffffu, v[e]);
-        if (lane == 0 && w > sm_ch[c0 + e]) atomicMax(&sm_ch[c0 + e], w);
+        for (int c8 = 0; c8 < 32; c8 += 8) {
+          const int c0 = cb * 32 + c8;
+          if (c0 < g.Cout) {  // Cout % 8 == 0
+            uint32_t v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              v[e] = live ? (__float_as_uint(__ldg(gp + (int64_t)(c0 + e) * g.L)) & 0x7fffffffu) : 0u;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              rm = max(rm, v[e]);
+              const uint32_t w = __reduce_max_sync(0xffffffffu, v[e]);
+              if (lane == c8 + e) chreg[cb] = max(chreg[cb], w);
+            }
+          }
+        }
       }
     }
     if (live) rowscale[m] = bwd_scale_from_maxbits(rm);
   }
+#pragma unroll
+  for (int cb = 0; cb < kCB; ++cb)
+    if (cb * 32 + lane < g.Cout && chreg[cb] != 0u) atomicMax(&sm_ch[cb * 32 + lane], chreg[cb]);
   __syncthreads();
   for (int c = threadIdx.x; c < g.Cout; c += 256)
     if (sm_ch[c] != 0u) atomicMax(&chmax[c], sm_ch[c]);
@@ -118,8 +146,9 @@ __global__ void __launch_bounds__(256) go_scales_kernel(Geo g, const float *__re
 // ---------------------------------------------------------------------------------------------------------------
 struct DgSmem {
   uint8_t *stage_base;
-  uint32_t full0, empty0, tfull0, tempty0;
+  uint32_t full0, empty0, tfull0, tempty0, dfull0, dempty0;
   uint32_t *tmem_slot;
+  uint8_t *dbuf;  // [2][128 * Kc] D bytes of the current / next chunk (dbulk)
   int *ftab;  // [F]: fold entry of unfold row f: offset inside the image << 7 | kx << 5 | tap
   int *tup;   // [NX][2][24]: complete tuple tt = 2v + eh of chunk i at [i][eh][v]: ((ci * H + ky) * W) << 2 | ky
 };
@@ -139,8 +168,11 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
     sm.full0 = smem_u32(aux);
     sm.empty0 = sm.full0 + 8 * kDgMaxStages;
     sm.tfull0 = sm.empty0 + 8 * kDgMaxStages;
-    sm.tempty0 = sm.tfull0 + 16;
-    sm.tmem_slot = reinterpret_cast<uint32_t *>(aux + 112);
+    sm.tempty0 = sm.tfull0 + 32;
+    sm.dfull0 = sm.tempty0 + 32;
+    sm.dempty0 = sm.dfull0 + 16;  // ends at byte 160
+    sm.tmem_slot = reinterpret_cast<uint32_t *>(aux + 160);
+    sm.dbuf = smem_raw + P.dbuf_off;
     sm.ftab = reinterpret_cast<int *>(smem_raw + P.ftab_off);
     sm.tup = reinterpret_cast<int *>(smem_raw + P.tup_off);
   }
@@ -150,12 +182,16 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
 
   if (threadIdx.x == 0) {
     for (int sidx = 0; sidx < P.stages; ++sidx) {
-      mbar_init(sm.full0 + 8 * sidx, kDgProducerThreads + 1);
+      mbar_init(sm.full0 + 8 * sidx, kDgProducerThreads / 32 + 1);  // one arrival per producer warp + the weight-tile copy
       mbar_init(sm.empty0 + 8 * sidx, 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(sm.tfull0 + 8 * b, 1);
       mbar_init(sm.tempty0 + 8 * b, kDgEpiWarps);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sm.dfull0 + 8 * b, 1);
+      mbar_init(sm.dempty0 + 8 * b, kDgProducerThreads / 32);
     }
     fence_barrier_init();
   }
@@ -222,35 +258,62 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
     if ((int)blockIdx.x < P.mtiles) {
       tile_ptrs(blockIdx.x, gop, dp, rsp);
       load_go(gop, rsp);
-      load_d(dp, 0);
+      if (!P.dbulk) load_d(dp, 0);
     }
-    uint32_t it = 0;
+    uint32_t chunk_it = 0;
+    int p_sidx = 0;       // pipeline stage and its phase as running counters
+    uint32_t p_phase = 0;
     for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
       const int nmt = mt + gridDim.x;
       const bool more_tiles = nmt < P.mtiles;
       if (more_tiles) tile_ptrs(nmt, gop_n, dp_n, rsp_n);
       // grad_out of the tile -> scaled fp16 pieces (once per tile)
+      if (!(P.dbg & 16)) {
 #pragma unroll
-      for (int q = 0; q < NPAIR; ++q) split_pieces<PB>(gnx[2 * q] * rs_n, gnx[2 * q + 1] * rs_n, p1[q], p2[q]);
-      for (int i = 0; i < g.NX; ++i) {
+        for (int q = 0; q < NPAIR; ++q) split_pieces<PB>(gnx[2 * q] * rs_n, gnx[2 * q + 1] * rs_n, p1[q], p2[q]);
+      }
+      for (int i = 0; i < g.NX; ++i, ++chunk_it) {
+        if (P.dbulk) {  // this chunk's D bytes were brought to shared memory by the loader thread
+          const uint32_t db = chunk_it & 1;
+          mbar_wait(sm.dfull0 + 8 * db, (chunk_it >> 1) & 1);
+          const uint8_t *src = sm.dbuf + (size_t)db * (kTcTileM * Kc) + r * Kc + h * CPT;
+          if constexpr (NW == 8) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(src), b4 = *reinterpret_cast<const uint4 *>(src + 16);
+            dnx[0] = a.x; dnx[1] = a.y; dnx[2] = a.z; dnx[3] = a.w; dnx[4] = b4.x; dnx[5] = b4.y; dnx[6] = b4.z; dnx[7] = b4.w;
+          } else if constexpr (NW == 4) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(src);
+            dnx[0] = a.x; dnx[1] = a.y; dnx[2] = a.z; dnx[3] = a.w;
+          } else {
+            const uint2 a = *reinterpret_cast<const uint2 *>(src);
+            dnx[0] = a.x; dnx[1] = a.y;
+          }
+        }
         // D bytes of two adjacent channels spread to the two halves of a register: [b(c), 0, b(c+1), 0]
 #pragma unroll
         for (int q = 0; q < NPAIR; ++q) sp[q] = __byte_perm(dnx[q >> 1], 0u, (q & 1) ? 0x4342 : 0x4140);
+        if (P.dbulk) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sm.dempty0 + 8 * (chunk_it & 1));
+        }
 #pragma unroll
-        for (int k = 0; k < NS; ++k, ++it) {
-          const int sidx = it % P.stages;
-          const uint32_t use = it / P.stages;
-          if (k == NS - 1) {  // the D bytes of the next chunk (or of the next tile's first chunk) start their trip now
+        for (int k = 0; k < NS; ++k) {
+          const int sidx = p_sidx;
+          const uint32_t use = p_phase;
+          if (++p_sidx == P.stages) { p_sidx = 0; p_phase ^= 1u; }
+          if (k == NS - 1 && !P.dbulk) {  // the D bytes of the next chunk (or of the next tile's first chunk) start their trip
             if (i + 1 < g.NX) load_d(dp, i + 1);
             else if (more_tiles) load_d(dp_n, 0);
           }
-          if (k == 0 && i + 1 == g.NX && more_tiles) load_go(gop_n, rsp_n);  // next tile's grad_out: a chunk ahead
+          if (k == 0 && i + 1 == g.NX && more_tiles && !(P.dbg & 16)) load_go(gop_n, rsp_n);  // next tile's grad_out: a chunk ahead
           mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
           uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
           if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
-            bulk_copy_g2s(smem_u32(st_ptr + kBwdPieces * (size_t)P.a_bytes), P.wtb + (size_t)(i * NS + k) * P.b_bytes,
-                          P.b_bytes, sm.full0 + 8 * sidx);
+            if (P.dbg & 8) mbar_arrive(sm.full0 + 8 * sidx);
+            else {
+              mbar_arrive_expect_tx(sm.full0 + 8 * sidx, P.b_bytes);
+              bulk_copy_g2s(smem_u32(st_ptr + kBwdPieces * (size_t)P.a_bytes), P.wtb + (size_t)(i * NS + k) * P.b_bytes,
+                            P.b_bytes, sm.full0 + 8 * sidx);
+            }
           }
           // count field k of both bytes -> fp16x2 (1024 + cnt * 4^k) -> cnt
           const uint32_t fmask = 0x00030003u << (2 * k);
@@ -258,6 +321,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
           const __half2 ok = __float2half2_rn(-1024.0f / (float)(1 << (2 * k)));
 #pragma unroll
           for (int cg8 = 0; cg8 < CPT / 8; ++cg8) {
+            if (P.dbg & 4) break;
             uint32_t a1[4], a2[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -270,8 +334,9 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
             *reinterpret_cast<uint4 *>(st_ptr + off) = make_uint4(a1[0], a1[1], a1[2], a1[3]);
             *reinterpret_cast<uint4 *>(st_ptr + P.a_bytes + off) = make_uint4(a2[0], a2[1], a2[2], a2[3]);
           }
-          fence_proxy_async();
-          mbar_arrive(sm.full0 + 8 * sidx);
+          fence_proxy_async();  // every thread publishes its own stores to the async proxy, then one arrival per warp
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sm.full0 + 8 * sidx);
         }
       }
       gop = gop_n; dp = dp_n; rsp = rsp_n;
@@ -282,23 +347,27 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
       // =========================== MMA issuer ===========================
       const uint32_t idesc = idesc_f16_f32(kTcTileM, Nf);
       const int ksteps = Kc >> 4;
-      uint32_t it = 0, acc_it = 0;
+      uint32_t a_buf = 0, a_use = 0;  // accumulator buffer and how often it has been used
+      int m_sidx = 0;
+      uint32_t m_phase = 0;
       for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
-        for (int i = 0; i < g.NX; ++i, ++acc_it) {
-          const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
-          mbar_wait<200>(sm.tempty0 + 8 * buf, (buse & 1) ^ 1);
+        for (int i = 0; i < g.NX; ++i) {
+          const uint32_t buf = a_buf, buse = a_use;
+          if (++a_buf == (uint32_t)P.nbuf) { a_buf = 0; ++a_use; }
+          mbar_wait<CIMQ_MMA_SLEEP>(sm.tempty0 + 8 * buf, (buse & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * Nf;
-          for (int k = 0; k < NS; ++k, ++it) {
-            const int sidx = it % P.stages;
-            const uint32_t use = it / P.stages;
-            mbar_wait<200>(sm.full0 + 8 * sidx, use & 1);
+          for (int k = 0; k < NS; ++k) {
+            const int sidx = m_sidx;
+            const uint32_t use = m_phase;
+            if (++m_sidx == P.stages) { m_sidx = 0; m_phase ^= 1u; }
+            mbar_wait<CIMQ_MMA_SLEEP>(sm.full0 + 8 * sidx, use & 1);
             tc_fence_after();
             const uint32_t a0 = smem_u32(sm.stage_base + (size_t)sidx * P.stage_bytes);
             const uint32_t b0 = a0 + kBwdPieces * P.a_bytes;
 #pragma unroll
             for (int pc = 0; pc < kBwdPieces; ++pc)
-              for (int ks = 0; ks < ksteps; ++ks) {
+              for (int ks = 0; ks < ksteps && !(P.dbg & 1); ++ks) {
                 const uint64_t adesc = make_smem_desc(a0 + pc * P.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
                 const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
                 umma_f16(d_tmem, adesc, bdesc, idesc, (k | pc | ks) != 0 ? 1u : 0u);
@@ -306,6 +375,21 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
             umma_commit(sm.empty0 + 8 * sidx);
           }
           umma_commit(sm.tfull0 + 8 * buf);
+        }
+      }
+    }
+    else if (warp == kDgMmaWarp + 1 && lane == 0 && P.dbulk) {
+      // =========================== D-byte loader ===========================
+      uint32_t chunk_it = 0;
+      for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
+        const int64_t m0 = (int64_t)mt * kTcTileM;
+        const uint32_t bytes = (uint32_t)(min((int64_t)kTcTileM, g.M - m0) * Kc);
+        for (int i = 0; i < g.NX; ++i, ++chunk_it) {
+          const uint32_t db = chunk_it & 1;
+          mbar_wait<100>(sm.dempty0 + 8 * db, ((chunk_it >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(sm.dfull0 + 8 * db, bytes);
+          bulk_copy_g2s(smem_u32(sm.dbuf + (size_t)db * (kTcTileM * Kc)), P.stateD + ((int64_t)i * g.M + m0) * g.Cout,
+                        bytes, sm.dfull0 + 8 * db);
         }
       }
     }
@@ -320,7 +404,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
     // fast fold: lanes are consecutive pixels of image rows; neighbours inside the row take part in the shuffles
     const int oxl = lane & (g.OW - 1);
     const float ml = (P.fast && oxl >= 1) ? 1.0f : 0.0f, mr = (P.fast && oxl + 1 < g.OW) ? 1.0f : 0.0f;
-    uint32_t acc_it = 0;
+    uint32_t a_buf = 0, a_use = 0;
     for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
       const int64_t m = (int64_t)mt * kTcTileM + r;
       const bool live = m < g.M;
@@ -341,10 +425,11 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
       }
       float *gxp = P.out + ((int64_t)eb * g.Cin * g.H + iy0) * g.W + ix0;  // generic: + (ci*H + ky)*W + kx
       float *gxc = gxp + g.pad;                                             // fast: + (ci*H + ky)*W, column ox
-      for (int i = 0; i < g.NX; ++i, ++acc_it) {
-        const uint32_t buf = acc_it & 1, buse = acc_it >> 1;
+      for (int i = 0; i < g.NX; ++i) {
+        const uint32_t buf = a_buf, buse = a_use;
+        if (++a_buf == (uint32_t)P.nbuf) { a_buf = 0; ++a_use; }
         const DgradCols dc = dgrad_cols(g, i);
-        const int ntup = P.fast ? dc.ntup : 0;
+        const int ntup = (P.dbg & 2) ? 0 : (P.fast ? dc.ntup : 0);
         const int *tup = sm.tup + i * kTupStride + eh * 24;
         mbar_wait(sm.tfull0 + 8 * buf, buse & 1);
         tc_fence_after();
@@ -377,7 +462,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
         }
         // ---- everything else, one unfolded element at a time: columns [3 * ntup, rows), split between the two warps
         const int c_begin = 3 * ntup;
-        for (int c0 = c_begin + 16 * eh; c0 < dc.rows; c0 += 32) {
+        for (int c0 = c_begin + 16 * eh; c0 < dc.rows && !(P.dbg & 2); c0 += 32) {
           int v[16];
           tmem_ld<16>(tcol + min(c0, Nf - 16), v);  // (the last batch may be shifted back to stay inside the buffer)
           tmem_ld_wait();
@@ -491,25 +576,33 @@ int launch_bwd_input_v2(const Geo &g, const float *go, const uint8_t *state, con
   P.b_bytes = (uint32_t)(P.Nf * P.Kc * 2);
   P.stage_bytes = kBwdPieces * P.a_bytes + P.b_bytes;
   P.fold = fold;
-  P.fast = (fold && g.K == 3 && g.stride == 1 && g.pad == 1 && (g.OW == 8 || g.OW == 16 || g.OW == 32)) ? 1 : 0;
+  P.fast = (fold && g.K == 3 && g.stride == 1 && g.pad == 1 && (g.OW == 8 || g.OW == 16 || g.OW == 32) &&
+            (g.L % kTcTileM == 0 || 2 * g.L == kTcTileM)) ? 1 : 0;  // a tile is rows of one image, or two whole images
   const size_t ftab_bytes = ((size_t)g.F * 4 + 15) & ~(size_t)15;
   const size_t tup_bytes = (size_t)g.NX * kTupStride * 4;
-  const size_t fixed = 128 + ftab_bytes + tup_bytes;
+  P.dbulk = (g.Cout == P.Kc && (reinterpret_cast<uintptr_t>(state) & 15u) == 0) ? 1 : 0;
+  const size_t dbuf_bytes = P.dbulk ? 2 * (size_t)kTcTileM * P.Kc : 0;
+  const size_t fixed = 256 + ftab_bytes + tup_bytes + 16 + dbuf_bytes;
   CIMQ_REQUIRE(fixed + P.stage_bytes <= kDgSmemBudget, "dgrad (v2): tile does not fit shared memory");
   int stages = (int)((kDgSmemBudget - fixed) / P.stage_bytes);
   if (stages > kDgMaxStages) stages = kDgMaxStages;
   P.stages = stages;
   P.aux_off = (uint32_t)((size_t)stages * P.stage_bytes);
-  P.ftab_off = P.aux_off + 128;
+  P.ftab_off = P.aux_off + 256;
   P.tup_off = P.ftab_off + (uint32_t)ftab_bytes;
-  // two accumulator buffers; the fast fold reads up to 18 columns past the second one
+  P.dbuf_off = P.tup_off + (uint32_t)((tup_bytes + 15) & ~(size_t)15);
+  // as many accumulator buffers as fit (the epilogue's drain then hides behind the next chunks' MMAs); the fast fold
+  // reads up to 18 columns past the last one
+  P.nbuf = (512 - (P.fast ? 32 : 0)) / P.Nf;
+  if (P.nbuf > 4) P.nbuf = 4;
   uint32_t cols = 32;
-  while (cols < 2u * P.Nf + (P.fast ? 32u : 0u)) cols <<= 1;
+  while (cols < (uint32_t)(P.nbuf * P.Nf) + (P.fast ? 32u : 0u)) cols <<= 1;
   P.tmem_cols = cols;
   P.go = go; P.stateD = state; P.s = s; P.out = out;
   P.rowscale = reinterpret_cast<const float *>(scales);
   const size_t smem = (size_t)stages * P.stage_bytes + fixed + 1024;
   const int grid = P.mtiles < 148 ? P.mtiles : 148;
+  if (const char *e = getenv("CIMQ_V2_DBG")) P.dbg = atoi(e);
 #define CIMQ_LAUNCH_DG2(NS_, CPT_)                                                                                  \
   do {                                                                                                              \
     CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_input_v2_kernel<NS_, CPT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \

@@ -9,6 +9,9 @@
 namespace cimq {
 namespace ptx {
 
+#ifndef CIMQ_MMA_SLEEP
+#define CIMQ_MMA_SLEEP 200  // ns between polls of an MMA-issuing thread that waits for operands
+#endif
 constexpr uint32_t kSpinLimit = 1u << 22;  // a dead pipeline traps (after ~1 s) instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -29,18 +32,33 @@ template <int kSleepNs = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done, spins = 0;
   do {
+#ifndef CIMQ_WAIT_HINT
+#define CIMQ_WAIT_HINT 20000
+#endif
+#if CIMQ_WAIT_HINT > 0
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)  // suspend-time hint (ns): fewer spin iterations
+        : "r"(bar), "r"(parity), "r"((uint32_t)CIMQ_WAIT_HINT)  // suspend-time hint (ns): fewer spin iterations
         : "memory");
+#else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+#endif
     if (!done) {
       // back off: a waiting role must not eat the issue slots of the role it waits for
       ++spins;
+#ifndef CIMQ_NO_SLEEP
       if constexpr (kSleepNs > 0) __nanosleep(kSleepNs);
       else if (spins > 2) __nanosleep(spins < 32 ? 40 : 200);
+#endif
       if (spins > kSpinLimit) __trap();
     }
   } while (!done);
