@@ -568,6 +568,7 @@ inline BwdPlan make_plan(const Geo &g) {
   if (tc_backward_supported(g) && bwd_tc_partial_bytes(g) > wpart) wpart = bwd_tc_partial_bytes(g);
   p.off_apart = p.off_wpart + align(wpart);
   p.alpha_splits_v2 = (148 * 6 + g.NX * g.NSA - 1) / (g.NX * g.NSA) + 1;
+  if (alpha_v3_supported(g) && alpha_v3_blocks(g) > p.alpha_splits_v2) p.alpha_splits_v2 = alpha_v3_blocks(g);
   const int asmax = p.alpha_splits > p.alpha_splits_v2 ? p.alpha_splits : p.alpha_splits_v2;
   p.off_scales = p.off_apart + align((int64_t)asmax * table_entries(g) * 4);
   p.total = p.off_scales + (v2_backward_supported(g) ? align(bwd_v2_scales_bytes(g)) : 0);
@@ -599,7 +600,15 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
   if (v2s && (gxq != nullptr || gwq != nullptr)) {
     if (launch_go_scales(g, go, scales, st)) return 1;
   }
-  if (v2s && galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
+  if (v2s && galpha != nullptr && alpha_v3_supported(g)) {
+    const uint8_t *cplanes = state2 + 2 * v2::plane_bytes(g);
+    if (launch_alpha_v3(g, go, cplanes, apart, st)) return 1;
+    const double numel = (double)g.B * g.NX * g.NSW * g.NSA * g.L * g.Cout;
+    const int64_t n = table_entries(g);
+    bwd_alpha_finish_kernel<<<(int)((n + 31) / 32), 256, 0, st>>>(g, alpha_v3_blocks(g), (float)(1.0 / sqrt(numel)), mask, apart,
+                                                                  galpha);
+    CIMQ_CUDA_OK(cudaGetLastError());
+  } else if (v2s && galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
     const int cblock = g.Cout > 128 ? (g.Cout % 128 == 0 ? 128 : 64) : g.Cout;  // channels per block (Cout % 16 == 0)
     const int nq = cblock / 4, pb = 8 * (32 / nq) * 8;  // pixels per block-iteration
     CIMQ_REQUIRE(32 % nq == 0, "conv_backward: alpha kernel needs 4, 8, 16 or 32 channel quads per block");

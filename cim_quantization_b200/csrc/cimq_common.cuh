@@ -154,6 +154,10 @@ int launch_weight_tiles_bwd2(const Geo &g, const int8_t *wcodes, void *tiles, cu
 // uint32 chmax[Cout] (bit pattern of the largest |grad_out| of the channel); bwd_v2_scales_bytes() bytes
 int64_t bwd_v2_scales_bytes(const Geo &g);
 int launch_go_scales(const Geo &g, const float *go, void *scales, cudaStream_t st);
+// grad_alpha from plane C, staged through shared memory (cim_alpha_v2.cu); writes alpha_v3_blocks() partials
+bool alpha_v3_supported(const Geo &g);
+int alpha_v3_blocks(const Geo &g);
+int launch_alpha_v3(const Geo &g, const float *go, const uint8_t *cplanes, float *partial, cudaStream_t st);
 int launch_bwd_input_v2(const Geo &g, const float *go, const uint8_t *state, const void *wtb, const float *s,
                         const void *scales, float *out, int fold, cudaStream_t st);
 
