@@ -156,8 +156,8 @@ int alpha_v3_blocks(const Geo &g) {
   const int ntiles = g.M / P;
   const int groups = (g.NX + v2::kAlphaMaxNXG - 1) / v2::kAlphaMaxNXG;
   int bx = 148 * 4 / groups;
-  if (bx < 1) bx = 1;
-  if (bx > ntiles) bx = ntiles;
+  if (bx > ntiles / 2) bx = ntiles / 2;  // at least two tiles per block (double buffering); small layers are latency
+  if (bx < 1) bx = 1;                    // bound and want many blocks, although every block writes one partial per entry
   return bx;
 }
 

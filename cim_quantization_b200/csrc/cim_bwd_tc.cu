@@ -65,7 +65,7 @@ struct BwdParams {
   int rk, prow;      // wgrad staging: rows per channel slot, staged row of (output row o, tap row ky) = o*prow + ky
   int xshared;       // wgrad staging: 1 = a tile is consecutive rows of ONE image and its output rows share input rows
                      // (prow == 1); 0 = every output row stages its own K rows (prow == K; also 1 for 1x1 kernels)
-  int async_rows;    // wgrad staging: rows arrive by 16-byte cp.async copies issued one chunk ahead
+  int async_rows;    // wgrad staging: rows arrive by cp.async copies issued one chunk ahead; value = piece size (16 or 8), 0 = off
   uint32_t raw_bytes;
   int gfast;         // wgrad: every 8-pixel group is an aligned run of one image row (or past the end)
   int co0;           // first output channel of this launch (layers with Cout > 128 run as blocks of 128 channels)
@@ -754,16 +754,21 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     auto issue_rows = [&](int i_, const int *tab, uint8_t *dstbuf) {
       const int lo_ = i_ * g.xbar, rows_ = min(rows_full, g.F - lo_);
       const int c_lo_ = lo_ / g.KK, nch_ = (lo_ + rows_ - 1) / g.KK - c_lo_ + 1;
-      const int cpr = g.W >> 4, total = nch_ * P.rk * cpr;
+      // pieces of 16 bytes, or of 8 for rows of 8 (mod 16) bytes (P.async_rows = piece size)
+      const int ps = P.async_rows, cpr = g.W / ps, total = nch_ * P.rk * cpr;
       for (int q = tid; q < total && !(P.dbg & 16); q += kWgProducerThreads) {
         const int rq = q / cpr, c16 = q - rq * cpr;
         const int sl = rq / P.rk, row = rq - sl * P.rk;
         const int off = tab[row];
         const bool ok = off != kNoRow;
-        const uint8_t *src = P.xcodes + (ok ? (size_t)(c_lo_ + sl) * HW + off + 16 * c16 : (size_t)0);
-        const uint32_t dst = smem_u32(dstbuf + ((size_t)rq << P.pitch_log2) + g.pad + P.col0 + 16 * c16);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u)
-                     : "memory");
+        const uint8_t *src = P.xcodes + (ok ? (size_t)(c_lo_ + sl) * HW + off + ps * c16 : (size_t)0);
+        const uint32_t dst = smem_u32(dstbuf + ((size_t)rq << P.pitch_log2) + g.pad + P.col0 + ps * c16);
+        if (ps == 16)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u)
+                       : "memory");
+        else
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(ok ? 8u : 0u)
+                       : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -1545,7 +1550,7 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
     while ((1 << owl) < g.OW) ++owl;
     // rows by 16-byte cp.async copies: 16-byte aligned rows on both sides (W % 16 == 0, image column 0 staged at
     // byte 16); otherwise 4-byte loads with image column -pad on a word boundary
-    const bool async_rows = g.W % 16 == 0 && g.pad <= 16 && (reinterpret_cast<uintptr_t>(xcodes) & 15u) == 0;
+    const bool async_rows = g.W % 8 == 0 && g.pad <= 16 && (reinterpret_cast<uintptr_t>(xcodes) & 15u) == 0;
     const int col0 = async_rows ? 16 - g.pad : (4 - g.pad % 4) % 4;
     const int needp = (g.OW - 1) + g.K + col0 + 4;  // + 4: the unaligned 8-byte window reads one word further
     int pl = 2;
@@ -1559,7 +1564,7 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
     const size_t raw = ((size_t)nch * rk * (1u << pl) + 8 + 15) & ~(size_t)15;
     if (pl <= 9 && rk <= 128 && 2 * raw + 2 * P.stage_bytes + kBarrierBytes <= kSmemBudget) {
       P.fastx = 1; P.ow_log2 = owl; P.rpt = rpt; P.pitch_log2 = pl; P.col0 = col0;
-      P.rk = rk; P.prow = shared_rows ? 1 : g.K; P.xshared = shared_rows ? 1 : 0; P.async_rows = async_rows ? 1 : 0;
+      P.rk = rk; P.prow = shared_rows ? 1 : g.K; P.xshared = shared_rows ? 1 : 0; P.async_rows = async_rows ? (g.W % 16 == 0 ? 16 : 8) : 0;
       P.raw_bytes = (uint32_t)raw;
     }
   }

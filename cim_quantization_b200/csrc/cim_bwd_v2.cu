@@ -93,10 +93,11 @@ __device__ __forceinline__ void red_add_pred(float *addr, float v, uint32_t pred
 // grad_out scales: rowscale[m] = 2^s with max_co |go[m, co]| * 2^s in [2^12, 2^13); chmax[co] = bit pattern of
 // max_m |go[m, co]| (atomicMax; zeroed by the caller).  One pass over grad_out, thread = pixel.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) go_scales_kernel(Geo g, const float *__restrict__ go, float *__restrict__ rowscale,
+constexpr int kScaleThreads = 128;  // thread = pixel; small blocks so that layers with few pixels still fill the SMs
+__global__ void __launch_bounds__(kScaleThreads) go_scales_kernel(Geo g, const float *__restrict__ go, float *__restrict__ rowscale,
                                                         uint32_t *__restrict__ chmax) {
   extern __shared__ uint32_t sm_ch[];  // [Cout]
-  for (int c = threadIdx.x; c < g.Cout; c += 256) sm_ch[c] = 0u;
+  for (int c = threadIdx.x; c < g.Cout; c += kScaleThreads) sm_ch[c] = 0u;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   // channel maxima stay in registers: lane l of a warp keeps the running maximum of channels c = l (mod 32)
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) go_scales_kernel(Geo g, const float *__re
   uint32_t chreg[kCB];
 #pragma unroll
   for (int cb = 0; cb < kCB; ++cb) chreg[cb] = 0u;
-  for (int m0 = blockIdx.x * 256; m0 < g.M; m0 += gridDim.x * 256) {
+  for (int m0 = blockIdx.x * kScaleThreads; m0 < g.M; m0 += gridDim.x * kScaleThreads) {
     const int m = m0 + threadIdx.x;
     const bool live = m < g.M;
     const int b = live ? m / g.L : 0, l = live ? m % g.L : 0;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) go_scales_kernel(Geo g, const float *__re
   for (int cb = 0; cb < kCB; ++cb)
     if (cb * 32 + lane < g.Cout && chreg[cb] != 0u) atomicMax(&sm_ch[cb * 32 + lane], chreg[cb]);
   __syncthreads();
-  for (int c = threadIdx.x; c < g.Cout; c += 256)
+  for (int c = threadIdx.x; c < g.Cout; c += kScaleThreads)
     if (sm_ch[c] != 0u) atomicMax(&chmax[c], sm_ch[c]);
 }
 
@@ -547,9 +548,9 @@ int launch_go_scales(const Geo &g, const float *go, void *scales, cudaStream_t s
   float *rowscale = reinterpret_cast<float *>(scales);
   uint32_t *chmax = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(scales) + (((int64_t)g.M * 4 + 255) & ~(int64_t)255));
   CIMQ_CUDA_OK(cudaMemsetAsync(chmax, 0, (size_t)g.Cout * 4, st));
-  int blocks = (g.M + 255) / 256;
-  if (blocks > 148 * 6) blocks = 148 * 6;
-  v2::go_scales_kernel<<<blocks, 256, (size_t)g.Cout * 4, st>>>(g, go, rowscale, chmax);
+  int blocks = (g.M + v2::kScaleThreads - 1) / v2::kScaleThreads;
+  if (blocks > 148 * 12) blocks = 148 * 12;
+  v2::go_scales_kernel<<<blocks, v2::kScaleThreads, (size_t)g.Cout * 4, st>>>(g, go, rowscale, chmax);
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
