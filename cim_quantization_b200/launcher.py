@@ -177,6 +177,19 @@ def install_child_hooks() -> None:
         dropin.install()
     import examples
     examples.get_freer_gpu = lambda: 0
+    # Reference defect worked around, in the spawned ranks only: get_summary_writer sets ``args.log_name`` on the first
+    # rank of a node alone (examples/__init__.py:466-476) but main_lsq.py:77 reads it on EVERY rank, so the reference's
+    # own DDP path dies with AttributeError on ranks > 0.  The other ranks get a scratch directory name of their own.
+    ref_writer = examples.get_summary_writer
+
+    def get_summary_writer(args, ngpus_per_node, model):
+        w = ref_writer(args, ngpus_per_node, model)
+        if not hasattr(args, "log_name"):
+            args.log_name = "logger/_rank%d" % int(getattr(args, "gpu", 0) or 0)
+            os.makedirs(args.log_name, exist_ok=True)
+        return w
+
+    examples.get_summary_writer = get_summary_writer
     stats = {"epochs": []}
 
     def sink(args):
