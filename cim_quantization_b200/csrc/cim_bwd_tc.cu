@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
 
   if (threadIdx.x == 0) {
     for (int sidx = 0; sidx < P.stages; ++sidx) {
-      mbar_init(cv.full0 + 8 * sidx, kWgProducerThreads);
+      mbar_init(cv.full0 + 8 * sidx, kWgProducerThreads / 32);
       mbar_init(cv.empty0 + 8 * sidx, 1);
     }
     mbar_init(cv.tfull0, 1);
@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     reg_alloc<kWgRegsProducer>();  // warpgroups 0-2; the registers come from warpgroup 3 (MMA issuer + idle warps)
     const int tid = threadIdx.x;
     const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
-    long long d_stage = 0, d_wait = 0, d_x = 0, d_g = 0;
+    long long d_stage = 0, d_wait = 0, d_x = 0, d_g = 0, d_bar = 0;
     // X tile items (crossbar row fr, 8-pixel group pg = x_pg0 + x_step * q, q < XI) of this thread
     // v2: threads [0, n_g) build G' (one 4-channel x 8-pixel item = 32 elements); with n_g = 256 the G' threads also
     // take ONE X item each (pixel groups 14, 15) and the other 128 threads fourteen (groups 0..13) -- measured: giving
@@ -1089,7 +1089,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
               }
             }
             fence_proxy_async();
-            mbar_arrive(cv.full0 + 8 * sidx);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cv.full0 + 8 * sidx);  // one arrival per warp (every thread fenced its own stores)
             d_g += CIMQ_TB() - tx1;
             continue;
           }
@@ -1130,7 +1131,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
               }
             }
             fence_proxy_async();
-            mbar_arrive(cv.full0 + 8 * sidx);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cv.full0 + 8 * sidx);  // one arrival per warp (every thread fenced its own stores)
             d_g += CIMQ_TB() - tx1;
             continue;
           }
@@ -1200,17 +1202,20 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
             *reinterpret_cast<uint4 *>(gb + 2 * (size_t)P.b_bytes + off) = make_uint4(lo3[0], lo3[1], lo3[2], lo3[3]);
           }
           fence_proxy_async();
-          mbar_arrive(cv.full0 + 8 * sidx);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(cv.full0 + 8 * sidx);  // one arrival per warp (every thread fenced its own stores)
           d_g += CIMQ_TB() - tx1;
         }
         if (P.async_rows) {  // my copies of the next chunk's rows have landed; publish them, retire this chunk's buffer
+          const long long tb0 = CIMQ_TB();
           asm volatile("cp.async.wait_group 0;" ::: "memory");
           named_barrier_sync(1, kWgProducerThreads);
+          d_bar += CIMQ_TB() - tb0;
         }
       }
       gpt = gpt_n;
     }
-    if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_stage; P.debug[2] = d_x; P.debug[3] = d_g; }
+    if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_stage; P.debug[2] = d_x; P.debug[3] = d_g; P.debug[7] = d_bar; }
   } else {
     reg_dealloc<kWgRegsMma>();
     // ------------------------------------------------------------------ MMA issuer

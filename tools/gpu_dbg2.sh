@@ -1,5 +1,2 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_v2.py tests/test_gpu_matrix.py tests/test_gpu_resnet20.py -m gpu -q -x 2>&1 | tail -3
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -2
-for b in 256 2048; do timeout 600 python tools/train_bench.py --batch $b --steps 10 2>/dev/null | tail -1 | cut -c1-200; done
-timeout 300 python tools/time_bwd.py --only v2 --cin 64 --cout 64 --hw 8 2>&1 | grep "wgrad\|dgrad\|alpha"
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_matrix.py tests/test_gpu_v2.py -m gpu -q -x 2>&1 | tail -3

@@ -10,6 +10,7 @@ p.add_argument("--adcbits", type=float, default=1.5)
 p.add_argument("--batch", type=int, default=256)
 p.add_argument("--iters", type=int, default=2)
 p.add_argument("--v1", action="store_true")
+p.add_argument("--timers", action="store_true", help="library built with `make TIMERS=1`: per-role cycle counters of the wgrad kernel (it runs last)")
 a = p.parse_args()
 adc = int(a.adcbits) if a.adcbits == int(a.adcbits) else a.adcbits
 B, C, HW = a.batch, 64, 32
@@ -31,8 +32,17 @@ table = L.adc_table(spec, s, aq, mask, alpha_scale=sc)
 wdig, wtiles = L.weight_prepare(spec, wc)
 go = torch.randn(B, C, HW * HW, device="cuda", generator=g)
 flags = 0 if a.v1 else L.FLAG_V2
+dbg = None
+if a.timers:
+    import ctypes
+    dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+    L.load().cimq_debug_set_timers(ctypes.c_void_p(dbg.data_ptr()))
 for it in range(a.iters):
     out, state = L.conv_forward(spec, xc, wc, wtiles, table, s, mask, save_state=True, flags=flags)
     L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask, need_alpha=aq is not None)
 torch.cuda.synchronize()
+if dbg is not None:
+    d = dbg.cpu().tolist()
+    for k, n in {0: "producer wait empty", 1: "producer chunk start (rows, gather)", 2: "producer X tile", 3: "producer G' tile", 7: "producer chunk-end barrier", 4: "mma wait full", 6: "mma total"}.items():
+        print(f"  wgrad timer {n:36s} {d[k] / 1e3:10.1f} kcycles")
 print("done")
