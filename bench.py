@@ -87,7 +87,7 @@ def workload_config(a):
     return {"workload": f"CiM conv layer microbench 3x3 {a.channels}->{a.channels} {a.hw}x{a.hw} "
                         f"w{a.nbits}a{a.nbits} xbar{a.xbar} adcbits{adc} fwd+bwd",
             "batch_per_gpu": a.batch, "xbar": a.xbar, "adcbits": adc,
-            "l2": "working set (x 67 MB, grad 67 MB, ADC state 335 MB) exceeds the 126 MB L2; no extra flush"}
+            "l2": "working set (x 67 MB, grad_out 67 MB, grad_x 67 MB, ADC state 419 MB) exceeds the 126 MB L2; no extra flush"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -728,23 +728,33 @@ def run_ours(a):
         fwd_name = ("conv_v2_kernel (CiM conv forward: tcgen05 kind::f8f6f4 -> fp16 TMEM partial sums, packed-half ADC "
                     "epilogue, kind::f16 A-from-TMEM shift-and-add)" if t["v2"]
                     else "conv_tc_kernel (CiM conv forward, tcgen05 kind::i8 + ADC epilogue)")
+        sfx = "_v2" if t["v2"] else ""
+        split_note = ("2x that in fp16 (grad_out scaled by a power of two per row / channel and split into two 9-bit "
+                      "pieces, exact piece * pass-count products)" if t["v2"] else
+                      "3x that in bf16 (hi/mid/lo split of grad)")
         cand = [
             (t_f, {"kernel": fwd_name, "bound": "tensor",
                    "achieved": fwd_ops / t_f / 1e9, "peak": int8_peak, "unit": "TOPS",
-                   "frac": fwd_ops / t_f / 1e9 / int8_peak, "traffic": _traffic_bytes(traffic, "conv_forward"),
+                   "frac": fwd_ops / t_f / 1e9 / int8_peak, "traffic": _traffic_bytes(traffic, "conv_forward" + sfx),
                    "algorithmic_bytes": alg_fwd,
                    "peak_source": peak_src + " x2 for 8-bit operands (no measured int8 / fp8 peak)",
                    "note": "algorithmic ops 2*NSW*NSA*MKN, one contraction per slice pair"}),
-            (t_bw, {"kernel": "bwd_weight_tc_kernel (+ finish; CiM conv wgrad, tcgen05 kind::f16 bf16x3)", "bound": "tensor",
+            (t_bw, {"kernel": ("bwd_weight_tc_kernel<V2> (+ go_scales, finish; CiM conv wgrad, tcgen05 kind::f16, grad_out as "
+                               "two fp16 pieces)" if t["v2"] else
+                               "bwd_weight_tc_kernel (+ finish; CiM conv wgrad, tcgen05 kind::f16 bf16x3)"), "bound": "tensor",
                     "achieved": wgrad_ops / t_bw / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
-                    "frac": wgrad_ops / t_bw / 1e9 / bf16_peak, "traffic": _traffic_bytes(traffic, "conv_wgrad"),
+                    "frac": wgrad_ops / t_bw / 1e9 / bf16_peak,
+                    "traffic": _traffic_bytes(traffic, "conv_wgrad" + sfx),
                     "algorithmic_bytes": alg_wgrad, "peak_source": peak_src,
-                    "note": "algorithmic flops 2*NSA*MKN; the kernel issues 3x that in bf16 (hi/mid/lo split of grad)"}),
-            (t_bx, {"kernel": "bwd_input_tc_kernel (CiM conv dgrad + fused fold, tcgen05 kind::f16 bf16x3)", "bound": "tensor",
+                    "note": "algorithmic flops 2*NSA*MKN; the kernel issues " + split_note}),
+            (t_bx, {"kernel": ("bwd_input_v2_kernel (+ go_scales; CiM conv dgrad + fold in the epilogue, tcgen05 kind::f16, "
+                               "grad_out as two fp16 pieces)" if t["v2"] else
+                               "bwd_input_tc_kernel (CiM conv dgrad + fused fold, tcgen05 kind::f16 bf16x3)"), "bound": "tensor",
                     "achieved": dgrad_ops / t_bx / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
-                    "frac": dgrad_ops / t_bx / 1e9 / bf16_peak, "traffic": _traffic_bytes(traffic, "conv_dgrad"),
+                    "frac": dgrad_ops / t_bx / 1e9 / bf16_peak,
+                    "traffic": _traffic_bytes(traffic, "conv_dgrad" + sfx),
                     "algorithmic_bytes": alg_dgrad, "peak_source": peak_src,
-                    "note": "algorithmic flops 2*NSW*MKN; the kernel issues 3x that in bf16 (hi/mid/lo split of grad)"}),
+                    "note": "algorithmic flops 2*NSW*MKN; the kernel issues " + split_note}),
         ]
         roof = max(cand, key=lambda c: c[0])[1]
         if roof.get("traffic"):
@@ -779,7 +789,11 @@ def run_ours(a):
             ref_cuda = reference_cuda_leg(torch, a, dev)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "8-bit digits (e4m3 / s8) -> fp16 / s32 partial sums (forward), f32 via bf16x3 (backward)", "data": "synthetic",
+                "vs_baseline": None,
+                "dtype": ("e4m3 digits -> fp16 partial sums in tensor memory (forward); fp32 grad_out as 2 fp16 pieces x exact "
+                          "small integers, fp32 accumulation (backward)" if t["v2"] else
+                          "u8 x s8 -> s32 partial sums (forward), f32 via bf16x3 (backward)"),
+                "data": "synthetic",
                 "config": dict(workload_config(a), cuda_graph=graph is not None,
                                tcgen05_forward=bool(info.tc_forward)),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps),

@@ -296,23 +296,22 @@ __global__ void __launch_bounds__(256, 3) bwd_alpha_v2_kernel(Geo g, int m_per_s
 
 // Block = 32 consecutive table entries x 8 slices of the split range, combined through shared memory in a fixed
 // order (deterministic).
-__global__ void __launch_bounds__(256) bwd_alpha_finish_kernel(Geo g, int nsplit, float gfac,
-                                                               const int8_t *__restrict__ mask,
-                                                               const float *__restrict__ partial,
-                                                               float *__restrict__ galpha) {
-  __shared__ float red[8][32];
+__global__ void __launch_bounds__(1024) bwd_alpha_finish_kernel(Geo g, int nsplit, float gfac,
+                                                                const int8_t *__restrict__ mask,
+                                                                const float *__restrict__ partial,
+                                                                float *__restrict__ galpha) {
+  __shared__ float red[32][32];
   const int64_t n = table_entries(g);
-  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5, nslice = blockDim.x >> 5;
   const int64_t e = (int64_t)blockIdx.x * 32 + lane;
   float v = 0.0f;
   if (e < n)
-    for (int sidx = slice; sidx < nsplit; sidx += 8) v += __ldg(partial + (int64_t)sidx * n + e);
+    for (int sidx = slice; sidx < nsplit; sidx += nslice) v += __ldg(partial + (int64_t)sidx * n + e);
   red[slice][lane] = v;
   __syncthreads();
   if (slice == 0 && e < n) {
     float t = red[0][lane];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) t += red[w][lane];
+    for (int w = 1; w < nslice; ++w) t += red[w][lane];
     const int q = (int)((e / g.Cout) % g.pairs);
     galpha[e] = t * gfac * (float)mask[q];  // lsq.py:306, 323-325 / 330-332
   }
@@ -605,8 +604,9 @@ int launch_conv_backward(const Geo &g, const float *go, const uint8_t *xcodes, c
     if (launch_alpha_v3(g, go, cplanes, apart, st)) return 1;
     const double numel = (double)g.B * g.NX * g.NSW * g.NSA * g.L * g.Cout;
     const int64_t n = table_entries(g);
-    bwd_alpha_finish_kernel<<<(int)((n + 31) / 32), 256, 0, st>>>(g, alpha_v3_blocks(g), (float)(1.0 / sqrt(numel)), mask, apart,
-                                                                  galpha);
+    // (hundreds of partials per entry: 32 slices of the partial range per block instead of 8)
+    bwd_alpha_finish_kernel<<<(int)((n + 31) / 32), alpha_v3_blocks(g) > 64 ? 1024 : 256, 0, st>>>(
+        g, alpha_v3_blocks(g), (float)(1.0 / sqrt(numel)), mask, apart, galpha);
     CIMQ_CUDA_OK(cudaGetLastError());
   } else if (v2s && galpha != nullptr && g.adc_mode != CIMQ_ADC_MULTIBIT) {
     const int cblock = g.Cout > 128 ? (g.Cout % 128 == 0 ? 128 : 64) : g.Cout;  // channels per block (Cout % 16 == 0)

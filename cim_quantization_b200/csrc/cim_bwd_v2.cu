@@ -93,9 +93,9 @@ __device__ __forceinline__ void red_add_pred(float *addr, float v, uint32_t pred
 // grad_out scales: rowscale[m] = 2^s with max_co |go[m, co]| * 2^s in [2^12, 2^13); chmax[co] = bit pattern of
 // max_m |go[m, co]| (atomicMax; zeroed by the caller).  One pass over grad_out, thread = pixel.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kScaleThreads = 128;  // thread = pixel; small blocks so that layers with few pixels still fill the SMs
+constexpr int kScaleThreads = 128;  // thread = four consecutive pixels (16-byte loads); small blocks fill the SMs on small layers
 __global__ void __launch_bounds__(kScaleThreads) go_scales_kernel(Geo g, const float *__restrict__ go, float *__restrict__ rowscale,
-                                                        uint32_t *__restrict__ chmax) {
+                                                                  uint32_t *__restrict__ chmax) {
   extern __shared__ uint32_t sm_ch[];  // [Cout]
   for (int c = threadIdx.x; c < g.Cout; c += kScaleThreads) sm_ch[c] = 0u;
   __syncthreads();
@@ -105,34 +105,40 @@ __global__ void __launch_bounds__(kScaleThreads) go_scales_kernel(Geo g, const f
   uint32_t chreg[kCB];
 #pragma unroll
   for (int cb = 0; cb < kCB; ++cb) chreg[cb] = 0u;
-  for (int m0 = blockIdx.x * kScaleThreads; m0 < g.M; m0 += gridDim.x * kScaleThreads) {
-    const int m = m0 + threadIdx.x;
-    const bool live = m < g.M;
-    const int b = live ? m / g.L : 0, l = live ? m % g.L : 0;
-    const float *gp = go + (int64_t)b * g.Cout * g.L + l;
-    uint32_t rm = 0u;
+  const int m4s = g.M >> 2;  // pixel quads (L % 4 == 0: a quad lies inside one image)
+  for (int q0 = blockIdx.x * kScaleThreads; q0 < m4s; q0 += gridDim.x * kScaleThreads) {
+    const int q = q0 + threadIdx.x;
+    const bool live = q < m4s;
+    const int m = live ? 4 * q : 0;
+    const int b = m / g.L, l = m % g.L;
+    const float4 *gp = reinterpret_cast<const float4 *>(go + (int64_t)b * g.Cout * g.L + l);
+    const int64_t cstride = g.L >> 2;  // float4 per channel row
+    uint32_t rm0 = 0u, rm1 = 0u, rm2 = 0u, rm3 = 0u;
 #pragma unroll
     for (int cb = 0; cb < kCB; ++cb) {
       if (cb * 32 < g.Cout) {
 #pragma unroll
         for (int c8 = 0; c8 < 32; c8 += 8) {
-          const int c0 = cb * 32 + c8;
-          if (c0 < g.Cout) {  // Cout % 8 == 0
-            uint32_t v[8];
+          if (cb * 32 + c8 < g.Cout) {  // Cout % 8 == 0
+            float4 v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              v[e] = live ? (__float_as_uint(__ldg(gp + (int64_t)(c0 + e) * g.L)) & 0x7fffffffu) : 0u;
+              v[e] = live ? __ldg(gp + (int64_t)(cb * 32 + c8 + e) * cstride) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              rm = max(rm, v[e]);
-              const uint32_t w = __reduce_max_sync(0xffffffffu, v[e]);
+              const uint32_t a0 = __float_as_uint(v[e].x) & 0x7fffffffu, a1 = __float_as_uint(v[e].y) & 0x7fffffffu;
+              const uint32_t a2 = __float_as_uint(v[e].z) & 0x7fffffffu, a3 = __float_as_uint(v[e].w) & 0x7fffffffu;
+              rm0 = max(rm0, a0); rm1 = max(rm1, a1); rm2 = max(rm2, a2); rm3 = max(rm3, a3);
+              const uint32_t w = __reduce_max_sync(0xffffffffu, max(max(a0, a1), max(a2, a3)));
               if (lane == c8 + e) chreg[cb] = max(chreg[cb], w);
             }
           }
         }
       }
     }
-    if (live) rowscale[m] = bwd_scale_from_maxbits(rm);
+    if (live)
+      *reinterpret_cast<float4 *>(rowscale + m) = make_float4(bwd_scale_from_maxbits(rm0), bwd_scale_from_maxbits(rm1),
+                                                              bwd_scale_from_maxbits(rm2), bwd_scale_from_maxbits(rm3));
   }
 #pragma unroll
   for (int cb = 0; cb < kCB; ++cb)
@@ -548,8 +554,10 @@ int launch_go_scales(const Geo &g, const float *go, void *scales, cudaStream_t s
   float *rowscale = reinterpret_cast<float *>(scales);
   uint32_t *chmax = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(scales) + (((int64_t)g.M * 4 + 255) & ~(int64_t)255));
   CIMQ_CUDA_OK(cudaMemsetAsync(chmax, 0, (size_t)g.Cout * 4, st));
-  int blocks = (g.M + v2::kScaleThreads - 1) / v2::kScaleThreads;
-  if (blocks > 148 * 12) blocks = 148 * 12;
+  CIMQ_REQUIRE(g.L % 4 == 0 && (reinterpret_cast<uintptr_t>(go) & 15u) == 0 && (reinterpret_cast<uintptr_t>(scales) & 15u) == 0,
+               "go_scales: grad_out rows must be 16-byte aligned");
+  int blocks = (g.M / 4 + v2::kScaleThreads - 1) / v2::kScaleThreads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
   v2::go_scales_kernel<<<blocks, v2::kScaleThreads, (size_t)g.Cout * 4, st>>>(g, go, rowscale, chmax);
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
