@@ -489,8 +489,9 @@ __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm,
       if (ENC == 1 && P.debug == reinterpret_cast<long long *>(1)) { /* development: skip the row assembly */ }
       else if (!K5 || g.K == 3) produce_fast<NSA, 3, ENC>(P, cl, st_ptr, raw, r, pix_base);
       else if constexpr (K5) produce_fast<NSA, 5, ENC>(P, cl, st_ptr, raw, r, pix_base);
-      fence_proxy_async();
-      mbar_arrive(sm.full0 + 8 * sidx);
+      fence_proxy_async();  // every thread publishes its own stores to the async proxy; one arrival per warp (every
+      __syncwarp();         // arrival wakes the warps sleeping on ANY mbarrier of the CTA: 128 per stage made them spin)
+      if ((tid & 31) == 0) mbar_arrive(sm.full0 + 8 * sidx);
       if (P.prefetch || P.tma_rows) {
         if (P.prefetch && more)
           stage_store<kPrefetchWords>(P, stt, ncl, 0, v, sm.raw + (size_t)((lit + 1) & 1) * P.raw_bytes, tid);
@@ -533,7 +534,8 @@ __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm,
       }
       produce_generic<NSA, ENC>(P, i, st_ptr, r, base, vm);
       fence_proxy_async();
-      mbar_arrive(sm.full0 + 8 * sidx);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(sm.full0 + 8 * sidx);
       advance(tile, i, ngroups);
       it += ngroups;
     }
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
 
   if (threadIdx.x == 0) {
     for (int sidx = 0; sidx < P.stages; ++sidx) {
-      mbar_init(sm.full0 + 8 * sidx, kProducerThreads + 1);
+      mbar_init(sm.full0 + 8 * sidx, kProducerWarps + 1);
       mbar_init(sm.empty0 + 8 * sidx, 1);
     }
     for (int b = 0; b < 2; ++b) {

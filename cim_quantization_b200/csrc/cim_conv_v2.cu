@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < T.stages; ++s) {
-      mbar_init(B.full0 + 8 * s, kProducerThreads + 1);
+      mbar_init(B.full0 + 8 * s, kProducerWarps + 1);  // one arrival per producer warp of the group + the weight-tile copy
       mbar_init(B.empty0 + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {

@@ -57,7 +57,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       ++spins;
 #ifndef CIMQ_NO_SLEEP
       if constexpr (kSleepNs > 0) __nanosleep(kSleepNs);
+#ifdef CIMQ_BACKOFF_NS
+      else __nanosleep(CIMQ_BACKOFF_NS);
+#else
       else if (spins > 2) __nanosleep(spins < 32 ? 40 : 200);
+#endif
 #endif
       if (spins > kSpinLimit) __trap();
     }
