@@ -90,6 +90,10 @@ EXPORTS = {
     "cimq_bn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                   C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cimq_bn_forward_quant": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p,
+                                        C.c_void_p]),
     "cimq_bn_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -411,8 +415,9 @@ def conv_psum_abs_sums(spec: LayerSpec, xcodes, wcodes):
 # ---- batch norm (+ residual) (+ ReLU) ------------------------------------------------------------------------
 @_on_tensor_device
 def bn_forward(x, residual, weight, bias, running_mean, running_var, training: bool, momentum: float, eps: float,
-               relu: bool):
-    """y, save_mean, save_invstd (None, None in inference)."""
+               relu: bool, next_quant=None):
+    """y, save_mean, save_invstd (None, None in inference) [, codes].  ``next_quant = (alpha_act, grad_scale, qp)`` of
+    the layer that consumes y: its activation codes are written by the same kernel (cimq_bn_forward_quant)."""
     b, c = x.shape[0], x.shape[1]
     hw = x.numel() // (b * c)
     y = torch.empty_like(x)
@@ -421,11 +426,20 @@ def bn_forward(x, residual, weight, bias, running_mean, running_var, training: b
         mean = torch.empty(c, dtype=torch.float32, device=x.device)
         invstd = torch.empty(c, dtype=torch.float32, device=x.device)
         ws = torch.empty(load().cimq_bn_workspace_bytes(b, c), dtype=torch.uint8, device=x.device)
-    _check(load().cimq_bn_forward(_ptr(x), _ptr(residual), _ptr(weight), _ptr(bias), _ptr(running_mean),
-                                  _ptr(running_var), int(training), float(momentum), float(eps), int(relu), b, c, hw,
-                                  _ptr(y), _ptr(mean), _ptr(invstd), _ptr(ws), _stream()))
+    if next_quant is None:
+        _check(load().cimq_bn_forward(_ptr(x), _ptr(residual), _ptr(weight), _ptr(bias), _ptr(running_mean),
+                                      _ptr(running_var), int(training), float(momentum), float(eps), int(relu), b, c, hw,
+                                      _ptr(y), _ptr(mean), _ptr(invstd), _ptr(ws), _stream()))
+        _count(2 if training else 1)
+        return y, mean, invstd
+    alpha_act, gscale, qp = next_quant
+    codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    _check(load().cimq_bn_forward_quant(_ptr(x), _ptr(residual), _ptr(weight), _ptr(bias), _ptr(running_mean),
+                                        _ptr(running_var), int(training), float(momentum), float(eps), int(relu), b, c,
+                                        hw, _ptr(y), _ptr(mean), _ptr(invstd), _ptr(ws), _ptr(alpha_act),
+                                        float(gscale), int(qp), _ptr(codes), _stream()))
     _count(2 if training else 1)
-    return y, mean, invstd
+    return y, mean, invstd, codes
 
 
 @_on_tensor_device

@@ -8,6 +8,7 @@
 // 16.8 MB.  Two launches per direction: per-block partial sums (fp32 in the block, double across blocks, fixed
 // order: deterministic), then the element-wise pass, whose blocks each re-reduce the few partials of their channel.
 #include "cimq_common.cuh"
+#include "lsq_code.cuh"
 
 namespace cimq {
 
@@ -64,7 +65,17 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
     const float *__restrict__ x, const float *__restrict__ residual, const float *__restrict__ weight,
     const float *__restrict__ bias, float *__restrict__ running_mean, float *__restrict__ running_var,
     const double2 *__restrict__ partial, int training, float momentum, float eps, int relu, int B, int C, int HW,
-    float *__restrict__ y, float *__restrict__ save_mean, float *__restrict__ save_invstd) {
+    float *__restrict__ y, float *__restrict__ save_mean, float *__restrict__ save_invstd,
+    const float *__restrict__ q_alpha, float q_g, float q_qp, uint8_t *__restrict__ codes) {
+  // codes != NULL: also emit the NEXT layer's activation codes rint(clamp(y / s, 0, qp)), s = grad_scale(q_alpha, q_g)
+  // (lsq.py:547-549) -- the same bytes cimq_lsq_quantize would compute from y, without reading y back.
+  StepSize qs;
+  qs.s = 1.0f; qs.r = 1.0f; qs.ok = true;
+  if (codes != nullptr) {
+    qs.s = grad_scale_value(__ldg(q_alpha), q_g);
+    qs.r = __frcp_rn(qs.s);
+    qs.ok = qs.s >= 1e-30f && qs.s <= 1e30f;
+  }
   __shared__ float sh[2];
   const int c = blockIdx.x, s = blockIdx.y, splits = gridDim.y;
   if (threadIdx.x == 0) {
@@ -116,6 +127,9 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
         }
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         y4[i] = o;
+        if (codes != nullptr)
+          reinterpret_cast<uint32_t *>(codes + off)[i] = lsq_code(o.x, qs, 0.0f, q_qp) | (lsq_code(o.y, qs, 0.0f, q_qp) << 8) |
+                                                         (lsq_code(o.z, qs, 0.0f, q_qp) << 16) | (lsq_code(o.w, qs, 0.0f, q_qp) << 24);
       }
     } else {
       for (int i = threadIdx.x; i < HW; i += kBnThreads) {
@@ -123,6 +137,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
         if (residual != nullptr) o += __ldg(residual + off + i);
         if (relu) o = fmaxf(o, 0.f);
         y[off + i] = o;
+        if (codes != nullptr) codes[off + i] = (uint8_t)lsq_code(o, qs, 0.0f, q_qp);
       }
     }
   }
@@ -245,12 +260,14 @@ int64_t bn_workspace_bytes(int B, int C) { return (int64_t)C * bn_splits(B, C) *
 int launch_bn_forward(const float *x, const float *residual, const float *weight, const float *bias,
                       float *running_mean, float *running_var, int training, float momentum, float eps, int relu,
                       int B, int C, int HW, float *y, float *save_mean, float *save_invstd, void *workspace,
-                      cudaStream_t st) {
+                      cudaStream_t st, const float *q_alpha, float q_g, int q_qp, uint8_t *codes) {
+  CIMQ_REQUIRE(codes == nullptr || (q_alpha != nullptr && q_qp > 0 && q_qp <= 255), "bn_forward: bad quantiser arguments");
   CIMQ_REQUIRE(x != nullptr && y != nullptr && B > 0 && C > 0 && HW > 0, "bn_forward: bad argument");
   CIMQ_REQUIRE(training ? (save_mean && save_invstd && workspace) : (running_mean && running_var),
                "bn_forward: missing statistics buffers");
   const dim3 grid(C, bn_splits(B, C));
-  const bool vec = HW % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(residual);
+  const bool vec = HW % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(residual) &&
+                   (reinterpret_cast<uintptr_t>(codes) & 3u) == 0;
   double2 *part = reinterpret_cast<double2 *>(workspace);
   if (training) {
     if (vec) bn_stats_kernel<true><<<grid, kBnThreads, 0, st>>>(x, B, C, HW, part);
@@ -260,11 +277,11 @@ int launch_bn_forward(const float *x, const float *residual, const float *weight
   if (vec)
     bn_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(x, residual, weight, bias, running_mean, running_var, part,
                                                        training, momentum, eps, relu, B, C, HW, y, save_mean,
-                                                       save_invstd);
+                                                       save_invstd, q_alpha, q_g, (float)q_qp, codes);
   else
     bn_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(x, residual, weight, bias, running_mean, running_var, part,
                                                         training, momentum, eps, relu, B, C, HW, y, save_mean,
-                                                        save_invstd);
+                                                        save_invstd, q_alpha, q_g, (float)q_qp, codes);
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -203,6 +203,16 @@ int cimq_bn_forward(const float *x, const float *residual, const float *weight, 
                            channels, hw, y, save_mean, save_invstd, workspace, as_stream(stream));
 }
 
+int cimq_bn_forward_quant(const float *x, const float *residual, const float *weight, const float *bias,
+                          float *running_mean, float *running_var, int32_t training, float momentum, float eps,
+                          int32_t relu, int32_t batch, int32_t channels, int32_t hw, float *y, float *save_mean,
+                          float *save_invstd, void *workspace, const float *next_alpha_act, float next_grad_scale,
+                          int32_t next_qp, uint8_t *next_codes, void *stream) {
+  return launch_bn_forward(x, residual, weight, bias, running_mean, running_var, training, momentum, eps, relu, batch,
+                           channels, hw, y, save_mean, save_invstd, workspace, as_stream(stream), next_alpha_act,
+                           next_grad_scale, next_qp, next_codes);
+}
+
 int cimq_bn_backward(const float *grad_y, const float *x, const float *y, const float *weight, const float *mean,
                      const float *invstd, int32_t training, int32_t relu, int32_t batch, int32_t channels, int32_t hw,
                      float *grad_x, float *grad_residual, float *grad_weight, float *grad_bias, void *workspace,

@@ -128,7 +128,8 @@ int64_t bn_workspace_bytes(int B, int C);
 int launch_bn_forward(const float *x, const float *residual, const float *weight, const float *bias,
                       float *running_mean, float *running_var, int training, float momentum, float eps, int relu,
                       int B, int C, int HW, float *y, float *save_mean, float *save_invstd, void *workspace,
-                      cudaStream_t st);
+                      cudaStream_t st, const float *q_alpha = nullptr, float q_g = 0.0f, int q_qp = 0,
+                      uint8_t *codes = nullptr);
 int launch_bn_backward(const float *gy, const float *x, const float *y, const float *weight, const float *save_mean,
                        const float *save_invstd, int training, int relu, int B, int C, int HW, float *gx, float *gres,
                        float *gweight, float *gbias, void *workspace, cudaStream_t st);

@@ -175,7 +175,7 @@ class _CimConv2dFusedV2(Function):
 
     @staticmethod
     def forward(ctx, x, weight, alpha_act, alpha_weight, alpha_cim, binary_mask, stride, padding, nbits_a, abitslice,
-                nbits_w, wbitslice, xbar, adcbits, nbits_alpha, flags):
+                nbits_w, wbitslice, xbar, adcbits, nbits_alpha, flags, xcodes_in=None):
         _require_cuda(x, weight, alpha_act, alpha_weight, alpha_cim)
         x = x.contiguous()
         weight = weight.contiguous()
@@ -192,7 +192,8 @@ class _CimConv2dFusedV2(Function):
         s, wcodes, alpha_q, aux, table, wtiles = _lib.layer_prepare(
             spec, weight.detach(), alpha_act.detach(), alpha_weight.detach(), ga, gw, a_cim, 1, 2 ** nbits_alpha - 1,
             mask)
-        xcodes = _lib.lsq_quantize(x.detach(), s[0:1], 0, qp_a)
+        # codes already written by the producer of x (batch_norm_act(..., next_conv=...))?
+        xcodes = xcodes_in if xcodes_in is not None else _lib.lsq_quantize(x.detach(), s[0:1], 0, qp_a)
         need_bwd = any(ctx.needs_input_grad)
         out, state = _lib.conv_forward(spec, xcodes, wcodes, wtiles, table, s, mask, save_state=need_bwd,
                                        flags=flags | _lib.FLAG_V2)
@@ -217,15 +218,15 @@ class _CimConv2dFusedV2(Function):
         gwt, g_aw = _lib.lsq_backward(gwq.view_as(weight), weight, s[1:2], qn_w, qp_w, gw)
         if need_alpha:
             galpha = _lib.alpha_quantize_backward(a_cim, galpha_q.view_as(a_cim), 1, 2 ** nbits_alpha - 1, aux)
-        return (gx, gwt, g_aa, g_aw, galpha) + (None,) * 11
+        return (gx, gwt, g_aa, g_aw, galpha) + (None,) * 12
 
 
 def cim_conv2d_v2(x, weight, alpha_act, alpha_weight, alpha_cim, binary_mask, stride, padding, nbits_a, abitslice,
-                  nbits_w, wbitslice, xbar, adcbits, nbits_alpha, flags: int = 0):
+                  nbits_w, wbitslice, xbar, adcbits, nbits_alpha, flags: int = 0, xcodes=None):
     """Fused CiM convolution of ``Conv2dLSQCiM`` (lsq.py:546-581) from the RAW ``alpha_cim`` parameter, for layers the
     v2 kernels cover (``_lib.layer_info(spec).tc_v2``, ``nbits_alpha <= 11``)."""
     return _CimConv2dFusedV2.apply(x, weight, alpha_act, alpha_weight, alpha_cim, binary_mask, stride, padding,
-                                   nbits_a, abitslice, nbits_w, wbitslice, xbar, adcbits, nbits_alpha, flags)
+                                   nbits_a, abitslice, nbits_w, wbitslice, xbar, adcbits, nbits_alpha, flags, xcodes)
 
 
 def _stochastic_seed() -> int:
@@ -347,8 +348,37 @@ class _BatchNormAct(torch.autograd.Function):
                 None, None, None, None)
 
 
-def batch_norm_act(x, bn: torch.nn.BatchNorm2d, residual=None, relu: bool = False):
-    """``relu?(bn(x) + residual?)`` with ``bn``'s parameters, buffers and train/eval mode."""
+class _BatchNormActQuant(torch.autograd.Function):
+    """:class:`_BatchNormAct` whose forward kernel also writes the activation codes of the layer that consumes its
+    output (resnet.py:83-86 + lsq.py:547-549 in one pass).  Returns ``(y, codes)``; codes carry no
+    gradient -- the consumer's quantiser backward works on y, as before."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, training, momentum, eps, relu, next_alpha,
+                next_gscale, next_qp):
+        x = x.contiguous()
+        res = residual.contiguous() if residual is not None else None
+        y, mean, invstd, codes = _lib.bn_forward(x, res, weight, bias, running_mean, running_var, training, momentum,
+                                                 eps, relu, next_quant=(next_alpha.detach(), next_gscale, next_qp))
+        if not training:
+            mean, invstd = running_mean, torch.rsqrt(running_var + eps)
+        ctx.save_for_backward(x, y if relu else None, weight, mean, invstd)
+        ctx.training, ctx.relu, ctx.has_res = training, relu, residual is not None
+        ctx.mark_non_differentiable(codes)
+        return y, codes
+
+    @staticmethod
+    def backward(ctx, gy, _gcodes):
+        x, y, weight, mean, invstd = ctx.saved_tensors
+        gx, gres, gw, gb = _lib.bn_backward(gy.contiguous(), x, y, weight, mean, invstd, ctx.training, ctx.relu,
+                                            ctx.has_res and ctx.needs_input_grad[1])
+        return (gx, gres, gw if weight is not None else None, gb if ctx.needs_input_grad[3] else None) + (None,) * 9
+
+
+def batch_norm_act(x, bn: torch.nn.BatchNorm2d, residual=None, relu: bool = False, next_conv=None):
+    """``relu?(bn(x) + residual?)`` with ``bn``'s parameters, buffers and train/eval mode.  With ``next_conv`` (a
+    ``Conv2dLSQCiM`` that will consume the result and whose step sizes are initialised) the return value is
+    ``(y, codes)``: pass ``codes`` to ``next_conv(y, xcodes=codes)``."""
     _require_cuda(x, residual)
     training = bn.training or not bn.track_running_stats
     momentum = 0.0 if bn.momentum is None else bn.momentum
@@ -356,5 +386,12 @@ def batch_norm_act(x, bn: torch.nn.BatchNorm2d, residual=None, relu: bool = Fals
         bn.num_batches_tracked.add_(1)
         if bn.momentum is None:
             momentum = 1.0 / float(bn.num_batches_tracked)
+    if next_conv is not None:
+        qp = 2 ** next_conv.nbits_a - 1
+        gscale = 1.0 / math.sqrt(x.numel() * qp)  # lsq.py:547 (the consumer sees a tensor of the same size)
+        return _BatchNormActQuant.apply(x, residual, bn.weight, bn.bias,
+                                        bn.running_mean if bn.track_running_stats else None,
+                                        bn.running_var if bn.track_running_stats else None, training, momentum, bn.eps,
+                                        relu, next_conv.alpha_act, gscale, qp)
     return _BatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean if bn.track_running_stats else None,
                                bn.running_var if bn.track_running_stats else None, training, momentum, bn.eps, relu)

@@ -17,13 +17,25 @@ from .modules import Conv2dLSQCiM
 FUSED_BN = True
 
 
-def _bn_act(x, bn, residual=None, relu=True):
+# the fused batch norm also writes the activation codes of the convolution that consumes its output
+# (one read of the fp32 activation and one launch less per layer); False keeps the separate quantiser kernel
+FUSED_QUANT = True
+
+
+def _bn_act(x, bn, residual=None, relu=True, next_conv=None):
+    """-> (y, codes-or-None)"""
     if FUSED_BN and x.is_cuda:
-        return CF.batch_norm_act(x, bn, residual, relu)
+        if (FUSED_QUANT and next_conv is not None and hasattr(next_conv, "accepts_codes") and next_conv.accepts_codes()):
+            return CF.batch_norm_act(x, bn, residual, relu, next_conv=next_conv)
+        return CF.batch_norm_act(x, bn, residual, relu), None
     out = bn(x)
     if residual is not None:
         out = out + residual
-    return F.relu(out) if relu else out
+    return (F.relu(out) if relu else out), None
+
+
+def _conv(conv, x, codes):
+    return conv(x, xcodes=codes) if codes is not None else conv(x)
 
 
 class _OptionA(nn.Module):
@@ -44,9 +56,12 @@ class BasicBlock(nn.Module):
         self.bn2 = nn.BatchNorm2d(planes)
         self.shortcut = _OptionA(planes) if (stride != 1 or in_planes != planes) else nn.Sequential()
 
-    def forward(self, x):
-        out = _bn_act(self.conv1(x), self.bn1)
-        return _bn_act(self.conv2(out), self.bn2, self.shortcut(x))
+    next_conv = None  # the convolution that consumes this block's output (set by ResNetCifar), for the fused quantiser
+
+    def forward(self, x, xcodes=None):
+        """-> (out, codes of out for ``self.next_conv`` or None)"""
+        out, c1 = _bn_act(_conv(self.conv1, x, xcodes), self.bn1, next_conv=self.conv2)
+        return _bn_act(_conv(self.conv2, out, c1), self.bn2, self.shortcut(x), next_conv=self.next_conv)
 
 
 class ResNetCifar(nn.Module):
@@ -71,9 +86,16 @@ class ResNetCifar(nn.Module):
             self.in_planes = planes
         return nn.Sequential(*layers)
 
+    def _blocks(self):
+        return [b for layer in (self.layer1, self.layer2, self.layer3) for b in layer]
+
     def forward(self, x):
-        out = _bn_act(self.conv1(x), self.bn1)
-        out = self.layer3(self.layer2(self.layer1(out)))
+        blocks = self._blocks()
+        for b, nxt in zip(blocks, blocks[1:] + [None]):  # (object.__setattr__: not a registered submodule)
+            object.__setattr__(b, "next_conv", nxt.conv1 if nxt is not None else None)
+        out, codes = _bn_act(self.conv1(x), self.bn1, next_conv=blocks[0].conv1)
+        for b in blocks:
+            out, codes = b(out, codes)
         out = F.adaptive_avg_pool2d(out, 1).flatten(1)
         return self.linear(out)
 

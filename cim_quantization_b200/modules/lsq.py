@@ -77,7 +77,16 @@ class _CiMForward:
         """``nbits_alpha``-bit range quantiser of alpha_cim, inside autograd (lsq.py:566-571): (alpha_q, step)."""
         return CF.alpha_quantize(self.alpha_cim, self.nbits_alpha)
 
-    def _cim_forward(self, x, w, stride, padding):
+    def accepts_codes(self, x_shape=None) -> bool:
+        """True when this layer can take its activation codes from the producer of its input
+        (``functional.batch_norm_act(..., next_conv=self)``): step sizes initialised, unsigned activations, and the
+        fused v2 path in use.  Checked on the host mirror of the init flags, no device read."""
+        init_done, init_cim_done = self._flags()
+        if not init_done or (self.alpha_cim is not None and not init_cim_done) or self.stochastic_quant:
+            return False
+        return self.nbits_alpha <= 11 and not (self.kernel_flags & _lib.FLAG_FORCE_SIMT) and self.abitslice == 1
+
+    def _cim_forward(self, x, w, stride, padding, xcodes=None):
         """[B,C,H,W] x [Cout,C,k,k] -> [B,Cout,OH,OW] through the crossbar model (adcbits != 0)."""
         if not x.is_cuda:
             raise RuntimeError(f"{type(self).__name__} (cim_quantization_b200) needs CUDA tensors; "
@@ -97,7 +106,8 @@ class _CiMForward:
                 and _lib.v2_usable(spec, self.alpha_cim is not None, True, self.kernel_flags)):
             return CF.cim_conv2d_v2(x, w, self.alpha_act, self.alpha_weight, self.alpha_cim, self.binary_mask, stride,
                                     padding, self.nbits_a, self.abitslice, self.nbits_w, self.wbitslice, self.xbar,
-                                    self.adcbits, self.nbits_alpha, self.kernel_flags)
+                                    self.adcbits, self.nbits_alpha, self.kernel_flags,
+                                    xcodes=xcodes if init_done and (init_cim_done or self.alpha_cim is None) else None)
         alpha_q, alpha_scale = self._alpha_q() if self.alpha_cim is not None else (None, None)
         if self.nbits_alpha > 11:  # the v2 kernels carry alpha_q / scale as an fp16 integer (< 2048)
             alpha_scale = None
@@ -123,13 +133,15 @@ class Conv2dLSQCiM(_Conv2dQCiM, _CiMForward):
         return CF._make_spec(x.shape, self.weight.shape, self.stride, self.padding, self.nbits_a, self.abitslice,
                              self.nbits_w, self.wbitslice, self.xbar, self.adcbits)
 
-    def forward(self, x):
+    def forward(self, x, xcodes=None):
+        """``xcodes`` (extension, optional): the uint8 activation codes of ``x`` already written by its producer
+        (``functional.batch_norm_act(..., next_conv=self)``); ignored unless :meth:`accepts_codes`."""
         if not x.is_cuda:
             raise RuntimeError("Conv2dLSQCiM (cim_quantization_b200) needs CUDA tensors; there is no CPU fallback")
         if self.dilation[0] != 1 or self.groups != 1:
             raise ValueError("Conv2dLSQCiM supports dilation=1, groups=1 (reference envelope, lsq.py:141,153)")
         if self.adcbits != 0:
-            out = self._cim_forward(x, self.weight, self.stride, self.padding)
+            out = self._cim_forward(x, self.weight, self.stride, self.padding, xcodes=xcodes)
             if self.bias is not None:
                 out = out + self.bias  # same broadcast as lsq.py:582-583
             return out

@@ -226,6 +226,16 @@ int cimq_bn_forward(const float *x, const float *residual, const float *weight, 
                     int32_t relu, int32_t batch, int32_t channels, int32_t hw, float *y, float *save_mean,
                     float *save_invstd, void *workspace, void *stream);
 
+/* The same, and -- SURVEY 8 f-2 -- the NEXT layer's activation quantiser (lsq.py:547-549) fused into the epilogue:
+ * next_codes [B,C,HW] uint8 = rint(clamp(y / s, 0, next_qp)) with s = grad_scale(next_alpha_act[0], next_grad_scale),
+ * byte-identical to cimq_lsq_quantize(y, cimq_step_sizes(...)[0], 0, next_qp); y is still written (the residual path and
+ * the quantiser's backward need it).  Replaces resnet.py:83-86 + the first line of the next Conv2dLSQCiM.forward. */
+int cimq_bn_forward_quant(const float *x, const float *residual, const float *weight, const float *bias,
+                          float *running_mean, float *running_var, int32_t training, float momentum, float eps,
+                          int32_t relu, int32_t batch, int32_t channels, int32_t hw, float *y, float *save_mean,
+                          float *save_invstd, void *workspace, const float *next_alpha_act, float next_grad_scale,
+                          int32_t next_qp, uint8_t *next_codes, void *stream);
+
 /* Gradients of the above: grad_x [B,C,HW], grad_residual (NULL if there was none; = grad_y where the ReLU passed),
  * grad_weight / grad_bias [C] (may be NULL).  y is the forward output (ReLU mask; may be NULL if relu == 0);
  * mean / invstd are save_mean / save_invstd of the forward (training) or the running statistics (inference). */

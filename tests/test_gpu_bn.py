@@ -55,3 +55,55 @@ def test_fused_bn_matches_float64_batchnorm(shape, residual, relu, training):
     assert rel_err(bn.running_mean.cpu().numpy(), bn64.running_mean.cpu().numpy()) < TOL
     assert rel_err(bn.running_var.cpu().numpy(), bn64.running_var.cpu().numpy()) < TOL
     assert int(bn.num_batches_tracked) == int(bn64.num_batches_tracked)
+
+
+@pytest.mark.parametrize("shape,res,relu", [((8, 16, 32, 32), False, True), ((4, 32, 16, 16), True, True),
+                                             ((3, 64, 7, 7), True, True), ((2, 16, 8, 8), False, False)])
+def test_bn_forward_quant_codes_equal_the_separate_quantiser(shape, res, relu):
+    """cimq_bn_forward_quant writes the consumer's activation codes in the batch-norm epilogue; they are
+    the bytes cimq_lsq_quantize computes from the fp32 output with the consumer's step size (lsq.py:547-549)."""
+    from cim_quantization_b200 import _lib as L
+    torch.manual_seed(3)
+    b, c, h, w = shape
+    x = torch.randn(shape, device="cuda") * 2.0 + 0.3
+    r = torch.randn(shape, device="cuda") if res else None
+    wt, bs = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    for qp, alpha in ((7, 0.31), (15, 0.173), (255, 0.0123)):
+        alpha_act = torch.tensor([alpha], device="cuda")
+        g = 1.0 / (x.numel() * qp) ** 0.5
+        y0, _, _ = L.bn_forward(x, r, wt, bs, rm.clone(), rv.clone(), True, 0.1, 1e-5, relu)
+        y1, _, _, codes = L.bn_forward(x, r, wt, bs, rm.clone(), rv.clone(), True, 0.1, 1e-5, relu,
+                                       next_quant=(alpha_act, g, qp))
+        assert torch.equal(y0, y1)
+        s = L.step_sizes(alpha_act, alpha_act, g, g)
+        ref = L.lsq_quantize(y0, s[0:1], 0, qp)
+        assert codes.dtype == torch.uint8 and torch.equal(codes, ref.view_as(codes))
+
+
+def test_resnet20_step_identical_with_and_without_fused_quantiser():
+    """The harness ResNet-20 with the batch-norm kernels writing the next layer's codes (harness.FUSED_QUANT) produces
+    the same logits and parameter gradients, bit for bit, as with the separate quantiser launches."""
+    from cim_quantization_b200 import harness
+    torch.manual_seed(0)
+    model = harness.convert_to_cim(harness.resnet20(), nbits_w=3, nbits_a=3, xbar=128, adcbits=1.5).cuda().train()
+    x = torch.randn(16, 3, 32, 32, device="cuda")
+    y = torch.randint(0, 10, (16,), device="cuda")
+    model(x)  # lazy initialisation of the step sizes
+    bn_state = {k: v.clone() for k, v in model.state_dict().items()}
+    results = []
+    from cim_quantization_b200 import _lib as L
+    L.set_deterministic(True)  # fixed-order fold instead of fp32 atomics in the dgrad epilogues
+    for fused in (False, True):
+        harness.FUSED_QUANT = fused
+        model.load_state_dict(bn_state)
+        for p in model.parameters():
+            p.grad = None
+        logits = model(x)
+        torch.nn.functional.cross_entropy(logits, y).backward()
+        results.append((logits.detach().clone(), [p.grad.clone() for p in model.parameters()]))
+    harness.FUSED_QUANT = True
+    L.set_deterministic(False)
+    assert torch.equal(results[0][0], results[1][0])
+    for g0, g1 in zip(results[0][1], results[1][1]):
+        assert torch.equal(g0, g1)

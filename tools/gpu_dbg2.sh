@@ -1,3 +1,2 @@
 #!/bin/bash
-timeout 300 python tools/time_fwd.py 2>&1 | grep "avg"
-timeout 300 python tools/time_bwd.py --only v2 2>&1 | grep "avg"
+timeout 900 python -m pytest tests/test_gpu_bn.py -m gpu -q -x -k "resnet20_step" 2>&1 | tail -12
