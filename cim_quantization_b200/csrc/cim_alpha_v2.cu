@@ -95,18 +95,21 @@ __device__ __forceinline__ void alpha_body(const AlphaParams &P, int i0, int npl
     __syncthreads();
     const uint8_t *buf = smem + (size_t)b * P.buf_bytes;
     const float *gs = reinterpret_cast<const float *>(buf + P.c_bytes) + c * P.gstride;
-    const uint8_t *bp = buf + ph * plane_px + c;
+    // one running pointer per owned plane (planes past the group's end alias the first: their sums are never written)
+    const uint8_t *bq[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) bq[q] = buf + (ph + q * P.phases < npl ? ph + q * P.phases : 0) * plane_px + c;
+#pragma unroll 4
     for (int p = 0; p < P.P; ++p) {
       const float gv = gs[p];
       gsum += gv;
       const float gsc = gv * 1.2676506002282294e30f;  // 2^100
 #pragma unroll
       for (int q = 0; q < PPT; ++q) {
-        if (ph + q * P.phases < npl) {
-          const uint32_t w = bp[q * P.phases * plane_px + p * g.Cout];
+        const uint32_t w = *bq[q];
+        bq[q] += g.Cout;
 #pragma unroll
-          for (int k = 0; k < NS; ++k) acc[q][k] = fmaf(gsc, __uint_as_float(w & (3u << (2 * k))), acc[q][k]);
-        }
+        for (int k = 0; k < NS; ++k) acc[q][k] = fmaf(gsc, __uint_as_float(w & (3u << (2 * k))), acc[q][k]);
       }
     }
     __syncthreads();  // the buffer is refilled by the copies issued at the top of the next iteration

@@ -1,2 +1,3 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_bn.py -m gpu -q -x -k "resnet20_step" 2>&1 | tail -12
+timeout 300 python tools/time_bwd.py --only v2 2>&1 | grep "alpha\|all"
+timeout 600 python -m pytest tests/test_gpu_v2.py tests/test_gpu_matrix.py -m gpu -q -x 2>&1 | tail -2
