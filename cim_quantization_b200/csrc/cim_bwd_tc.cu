@@ -77,6 +77,7 @@ struct BwdParams {
   int fold;  // dgrad: 1 = the epilogue folds (col2im) straight into grad_x with fp32 reductions; 0 = writes gxu[b][f][l]
   int v2;    // 1 = `state` holds the v2 byte planes (cim_v2.cuh): D [NX][M][Cout] for dgrad, W for wgrad
   const uint8_t *state2, *state2w;
+  uint32_t xt_off;     // wgrad: byte offset of the per-(chunk, crossbar row) index tables inside the dynamic shared memory
   const uint32_t *chmax;  // v2 wgrad: bit pattern of max |grad_out| per output channel (launch_go_scales)
   const float *go;
   const uint32_t *state;
@@ -576,6 +577,7 @@ __device__ __noinline__ uint2 gather_codes_generic(GatherGeo g, const uint8_t *_
   return make_uint2(c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24), c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24));
 }
 
+__host__ __device__ inline size_t wg_table_bytes(int nxg) { return (size_t)nxg * (sizeof(int4) + 128 * sizeof(uint32_t)); }  // index tables
 constexpr int kWgLBO = 144;  // padded K-stride of the G' tiles: producer lanes run along K (bank-conflict free)
 
 // ---- wgrad X tile (im2col^T digit planes), v2 fast path: item counts and strides are compile-time per thread role so
@@ -703,6 +705,26 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     const int gpg = tid & 15, gco0 = tid >> 4;
     float gvc[3][8];
     uint32_t swc[3][8];
+    // ---- index tables of this CTA's chunks (built once): xt_chunk[c] = {lo, rows, first channel, channels touched},
+    // xt_row[c][fr] = valid << 31 | kx << 24 | ky << 16 | (channel - first channel)
+    int4 *xt_chunk = reinterpret_cast<int4 *>(smem_raw + P.xt_off);
+    uint32_t *xt_row = reinterpret_cast<uint32_t *>(smem_raw + P.xt_off + (size_t)P.nxg * sizeof(int4));
+    for (int e = tid; e < (i_end - i_begin) * 128; e += kWgProducerThreads) {
+      const int c = e >> 7, r = e & 127;
+      const int lo_ = (i_begin + c) * g.xbar, rows_ = min(rows_full, g.F - lo_);
+      const int c_lo_ = lo_ / g.KK;
+      uint32_t v = 0u;
+      if (r < rows_) {
+        const int f = lo_ + r, ci_ = f / g.KK, tap = f % g.KK;
+        v = 0x80000000u | ((uint32_t)(tap % g.K) << 24) | ((uint32_t)(tap / g.K) << 16) | (uint32_t)ci_;
+      }
+      xt_row[e] = v;
+      if (r == 0) xt_chunk[c] = make_int4(lo_, rows_, c_lo_, (lo_ + rows_ - 1) / g.KK - c_lo_ + 1);
+    }
+    named_barrier_sync(1, kWgProducerThreads);
+    const int ir_cpr = P.async_rows ? g.W / P.async_rows : 1;
+    const int ir_rq = tid / ir_cpr, ir_c16 = tid - ir_rq * ir_cpr;
+    const int ir_sl = ir_rq / (P.rk > 0 ? P.rk : 1), ir_row = ir_rq - ir_sl * (P.rk > 0 ? P.rk : 1);
     auto pix_group = [&](int mt_) {  // {image, output row, first output column, kind} of this thread's pixel group
       const int64_t m = (int64_t)mt_ * kTcTileM + gpg * 8;
       int4 e = make_int4(0, 0, 0, -1);
@@ -752,13 +774,14 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     };
     // async staging of the channels crossbar i_ touches: 16-byte pieces, zero-fill for rows outside the image
     auto issue_rows = [&](int i_, const int *tab, uint8_t *dstbuf) {
-      const int lo_ = i_ * g.xbar, rows_ = min(rows_full, g.F - lo_);
-      const int c_lo_ = lo_ / g.KK, nch_ = (lo_ + rows_ - 1) / g.KK - c_lo_ + 1;
+      const int4 ci_ = xt_chunk[i_ - i_begin];
+      const int c_lo_ = ci_.z, nch_ = ci_.w;
       // pieces of 16 bytes, or of 8 for rows of 8 (mod 16) bytes (P.async_rows = piece size)
-      const int ps = P.async_rows, cpr = g.W / ps, total = nch_ * P.rk * cpr;
+      const int ps = P.async_rows, cpr = ir_cpr, total = nch_ * P.rk * cpr;
       for (int q = tid; q < total && !(P.dbg & 16); q += kWgProducerThreads) {
-        const int rq = q / cpr, c16 = q - rq * cpr;
-        const int sl = rq / P.rk, row = rq - sl * P.rk;
+        int rq, c16, sl, row;
+        if (q == tid) { rq = ir_rq; c16 = ir_c16; sl = ir_sl; row = ir_row; }  // (the common case: one piece per thread)
+        else { rq = q / cpr; c16 = q - rq * cpr; sl = rq / P.rk; row = rq - sl * P.rk; }
         const int off = tab[row];
         const bool ok = off != kNoRow;
         const uint8_t *src = P.xcodes + (ok ? (size_t)(c_lo_ + sl) * HW + off + ps * c16 : (size_t)0);
@@ -878,12 +901,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
       }
       const int4 *ptab = cv.pixtab + tpar * 16;
       for (int i = i_begin; i < i_end; ++i, ++chunk_it) {
-        const int lo = i * g.xbar;
-        const int rows = min(rows_full, g.F - lo);
-        const bool frow = fr < rows;
-        int ci = 0, ky = 0, kx = 0;
-        if (frow) { const int f = lo + fr; ci = f / g.KK; const int tap = f % g.KK; ky = tap / g.K; kx = tap % g.K; }
-        const int c_lo = lo / g.KK;
+        // (channel, tap) of this thread's crossbar row and the chunk's channel range: from the tables built at kernel
+        // start -- five divisions by run-time values per chunk and thread were a quarter of the producers' instructions
+        const int4 cinf = xt_chunk[i - i_begin];  // {lo, rows, c_lo, nch}
+        const int lo = cinf.x, rows = cinf.y, c_lo = cinf.z;
+        const uint32_t xinf = xt_row[(i - i_begin) * 128 + fr];
+        const bool frow = (xinf >> 31) != 0;
+        const int ci = (int)(xinf & 0xffffu), ky = (int)((xinf >> 16) & 0xffu), kx = (int)((xinf >> 24) & 0x7fu);
         const int st_next = (i + 1) / P.sdiv, st_first = i_begin / P.sdiv;  // state (crossbar) index of the next chunk
         uint8_t *raw = cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes;
         const long long ts0 = CIMQ_TB();
@@ -1547,6 +1571,9 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
   P.stage_bytes = P.a_bytes + (v2 ? v2::kBwdPieces : 3) * P.b_bytes;
   CIMQ_REQUIRE(!v2 || scales != nullptr, "wgrad (v2): the grad_out scales are missing");
   if (v2) P.chmax = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(scales) + (((int64_t)g0.M * 4 + 255) & ~(int64_t)255));
+  int groups = 1;
+  const int ctas = wgrad_ctas(g, v2, &P.nxg, &groups);
+  const size_t tbytes = wg_table_bytes(P.nxg);
   // staged activation rows (stride 1, output width a power of two between 8 and 128, 4-byte aligned rows)
   P.fastx = 0; P.raw_bytes = 0;
   if (g.stride == 1 && g.W % 4 == 0 && g.OW >= 8 && g.OW <= kTcTileM && (g.OW & (g.OW - 1)) == 0 &&
@@ -1567,25 +1594,24 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
     const bool shared_rows = g.L % kTcTileM == 0;
     const int rk = shared_rows ? rpt - 1 + g.K : rpt * g.K;
     const size_t raw = ((size_t)nch * rk * (1u << pl) + 8 + 15) & ~(size_t)15;
-    if (pl <= 9 && rk <= 128 && 2 * raw + 2 * P.stage_bytes + kBarrierBytes <= kSmemBudget) {
+    if (pl <= 9 && rk <= 128 && 2 * raw + 2 * P.stage_bytes + kBarrierBytes + tbytes + 16 <= kSmemBudget) {
       P.fastx = 1; P.ow_log2 = owl; P.rpt = rpt; P.pitch_log2 = pl; P.col0 = col0;
       P.rk = rk; P.prow = shared_rows ? 1 : g.K; P.xshared = shared_rows ? 1 : 0; P.async_rows = async_rows ? (g.W % 16 == 0 ? 16 : 8) : 0;
       P.raw_bytes = (uint32_t)raw;
     }
   }
-  int stages = (int)((kSmemBudget - kBarrierBytes - 2 * (size_t)P.raw_bytes) / P.stage_bytes);
+  int stages = (int)((kSmemBudget - kBarrierBytes - 2 * (size_t)P.raw_bytes - tbytes - 16) / P.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   CIMQ_REQUIRE(stages >= 1, "wgrad tile does not fit shared memory");
   P.stages = stages;
   P.gfast = (g.L % 8 == 0 && g.OW % 8 == 0 && g.M % 8 == 0 && g.M >= 8 &&
              (reinterpret_cast<uintptr_t>(go) & 15u) == 0 && (reinterpret_cast<uintptr_t>(state) & 15u) == 0) ? 1 : 0;
-  int groups = 1;
-  const int ctas = wgrad_ctas(g, v2, &P.nxg, &groups);
   uint32_t cols = 32;
   while (cols < (uint32_t)(P.nxg * P.Kc)) cols <<= 1;
   P.tmem_cols = cols;
   P.go = go; P.state = state; P.xcodes = xcodes; P.s = s; P.mask = mask; P.out = partial;
-  const size_t smem = (size_t)stages * P.stage_bytes + kBarrierBytes + 2 * (size_t)P.raw_bytes + 1024;
+  P.xt_off = (uint32_t)(((size_t)stages * P.stage_bytes + kBarrierBytes + 2 * (size_t)P.raw_bytes + 15) & ~(size_t)15);
+  const size_t smem = (size_t)P.xt_off + tbytes + 1024;
   dim3 grid(ctas, groups);
   if (const char *e = getenv("CIMQ_V2_DBG")) P.dbg = v2 ? atoi(e) : 0;
 #define CIMQ_LAUNCH_WGRAD(W, A, T, ...)                                        \
