@@ -91,6 +91,7 @@ struct Smem {
   int *rowoff;           // 2 * 128 ints: global offset of staged row (orow, ky) or kNoRow
   uint32_t full0, empty0, tfull0, tempty0;
   uint32_t *tmem_slot;
+  const ChunkLayout *cltab = nullptr;  // [NX] chunk layouts precomputed in shared memory (v2 kernel), or NULL
 };
 constexpr size_t kAuxBytes = 2048;  // barriers, tmem slot, rowoff table
 
@@ -222,8 +223,9 @@ __device__ __forceinline__ void stage_issue_async(const TcParams &P, const Chunk
   const int cpr = g.W >> 4;  // 16-byte pieces per row
   const int total = nslots * P.rk * cpr, HW = g.H * g.W;
   const int ch_head = cl.nhead > 0 ? cl.cf0 - 1 : cl.cf0 + cl.nfull, ch_tail = cl.cf0 + cl.nfull;
+  const int cshift = (cpr & (cpr - 1)) == 0 ? 31 - __clz(cpr) : -1;  // (row widths of 16 * 2^n bytes: a shift)
   for (int q = tid; q < total; q += kProducerThreads) {
-    const int rq = q / cpr, c16 = q - rq * cpr;
+    const int rq = cshift >= 0 ? q >> cshift : q / cpr, c16 = q - rq * cpr;
     const int sl = (int)__umulhi((uint32_t)rq, P.rk_magic), row = rq - sl * P.rk;
     const int off = rowoff[row];
     const bool ok = off != kNoRow;
@@ -411,6 +413,15 @@ __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm,
   const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   long long d_wait = 0, d_prod = 0, d_tile = 0;
   uint32_t it = (uint32_t)gidx, lit = 0;  // global / group-local stage counters
+  // stage slot / use count of stage `it` as running counters, chunk layouts from a table where the kernel provides one:
+  // divisions by run-time values (it % stages, the four of chunk_layout) were a sizeable part of a producer stage
+  int p_sidx = gidx % P.stages;
+  uint32_t p_use = (uint32_t)(gidx / P.stages);
+  auto next_slot = [&]() {
+    p_sidx += ngroups;
+    while (p_sidx >= P.stages) { p_sidx -= P.stages; ++p_use; }
+  };
+  auto layout_of = [&](int i_) { return sm.cltab != nullptr ? sm.cltab[i_] : chunk_layout(g, i_); };
   // (tile, i) of stage `it`: advance by n stages
   auto advance = [&](int &tile_, int &i_, int n) {
     i_ += n;
@@ -431,20 +442,20 @@ __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm,
         for (uint32_t q = tid * 16u; q < 2u * P.raw_bytes; q += kProducerThreads * 16u)
           *reinterpret_cast<uint4 *>(sm.raw + q) = make_uint4(0u, 0u, 0u, 0u);
         named_barrier_sync(bar, kProducerThreads);
-        stage_issue_async(P, chunk_layout(g, i), sm.rowoff, sm.raw, tid);
+        stage_issue_async(P, layout_of(i), sm.rowoff, sm.raw, tid);
         stage_async_wait();
         named_barrier_sync(bar, kProducerThreads);
       }
       if (P.prefetch) {
-        const ChunkLayout cl0 = chunk_layout(g, i);
+        const ChunkLayout cl0 = layout_of(i);
         stage_load<kPrefetchWords>(P, stt, cl0, sm.rowoff, 0, v);
         stage_store<kPrefetchWords>(P, stt, cl0, 0, v, sm.raw, tid);
         named_barrier_sync(bar, kProducerThreads);
       }
     }
     while (tile < ntiles) {
-      const int ct = tile % P.nct;
-      const ChunkLayout cl = chunk_layout(g, i);
+      const int ct = P.nct == 1 ? 0 : tile % P.nct;
+      const ChunkLayout cl = layout_of(i);
       uint8_t *raw = sm.raw + (size_t)(lit & 1) * P.raw_bytes;
       // the group's next stage
       int ni = i, ntile = tile;
@@ -453,7 +464,7 @@ __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm,
       const bool more = ntile < ntiles;
       ChunkLayout ncl = cl;
       if (more) {
-        ncl = chunk_layout(g, ni);
+        ncl = layout_of(ni);
         if (ntile != tile) {  // new tile: publish its row table first (its buffer was last read a whole tile ago)
           stage_set_rowoff(P, ntile / P.nct, sm.rowoff + ntpar * 128, tid);
           named_barrier_sync(bar, kProducerThreads);
@@ -474,8 +485,9 @@ __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm,
         }
         named_barrier_sync(bar, kProducerThreads);
       }
-      const int sidx = it % P.stages;
-      const uint32_t use = it / P.stages;
+      const int sidx = p_sidx;
+      const uint32_t use = p_use;
+      next_slot();
       long long t0 = CIMQ_T0();
       mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
       long long t1 = CIMQ_T0();
@@ -523,8 +535,9 @@ __device__ __forceinline__ void producer_loop(const TcParams &P, const Smem &sm,
               if (iy0 + ky >= 0 && iy0 + ky < g.H && ix0 + kx >= 0 && ix0 + kx < g.W) vm |= 1u << (ky * g.K + kx);
         }
       }
-      const int sidx = it % P.stages;
-      const uint32_t use = it / P.stages;
+      const int sidx = p_sidx;
+      const uint32_t use = p_use;
+      next_slot();
       mbar_wait(sm.empty0 + 8 * sidx, (use & 1) ^ 1);
       uint8_t *st_ptr = sm.stage_base + (size_t)sidx * P.stage_bytes;
       if (tid == 0) {

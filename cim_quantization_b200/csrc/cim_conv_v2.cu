@@ -181,6 +181,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
   sm.tmem_slot = reinterpret_cast<uint32_t *>(pp + 192);
   sm.rowoff = reinterpret_cast<int *>(pp + 256);  // per producer group 2 x 128 ints
   sm.ttab = nullptr;
+  ChunkLayout *cltab = reinterpret_cast<ChunkLayout *>(pp + 256 + kProducerGroups * 2 * 128 * 4);  // [NX] (<= 64 chunks)
+  sm.cltab = g.NX <= (int)((kAuxBytes - 256 - kProducerGroups * 1024) / sizeof(ChunkLayout)) ? cltab : nullptr;
+  if (sm.cltab != nullptr && (int)threadIdx.x < g.NX) cltab[threadIdx.x] = chunk_layout(g, threadIdx.x);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
