@@ -158,6 +158,7 @@ struct DgSmem {
   uint8_t *dbuf;  // [2][128 * Kc] D bytes of the current / next chunk (dbulk)
   int *ftab;  // [F]: fold entry of unfold row f: offset inside the image << 7 | kx << 5 | tap
   int *tup;   // [NX][2][24]: complete tuple tt = 2v + eh of chunk i at [i][eh][v]: ((ci * H + ky) * W) << 2 | ky
+  DgradCols *dcols;  // [NX] column layout of every chunk (computed once: three run-time divisions each)
 };
 
 // NS: digit planes per operand; CPT: channels per producer thread (Kc / 2)
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
     sm.dbuf = smem_raw + P.dbuf_off;
     sm.ftab = reinterpret_cast<int *>(smem_raw + P.ftab_off);
     sm.tup = reinterpret_cast<int *>(smem_raw + P.tup_off);
+    sm.dcols = reinterpret_cast<DgradCols *>(smem_raw + P.tup_off + (size_t)g.NX * kTupStride * 4);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Kc = P.Kc, Nf = P.Nf;
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
     }
     sm.tup[e] = val;
   }
+  if ((int)threadIdx.x < g.NX) sm.dcols[threadIdx.x] = dgrad_cols(g, threadIdx.x);
   if (warp == kDgMmaWarp) tmem_alloc(smem_u32(sm.tmem_slot), P.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
       for (int i = 0; i < g.NX; ++i) {
         const uint32_t buf = a_buf, buse = a_use;
         if (++a_buf == (uint32_t)P.nbuf) { a_buf = 0; ++a_use; }
-        const DgradCols dc = dgrad_cols(g, i);
+        const DgradCols dc = sm.dcols[i];
         const int ntup = (P.dbg & 2) ? 0 : (P.fast ? dc.ntup : 0);
         const int *tup = sm.tup + i * kTupStride + eh * 24;
         mbar_wait(sm.tfull0 + 8 * buf, buse & 1);
@@ -588,7 +591,7 @@ int launch_bwd_input_v2(const Geo &g, const float *go, const uint8_t *state, con
   P.fast = (fold && g.K == 3 && g.stride == 1 && g.pad == 1 && (g.OW == 8 || g.OW == 16 || g.OW == 32) &&
             (g.L % kTcTileM == 0 || 2 * g.L == kTcTileM)) ? 1 : 0;  // a tile is rows of one image, or two whole images
   const size_t ftab_bytes = ((size_t)g.F * 4 + 15) & ~(size_t)15;
-  const size_t tup_bytes = (size_t)g.NX * kTupStride * 4;
+  const size_t tup_bytes = (size_t)g.NX * (kTupStride * 4 + sizeof(v2::DgradCols));
   P.dbulk = (g.Cout == P.Kc && (reinterpret_cast<uintptr_t>(state) & 15u) == 0) ? 1 : 0;
   const size_t dbuf_bytes = P.dbulk ? 2 * (size_t)kTcTileM * P.Kc : 0;
   const size_t fixed = 256 + ftab_bytes + tup_bytes + 16 + dbuf_bytes;
