@@ -857,387 +857,414 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         v2_load_w(blockIdx.x, i_begin);
       }
     }
-    for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
-      const int64_t m0 = (int64_t)mt * kTcTileM;
-      if constexpr (V2) {
-        if (g_thread && !(P.dbg & 32)) {  // this tile's grad_out (loaded during the previous tile's last stage) -> scaled fp16 pieces
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float v0 = gs2[c][2 * q] * chs[c], v1 = gs2[c][2 * q + 1] * chs[c];
-              constexpr uint32_t kMask = 0xffffffffu << (24 - PB2), kRnd = 1u << (23 - PB2);
-              const float a0 = __uint_as_float((__float_as_uint(v0) + kRnd) & kMask);
-              const float a1 = __uint_as_float((__float_as_uint(v1) + kRnd) & kMask);
-              const float r0 = v0 - a0, r1 = v1 - a1;
-              const float b0 = __uint_as_float((__float_as_uint(r0) + kRnd) & kMask);
-              const float b1 = __uint_as_float((__float_as_uint(r1) + kRnd) & kMask);
-              const __half2 h1 = __floats2half2_rn(a0, a1), h2v = __floats2half2_rn(b0, b1);
-              gp1[c][q] = *reinterpret_cast<const uint32_t *>(&h1);
-              gp2[c][q] = *reinterpret_cast<const uint32_t *>(&h2v);
-            }
-        }
-      }
-      const int mt_n = mt + gridDim.x;
-      if (gcache && mt_n < P.mtiles) gpt_n = pix_group(mt_n);
-      // per 8-pixel group: image, output row, first output column; fast = one image row, fully valid, aligned
-      if (tid < 16) {
-        const int64_t m = m0 + tid * 8;
-        int4 e = make_int4(0, 0, 0, -1);  // w = -1: entirely past the end
-        if (m < g.M) {
-          const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
-          e = make_int4(b, oy, ox, (aligned && m + 7 < g.M && ox + 7 < g.OW) ? 1 : 0);
-        }
-        cv.pixtab[tpar * 16 + tid] = e;
-      }
-      int *rowoff = cv.rowoff + tpar * 128;
-      // async staging fills the table of a tile one chunk before the tile starts (below); the first tile's here
-      if (P.fastx && (!P.async_rows || mt == (int)blockIdx.x)) fill_rowoff(mt, rowoff);
-      named_barrier_sync(1, kWgProducerThreads);
-      if (P.async_rows && mt == (int)blockIdx.x) {  // rows of the very first chunk
-        issue_rows(i_begin, rowoff, cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        named_barrier_sync(1, kWgProducerThreads);
-      }
-      const int4 *ptab = cv.pixtab + tpar * 16;
-      for (int i = i_begin; i < i_end; ++i, ++chunk_it) {
-        // (channel, tap) of this thread's crossbar row and the chunk's channel range: from the tables built at kernel
-        // start -- five divisions by run-time values per chunk and thread were a quarter of the producers' instructions
-        const int4 cinf = xt_chunk[i - i_begin];  // {lo, rows, c_lo, nch}
-        const int lo = cinf.x, rows = cinf.y, c_lo = cinf.z;
-        const uint32_t xinf = xt_row[(i - i_begin) * 128 + fr];
-        const bool frow = (xinf >> 31) != 0;
-        const int ci = (int)(xinf & 0xffffu), ky = (int)((xinf >> 16) & 0xffu), kx = (int)((xinf >> 24) & 0x7fu);
-        const int st_next = (i + 1) / P.sdiv, st_first = i_begin / P.sdiv;  // state (crossbar) index of the next chunk
-        uint8_t *raw = cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes;
-        const long long ts0 = CIMQ_TB();
-        if (P.async_rows) {
-          // the rows of this chunk are already in raw[chunk_it & 1]; start the next chunk's (or next tile's first)
-          uint8_t *nbuf = cv.raw + (size_t)((chunk_it + 1) & 1) * P.raw_bytes;
-          if (i + 1 < i_end) {
-            issue_rows(i + 1, rowoff, nbuf);
-          } else if (mt_n < P.mtiles) {
-            fill_rowoff(mt_n, cv.rowoff + (tpar ^ 1) * 128);
-            named_barrier_sync(1, kWgProducerThreads);
-            issue_rows(i_begin, cv.rowoff + (tpar ^ 1) * 128, nbuf);
-          }
-        } else if (P.fastx) {
-          // stage the input rows of the channels this crossbar touches (once per chunk, shared by all planes)
-          const int nch = (lo + rows - 1) / g.KK - c_lo + 1;
-          const int wpr_log2 = P.pitch_log2 - 2;
-          const int xw = tid & ((1 << wpr_log2) - 1);
-          const int rstep = kWgProducerThreads >> wpr_log2;
-          const int rk = P.rk;
-          const int total_rows = nch * rk;
-          const int ix = 4 * xw - P.col0 - g.pad;
-          const bool xok = ix >= 0 && ix < g.W;
-          int row = tid >> wpr_log2, sl = 0;
-          while (row >= rk) { row -= rk; ++sl; }
-          for (int r0 = tid >> wpr_log2; r0 < total_rows; r0 += 4 * rstep) {
-            uint32_t v[4];
-            int dsto[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              v[u] = 0u;
-              dsto[u] = -1;
-              if (r0 + u * rstep < total_rows) {
-                const int off = rowoff[row];
-                if (xok && off != kNoRow)
-                  v[u] = __ldg(reinterpret_cast<const uint32_t *>(P.xcodes + (size_t)(c_lo + sl) * HW + off + 4 * xw));
-                dsto[u] = sl * slot_bytes + (row << P.pitch_log2) + 4 * xw;
+    // The tile loop is instantiated per thread ROLE where the roles are fixed (v2 with 256 G' threads: 1 = G' thread with
+    // one X item, 2 = X thread with fourteen; 0 = decided at run time): the G' registers (pieces, paired W bytes, raw
+    // grad_out) and the X registers (gathered codes of 14 items) then never live in the same thread.
+    auto run_tiles = [&](auto role_tag) {
+      constexpr int ROLE = decltype(role_tag)::value;
+      constexpr int XIr = ROLE == 1 ? 1 : XI;
+      const bool gthr = ROLE == 1 || (ROLE == 0 && g_thread);
+      const int xc = ROLE == 1 ? 1 : (ROLE == 2 ? 14 : x_cnt);
+      for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
+        const int64_t m0 = (int64_t)mt * kTcTileM;
+        if constexpr (V2) {
+          if (gthr && !(P.dbg & 32)) {  // this tile's grad_out (loaded during the previous tile's last stage) -> scaled fp16 pieces
+  #pragma unroll
+            for (int c = 0; c < 4; ++c)
+  #pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float v0 = gs2[c][2 * q] * chs[c], v1 = gs2[c][2 * q + 1] * chs[c];
+                constexpr uint32_t kMask = 0xffffffffu << (24 - PB2), kRnd = 1u << (23 - PB2);
+                const float a0 = __uint_as_float((__float_as_uint(v0) + kRnd) & kMask);
+                const float a1 = __uint_as_float((__float_as_uint(v1) + kRnd) & kMask);
+                const float r0 = v0 - a0, r1 = v1 - a1;
+                const float b0 = __uint_as_float((__float_as_uint(r0) + kRnd) & kMask);
+                const float b1 = __uint_as_float((__float_as_uint(r1) + kRnd) & kMask);
+                const __half2 h1 = __floats2half2_rn(a0, a1), h2v = __floats2half2_rn(b0, b1);
+                gp1[c][q] = *reinterpret_cast<const uint32_t *>(&h1);
+                gp2[c][q] = *reinterpret_cast<const uint32_t *>(&h2v);
               }
-              row += rstep;
-              while (row >= rk) { row -= rk; ++sl; }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (dsto[u] >= 0) *reinterpret_cast<uint32_t *>(raw + dsto[u]) = v[u];
           }
+        }
+        const int mt_n = mt + gridDim.x;
+        if (gcache && mt_n < P.mtiles) gpt_n = pix_group(mt_n);
+        // per 8-pixel group: image, output row, first output column; fast = one image row, fully valid, aligned
+        if (tid < 16) {
+          const int64_t m = m0 + tid * 8;
+          int4 e = make_int4(0, 0, 0, -1);  // w = -1: entirely past the end
+          if (m < g.M) {
+            const int b = (int)(m / g.L), l = (int)(m % g.L), oy = l / g.OW, ox = l % g.OW;
+            e = make_int4(b, oy, ox, (aligned && m + 7 < g.M && ox + 7 < g.OW) ? 1 : 0);
+          }
+          cv.pixtab[tpar * 16 + tid] = e;
+        }
+        int *rowoff = cv.rowoff + tpar * 128;
+        // async staging fills the table of a tile one chunk before the tile starts (below); the first tile's here
+        if (P.fastx && (!P.async_rows || mt == (int)blockIdx.x)) fill_rowoff(mt, rowoff);
+        named_barrier_sync(1, kWgProducerThreads);
+        if (P.async_rows && mt == (int)blockIdx.x) {  // rows of the very first chunk
+          issue_rows(i_begin, rowoff, cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes);
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
           named_barrier_sync(1, kWgProducerThreads);
         }
-        // ---- the activation codes of this thread's X items (row fr, 8-pixel group pg = tid/128 + 3q), gathered once
-        // per chunk: the NSA digit planes below only shift and mask them
-        uint32_t xlo[XI], xhi[XI];
-        const bool xfast = V2 && P.fastx;  // (v2 layers have 1-bit digits)
-        if (xfast && !(P.dbg & 8)) {
-          const uint8_t *src_row = raw + (size_t)(ci - c_lo) * slot_bytes + ((size_t)ky << P.pitch_log2) + kx + P.col0;
-          const int rps = P.pitch_log2 + (P.prow == 1 ? 0 : (g.K == 1 ? 0 : -1));  // row pitch shift (see below)
-          (void)rps;
-          // output row r of the tile is staged r * prow rows further down; prow is 1 or K (not a power of two in
-          // general), so the row offset is a multiply
-          const int rowb = P.prow << P.pitch_log2;
-          auto gather = [&](auto cnt, auto stp) {
-#pragma unroll
-            for (int q = 0; q < decltype(cnt)::value; ++q) {
-              const int p0 = (x_pg0 + decltype(stp)::value * q) * 8;
-              uint32_t lo8 = 0u, hi8 = 0u;
-              if (frow) {
-                const uint8_t *src = src_row + (p0 >> P.ow_log2) * rowb + (p0 & ((1 << P.ow_log2) - 1));
+        const int4 *ptab = cv.pixtab + tpar * 16;
+        for (int i = i_begin; i < i_end; ++i, ++chunk_it) {
+          // (channel, tap) of this thread's crossbar row and the chunk's channel range: from the tables built at kernel
+          // start -- five divisions by run-time values per chunk and thread were a quarter of the producers' instructions
+          const int4 cinf = xt_chunk[i - i_begin];  // {lo, rows, c_lo, nch}
+          const int lo = cinf.x, rows = cinf.y, c_lo = cinf.z;
+          const uint32_t xinf = xt_row[(i - i_begin) * 128 + fr];
+          const bool frow = (xinf >> 31) != 0;
+          const int ci = (int)(xinf & 0xffffu), ky = (int)((xinf >> 16) & 0xffu), kx = (int)((xinf >> 24) & 0x7fu);
+          const int st_next = (i + 1) / P.sdiv, st_first = i_begin / P.sdiv;  // state (crossbar) index of the next chunk
+          uint8_t *raw = cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes;
+          const long long ts0 = CIMQ_TB();
+          if (P.async_rows) {
+            // the rows of this chunk are already in raw[chunk_it & 1]; start the next chunk's (or next tile's first)
+            uint8_t *nbuf = cv.raw + (size_t)((chunk_it + 1) & 1) * P.raw_bytes;
+            if (i + 1 < i_end) {
+              issue_rows(i + 1, rowoff, nbuf);
+            } else if (mt_n < P.mtiles) {
+              fill_rowoff(mt_n, cv.rowoff + (tpar ^ 1) * 128);
+              named_barrier_sync(1, kWgProducerThreads);
+              issue_rows(i_begin, cv.rowoff + (tpar ^ 1) * 128, nbuf);
+            }
+          } else if (P.fastx) {
+            // stage the input rows of the channels this crossbar touches (once per chunk, shared by all planes)
+            const int nch = (lo + rows - 1) / g.KK - c_lo + 1;
+            const int wpr_log2 = P.pitch_log2 - 2;
+            const int xw = tid & ((1 << wpr_log2) - 1);
+            const int rstep = kWgProducerThreads >> wpr_log2;
+            const int rk = P.rk;
+            const int total_rows = nch * rk;
+            const int ix = 4 * xw - P.col0 - g.pad;
+            const bool xok = ix >= 0 && ix < g.W;
+            int row = tid >> wpr_log2, sl = 0;
+            while (row >= rk) { row -= rk; ++sl; }
+            for (int r0 = tid >> wpr_log2; r0 < total_rows; r0 += 4 * rstep) {
+              uint32_t v[4];
+              int dsto[4];
+  #pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                v[u] = 0u;
+                dsto[u] = -1;
+                if (r0 + u * rstep < total_rows) {
+                  const int off = rowoff[row];
+                  if (xok && off != kNoRow)
+                    v[u] = __ldg(reinterpret_cast<const uint32_t *>(P.xcodes + (size_t)(c_lo + sl) * HW + off + 4 * xw));
+                  dsto[u] = sl * slot_bytes + (row << P.pitch_log2) + 4 * xw;
+                }
+                row += rstep;
+                while (row >= rk) { row -= rk; ++sl; }
+              }
+  #pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (dsto[u] >= 0) *reinterpret_cast<uint32_t *>(raw + dsto[u]) = v[u];
+            }
+            named_barrier_sync(1, kWgProducerThreads);
+          }
+          // ---- the activation codes of this thread's X items (row fr, 8-pixel group pg = tid/128 + 3q), gathered once
+          // per chunk: the NSA digit planes below only shift and mask them
+          uint32_t xlo[XIr], xhi[XIr];
+          const bool xfast = V2 && P.fastx;  // (v2 layers have 1-bit digits)
+          if (xfast && !(P.dbg & 8)) {
+            const uint8_t *src_row = raw + (size_t)(ci - c_lo) * slot_bytes + ((size_t)ky << P.pitch_log2) + kx + P.col0;
+            const int rps = P.pitch_log2 + (P.prow == 1 ? 0 : (g.K == 1 ? 0 : -1));  // row pitch shift (see below)
+            (void)rps;
+            // output row r of the tile is staged r * prow rows further down; prow is 1 or K (not a power of two in
+            // general), so the row offset is a multiply
+            const int rowb = P.prow << P.pitch_log2;
+            auto gather = [&](auto cnt, auto stp) {
+  #pragma unroll
+              for (int q = 0; q < decltype(cnt)::value; ++q) {
+                const int p0 = (x_pg0 + decltype(stp)::value * q) * 8;
+                uint32_t lo8 = 0u, hi8 = 0u;
+                if (frow) {
+                  const uint8_t *src = src_row + (p0 >> P.ow_log2) * rowb + (p0 & ((1 << P.ow_log2) - 1));
+                  const uint32_t sa = smem_u32(src);
+                  const uint32_t *al = reinterpret_cast<const uint32_t *>(src - (sa & 3u));
+                  const uint32_t w0 = al[0], w1 = al[1], w2 = al[2];
+                  const uint32_t bsh = (sa & 3u) * 8u;
+                  lo8 = __funnelshift_r(w0, w1, bsh);
+                  hi8 = __funnelshift_r(w1, w2, bsh);
+                }
+                xlo[q] = lo8;
+                xhi[q] = hi8;
+              }
+            };
+            if constexpr (ROLE == 1) gather(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+            else if constexpr (ROLE == 2) gather(std::integral_constant<int, 14>{}, std::integral_constant<int, 1>{});
+            else {
+              if (xc == 14) gather(std::integral_constant<int, 14>{}, std::integral_constant<int, 1>{});
+              else if (xc == 8) gather(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
+              else if (xc == 1) gather(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+            }
+          }
+  #pragma unroll
+          for (int q = 0; q < XIr; ++q) {
+            if (xfast) break;
+            const int pg = x_pg0 + x_step * q;
+            xlo[q] = 0u;
+            xhi[q] = 0u;
+            if (pg < 16 && q < xc) {
+            uint32_t lo8 = 0u, hi8 = 0u;
+            if (frow) {
+              if (P.fastx) {
+                const int p0 = pg * 8;
+                const uint8_t *src = raw + (size_t)(ci - c_lo) * slot_bytes +
+                                     ((((p0 >> P.ow_log2) * P.prow) + ky) << P.pitch_log2) +
+                                     (p0 & ((1 << P.ow_log2) - 1)) + kx + P.col0;
                 const uint32_t sa = smem_u32(src);
                 const uint32_t *al = reinterpret_cast<const uint32_t *>(src - (sa & 3u));
                 const uint32_t w0 = al[0], w1 = al[1], w2 = al[2];
                 const uint32_t bsh = (sa & 3u) * 8u;
                 lo8 = __funnelshift_r(w0, w1, bsh);
                 hi8 = __funnelshift_r(w1, w2, bsh);
+              } else {  // geometries without staged rows: out of line, it would be inlined six times here
+                const uint2 c8 = gather_codes_generic(GatherGeo{g.stride, g.pad, g.H, g.W, g.Cin, g.L, g.OW, g.M}, P.xcodes,
+                                                      ptab[pg], ci, ky, kx, m0 + pg * 8);
+                lo8 = c8.x;
+                hi8 = c8.y;
               }
+            }
               xlo[q] = lo8;
               xhi[q] = hi8;
             }
-          };
-          if (x_cnt == 14) gather(std::integral_constant<int, 14>{}, std::integral_constant<int, 1>{});
-          else if (x_cnt == 8) gather(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
-          else if (x_cnt == 1) gather(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
-        }
-#pragma unroll
-        for (int q = 0; q < XI; ++q) {
-          if (xfast) break;
-          const int pg = x_pg0 + x_step * q;
-          xlo[q] = 0u;
-          xhi[q] = 0u;
-          if (pg < 16 && q < x_cnt) {
-          uint32_t lo8 = 0u, hi8 = 0u;
-          if (frow) {
-            if (P.fastx) {
-              const int p0 = pg * 8;
-              const uint8_t *src = raw + (size_t)(ci - c_lo) * slot_bytes +
-                                   ((((p0 >> P.ow_log2) * P.prow) + ky) << P.pitch_log2) +
-                                   (p0 & ((1 << P.ow_log2) - 1)) + kx + P.col0;
-              const uint32_t sa = smem_u32(src);
-              const uint32_t *al = reinterpret_cast<const uint32_t *>(src - (sa & 3u));
-              const uint32_t w0 = al[0], w1 = al[1], w2 = al[2];
-              const uint32_t bsh = (sa & 3u) * 8u;
-              lo8 = __funnelshift_r(w0, w1, bsh);
-              hi8 = __funnelshift_r(w1, w2, bsh);
-            } else {  // geometries without staged rows: out of line, it would be inlined six times here
-              const uint2 c8 = gather_codes_generic(GatherGeo{g.stride, g.pad, g.H, g.W, g.Cin, g.L, g.OW, g.M}, P.xcodes,
-                                                    ptab[pg], ci, ky, kx, m0 + pg * 8);
-              lo8 = c8.x;
-              hi8 = c8.y;
-            }
           }
-            xlo[q] = lo8;
-            xhi[q] = hi8;
-          }
-        }
-        d_stage += CIMQ_TB() - ts0;
-        if constexpr (V2) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) wsp[c][q] = __byte_perm(wnx2[2 * q], wnx2[2 * q + 1], c | ((4 + c) << 8));
-        }
-        for (int j = 0; j < NSA; ++j, ++it) {
-          // (stage index and phase as running counters: `it % stages` is a division by a run-time value)
-          const int sidx = p_sidx;
-          const uint32_t use = p_phase;
-          if (++p_sidx == P.stages) { p_sidx = 0; p_phase ^= 1u; }
-          const long long tw0 = CIMQ_TB();
-          mbar_wait(cv.empty0 + 8 * sidx, (use & 1) ^ 1);
-          const long long tw1 = CIMQ_TB();
-          d_wait += tw1 - tw0;
-          uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
-          // ---- X_j tile [128 crossbar rows x 128 pixels] (bf16 digits); item = (row fr, 8-pixel group pg)
-          const int sh = g.abs_ * j;
-          // v2: fp16 operands (the G' pieces are fp16); the digit carries the slice weight 2^j (mask[k][j] * 2^(-wbs*k)
-          // = 2^j for 1-bit slices, lsq.py:306, 363-364), the pass COUNT of plane W multiplies grad_out
-          const uint32_t one_bf = V2 ? 0x3C00u + ((uint32_t)j << 10) : 0x3F80u;
-          if (xfast && !(P.dbg & 2)) {
-            uint8_t *dst = st_ptr + tc_tile_offset16(fr, x_pg0 * 8, kTcLBO, a_sbo);
-            const uint32_t cmul = one_bf >> sh;  // the 16-bit pattern of 1.0 divided by the bit weight of the digit
-            if (x_cnt == 14) x_store_fast<14, 1, XI>(dst, xlo, xhi, sh, cmul);
-            else if (x_cnt == 8) x_store_fast<8, 2, XI>(dst, xlo, xhi, sh, cmul);
-            else if (x_cnt == 1) x_store_fast<1, 1, XI>(dst, xlo, xhi, sh, cmul);
-          }
-#pragma unroll
-          for (int q = 0; q < XI; ++q) {
-            if (xfast) break;
-            const int pg = x_pg0 + x_step * q;
-            if (pg >= 16 || q >= x_cnt) continue;
-            const uint32_t lo8 = xlo[q], hi8 = xhi[q];
-            uint32_t d[4];
-            if (g.amask == 1) {  // 1-bit digits: bf16(1) = 0x3F80; spread two bytes to 16-bit lanes, one multiply
-              const uint32_t tl = (lo8 >> sh) & 0x01010101u, th = (hi8 >> sh) & 0x01010101u;
-              d[0] = __byte_perm(tl, 0u, 0x4140) * one_bf;
-              d[1] = __byte_perm(tl, 0u, 0x4342) * one_bf;
-              d[2] = __byte_perm(th, 0u, 0x4140) * one_bf;
-              d[3] = __byte_perm(th, 0u, 0x4342) * one_bf;
-            } else {
-              const uint32_t am = (uint32_t)g.amask;
-#pragma unroll
-              for (int e2 = 0; e2 < 4; ++e2) {
-                const uint32_t wsrc = e2 < 2 ? lo8 : hi8;
-                const uint32_t b0 = (wsrc >> (16 * (e2 & 1) + sh)) & am, b1 = (wsrc >> (16 * (e2 & 1) + 8 + sh)) & am;
-                d[e2] = cvt_bf16x2((float)b1, (float)b0);
-              }
-            }
-            *reinterpret_cast<uint4 *>(st_ptr + tc_tile_offset16(fr, pg * 8, kTcLBO, a_sbo)) =
-                make_uint4(d[0], d[1], d[2], d[3]);
-          }
-          // ---- G'_j tiles (3 bf16 terms) [Cout x 128 pixels]; item = (channel co, 8-pixel group pg), lanes along pixels
-          const long long tx1 = CIMQ_TB();
-          d_x += tx1 - tw1;
-          uint8_t *gb = st_ptr + P.a_bytes;
+          d_stage += CIMQ_TB() - ts0;
           if constexpr (V2) {
-            // G'_j[co, m] = (go * 2^s_co as two fp16 pieces) * (pass count of activation slice j): exact products
-            if (g_thread) {
-              const bool last_j = j + 1 == NSA;
-              const bool next_chunk = i + 1 < i_end, next_tile = !next_chunk && mt_n < P.mtiles;
-              if (last_j) {  // the W bytes of the next chunk (or of the next tile's first chunk) start their trip now
-                if (next_chunk) v2_load_w(mt, i + 1);
-                else if (next_tile) v2_load_w(mt_n, i_begin);
-              }
-              if (j == 0 && next_tile) {  // next tile's grad_out: three stages ahead of its split
-#pragma unroll
-                for (int c = 0; c < 4; ++c) v2_load_go(mt_n, c);
-              }
-              // count field j of both bytes -> fp16x2 (1024 + cnt * 4^j) -> cnt
-              const uint32_t fmask = 0x00030003u << (2 * j);
-              const __half2 sk = __float2half2_rn(1.0f / (float)(1 << (2 * j)));
-              const __half2 ok = __float2half2_rn(-1024.0f / (float)(1 << (2 * j)));
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                if (P.dbg & 4) break;
-                uint32_t a1[4], a2[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const uint32_t fw = (wsp[c][q] & fmask) | 0x64006400u;
-                  const __half2 cnt = __hfma2(*reinterpret_cast<const __half2 *>(&fw), sk, ok);
-                  const __half2 r1 = __hmul2(*reinterpret_cast<const __half2 *>(&gp1[c][q]), cnt);
-                  const __half2 r2 = __hmul2(*reinterpret_cast<const __half2 *>(&gp2[c][q]), cnt);
-                  a1[q] = *reinterpret_cast<const uint32_t *>(&r1);
-                  a2[q] = *reinterpret_cast<const uint32_t *>(&r2);
-                }
-                const uint32_t off = tc_tile_offset16(4 * gq2 + c, gpg2 * 8, kWgLBO, b_sbo);
-                *reinterpret_cast<uint4 *>(gb + off) = make_uint4(a1[0], a1[1], a1[2], a1[3]);
-                *reinterpret_cast<uint4 *>(gb + P.b_bytes + off) = make_uint4(a2[0], a2[1], a2[2], a2[3]);
-              }
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(cv.full0 + 8 * sidx);  // one arrival per warp (every thread fenced its own stores)
-            d_g += CIMQ_TB() - tx1;
-            continue;
+  #pragma unroll
+            for (int c = 0; c < 4; ++c)
+  #pragma unroll
+              for (int q = 0; q < 4; ++q) wsp[c][q] = __byte_perm(wnx2[2 * q], wnx2[2 * q + 1], c | ((4 + c) << 8));
           }
-          float wv[NSW];
-#pragma unroll
-          for (int k = 0; k < NSW; ++k) wv[k] = cv.wtab[k * NSA + j];
-          const uint32_t lutj = smem_u32(cv.lut + j * 16);
-          const int pg = tid & 15;
-          if (gcache) {
-            if constexpr (kCacheOk) {
-              const bool last_j = j + 1 == NSA;
-              const bool next_chunk = i + 1 < i_end, next_tile = !next_chunk && mt_n < P.mtiles;
-#pragma unroll
-              for (int q = 0; q < 3; ++q) {
-                const int co = gco0 + 24 * q;
-                if (co < Kc) {
-                  float v[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    v[e] = gvc[q][e] *
-                           lds_const_f32(lutj + 4u * ((swc[q][e] >> (CBits::CB + j * NSW)) & ((1u << NSW) - 1u)));
-                  if (last_j) {  // last use of this item's state words (and, at the last chunk, of its grad_out)
-                    if (next_chunk) load_state(gpt, mt, st_next, co, swc[q]);
-                    else if (next_tile) {
-                      load_state(gpt_n, mt_n, st_first, co, swc[q]);
-                      load_go(gpt_n, mt_n, co, gvc[q]);
-                    }
-                  }
-                  uint32_t hi[4], mid[4], lo3[4];
-#pragma unroll
-                  for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo3[e2]);
-                  const uint32_t off = tc_tile_offset16(co, pg * 8, kWgLBO, b_sbo);
-                  *reinterpret_cast<uint4 *>(gb + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                  *reinterpret_cast<uint4 *>(gb + P.b_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-                  *reinterpret_cast<uint4 *>(gb + 2 * (size_t)P.b_bytes + off) =
-                      make_uint4(lo3[0], lo3[1], lo3[2], lo3[3]);
-                }
+          for (int j = 0; j < NSA; ++j, ++it) {
+            // (stage index and phase as running counters: `it % stages` is a division by a run-time value)
+            const int sidx = p_sidx;
+            const uint32_t use = p_phase;
+            if (++p_sidx == P.stages) { p_sidx = 0; p_phase ^= 1u; }
+            const long long tw0 = CIMQ_TB();
+            mbar_wait(cv.empty0 + 8 * sidx, (use & 1) ^ 1);
+            const long long tw1 = CIMQ_TB();
+            d_wait += tw1 - tw0;
+            uint8_t *st_ptr = cv.stage_base + (size_t)sidx * P.stage_bytes;
+            // ---- X_j tile [128 crossbar rows x 128 pixels] (bf16 digits); item = (row fr, 8-pixel group pg)
+            const int sh = g.abs_ * j;
+            // v2: fp16 operands (the G' pieces are fp16); the digit carries the slice weight 2^j (mask[k][j] * 2^(-wbs*k)
+            // = 2^j for 1-bit slices, lsq.py:306, 363-364), the pass COUNT of plane W multiplies grad_out
+            const uint32_t one_bf = V2 ? 0x3C00u + ((uint32_t)j << 10) : 0x3F80u;
+            if (xfast && !(P.dbg & 2)) {
+              uint8_t *dst = st_ptr + tc_tile_offset16(fr, x_pg0 * 8, kTcLBO, a_sbo);
+              const uint32_t cmul = one_bf >> sh;  // the 16-bit pattern of 1.0 divided by the bit weight of the digit
+              if constexpr (ROLE == 1) x_store_fast<1, 1, XIr>(dst, xlo, xhi, sh, cmul);
+              else if constexpr (ROLE == 2) x_store_fast<14, 1, XIr>(dst, xlo, xhi, sh, cmul);
+              else {
+                if (xc == 14) x_store_fast<14, 1, XIr>(dst, xlo, xhi, sh, cmul);
+                else if (xc == 8) x_store_fast<8, 2, XIr>(dst, xlo, xhi, sh, cmul);
+                else if (xc == 1) x_store_fast<1, 1, XIr>(dst, xlo, xhi, sh, cmul);
               }
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(cv.full0 + 8 * sidx);  // one arrival per warp (every thread fenced its own stores)
-            d_g += CIMQ_TB() - tx1;
-            continue;
-          }
-          const int4 pt = ptab[pg];
-          const int64_t mg = m0 + pg * 8;
-          // loads of the next channel are issued before the current one is processed (latency hiding)
-          auto load_g = [&](int co, float (&gv)[8], uint32_t (&sw)[8][CBits::CWN]) {
-            const uint32_t *sp = P.state + ((int64_t)((i / P.sdiv) * g.Cout + P.co0 + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
-            if (pt.w == 1) {
-              const float4 *gp = reinterpret_cast<const float4 *>(
-                  P.go + ((int64_t)pt.x * g.Cout + P.co0 + co) * g.L + pt.y * g.OW + pt.z);
-              const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
-              gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w;
-              gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
-#pragma unroll
-              for (int w = 0; w < CBits::CWN; ++w) {
-                const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(sp + (int64_t)w * g.M));
-                const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(sp + (int64_t)w * g.M) + 1);
-                sw[0][w] = s0.x; sw[1][w] = s0.y; sw[2][w] = s0.z; sw[3][w] = s0.w;
-                sw[4][w] = s1.x; sw[5][w] = s1.y; sw[6][w] = s1.z; sw[7][w] = s1.w;
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int64_t m = mg + e;
-                gv[e] = 0.0f;
-#pragma unroll
-                for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = 0xffffffffu;
-                if (m < g.M) {
-                  const int b = (int)(m / g.L), l = (int)(m % g.L);
-                  gv[e] = __ldg(&P.go[((int64_t)b * g.Cout + P.co0 + co) * g.L + l]);
-#pragma unroll
-                  for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = __ldg(sp + (int64_t)w * g.M + e);
-                }
-              }
-            }
-          };
-          float gv_n[8];
-          uint32_t sw_n[8][CBits::CWN];
-          const int co0 = tid >> 4;  // 0..23
-          if (co0 < Kc) load_g(co0, gv_n, sw_n);
-          for (int co = co0; co < Kc; co += 24) {
-            float gv[8];
-            uint32_t sw[8][CBits::CWN];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              gv[e] = gv_n[e];
-#pragma unroll
-              for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = sw_n[e][w];
-            }
-            if (co + 24 < Kc) load_g(co + 24, gv_n, sw_n);
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if constexpr (kLut && CBits::CWN == 1) {
-                v[e] = gv[e] * lds_const_f32(lutj + 4u * ((sw[e][0] >> (CBits::CB + j * NSW)) & ((1u << NSW) - 1u)));
+  #pragma unroll
+            for (int q = 0; q < XIr; ++q) {
+              if (xfast) break;
+              const int pg = x_pg0 + x_step * q;
+              if (pg >= 16 || q >= xc) continue;
+              const uint32_t lo8 = xlo[q], hi8 = xhi[q];
+              uint32_t d[4];
+              if (g.amask == 1) {  // 1-bit digits: bf16(1) = 0x3F80; spread two bytes to 16-bit lanes, one multiply
+                const uint32_t tl = (lo8 >> sh) & 0x01010101u, th = (hi8 >> sh) & 0x01010101u;
+                d[0] = __byte_perm(tl, 0u, 0x4140) * one_bf;
+                d[1] = __byte_perm(tl, 0u, 0x4342) * one_bf;
+                d[2] = __byte_perm(th, 0u, 0x4140) * one_bf;
+                d[3] = __byte_perm(th, 0u, 0x4342) * one_bf;
               } else {
-                v[e] = gv[e] * pass_weight<NSW, CBits::CWN>(sw[e], CBits::CB + j * NSW, 1, wv);
+                const uint32_t am = (uint32_t)g.amask;
+  #pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  const uint32_t wsrc = e2 < 2 ? lo8 : hi8;
+                  const uint32_t b0 = (wsrc >> (16 * (e2 & 1) + sh)) & am, b1 = (wsrc >> (16 * (e2 & 1) + 8 + sh)) & am;
+                  d[e2] = cvt_bf16x2((float)b1, (float)b0);
+                }
               }
+              *reinterpret_cast<uint4 *>(st_ptr + tc_tile_offset16(fr, pg * 8, kTcLBO, a_sbo)) =
+                  make_uint4(d[0], d[1], d[2], d[3]);
             }
-            uint32_t hi[4], mid[4], lo3[4];
-#pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo3[e2]);
-            const uint32_t off = tc_tile_offset16(co, pg * 8, kWgLBO, b_sbo);
-            *reinterpret_cast<uint4 *>(gb + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4 *>(gb + P.b_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-            *reinterpret_cast<uint4 *>(gb + 2 * (size_t)P.b_bytes + off) = make_uint4(lo3[0], lo3[1], lo3[2], lo3[3]);
+            // ---- G'_j tiles (3 bf16 terms) [Cout x 128 pixels]; item = (channel co, 8-pixel group pg), lanes along pixels
+            const long long tx1 = CIMQ_TB();
+            d_x += tx1 - tw1;
+            uint8_t *gb = st_ptr + P.a_bytes;
+            if constexpr (V2) {
+              // G'_j[co, m] = (go * 2^s_co as two fp16 pieces) * (pass count of activation slice j): exact products
+              if (gthr) {
+                const bool last_j = j + 1 == NSA;
+                const bool next_chunk = i + 1 < i_end, next_tile = !next_chunk && mt_n < P.mtiles;
+                if (last_j) {  // the W bytes of the next chunk (or of the next tile's first chunk) start their trip now
+                  if (next_chunk) v2_load_w(mt, i + 1);
+                  else if (next_tile) v2_load_w(mt_n, i_begin);
+                }
+                if (j == 0 && next_tile) {  // next tile's grad_out: three stages ahead of its split
+  #pragma unroll
+                  for (int c = 0; c < 4; ++c) v2_load_go(mt_n, c);
+                }
+                // count field j of both bytes -> fp16x2 (1024 + cnt * 4^j) -> cnt
+                const uint32_t fmask = 0x00030003u << (2 * j);
+                const __half2 sk = __float2half2_rn(1.0f / (float)(1 << (2 * j)));
+                const __half2 ok = __float2half2_rn(-1024.0f / (float)(1 << (2 * j)));
+  #pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  if (P.dbg & 4) break;
+                  uint32_t a1[4], a2[4];
+  #pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const uint32_t fw = (wsp[c][q] & fmask) | 0x64006400u;
+                    const __half2 cnt = __hfma2(*reinterpret_cast<const __half2 *>(&fw), sk, ok);
+                    const __half2 r1 = __hmul2(*reinterpret_cast<const __half2 *>(&gp1[c][q]), cnt);
+                    const __half2 r2 = __hmul2(*reinterpret_cast<const __half2 *>(&gp2[c][q]), cnt);
+                    a1[q] = *reinterpret_cast<const uint32_t *>(&r1);
+                    a2[q] = *reinterpret_cast<const uint32_t *>(&r2);
+                  }
+                  const uint32_t off = tc_tile_offset16(4 * gq2 + c, gpg2 * 8, kWgLBO, b_sbo);
+                  *reinterpret_cast<uint4 *>(gb + off) = make_uint4(a1[0], a1[1], a1[2], a1[3]);
+                  *reinterpret_cast<uint4 *>(gb + P.b_bytes + off) = make_uint4(a2[0], a2[1], a2[2], a2[3]);
+                }
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(cv.full0 + 8 * sidx);  // one arrival per warp (every thread fenced its own stores)
+              d_g += CIMQ_TB() - tx1;
+              continue;
+            }
+            float wv[NSW];
+  #pragma unroll
+            for (int k = 0; k < NSW; ++k) wv[k] = cv.wtab[k * NSA + j];
+            const uint32_t lutj = smem_u32(cv.lut + j * 16);
+            const int pg = tid & 15;
+            if (gcache) {
+              if constexpr (kCacheOk) {
+                const bool last_j = j + 1 == NSA;
+                const bool next_chunk = i + 1 < i_end, next_tile = !next_chunk && mt_n < P.mtiles;
+  #pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                  const int co = gco0 + 24 * q;
+                  if (co < Kc) {
+                    float v[8];
+  #pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                      v[e] = gvc[q][e] *
+                             lds_const_f32(lutj + 4u * ((swc[q][e] >> (CBits::CB + j * NSW)) & ((1u << NSW) - 1u)));
+                    if (last_j) {  // last use of this item's state words (and, at the last chunk, of its grad_out)
+                      if (next_chunk) load_state(gpt, mt, st_next, co, swc[q]);
+                      else if (next_tile) {
+                        load_state(gpt_n, mt_n, st_first, co, swc[q]);
+                        load_go(gpt_n, mt_n, co, gvc[q]);
+                      }
+                    }
+                    uint32_t hi[4], mid[4], lo3[4];
+  #pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo3[e2]);
+                    const uint32_t off = tc_tile_offset16(co, pg * 8, kWgLBO, b_sbo);
+                    *reinterpret_cast<uint4 *>(gb + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(gb + P.b_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+                    *reinterpret_cast<uint4 *>(gb + 2 * (size_t)P.b_bytes + off) =
+                        make_uint4(lo3[0], lo3[1], lo3[2], lo3[3]);
+                  }
+                }
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(cv.full0 + 8 * sidx);  // one arrival per warp (every thread fenced its own stores)
+              d_g += CIMQ_TB() - tx1;
+              continue;
+            }
+            const int4 pt = ptab[pg];
+            const int64_t mg = m0 + pg * 8;
+            // loads of the next channel are issued before the current one is processed (latency hiding)
+            auto load_g = [&](int co, float (&gv)[8], uint32_t (&sw)[8][CBits::CWN]) {
+              const uint32_t *sp = P.state + ((int64_t)((i / P.sdiv) * g.Cout + P.co0 + co) * CBits::SWORDS + CBits::CW0) * g.M + mg;
+              if (pt.w == 1) {
+                const float4 *gp = reinterpret_cast<const float4 *>(
+                    P.go + ((int64_t)pt.x * g.Cout + P.co0 + co) * g.L + pt.y * g.OW + pt.z);
+                const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+                gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w;
+                gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
+  #pragma unroll
+                for (int w = 0; w < CBits::CWN; ++w) {
+                  const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(sp + (int64_t)w * g.M));
+                  const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(sp + (int64_t)w * g.M) + 1);
+                  sw[0][w] = s0.x; sw[1][w] = s0.y; sw[2][w] = s0.z; sw[3][w] = s0.w;
+                  sw[4][w] = s1.x; sw[5][w] = s1.y; sw[6][w] = s1.z; sw[7][w] = s1.w;
+                }
+              } else {
+  #pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int64_t m = mg + e;
+                  gv[e] = 0.0f;
+  #pragma unroll
+                  for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = 0xffffffffu;
+                  if (m < g.M) {
+                    const int b = (int)(m / g.L), l = (int)(m % g.L);
+                    gv[e] = __ldg(&P.go[((int64_t)b * g.Cout + P.co0 + co) * g.L + l]);
+  #pragma unroll
+                    for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = __ldg(sp + (int64_t)w * g.M + e);
+                  }
+                }
+              }
+            };
+            float gv_n[8];
+            uint32_t sw_n[8][CBits::CWN];
+            const int co0 = tid >> 4;  // 0..23
+            if (co0 < Kc) load_g(co0, gv_n, sw_n);
+            for (int co = co0; co < Kc; co += 24) {
+              float gv[8];
+              uint32_t sw[8][CBits::CWN];
+  #pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                gv[e] = gv_n[e];
+  #pragma unroll
+                for (int w = 0; w < CBits::CWN; ++w) sw[e][w] = sw_n[e][w];
+              }
+              if (co + 24 < Kc) load_g(co + 24, gv_n, sw_n);
+              float v[8];
+  #pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                if constexpr (kLut && CBits::CWN == 1) {
+                  v[e] = gv[e] * lds_const_f32(lutj + 4u * ((sw[e][0] >> (CBits::CB + j * NSW)) & ((1u << NSW) - 1u)));
+                } else {
+                  v[e] = gv[e] * pass_weight<NSW, CBits::CWN>(sw[e], CBits::CB + j * NSW, 1, wv);
+                }
+              }
+              uint32_t hi[4], mid[4], lo3[4];
+  #pragma unroll
+              for (int e2 = 0; e2 < 4; ++e2) split3x2(v[2 * e2], v[2 * e2 + 1], hi[e2], mid[e2], lo3[e2]);
+              const uint32_t off = tc_tile_offset16(co, pg * 8, kWgLBO, b_sbo);
+              *reinterpret_cast<uint4 *>(gb + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4 *>(gb + P.b_bytes + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+              *reinterpret_cast<uint4 *>(gb + 2 * (size_t)P.b_bytes + off) = make_uint4(lo3[0], lo3[1], lo3[2], lo3[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cv.full0 + 8 * sidx);  // one arrival per warp (every thread fenced its own stores)
+            d_g += CIMQ_TB() - tx1;
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(cv.full0 + 8 * sidx);  // one arrival per warp (every thread fenced its own stores)
-          d_g += CIMQ_TB() - tx1;
+          if (P.async_rows) {  // my copies of the next chunk's rows have landed; publish them, retire this chunk's buffer
+            const long long tb0 = CIMQ_TB();
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            named_barrier_sync(1, kWgProducerThreads);
+            d_bar += CIMQ_TB() - tb0;
+          }
         }
-        if (P.async_rows) {  // my copies of the next chunk's rows have landed; publish them, retire this chunk's buffer
-          const long long tb0 = CIMQ_TB();
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          named_barrier_sync(1, kWgProducerThreads);
-          d_bar += CIMQ_TB() - tb0;
-        }
+        gpt = gpt_n;
       }
-      gpt = gpt_n;
+    };
+    if constexpr (V2) {
+      if (n_g == 256) {
+        if (g_thread) run_tiles(std::integral_constant<int, 1>{});
+        else run_tiles(std::integral_constant<int, 2>{});
+      } else {
+        run_tiles(std::integral_constant<int, 0>{});
+      }
+    } else {
+      run_tiles(std::integral_constant<int, 0>{});
     }
     if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_stage; P.debug[2] = d_x; P.debug[3] = d_g; P.debug[7] = d_bar; }
   } else {
