@@ -857,14 +857,15 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         v2_load_w(blockIdx.x, i_begin);
       }
     }
-    // The tile loop is instantiated per thread ROLE where the roles are fixed (v2 with 256 G' threads: 1 = G' thread with
-    // one X item, 2 = X thread with fourteen; 0 = decided at run time): the G' registers (pieces, paired W bytes, raw
+    // The tile loop is instantiated per thread ROLE (v2 at 64 channels: 1 = G' thread with one X item, 2 = X thread with
+    // fourteen; v2 at 16 / 32 channels: 3 = G' thread, 4 = X thread with eight items or none; v1: 0 = one for all): the G' registers (pieces, paired W bytes, raw
     // grad_out) and the X registers (gathered codes of 14 items) then never live in the same thread.
     auto run_tiles = [&](auto role_tag) {
       constexpr int ROLE = decltype(role_tag)::value;
-      constexpr int XIr = ROLE == 1 ? 1 : XI;
-      const bool gthr = ROLE == 1 || (ROLE == 0 && g_thread);
-      const int xc = ROLE == 1 ? 1 : (ROLE == 2 ? 14 : x_cnt);
+      constexpr int XIr = (ROLE == 1 || ROLE == 3) ? 1 : XI;
+      const bool gthr = ROLE == 1 || ROLE == 3 || (ROLE == 0 && g_thread);
+      // X items of the thread: compile-time where the role fixes them (the run-time branches cost 10 % at 64 channels)
+      const int xc = ROLE == 1 ? 1 : (ROLE == 2 ? 14 : (ROLE == 3 ? 0 : x_cnt));
       for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
         const int64_t m0 = (int64_t)mt * kTcTileM;
         if constexpr (V2) {
@@ -994,7 +995,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
             };
             if constexpr (ROLE == 1) gather(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
             else if constexpr (ROLE == 2) gather(std::integral_constant<int, 14>{}, std::integral_constant<int, 1>{});
-            else {
+            else if constexpr (ROLE == 3) { /* no X items */ }
+            else if constexpr (ROLE == 4) {
+              if (xc == 8) gather(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
+            } else {
               if (xc == 14) gather(std::integral_constant<int, 14>{}, std::integral_constant<int, 1>{});
               else if (xc == 8) gather(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
               else if (xc == 1) gather(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
@@ -1058,7 +1062,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
               const uint32_t cmul = one_bf >> sh;  // the 16-bit pattern of 1.0 divided by the bit weight of the digit
               if constexpr (ROLE == 1) x_store_fast<1, 1, XIr>(dst, xlo, xhi, sh, cmul);
               else if constexpr (ROLE == 2) x_store_fast<14, 1, XIr>(dst, xlo, xhi, sh, cmul);
-              else {
+              else if constexpr (ROLE == 3) { /* no X items */ }
+              else if constexpr (ROLE == 4) {
+                if (xc == 8) x_store_fast<8, 2, XIr>(dst, xlo, xhi, sh, cmul);
+              } else {
                 if (xc == 14) x_store_fast<14, 1, XIr>(dst, xlo, xhi, sh, cmul);
                 else if (xc == 8) x_store_fast<8, 2, XIr>(dst, xlo, xhi, sh, cmul);
                 else if (xc == 1) x_store_fast<1, 1, XIr>(dst, xlo, xhi, sh, cmul);
@@ -1261,7 +1268,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         if (g_thread) run_tiles(std::integral_constant<int, 1>{});
         else run_tiles(std::integral_constant<int, 2>{});
       } else {
-        run_tiles(std::integral_constant<int, 0>{});
+        if (g_thread) run_tiles(std::integral_constant<int, 3>{});
+        else run_tiles(std::integral_constant<int, 4>{});
       }
     } else {
       run_tiles(std::integral_constant<int, 0>{});
