@@ -673,16 +673,16 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     long long d_stage = 0, d_wait = 0, d_x = 0, d_g = 0, d_bar = 0;
     // X tile items (crossbar row fr, 8-pixel group pg = x_pg0 + x_step * q, q < XI) of this thread
     // v2: threads [0, n_g) build G' (one 4-channel x 8-pixel item = 32 elements); with n_g = 256 the G' threads also
-    // take ONE X item each (pixel groups 14, 15) and the other 128 threads fourteen (groups 0..13) -- measured: giving
-    // the G' threads three X items each costs 10 %, they are the critical path; with fewer G' threads the 256 threads
-    // after them take eight X items each.
+    // take three X items each (pixel groups 10..15) and the other 128 threads ten (groups 0..9) -- measured with the
+    // per-role instantiation of the tile loop below: 14/1 346 us, 12/2 336, 10/3 330, 8/4 345; with fewer G' threads
+    // the 256 threads after them take eight X items each.
     constexpr int XI = V2 ? 14 : 6;
     const int n_g = V2 ? 4 * Kc : 0;
     int fr, x_pg0, x_step, x_cnt;
     if (!V2) { fr = tid & 127; x_pg0 = tid >> 7; x_step = 3; x_cnt = 6; }
     else if (n_g == 256) {
-      if (tid >= 256) { fr = tid - 256; x_pg0 = 0; x_step = 1; x_cnt = 14; }
-      else { fr = tid & 127; x_pg0 = 14 + (tid >> 7); x_step = 1; x_cnt = 1; }
+      if (tid >= 256) { fr = tid - 256; x_pg0 = 0; x_step = 1; x_cnt = 10; }
+      else { fr = tid & 127; x_pg0 = 10 + 3 * (tid >> 7); x_step = 1; x_cnt = 3; }
     } else {
       const int xt = tid - n_g;
       fr = xt & 127; x_pg0 = xt >> 7; x_step = 2;
@@ -862,10 +862,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     // grad_out) and the X registers (gathered codes of 14 items) then never live in the same thread.
     auto run_tiles = [&](auto role_tag) {
       constexpr int ROLE = decltype(role_tag)::value;
-      constexpr int XIr = (ROLE == 1 || ROLE == 3) ? 1 : XI;
+      constexpr int XIr = ROLE == 1 ? 3 : (ROLE == 3 ? 1 : XI);
       const bool gthr = ROLE == 1 || ROLE == 3 || (ROLE == 0 && g_thread);
       // X items of the thread: compile-time where the role fixes them (the run-time branches cost 10 % at 64 channels)
-      const int xc = ROLE == 1 ? 1 : (ROLE == 2 ? 14 : (ROLE == 3 ? 0 : x_cnt));
+      const int xc = ROLE == 1 ? 3 : (ROLE == 2 ? 10 : (ROLE == 3 ? 0 : x_cnt));
       for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
         const int64_t m0 = (int64_t)mt * kTcTileM;
         if constexpr (V2) {
@@ -993,8 +993,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
                 xhi[q] = hi8;
               }
             };
-            if constexpr (ROLE == 1) gather(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
-            else if constexpr (ROLE == 2) gather(std::integral_constant<int, 14>{}, std::integral_constant<int, 1>{});
+            if constexpr (ROLE == 1) gather(std::integral_constant<int, 3>{}, std::integral_constant<int, 1>{});
+            else if constexpr (ROLE == 2) gather(std::integral_constant<int, 10>{}, std::integral_constant<int, 1>{});
             else if constexpr (ROLE == 3) { /* no X items */ }
             else if constexpr (ROLE == 4) {
               if (xc == 8) gather(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
@@ -1060,8 +1060,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
             if (xfast && !(P.dbg & 2)) {
               uint8_t *dst = st_ptr + tc_tile_offset16(fr, x_pg0 * 8, kTcLBO, a_sbo);
               const uint32_t cmul = one_bf >> sh;  // the 16-bit pattern of 1.0 divided by the bit weight of the digit
-              if constexpr (ROLE == 1) x_store_fast<1, 1, XIr>(dst, xlo, xhi, sh, cmul);
-              else if constexpr (ROLE == 2) x_store_fast<14, 1, XIr>(dst, xlo, xhi, sh, cmul);
+              if constexpr (ROLE == 1) x_store_fast<3, 1, XIr>(dst, xlo, xhi, sh, cmul);
+              else if constexpr (ROLE == 2) x_store_fast<10, 1, XIr>(dst, xlo, xhi, sh, cmul);
               else if constexpr (ROLE == 3) { /* no X items */ }
               else if constexpr (ROLE == 4) {
                 if (xc == 8) x_store_fast<8, 2, XIr>(dst, xlo, xhi, sh, cmul);
