@@ -474,22 +474,13 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
         const int c_begin = 3 * ntup;
         for (int c0 = c_begin + 16 * eh; c0 < dc.rows && !(P.dbg & 2); c0 += 32) {
           int v[16];
-          tmem_ld<16>(tcol + min(c0, Nf - 16), v);  // (the last batch may be shifted back to stay inside the buffer)
+          tmem_ld<16>(tcol + c0, v);  // (fast fold: c0 is not a multiple of 16 and the read may run into the slack columns)
           tmem_ld_wait();
-          const int shift = c0 - min(c0, Nf - 16);
 #pragma unroll
           for (int cc = 0; cc < 16; ++cc) {
             const int col = c0 + cc;
             if (col < dc.rows) {  // warp-uniform
-              // value of column `col` sits at v[cc + shift]; shift > 0 only for the (rare) shifted last batch
-              float val;
-              if (shift == 0) val = __int_as_float(v[cc]);
-              else {
-                val = 0.0f;
-#pragma unroll
-                for (int z = 0; z < 16; ++z)
-                  if (z == cc + shift) val = __int_as_float(v[z]);
-              }
+              const float val = __int_as_float(v[cc]);
               const int f = dgrad_col_f(g, dc, col);
               if (P.fold) {
                 const int ent = sm.ftab[f];
