@@ -18,6 +18,11 @@
 //                            place, as GEMM2's A operand (tcgen05.st); the backward's inputs are accumulated as
 //                            small integers in packed-half registers (see cim_v2.cuh) and leave as bytes.
 //   constants (warp 17)      one bulk copy per chunk: thresholds + B2 slabs -> shared memory (double buffered).
+// Measured alternatives (B200, microbench layer; training / inference forward, baseline 334 / 221 us): 16 epilogue warps
+// with 16 channels per thread and two producer groups (88 / 72 registers): 338 / 230; 16 epilogue warps and ONE producer
+// group (96 / 80 registers): 328 / 251.  The epilogue warps are the busy role (ncu: ~45 % of the stall samples, almost no
+// waiting) while the producers wait 40 % of their time, but halving the work per epilogue thread does not shorten the
+// per-plane chain tcgen05.ld -> quantise -> tcgen05.st -> fence -> arrive.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
