@@ -305,8 +305,18 @@ __global__ void __launch_bounds__(1024) bwd_alpha_finish_kernel(Geo g, int nspli
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5, nslice = blockDim.x >> 5;
   const int64_t e = (int64_t)blockIdx.x * 32 + lane;
   float v = 0.0f;
-  if (e < n)
-    for (int sidx = slice; sidx < nsplit; sidx += nslice) v += __ldg(partial + (int64_t)sidx * n + e);
+  if (e < n) {
+    // four loads in flight (fixed summation order: deterministic)
+    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+    int sidx = slice;
+    for (; sidx + 3 * nslice < nsplit; sidx += 4 * nslice) {
+      const float a0 = __ldg(partial + (int64_t)sidx * n + e), a1 = __ldg(partial + (int64_t)(sidx + nslice) * n + e);
+      const float a2 = __ldg(partial + (int64_t)(sidx + 2 * nslice) * n + e), a3 = __ldg(partial + (int64_t)(sidx + 3 * nslice) * n + e);
+      v0 += a0; v1 += a1; v2 += a2; v3 += a3;
+    }
+    for (; sidx < nsplit; sidx += nslice) v0 += __ldg(partial + (int64_t)sidx * n + e);
+    v = (v0 + v1) + (v2 + v3);
+  }
   red[slice][lane] = v;
   __syncthreads();
   if (slice == 0 && e < n) {

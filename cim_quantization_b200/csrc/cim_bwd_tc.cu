@@ -1372,8 +1372,17 @@ __global__ void __launch_bounds__(256) bwd_weight_tc_finish_kernel(Geo g, int np
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int64_t e = (int64_t)blockIdx.x * 32 + lane;  // e = f * Cout + co
   float v = 0.0f;
-  if (e < n)
-    for (int p = slice; p < nparts; p += 8) v += __ldg(partial + (int64_t)p * n + e);
+  if (e < n) {
+    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;  // four loads in flight, fixed summation order
+    int p = slice;
+    for (; p + 24 < nparts; p += 32) {
+      const float a0 = __ldg(partial + (int64_t)p * n + e), a1 = __ldg(partial + (int64_t)(p + 8) * n + e);
+      const float a2 = __ldg(partial + (int64_t)(p + 16) * n + e), a3 = __ldg(partial + (int64_t)(p + 24) * n + e);
+      v0 += a0; v1 += a1; v2 += a2; v3 += a3;
+    }
+    for (; p < nparts; p += 8) v0 += __ldg(partial + (int64_t)p * n + e);
+    v = (v0 + v1) + (v2 + v3);
+  }
   red[slice][lane] = v;
   __syncthreads();
   if (slice == 0 && e < n) {

@@ -118,14 +118,14 @@ __global__ void __launch_bounds__(kScaleThreads) go_scales_kernel(Geo g, const f
     for (int cb = 0; cb < kCB; ++cb) {
       if (cb * 32 < g.Cout) {
 #pragma unroll
-        for (int c8 = 0; c8 < 32; c8 += 8) {
-          if (cb * 32 + c8 < g.Cout) {  // Cout % 8 == 0
-            float4 v[8];
+        for (int c8 = 0; c8 < 32; c8 += 16) {
+          if (cb * 32 + c8 < g.Cout) {  // Cout % 16 == 0
+            float4 v[16];  // sixteen 16-byte loads in flight per thread: the kernel is latency bound
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
+            for (int e = 0; e < 16; ++e)
               v[e] = live ? __ldg(gp + (int64_t)(cb * 32 + c8 + e) * cstride) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < 16; ++e) {
               const uint32_t a0 = __float_as_uint(v[e].x) & 0x7fffffffu, a1 = __float_as_uint(v[e].y) & 0x7fffffffu;
               const uint32_t a2 = __float_as_uint(v[e].z) & 0x7fffffffu, a3 = __float_as_uint(v[e].w) & 0x7fffffffu;
               rm0 = max(rm0, a0); rm1 = max(rm1, a1); rm2 = max(rm2, a2); rm3 = max(rm3, a3);
