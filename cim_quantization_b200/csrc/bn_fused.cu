@@ -29,6 +29,26 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
   return t;  // valid in thread 0
 }
 
+// The float4 items of block (c, s) -- images b = s, s + splits, ... of channel c, HW / 4 items each -- as ONE flat range:
+// with one image per loop iteration a block of 256 threads had a single load in flight per thread (16x16 and 8x8 layers
+// used 64 / 16 of its threads) and the kernels were latency bound at 1.3 TB/s.  kBnUnroll items per thread are loaded
+// before the first one is used.
+constexpr int kBnUnroll = 4;
+struct BnItems {
+  int total, hw4, shift, s, splits, C, c;
+  __device__ __forceinline__ BnItems(int B, int C_, int HW, int c_, int s_, int splits_) {
+    hw4 = HW >> 2; s = s_; splits = splits_; C = C_; c = c_;
+    shift = (hw4 & (hw4 - 1)) == 0 ? 31 - __clz(hw4) : -1;
+    const int nb = s_ < B ? (B - s_ + splits_ - 1) / splits_ : 0;
+    total = nb * hw4;
+  }
+  // float4 index (into the [B, C, HW/4] tensor) of flat item t
+  __device__ __forceinline__ int64_t at(int t) const {
+    const int bi = shift >= 0 ? t >> shift : t / hw4, i = t - bi * hw4;
+    return ((int64_t)(s + bi * splits) * C + c) * hw4 + i;
+  }
+};
+
 // forward pass 1: partial[c][s] = {sum x, sum x^2} over the images b = s, s+splits, ...
 template <bool VEC>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float *__restrict__ x, int B, int C, int HW,
@@ -36,16 +56,26 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float *__res
   __shared__ float red[kBnThreads / 32];
   const int c = blockIdx.x, s = blockIdx.y, splits = gridDim.y;
   float s1 = 0.0f, s2 = 0.0f;
-  for (int b = s; b < B; b += splits) {
-    const float *p = x + ((int64_t)b * C + c) * HW;
-    if (VEC) {
-      const float4 *p4 = reinterpret_cast<const float4 *>(p);
-      for (int i = threadIdx.x; i < HW / 4; i += kBnThreads) {
-        const float4 v = __ldg(p4 + i);
-        s1 += (v.x + v.y) + (v.z + v.w);
-        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  if (VEC) {
+    const BnItems it(B, C, HW, c, s, splits);
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (int t0 = threadIdx.x; t0 < it.total; t0 += kBnUnroll * kBnThreads) {
+      float4 v[kBnUnroll];
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const int t = t0 + u * kBnThreads;
+        v[u] = t < it.total ? __ldg(x4 + it.at(t)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    } else {
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        s1 += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+        s2 += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w);
+      }
+    }
+  }
+  for (int b = s; b < B && !VEC; b += splits) {
+    const float *p = x + ((int64_t)b * C + c) * HW;
+    {
       for (int i = threadIdx.x; i < HW; i += kBnThreads) {
         const float v = __ldg(p + i);
         s1 += v;
@@ -111,27 +141,39 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
   __syncthreads();
   const float mean = sh[0];
   const float g = (weight != nullptr ? weight[c] : 1.0f) * sh[1], be = bias != nullptr ? bias[c] : 0.0f;
-  for (int b = s; b < B; b += splits) {
-    const int64_t off = ((int64_t)b * C + c) * HW;
-    if (VEC) {
-      const float4 *p4 = reinterpret_cast<const float4 *>(x + off);
-      const float4 *r4 = residual != nullptr ? reinterpret_cast<const float4 *>(residual + off) : nullptr;
-      float4 *y4 = reinterpret_cast<float4 *>(y + off);
-      for (int i = threadIdx.x; i < HW / 4; i += kBnThreads) {
-        const float4 v = __ldg(p4 + i);
-        float4 o = make_float4(fmaf(v.x - mean, g, be), fmaf(v.y - mean, g, be), fmaf(v.z - mean, g, be),
-                               fmaf(v.w - mean, g, be));
-        if (r4 != nullptr) {
-          const float4 r = __ldg(r4 + i);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
-        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        y4[i] = o;
-        if (codes != nullptr)
-          reinterpret_cast<uint32_t *>(codes + off)[i] = lsq_code(o.x, qs, 0.0f, q_qp) | (lsq_code(o.y, qs, 0.0f, q_qp) << 8) |
-                                                         (lsq_code(o.z, qs, 0.0f, q_qp) << 16) | (lsq_code(o.w, qs, 0.0f, q_qp) << 24);
+  if (VEC) {
+    const BnItems it(B, C, HW, c, s, splits);
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    const float4 *r4 = reinterpret_cast<const float4 *>(residual);
+    float4 *y4 = reinterpret_cast<float4 *>(y);
+    uint32_t *c4 = reinterpret_cast<uint32_t *>(codes);
+    for (int t0 = threadIdx.x; t0 < it.total; t0 += kBnUnroll * kBnThreads) {
+      float4 v[kBnUnroll], r[kBnUnroll];
+      int64_t idx[kBnUnroll];
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const int t = t0 + u * kBnThreads;
+        idx[u] = t < it.total ? it.at(t) : -1;
+        v[u] = idx[u] >= 0 ? __ldg(x4 + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        r[u] = (idx[u] >= 0 && r4 != nullptr) ? __ldg(r4 + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    } else {
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        if (idx[u] < 0) continue;
+        float4 o = make_float4(fmaf(v[u].x - mean, g, be), fmaf(v[u].y - mean, g, be), fmaf(v[u].z - mean, g, be),
+                               fmaf(v[u].w - mean, g, be));
+        if (r4 != nullptr) { o.x += r[u].x; o.y += r[u].y; o.z += r[u].z; o.w += r[u].w; }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        y4[idx[u]] = o;
+        if (codes != nullptr)
+          c4[idx[u]] = lsq_code(o.x, qs, 0.0f, q_qp) | (lsq_code(o.y, qs, 0.0f, q_qp) << 8) |
+                       (lsq_code(o.z, qs, 0.0f, q_qp) << 16) | (lsq_code(o.w, qs, 0.0f, q_qp) << 24);
+      }
+    }
+  }
+  for (int b = s; b < B && !VEC; b += splits) {
+    const int64_t off = ((int64_t)b * C + c) * HW;
+    {
       for (int i = threadIdx.x; i < HW; i += kBnThreads) {
         float o = fmaf(__ldg(x + off + i) - mean, g, be);
         if (residual != nullptr) o += __ldg(residual + off + i);
@@ -154,24 +196,35 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_stats_kernel(const float *_
   const int c = blockIdx.x, s = blockIdx.y, splits = gridDim.y;
   const float mean = save_mean[c];
   float s1 = 0.0f, s2 = 0.0f;
-  for (int b = s; b < B; b += splits) {
-    const int64_t off = ((int64_t)b * C + c) * HW;
-    if (VEC) {
-      const float4 *g4 = reinterpret_cast<const float4 *>(gy + off);
-      const float4 *x4 = reinterpret_cast<const float4 *>(x + off);
-      const float4 *y4 = reinterpret_cast<const float4 *>(y + off);
-      for (int i = threadIdx.x; i < HW / 4; i += kBnThreads) {
-        float4 d = __ldg(g4 + i);
-        const float4 v = __ldg(x4 + i);
-        if (relu) {
-          const float4 o = __ldg(y4 + i);
-          d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
-          d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
-        }
-        s1 += (d.x + d.y) + (d.z + d.w);
-        s2 += (d.x * (v.x - mean) + d.y * (v.y - mean)) + (d.z * (v.z - mean) + d.w * (v.w - mean));
+  if (VEC) {
+    const BnItems it(B, C, HW, c, s, splits);
+    const float4 *g4 = reinterpret_cast<const float4 *>(gy);
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    const float4 *y4 = reinterpret_cast<const float4 *>(y);
+    for (int t0 = threadIdx.x; t0 < it.total; t0 += kBnUnroll * kBnThreads) {
+      float4 d[kBnUnroll], v[kBnUnroll], o[kBnUnroll];
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const int t = t0 + u * kBnThreads;
+        const bool ok = t < it.total;
+        const int64_t idx = ok ? it.at(t) : 0;
+        d[u] = ok ? __ldg(g4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u] = ok ? __ldg(x4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        o[u] = (ok && relu) ? __ldg(y4 + idx) : make_float4(1.f, 1.f, 1.f, 1.f);
       }
-    } else {
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        float4 dd = d[u];
+        dd.x = o[u].x > 0.f ? dd.x : 0.f; dd.y = o[u].y > 0.f ? dd.y : 0.f;
+        dd.z = o[u].z > 0.f ? dd.z : 0.f; dd.w = o[u].w > 0.f ? dd.w : 0.f;
+        s1 += (dd.x + dd.y) + (dd.z + dd.w);
+        s2 += (dd.x * (v[u].x - mean) + dd.y * (v[u].y - mean)) + (dd.z * (v[u].z - mean) + dd.w * (v[u].w - mean));
+      }
+    }
+  }
+  for (int b = s; b < B && !VEC; b += splits) {
+    const int64_t off = ((int64_t)b * C + c) * HW;
+    {
       for (int i = threadIdx.x; i < HW; i += kBnThreads) {
         float d = __ldg(gy + off + i);
         if (relu && !(__ldg(y + off + i) > 0.f)) d = 0.f;
@@ -214,27 +267,40 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
   __syncthreads();
   const float m1 = sh[0], m2 = sh[1];
   const float k = (weight != nullptr ? weight[c] : 1.0f) * invstd;
-  for (int b = s; b < B; b += splits) {
-    const int64_t off = ((int64_t)b * C + c) * HW;
-    if (VEC) {
-      const float4 *g4 = reinterpret_cast<const float4 *>(gy + off);
-      const float4 *x4 = reinterpret_cast<const float4 *>(x + off);
-      const float4 *y4 = reinterpret_cast<const float4 *>(y + off);
-      float4 *o4 = reinterpret_cast<float4 *>(gx + off);
-      float4 *r4 = gres != nullptr ? reinterpret_cast<float4 *>(gres + off) : nullptr;
-      for (int i = threadIdx.x; i < HW / 4; i += kBnThreads) {
-        float4 d = __ldg(g4 + i);
-        const float4 v = __ldg(x4 + i);
-        if (relu) {
-          const float4 o = __ldg(y4 + i);
-          d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
-          d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
-        }
-        if (r4 != nullptr) r4[i] = d;
-        o4[i] = make_float4(k * (d.x - m1 - (v.x - mean) * m2), k * (d.y - m1 - (v.y - mean) * m2),
-                            k * (d.z - m1 - (v.z - mean) * m2), k * (d.w - m1 - (v.w - mean) * m2));
+  if (VEC) {
+    const BnItems it(B, C, HW, c, s, splits);
+    const float4 *g4 = reinterpret_cast<const float4 *>(gy);
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    const float4 *y4 = reinterpret_cast<const float4 *>(y);
+    float4 *o4 = reinterpret_cast<float4 *>(gx);
+    float4 *r4 = reinterpret_cast<float4 *>(gres);
+    for (int t0 = threadIdx.x; t0 < it.total; t0 += kBnUnroll * kBnThreads) {
+      float4 d[kBnUnroll], v[kBnUnroll], o[kBnUnroll];
+      int64_t idx[kBnUnroll];
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const int t = t0 + u * kBnThreads;
+        idx[u] = t < it.total ? it.at(t) : -1;
+        const bool ok = idx[u] >= 0;
+        d[u] = ok ? __ldg(g4 + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u] = ok ? __ldg(x4 + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        o[u] = (ok && relu) ? __ldg(y4 + idx[u]) : make_float4(1.f, 1.f, 1.f, 1.f);
       }
-    } else {
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        if (idx[u] < 0) continue;
+        float4 dd = d[u];
+        dd.x = o[u].x > 0.f ? dd.x : 0.f; dd.y = o[u].y > 0.f ? dd.y : 0.f;
+        dd.z = o[u].z > 0.f ? dd.z : 0.f; dd.w = o[u].w > 0.f ? dd.w : 0.f;
+        if (r4 != nullptr) r4[idx[u]] = dd;
+        o4[idx[u]] = make_float4(k * (dd.x - m1 - (v[u].x - mean) * m2), k * (dd.y - m1 - (v[u].y - mean) * m2),
+                                 k * (dd.z - m1 - (v[u].z - mean) * m2), k * (dd.w - m1 - (v[u].w - mean) * m2));
+      }
+    }
+  }
+  for (int b = s; b < B && !VEC; b += splits) {
+    const int64_t off = ((int64_t)b * C + c) * HW;
+    {
       for (int i = threadIdx.x; i < HW; i += kBnThreads) {
         float d = __ldg(gy + off + i);
         if (relu && !(__ldg(y + off + i) > 0.f)) d = 0.f;
