@@ -143,6 +143,128 @@ __global__ void __launch_bounds__(kAlphaThreads, 4) bwd_alpha_v3_kernel(const Al
   else alpha_body<NS, kAlphaMaxNXG * NS>(P, i0, npl, smem_alpha);
 }
 
+
+// ---- compile-time variant (Cout = 16 / 32 / 64 / 128): thread = (channel c, pixel phase sub) owns EVERY plane of its
+// channel at the pixels sub, sub + PH, ... of the tile.  The mapping above gives a thread whole planes: at 16 channels
+// (6 planes, 16 threads per channel) 10 of 16 threads had nothing to do, at 32 channels (9 planes, 8 threads) one thread
+// of eight had two planes -- those layers ran at a quarter / a half of the 64-channel rate per partial sum.  Here the
+// work is 4 pixels x all planes for every thread, grad_out is read once per pixel for all planes, a tile is always
+// 1024 bytes per plane (PX = 1024 / Cout pixels) and every shared-memory address is base + immediate (no pointer
+// updates): 7 instructions per state byte (byte load, 3 masks, 3 FMAs).  The PH sums of a channel are added through
+// shared memory once, at the end of the block.
+template <int NS, int NPL, int COUT>
+__device__ __forceinline__ void alpha_body_ct(const AlphaParams &P, int i0, uint8_t *smem) {
+  constexpr int PH = kAlphaThreads / COUT, PX = 1024 / COUT, PT = PX / PH, GS = PX + 1;
+  constexpr uint32_t CB = NPL * 1024u, BUF = (CB + COUT * GS * 4u + 15u) & ~15u;
+  static_assert(PT == 4, "four pixels per thread and tile");
+  const Geo &g = P.g;
+  const int tid = threadIdx.x;
+  const int c = tid % COUT, sub = tid / COUT;
+  float acc[NPL][NS], gsum = 0.0f;
+#pragma unroll
+  for (int q = 0; q < NPL; ++q)
+#pragma unroll
+    for (int k = 0; k < NS; ++k) acc[q][k] = 0.0f;
+
+  auto issue = [&](int tile, int b) {
+    const int64_t m0 = (int64_t)tile * PX;
+    const uint32_t sbuf = (uint32_t)__cvta_generic_to_shared(smem + (size_t)b * BUF);
+    const uint8_t *cbase = P.cplanes + ((int64_t)i0 * NS * g.M + m0) * COUT;
+#pragma unroll
+    for (int q0 = 0; q0 < NPL * 64; q0 += kAlphaThreads) {  // 64 16-byte chunks per plane
+      const int q = q0 + tid;
+      if (NPL * 64 % kAlphaThreads == 0 || q < NPL * 64) {
+        const int pl = q >> 6, ch16 = (q & 63) << 4;
+        cp_async16(sbuf + pl * 1024 + ch16, cbase + (int64_t)pl * g.M * COUT + ch16);
+      }
+    }
+    const int bimg = (int)(m0 / g.L), l0 = (int)(m0 % g.L);
+    const float *gbase = P.go + (int64_t)bimg * COUT * g.L + l0;
+#pragma unroll
+    for (int q0 = 0; q0 < 1024; q0 += kAlphaThreads) {  // Cout runs of PX floats
+      const int q = q0 + tid, cc = q / PX, p = q % PX;
+      cp_async4(sbuf + CB + (uint32_t)(cc * GS + p) * 4u, gbase + (int64_t)cc * g.L + p);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int tile = blockIdx.x, b = 0;
+  if (tile < P.ntiles) issue(tile, 0);
+  for (; tile < P.ntiles; tile += gridDim.x, b ^= 1) {
+    const int nxt = tile + gridDim.x;
+    if (nxt < P.ntiles) {
+      issue(nxt, b ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint8_t *bp = smem + (size_t)b * BUF + sub * COUT + c;
+    const float *gs = reinterpret_cast<const float *>(smem + (size_t)b * BUF + CB) + c * GS + sub;
+#pragma unroll
+    for (int t = 0; t < PT; ++t) {
+      const float gv = gs[t * PH];
+      gsum += gv;
+      const float gsc = gv * 1.2676506002282294e30f;  // 2^100
+#pragma unroll
+      for (int q = 0; q < NPL; ++q) {
+        const uint32_t w = bp[q * 1024 + t * PH * COUT];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) acc[q][k] = fmaf(gsc, __uint_as_float(w & (3u << (2 * k))), acc[q][k]);
+      }
+    }
+    __syncthreads();  // the buffer is refilled by the copies issued at the top of the next iteration
+  }
+
+  // ---- add the PH pixel phases of each channel (fixed order), undo the scaling, subtract sum go
+  constexpr int NV = NPL * NS;
+  float *red = reinterpret_cast<float *>(smem);  // [NV + 1][PH][COUT]
+#pragma unroll
+  for (int q = 0; q < NPL; ++q)
+#pragma unroll
+    for (int k = 0; k < NS; ++k) red[((q * NS + k) * PH + sub) * COUT + c] = acc[q][k];
+  red[(NV * PH + sub) * COUT + c] = gsum;
+  __syncthreads();
+  float gt = 0.0f;
+#pragma unroll
+  for (int s = 0; s < PH; ++s) gt += red[(NV * PH + s) * COUT + c];
+  const int64_t n = table_entries(g);
+  for (int v = sub; v < NV; v += PH) {
+    float a = 0.0f;
+#pragma unroll
+    for (int s = 0; s < PH; ++s) a += red[(v * PH + s) * COUT + c];
+    const int pl = v / NS, k = v % NS;
+    const int i = i0 + pl / NS, j = pl % NS;
+    P.partial[(int64_t)blockIdx.x * n + ((int64_t)i * g.pairs + k * g.NSA + j) * COUT + c] =
+        a * exp2f((float)(49 - 2 * k)) - gt;
+  }
+}
+
+template <int NS, int COUT>
+__global__ void __launch_bounds__(kAlphaThreads, 4) bwd_alpha_ct_kernel(const AlphaParams P) {
+  extern __shared__ __align__(16) uint8_t smem_alpha[];
+  const int i0 = blockIdx.y * kAlphaMaxNXG;
+  switch (min(kAlphaMaxNXG, P.g.NX - i0)) {
+    case 1: alpha_body_ct<NS, 1 * NS, COUT>(P, i0, smem_alpha); break;
+    case 2: alpha_body_ct<NS, 2 * NS, COUT>(P, i0, smem_alpha); break;
+    case 3: alpha_body_ct<NS, 3 * NS, COUT>(P, i0, smem_alpha); break;
+    case 4: alpha_body_ct<NS, 4 * NS, COUT>(P, i0, smem_alpha); break;
+    default: alpha_body_ct<NS, 5 * NS, COUT>(P, i0, smem_alpha); break;
+  }
+}
+
+template <int NS, int COUT>
+int launch_alpha_ct(const AlphaParams &P, dim3 grid, int nxg, cudaStream_t st) {
+  constexpr int PX = 1024 / COUT;
+  const size_t buf = ((size_t)nxg * NS * 1024 + (size_t)COUT * (PX + 1) * 4 + 15) & ~(size_t)15;
+  const size_t red = ((size_t)nxg * NS * NS + 1) * kAlphaThreads * 4;
+  const size_t smem = 2 * buf > red ? 2 * buf : red;
+  CIMQ_CUDA_OK(cudaFuncSetAttribute(bwd_alpha_ct_kernel<NS, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bwd_alpha_ct_kernel<NS, COUT><<<grid, kAlphaThreads, smem, st>>>(P);
+  CIMQ_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 }  // namespace v2
 
@@ -154,8 +276,13 @@ bool alpha_v3_supported(const Geo &g) {
 }
 
 // number of per-block partials the launch below writes (the finish kernel sums them): blocks along x
+// the compile-time variant covers Cout = 16 / 32 / 64 / 128 when its tile (1024 / Cout pixels) divides an image
+static bool alpha_ct_geo(const Geo &g) {
+  return (g.Cout == 16 || g.Cout == 32 || g.Cout == 64 || g.Cout == 128) && g.L % (1024 / g.Cout) == 0 && g.NSW == g.NSA;
+}
+
 int alpha_v3_blocks(const Geo &g) {
-  const int P = g.L % 16 == 0 ? 16 : 8;
+  const int P = alpha_ct_geo(g) ? 1024 / g.Cout : (g.L % 16 == 0 ? 16 : 8);
   const int ntiles = g.M / P;
   const int groups = (g.NX + v2::kAlphaMaxNXG - 1) / v2::kAlphaMaxNXG;
   int bx = 148 * 4 / groups;
@@ -178,6 +305,21 @@ int launch_alpha_v3(const Geo &g, const float *go, const uint8_t *cplanes, float
   P.c_bytes = (uint32_t)(nxg * g.NSA * P.P * g.Cout);
   P.buf_bytes = (P.c_bytes + (uint32_t)(g.Cout * P.gstride * 4) + 15u) & ~15u;
   P.go = go; P.cplanes = cplanes; P.partial = partial;
+  if (alpha_ct_geo(g)) {
+    CIMQ_REQUIRE((reinterpret_cast<uintptr_t>(cplanes) & 15u) == 0, "alpha-grad (v2): state planes must be 16-byte aligned");
+    P.P = 1024 / g.Cout;
+    P.ntiles = g.M / P.P;
+    const dim3 grid(alpha_v3_blocks(g), (g.NX + kAlphaMaxNXG - 1) / kAlphaMaxNXG);
+#define CIMQ_ALPHA_CT(NS_)                                                        \
+    switch (g.Cout) {                                                             \
+      case 16: return launch_alpha_ct<NS_, 16>(P, grid, nxg, st);                 \
+      case 32: return launch_alpha_ct<NS_, 32>(P, grid, nxg, st);                 \
+      case 64: return launch_alpha_ct<NS_, 64>(P, grid, nxg, st);                 \
+      default: return launch_alpha_ct<NS_, 128>(P, grid, nxg, st);                \
+    }
+    if (g.NSW == 3) { CIMQ_ALPHA_CT(3) } else if (g.NSW == 2) { CIMQ_ALPHA_CT(2) }
+#undef CIMQ_ALPHA_CT
+  }
   const size_t smem = 2 * (size_t)P.buf_bytes;
   CIMQ_REQUIRE(smem <= 200 * 1024, "alpha-grad (v2): tile does not fit shared memory");
   CIMQ_REQUIRE((reinterpret_cast<uintptr_t>(cplanes) & 15u) == 0, "alpha-grad (v2): state planes must be 16-byte aligned");

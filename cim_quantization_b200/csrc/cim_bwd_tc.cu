@@ -1658,6 +1658,7 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
   const size_t smem = (size_t)P.xt_off + tbytes + 1024;
   dim3 grid(ctas, groups);
   if (const char *e = getenv("CIMQ_V2_DBG")) P.dbg = v2 ? atoi(e) : 0;
+  if (const char *e = getenv("CIMQ_V2_DBG_WG")) P.dbg = v2 ? atoi(e) : 0;  // (this kernel only)
 #define CIMQ_LAUNCH_WGRAD(W, A, T, ...)                                        \
   do {                                                                         \
     if (launch_wgrad_instance<W, A, T>(P, grid, smem, st)) return 1;            \

@@ -10,10 +10,13 @@ p.add_argument("--adcbits", type=float, default=1.5)
 p.add_argument("--batch", type=int, default=256)
 p.add_argument("--iters", type=int, default=2)
 p.add_argument("--v1", action="store_true")
+p.add_argument("--channels", type=int, default=64)
+p.add_argument("--hw", type=int, default=32)
+p.add_argument("--time", action="store_true", help="print CUDA-event times of the forward and the backward call")
 p.add_argument("--timers", action="store_true", help="library built with `make TIMERS=1`: per-role cycle counters of the wgrad kernel (it runs last)")
 a = p.parse_args()
 adc = int(a.adcbits) if a.adcbits == int(a.adcbits) else a.adcbits
-B, C, HW = a.batch, 64, 32
+B, C, HW = a.batch, a.channels, a.hw
 spec = L.LayerSpec(B, C, HW, C, 3, 1, 1, 3, 1, 3, 1, a.xbar, adc)
 g = torch.Generator(device="cuda").manual_seed(0)
 x = torch.relu(torch.randn(B, C, HW, HW, device="cuda", generator=g))
@@ -37,10 +40,16 @@ if a.timers:
     import ctypes
     dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
     L.load().cimq_debug_set_timers(ctypes.c_void_p(dbg.data_ptr()))
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 for it in range(a.iters):
+    ev[0].record()
     out, state = L.conv_forward(spec, xc, wc, wtiles, table, s, mask, save_state=True, flags=flags)
+    ev[1].record()
     L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask, need_alpha=aq is not None)
+    ev[2].record()
 torch.cuda.synchronize()
+if a.time:
+    print(f"forward {ev[0].elapsed_time(ev[1]) * 1e3:.1f} us   backward {ev[1].elapsed_time(ev[2]) * 1e3:.1f} us")
 if dbg is not None:
     d = dbg.cpu().tolist()
     for k, n in {0: "producer wait empty", 1: "producer chunk start (rows, gather)", 2: "producer X tile", 3: "producer G' tile", 7: "producer chunk-end barrier", 4: "mma wait full", 6: "mma total"}.items():
