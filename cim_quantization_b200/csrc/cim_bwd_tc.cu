@@ -629,7 +629,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
   const Geo &g = P.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const Carve cv = carve_smem(smem_raw, P.stages, P.stage_bytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the warp index through a shuffle: the compiler then knows that the role branches below are warp-uniform and keeps
+  // the MMA issuer's descriptors in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int Kc = P.Kc;                            // Cout = UMMA N
   const uint32_t a_sbo = 128u * 16u;              // X tile: 8 rows x 128 pixels bf16, LBO 128
   // G' tile: 16 k-groups of 144 bytes per 8 rows (+ 16 bytes in the v2 variant, whose producer lanes run along the
@@ -1278,7 +1280,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
   } else {
     reg_dealloc<kWgRegsMma>();
     // ------------------------------------------------------------------ MMA issuer
-    if (warp == kMmaWarp && lane == 0 && has_work) {
+    if (warp == kMmaWarp && has_work) {  // the whole warp walks the loop (uniform control flow); lane 0 issues
       const uint32_t idesc = V2 ? idesc_f16_f32(128, Kc) : idesc_bf16_f32(128, Kc);
       constexpr int kPieces = V2 ? v2::kBwdPieces : 3;  // terms of the real-valued operand
       uint32_t it = 0;
@@ -1288,6 +1290,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
       const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
       long long d_full = 0;
       const long long t_begin = CIMQ_TB();
+      const uint32_t stage0 = smem_u32(cv.stage_base);
       for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, first_tile = false) {
         for (int i = i_begin; i < i_end; ++i) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(i - i_begin) * Kc;
@@ -1299,20 +1302,29 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
             mbar_wait<CIMQ_MMA_SLEEP>(cv.full0 + 8 * sidx, use & 1);
             d_full += CIMQ_TB() - tf0;
             tc_fence_after();
-            const uint32_t a0 = smem_u32(cv.stage_base + (size_t)sidx * P.stage_bytes);
-            const uint32_t b0 = a0 + P.a_bytes;
-            for (int sp = 0; sp < kPieces; ++sp)
-              for (int ks = 0; ks < 8 && !(P.dbg & 1); ++ks) {  // 128 pixels = 8 x K16
-                const uint64_t adesc = make_smem_desc(a0 + ks * 2 * kTcLBO, kTcLBO, a_sbo);
-                const uint64_t bdesc = make_smem_desc(b0 + sp * P.b_bytes + ks * 2 * kWgLBO, kWgLBO, b_sbo);
-                umma_f16(d_tmem, adesc, bdesc, idesc, (first_tile && j == 0 && sp == 0 && ks == 0) ? 0u : 1u);
+            const uint32_t a0 = stage0 + (uint32_t)sidx * P.stage_bytes;
+            // one descriptor per operand and stage; the k-steps and pieces only add to its address field (bits 0-13,
+            // address >> 4: shared memory ends below 2^18, so the sum never carries out of the field)
+            const uint64_t adesc0 = make_smem_desc(a0, kTcLBO, a_sbo);
+            const uint64_t bdesc0 = make_smem_desc(a0 + P.a_bytes, kWgLBO, b_sbo);
+            if (lane == 0) {
+              if (!(P.dbg & 1)) {
+#pragma unroll
+                for (int sp = 0; sp < kPieces; ++sp)
+#pragma unroll
+                  for (int ks = 0; ks < 8; ++ks)  // 128 pixels = 8 x K16
+                    umma_f16(d_tmem, adesc0 + (uint64_t)((ks * 2 * kTcLBO) >> 4),
+                             bdesc0 + (uint64_t)((sp * P.b_bytes + ks * 2 * kWgLBO) >> 4), idesc,
+                             (first_tile && j == 0 && sp == 0 && ks == 0) ? 0u : 1u);
               }
-            umma_commit(cv.empty0 + 8 * sidx);
+              umma_commit(cv.empty0 + 8 * sidx);
+            }
+            __syncwarp();
           }
         }
       }
-      umma_commit(cv.tfull0);  // every accumulation of this CTA is complete
-      if (dbg) { P.debug[4] = d_full; P.debug[6] = clock64() - t_begin; }
+      if (lane == 0) umma_commit(cv.tfull0);  // every accumulation of this CTA is complete
+      if (dbg && lane == 0) { P.debug[4] = d_full; P.debug[6] = clock64() - t_begin; }
     }
   }
   if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + kEpilogueWarps) {
