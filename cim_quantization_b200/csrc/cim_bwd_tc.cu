@@ -62,6 +62,7 @@ struct BwdParams {
   int nxg, chunk0;  // wgrad: crossbars handled by this launch's blockIdx.y group
   // wgrad staged activation rows (same geometry as the forward producer, stride 1 only)
   int fastx, ow_log2, rpt, pitch_log2, col0;
+  int pitch, slot_bytes;  // wgrad staging: bytes per staged row / per channel slot (rk rows + bank padding), see tune_row_layout
   int rk, prow;      // wgrad staging: rows per channel slot, staged row of (output row o, tap row ky) = o*prow + ky
   int xshared;       // wgrad staging: 1 = a tile is consecutive rows of ONE image and its output rows share input rows
                      // (prow == 1); 0 = every output row stages its own K rows (prow == K; also 1 for 1x1 kernels)
@@ -629,6 +630,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
   const Geo &g = P.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const Carve cv = carve_smem(smem_raw, P.stages, P.stage_bytes);
+  if (kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) P.debug[10] = clock64();  // (absolute: entry)
   // (the warp index through a shuffle: the compiler then knows that the role branches below are warp-uniform and keeps
   // the MMA issuer's descriptors in uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -666,12 +668,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
   const uint32_t tmem_base = *cv.tmem_slot;
   const int rows_full = g.xbar < g.F ? g.xbar : g.F;
   const bool has_work = blockIdx.x < P.mtiles;
+  if (kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) P.debug[11] = clock64();  // prologue done
 
   if (warp < 12) {
     // ------------------------------------------------------------------ producers (384 threads)
     reg_alloc<kWgRegsProducer>();  // warpgroups 0-2; the registers come from warpgroup 3 (MMA issuer + idle warps)
     const int tid = threadIdx.x;
-    const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x == (P.dbg >> 8);  // (timed thread: CIMQ_V2_DBG_WG >> 8)
     long long d_stage = 0, d_wait = 0, d_x = 0, d_g = 0, d_bar = 0;
     // X tile items (crossbar row fr, 8-pixel group pg = x_pg0 + x_step * q, q < XI) of this thread
     // v2: threads [0, n_g) build G' (one 4-channel x 8-pixel item = 32 elements); with n_g = 256 the G' threads also
@@ -691,8 +694,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
       x_cnt = (xt >= 0 && xt < 256) ? 8 : 0;
     }
     const bool aligned = (g.L % 8) == 0 && (g.OW % 8) == 0;
-    const int pitch = 1 << P.pitch_log2;
-    const int slot_bytes = P.rk * pitch;
+    const int pitch = P.pitch;
+    const int slot_bytes = P.slot_bytes;
     const int HW = g.H * g.W;
     uint32_t it = 0, chunk_it = 0;
     int p_sidx = 0;
@@ -787,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         const int off = tab[row];
         const bool ok = off != kNoRow;
         const uint8_t *src = P.xcodes + (ok ? (size_t)(c_lo_ + sl) * HW + off + ps * c16 : (size_t)0);
-        const uint32_t dst = smem_u32(dstbuf + ((size_t)rq << P.pitch_log2) + g.pad + P.col0 + ps * c16);
+        const uint32_t dst = smem_u32(dstbuf + (size_t)sl * slot_bytes + (size_t)row * pitch + g.pad + P.col0 + ps * c16);
         if (ps == 16)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u)
                        : "memory");
@@ -971,12 +974,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           uint32_t xlo[XIr], xhi[XIr];
           const bool xfast = V2 && P.fastx;  // (v2 layers have 1-bit digits)
           if (xfast && !(P.dbg & 8)) {
-            const uint8_t *src_row = raw + (size_t)(ci - c_lo) * slot_bytes + ((size_t)ky << P.pitch_log2) + kx + P.col0;
-            const int rps = P.pitch_log2 + (P.prow == 1 ? 0 : (g.K == 1 ? 0 : -1));  // row pitch shift (see below)
-            (void)rps;
+            const uint8_t *src_row = raw + (size_t)(ci - c_lo) * slot_bytes + (size_t)ky * pitch + kx + P.col0;
             // output row r of the tile is staged r * prow rows further down; prow is 1 or K (not a power of two in
             // general), so the row offset is a multiply
-            const int rowb = P.prow << P.pitch_log2;
+            const int rowb = P.prow * pitch;
             auto gather = [&](auto cnt, auto stp) {
   #pragma unroll
               for (int q = 0; q < decltype(cnt)::value; ++q) {
@@ -1018,7 +1019,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
               if (P.fastx) {
                 const int p0 = pg * 8;
                 const uint8_t *src = raw + (size_t)(ci - c_lo) * slot_bytes +
-                                     ((((p0 >> P.ow_log2) * P.prow) + ky) << P.pitch_log2) +
+                                     (((p0 >> P.ow_log2) * P.prow) + ky) * pitch +
                                      (p0 & ((1 << P.ow_log2) - 1)) + kx + P.col0;
                 const uint32_t sa = smem_u32(src);
                 const uint32_t *al = reinterpret_cast<const uint32_t *>(src - (sa & 3u));
@@ -1324,7 +1325,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         }
       }
       if (lane == 0) umma_commit(cv.tfull0);  // every accumulation of this CTA is complete
-      if (dbg && lane == 0) { P.debug[4] = d_full; P.debug[6] = clock64() - t_begin; }
+      if (dbg && lane == 0) { P.debug[4] = d_full; P.debug[6] = clock64() - t_begin; P.debug[12] = t_begin; P.debug[13] = clock64(); }
     }
   }
   if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + kEpilogueWarps) {
@@ -1337,6 +1338,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
       mbar_wait(cv.tfull0, 0);
       tc_fence_after();
     }
+    if (kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && warp == kEpilogueWarp0 && lane == 0) P.debug[14] = clock64();
     for (int i = i_begin; i < i_end; ++i) {
       const int lo = i * g.xbar;
       const int rows = min(rows_full, g.F - lo);
@@ -1367,6 +1369,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
 
   tc_fence_before();
   __syncthreads();
+  if (kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) P.debug[15] = clock64();  // all roles done
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, P.tmem_cols);
@@ -1609,6 +1612,44 @@ int launch_bwd_input_tc(const Geo &g0, const float *go, const uint32_t *state, c
   return 0;
 }
 
+// Bank layout of the staged activation rows (async staging).  A producer warp gathers 32 consecutive crossbar rows
+// = (channel, ky, kx) triples; its lanes read row ky of channel slot (channel - first channel), byte kx + col0 + pixel
+// offset.  With a power-of-two row pitch and slot = rk * pitch (64 B, 384 B at 32x32 images) every channel and every
+// second ky fell on the same banks: 8.4 wavefronts per load instruction, 16 M conflict wavefronts of 62 M at the
+// microbench layer (ncu l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld).  Pitch and slot padding (16-byte steps:
+// the cp.async pieces stay aligned) are picked to minimise the worst distinct-words-per-bank count over the warps of
+// all crossbars.
+static void tune_row_layout(const Geo &g, int rk, int needp, int col0, int *pitch_out, int *slot_out) {
+  const int rows_full = g.xbar < g.F ? g.xbar : g.F;
+  const int base = (needp + 15) & ~15;
+  long best = -1;
+  for (int pitch = base; pitch <= base + 48; pitch += 16)
+    for (int pad = 0; pad < 128; pad += 16) {
+      const int slot = rk * pitch + pad;
+      long cost = 0;
+      for (int i = 0; i < g.NX; ++i) {
+        const int lo = i * g.xbar, rows = rows_full < g.F - lo ? rows_full : g.F - lo, c_lo = lo / g.KK;
+        for (int w0 = 0; w0 < rows; w0 += 32)
+          for (int word = 0; word < 3; ++word) {  // the three aligned words of an 8-byte window
+            int seen[32][32], nseen[32];
+            for (int b = 0; b < 32; ++b) nseen[b] = 0;
+            int worst = 0;
+            for (int r = w0; r < w0 + 32 && r < rows; ++r) {
+              const int f = lo + r, ci = f / g.KK - c_lo, tap = f % g.KK, ky = tap / g.K, kx = tap % g.K;
+              const int wa = ((ci * slot + ky * pitch + kx + col0) >> 2) + word, b = wa & 31;
+              bool dup = false;
+              for (int q = 0; q < nseen[b]; ++q) dup = dup || seen[b][q] == wa;
+              if (!dup) seen[b][nseen[b]++] = wa;
+              if (nseen[b] > worst) worst = nseen[b];
+            }
+            cost += worst;
+          }
+      }
+      cost = cost * 4096 + slot;  // ties: the smaller buffer
+      if (best < 0 || cost < best) { best = cost; *pitch_out = pitch; *slot_out = slot; }
+    }
+}
+
 int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, const uint32_t *state,
                          const float *s, const int8_t *mask, float *partial, float *gw, bool v2, const void *scales,
                          cudaStream_t st) {
@@ -1649,9 +1690,11 @@ int launch_bwd_weight_tc(const Geo &g0, const float *go, const uint8_t *xcodes, 
     const int rpt = kTcTileM / g.OW;
     const bool shared_rows = g.L % kTcTileM == 0;
     const int rk = shared_rows ? rpt - 1 + g.K : rpt * g.K;
-    const size_t raw = ((size_t)nch * rk * (1u << pl) + 8 + 15) & ~(size_t)15;
+    int pitch = 1 << pl, slot = rk * pitch;  // synchronous staging maps threads to the words of a power-of-two row
+    if (async_rows) tune_row_layout(g, rk, needp, col0, &pitch, &slot);
+    const size_t raw = ((size_t)nch * slot + 8 + 15) & ~(size_t)15;
     if (pl <= 9 && rk <= 128 && 2 * raw + 2 * P.stage_bytes + kBarrierBytes + tbytes + 16 <= kSmemBudget) {
-      P.fastx = 1; P.ow_log2 = owl; P.rpt = rpt; P.pitch_log2 = pl; P.col0 = col0;
+      P.fastx = 1; P.ow_log2 = owl; P.rpt = rpt; P.pitch_log2 = pl; P.col0 = col0; P.pitch = pitch; P.slot_bytes = slot;
       P.rk = rk; P.prow = shared_rows ? 1 : g.K; P.xshared = shared_rows ? 1 : 0; P.async_rows = async_rows ? (g.W % 16 == 0 ? 16 : 8) : 0;
       P.raw_bytes = (uint32_t)raw;
     }

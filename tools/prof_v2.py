@@ -54,4 +54,8 @@ if dbg is not None:
     d = dbg.cpu().tolist()
     for k, n in {0: "producer wait empty", 1: "producer chunk start (rows, gather)", 2: "producer X tile", 3: "producer G' tile", 7: "producer chunk-end barrier", 4: "mma wait full", 6: "mma total"}.items():
         print(f"  wgrad timer {n:36s} {d[k] / 1e3:10.1f} kcycles")
+    if d[10]:
+        t0 = d[10]
+        print("  wgrad block 0 (cycles after entry): prologue done %d, MMA issuer starts %d, last commit %d, epilogue starts %d, all done %d"
+              % (d[11] - t0, d[12] - t0, d[13] - t0, d[14] - t0, d[15] - t0))
 print("done")
