@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     reg_alloc<kWgRegsProducer>();  // warpgroups 0-2; the registers come from warpgroup 3 (MMA issuer + idle warps)
     const int tid = threadIdx.x;
     const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x == (P.dbg >> 8);  // (timed thread: CIMQ_V2_DBG_WG >> 8)
-    long long d_stage = 0, d_wait = 0, d_x = 0, d_g = 0, d_bar = 0;
+    long long d_stage = 0, d_wait = 0, d_x = 0, d_g = 0, d_bar = 0, d_conv = 0, d_tbar = 0;
     // X tile items (crossbar row fr, 8-pixel group pg = x_pg0 + x_step * q, q < XI) of this thread
     // v2: threads [0, n_g) build G' (one 4-channel x 8-pixel item = 32 elements); with n_g = 256 the G' threads also
     // take three X items each (pixel groups 10..15) and the other 128 threads ten (groups 0..9) -- measured with the
@@ -873,6 +873,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
       const int xc = ROLE == 1 ? 3 : (ROLE == 2 ? 10 : (ROLE == 3 ? 0 : x_cnt));
       for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x, tpar ^= 1) {
         const int64_t m0 = (int64_t)mt * kTcTileM;
+        const long long tt0 = CIMQ_TB();
         if constexpr (V2) {
           if (gthr && !(P.dbg & 32)) {  // this tile's grad_out (loaded during the previous tile's last stage) -> scaled fp16 pieces
   #pragma unroll
@@ -907,7 +908,10 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
         int *rowoff = cv.rowoff + tpar * 128;
         // async staging fills the table of a tile one chunk before the tile starts (below); the first tile's here
         if (P.fastx && (!P.async_rows || mt == (int)blockIdx.x)) fill_rowoff(mt, rowoff);
+        const long long tt1 = CIMQ_TB();
         named_barrier_sync(1, kWgProducerThreads);
+        d_conv += tt1 - tt0;
+        d_tbar += CIMQ_TB() - tt1;
         if (P.async_rows && mt == (int)blockIdx.x) {  // rows of the very first chunk
           issue_rows(i_begin, rowoff, cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes);
           asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1113,6 +1117,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
                   else if (next_tile) v2_load_w(mt_n, i_begin);
                 }
                 if (j == 0 && next_tile) {  // next tile's grad_out: three stages ahead of its split
+                  // (measured: issuing these loads after the stage's arrival instead, one stage earlier for the W bytes,
+                  // made the kernel 4 % slower)
   #pragma unroll
                   for (int c = 0; c < 4; ++c) v2_load_go(mt_n, c);
                 }
@@ -1277,7 +1283,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     } else {
       run_tiles(std::integral_constant<int, 0>{});
     }
-    if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_stage; P.debug[2] = d_x; P.debug[3] = d_g; P.debug[7] = d_bar; }
+    if (dbg) { P.debug[0] = d_wait; P.debug[1] = d_stage; P.debug[2] = d_x; P.debug[3] = d_g; P.debug[7] = d_bar; P.debug[16] = d_conv; P.debug[17] = d_tbar; }
   } else {
     reg_dealloc<kWgRegsMma>();
     // ------------------------------------------------------------------ MMA issuer

@@ -38,7 +38,7 @@ flags = 0 if a.v1 else L.FLAG_V2
 dbg = None
 if a.timers:
     import ctypes
-    dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(32, dtype=torch.int64, device="cuda")
     L.load().cimq_debug_set_timers(ctypes.c_void_p(dbg.data_ptr()))
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 for it in range(a.iters):
@@ -52,7 +52,7 @@ if a.time:
     print(f"forward {ev[0].elapsed_time(ev[1]) * 1e3:.1f} us   backward {ev[1].elapsed_time(ev[2]) * 1e3:.1f} us")
 if dbg is not None:
     d = dbg.cpu().tolist()
-    for k, n in {0: "producer wait empty", 1: "producer chunk start (rows, gather)", 2: "producer X tile", 3: "producer G' tile", 7: "producer chunk-end barrier", 4: "mma wait full", 6: "mma total"}.items():
+    for k, n in {0: "producer wait empty", 1: "producer chunk start (rows, gather)", 2: "producer X tile", 3: "producer G' tile", 7: "producer chunk-end barrier", 16: "producer tile start (pieces, tables)", 17: "producer tile-start barrier", 4: "mma wait full", 6: "mma total"}.items():
         print(f"  wgrad timer {n:36s} {d[k] / 1e3:10.1f} kcycles")
     if d[10]:
         t0 = d[10]
