@@ -148,6 +148,70 @@ __global__ void __launch_bounds__(kScaleThreads) go_scales_kernel(Geo g, const f
     if (sm_ch[c] != 0u) atomicMax(&chmax[c], sm_ch[c]);
 }
 
+// Small layers (fewer than ~300 blocks of 512 pixels): the four warps of a block share 32 pixel quads and split the
+// CHANNELS, four times as many blocks and a quarter of the loads per thread -- the 8x8 / 16x16 layers of a ResNet at
+// batch 256 were 32 / 128 blocks of the kernel above, 15 us of load latency each.  E = loads in flight per batch.
+template <int E>
+__global__ void __launch_bounds__(kScaleThreads) go_scales_split_kernel(Geo g, const float *__restrict__ go,
+                                                                        float *__restrict__ rowscale,
+                                                                        uint32_t *__restrict__ chmax) {
+  __shared__ uint4 rm_s[4][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cpw = g.Cout >> 2;  // channels per warp (a multiple of E)
+  constexpr int kCB = 4;        // 32-channel blocks per warp (Cout <= 512)
+  uint32_t chreg[kCB];
+#pragma unroll
+  for (int cb = 0; cb < kCB; ++cb) chreg[cb] = 0u;
+  const int m4s = g.M >> 2;
+  for (int q0 = blockIdx.x * 32; q0 < m4s; q0 += gridDim.x * 32) {
+    const int q = q0 + lane;
+    const bool live = q < m4s;
+    const int m = live ? 4 * q : 0;
+    const int b = m / g.L, l = m % g.L;
+    const float4 *gp = reinterpret_cast<const float4 *>(go + ((int64_t)b * g.Cout + w * cpw) * g.L + l);
+    const int64_t cstride = g.L >> 2;
+    uint32_t rm0 = 0u, rm1 = 0u, rm2 = 0u, rm3 = 0u;
+#pragma unroll
+    for (int cb = 0; cb < kCB; ++cb) {
+      if (cb * 32 < cpw) {
+#pragma unroll
+        for (int c8 = 0; c8 < 32; c8 += E) {
+          if (cb * 32 + c8 < cpw) {
+            float4 v[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+              v[e] = live ? __ldg(gp + (int64_t)(cb * 32 + c8 + e) * cstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              const uint32_t a0 = __float_as_uint(v[e].x) & 0x7fffffffu, a1 = __float_as_uint(v[e].y) & 0x7fffffffu;
+              const uint32_t a2 = __float_as_uint(v[e].z) & 0x7fffffffu, a3 = __float_as_uint(v[e].w) & 0x7fffffffu;
+              rm0 = max(rm0, a0); rm1 = max(rm1, a1); rm2 = max(rm2, a2); rm3 = max(rm3, a3);
+              const uint32_t wm = __reduce_max_sync(0xffffffffu, max(max(a0, a1), max(a2, a3)));
+              if (lane == c8 + e) chreg[cb] = max(chreg[cb], wm);
+            }
+          }
+        }
+      }
+    }
+    rm_s[w][lane] = make_uint4(rm0, rm1, rm2, rm3);
+    __syncthreads();
+    if (w == 0 && live) {
+      uint4 a = rm_s[0][lane];
+#pragma unroll
+      for (int ww = 1; ww < 4; ++ww) {
+        const uint4 o = rm_s[ww][lane];
+        a.x = max(a.x, o.x); a.y = max(a.y, o.y); a.z = max(a.z, o.z); a.w = max(a.w, o.w);
+      }
+      *reinterpret_cast<float4 *>(rowscale + m) = make_float4(bwd_scale_from_maxbits(a.x), bwd_scale_from_maxbits(a.y),
+                                                              bwd_scale_from_maxbits(a.z), bwd_scale_from_maxbits(a.w));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int cb = 0; cb < kCB; ++cb)
+    if (cb * 32 + lane < cpw && chreg[cb] != 0u) atomicMax(&chmax[w * cpw + cb * 32 + lane], chreg[cb]);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // dgrad
 // ---------------------------------------------------------------------------------------------------------------
@@ -552,6 +616,14 @@ int launch_go_scales(const Geo &g, const float *go, void *scales, cudaStream_t s
                "go_scales: grad_out rows must be 16-byte aligned");
   int blocks = (g.M / 4 + v2::kScaleThreads - 1) / v2::kScaleThreads;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 148 * 2 && g.Cout % 16 == 0 && g.Cout <= 512) {  // small layer: split the channels over the warps
+    int sb = (g.M / 4 + 31) / 32;
+    if (sb > 148 * 4) sb = 148 * 4;
+    if (g.Cout % 32 == 0) v2::go_scales_split_kernel<8><<<sb, v2::kScaleThreads, 0, st>>>(g, go, rowscale, chmax);
+    else v2::go_scales_split_kernel<4><<<sb, v2::kScaleThreads, 0, st>>>(g, go, rowscale, chmax);
+    CIMQ_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   v2::go_scales_kernel<<<blocks, v2::kScaleThreads, (size_t)g.Cout * 4, st>>>(g, go, rowscale, chmax);
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
