@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
   sm.cltab = g.NX <= (int)((kAuxBytes - 256 - kProducerGroups * 1024) / sizeof(ChunkLayout)) ? cltab : nullptr;
   if (sm.cltab != nullptr && (int)threadIdx.x < g.NX) cltab[threadIdx.x] = chunk_layout(g, threadIdx.x);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // (provably warp-uniform)
   if (threadIdx.x == 0) {
     for (int s = 0; s < T.stages; ++s) {
       mbar_init(B.full0 + 8 * s, kProducerWarps + 1);  // one arrival per producer warp of the group + the weight-tile copy
@@ -227,17 +227,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
     }
   } else if (warp >= kMmaWarp) {
     reg_dealloc<kRegsMma>();
-    if (warp == kMmaWarp && lane == 0) {
+    if (warp == kMmaWarp) {
       // =========================== GEMM1 issuer ===========================
+      // (the whole warp walks the loops -- uniform control flow keeps descriptors and counters in uniform registers, a
+      // single-lane branch made the compiler wrap every MMA in an elect / broadcast loop -- and lane 0 issues)
       // partial sums of one activation digit plane per TMEM buffer; runs ahead of the epilogue by one plane.  Its
       // commits track only its own MMAs: a stage is released as soon as the GEMM1s that read it are done.
       const uint32_t idesc1 = idesc_e4m3_f16(kTcTileM, N1);
       const uint32_t sbo = 8u * (uint32_t)T.Kp;
-      uint32_t it = 0, pl = 0;
+      uint32_t pl = 0;
+      int m_sidx = 0;       // pipeline stage and its use count as running counters (no division by a run-time value)
+      uint32_t m_use = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int i = 0; i < g.NX; ++i, ++it) {
-          const int sidx = it % T.stages;
-          const uint32_t use = it / T.stages;
+        for (int i = 0; i < g.NX; ++i) {
+          const int sidx = m_sidx;
+          const uint32_t use = m_use;
+          if (++m_sidx == T.stages) { m_sidx = 0; ++m_use; }
           const int rows = min(rows_full, g.F - i * g.xbar);
           const int ksteps = (rows + 31) >> 5;
           mbar_wait(B.full0 + 8 * sidx, use & 1);
@@ -249,18 +254,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
             mbar_wait(B.tempty0 + 8 * buf, ((pl >> 1) & 1) ^ 1);  // GEMM2 of the plane two back has read its codes
             tc_fence_after();
             const uint32_t d1 = tmem_base + buf * N1;
-            for (int ks = 0; ks < ksteps && !(P.dbg & 2); ++ks) {
-              const uint64_t adesc = make_smem_desc(a0 + j * T.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
-              const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
-              umma_f8(d1, adesc, bdesc, idesc1, ks > 0 ? 1u : 0u);
+            if (lane == 0) {
+              for (int ks = 0; ks < ksteps && !(P.dbg & 2); ++ks) {
+                const uint64_t adesc = make_smem_desc(a0 + j * T.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
+                const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
+                umma_f8(d1, adesc, bdesc, idesc1, ks > 0 ? 1u : 0u);
+              }
+              umma_commit(B.tfull0 + 8 * buf);
+              if (j == NS - 1) umma_commit(B.empty0 + 8 * sidx);  // stage consumed -> producers
             }
-            umma_commit(B.tfull0 + 8 * buf);
-            if (j == NS - 1) umma_commit(B.empty0 + 8 * sidx);  // stage consumed -> producers
+            __syncwarp();
           }
         }
       }
-    } else if (warp == kMma2Warp && lane == 0) {
-      // =========================== GEMM2 issuer ===========================
+    } else if (warp == kMma2Warp) {
+      // =========================== GEMM2 issuer (whole warp, lane 0 issues) ===========================
       // shift-and-add of one plane as soon as its codes are in tensor memory: a thread of its own, so that waiting
       // for the epilogue never delays the next GEMM1
       const uint32_t idesc2 = idesc_f16_f32(kTcTileM, 16);
@@ -280,19 +288,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_v2_kernel(const V2Params P) 
             tc_fence_after();
             const uint32_t a2 = tmem_base + buf * N1;
             const uint32_t b2 = cb_addr + cpar * P.block_bytes + P.b2_off + (uint32_t)(j * NS * G) * kSlabBytes;
+            if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < NS; ++k)
+              for (int k = 0; k < NS; ++k)
 #pragma unroll
-              for (int gi = 0; gi < G; ++gi) {
-                if (P.dbg & 1) continue;
-                const int h = (16 * gi) / CH;
-                const uint32_t acol = a2 + k * CT + h * CH + (16 * gi - h * CH) / 2;
-                const uint64_t bdesc = make_smem_desc(b2 + (uint32_t)(k * G + gi) * kSlabBytes, kTcLBO, 256u);
-                umma_f16_ts(d2 + 16 * gi, acol, bdesc, idesc2, (i | j | k) != 0 ? 1u : 0u);
-              }
-            umma_commit(B.tempty0 + 8 * buf);                      // partial-sum buffer free again
-            if (j == NS - 1) umma_commit(B.cempty0 + 8 * cpar);    // constants of the chunk no longer read by the MMA
-            if (i == g.NX - 1 && j == NS - 1) umma_commit(B.d2full0 + 8 * tb);
+                for (int gi = 0; gi < G; ++gi) {
+                  if (P.dbg & 1) continue;
+                  const int h = (16 * gi) / CH;
+                  const uint32_t acol = a2 + k * CT + h * CH + (16 * gi - h * CH) / 2;
+                  const uint64_t bdesc = make_smem_desc(b2 + (uint32_t)(k * G + gi) * kSlabBytes, kTcLBO, 256u);
+                  umma_f16_ts(d2 + 16 * gi, acol, bdesc, idesc2, (i | j | k) != 0 ? 1u : 0u);
+                }
+              umma_commit(B.tempty0 + 8 * buf);                      // partial-sum buffer free again
+              if (j == NS - 1) umma_commit(B.cempty0 + 8 * cpar);    // constants of the chunk no longer read by the MMA
+              if (i == g.NX - 1 && j == NS - 1) umma_commit(B.d2full0 + 8 * tb);
+            }
+            __syncwarp();
           }
         }
       }
