@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
   const Geo &g = P.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const Carve cv = carve_smem(smem_raw, P.stages, P.stage_bytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // (provably warp-uniform)
   const int Kc = P.Kc, Nf = P.Nf;
   const uint32_t sbo = (uint32_t)Kc * 16u;  // 8 rows x Kc bf16
 
@@ -418,12 +418,14 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
   } else if (warp >= kMmaWarp) {
     reg_dealloc<kDgRegsMma>();  // warpgroup 3: the MMA issuer and three idle warps
     if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp walks the loops, lane 0 issues)
+    {
       const uint32_t idesc = idesc_bf16_f32(kTcTileM, Nf);
       const int ksteps = Kc >> 4;
-      uint32_t it = 0, acc_it = 0;
-      const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0;
+      uint32_t acc_it = 0;
+      int m_sidx = 0;  // pipeline stage and its use count as running counters
+      uint32_t m_use = 0;
+      const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && lane == 0;
       long long d_full = 0, d_tempty = 0;
       const long long t_begin = CIMQ_TB();
       for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
@@ -434,24 +436,28 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_input_tc_kernel(const BwdPara
           d_tempty += CIMQ_TB() - ta;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * Nf;
-          for (int k = 0; k < NSW; ++k, ++it) {
-            const int sidx = it % P.stages;
-            const uint32_t use = it / P.stages;
+          for (int k = 0; k < NSW; ++k) {
+            const int sidx = m_sidx;
+            const uint32_t use = m_use;
+            if (++m_sidx == P.stages) { m_sidx = 0; ++m_use; }
             const long long tb = CIMQ_TB();
             mbar_wait<400>(cv.full0 + 8 * sidx, use & 1);
             d_full += CIMQ_TB() - tb;
             tc_fence_after();
             const uint32_t a0 = smem_u32(cv.stage_base + (size_t)sidx * P.stage_bytes);
             const uint32_t b0 = a0 + 3 * P.a_bytes;
-            for (int sp = 0; sp < 3; ++sp)
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t adesc = make_smem_desc(a0 + sp * P.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
-                const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
-                umma_f16(d_tmem, adesc, bdesc, idesc, (k | sp | ks) != 0 ? 1u : 0u);
-              }
-            umma_commit(cv.empty0 + 8 * sidx);
+            if (lane == 0) {
+              for (int sp = 0; sp < 3; ++sp)
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint64_t adesc = make_smem_desc(a0 + sp * P.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
+                  const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
+                  umma_f16(d_tmem, adesc, bdesc, idesc, (k | sp | ks) != 0 ? 1u : 0u);
+                }
+              umma_commit(cv.empty0 + 8 * sidx);
+              if (k == NSW - 1) umma_commit(cv.tfull0 + 8 * buf);
+            }
+            __syncwarp();
           }
-          umma_commit(cv.tfull0 + 8 * buf);
         }
       }
       if (dbg) { P.debug[4] = d_full; P.debug[5] = d_tempty; P.debug[6] = clock64() - t_begin; }

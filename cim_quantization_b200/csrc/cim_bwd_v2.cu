@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
     sm.tup = reinterpret_cast<int *>(smem_raw + P.tup_off);
     sm.dcols = reinterpret_cast<DgradCols *>(smem_raw + P.tup_off + (size_t)g.NX * kTupStride * 4);
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // (provably warp-uniform)
   const int Kc = P.Kc, Nf = P.Nf;
   const uint32_t sbo = (uint32_t)Kc * 16u;  // 8 rows x Kc fp16
 
@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
     }
   } else if (warp >= kDgMmaWarp) {
     reg_dealloc<kDgRegsMma>();
-    if (warp == kDgMmaWarp && lane == 0) {
-      // =========================== MMA issuer ===========================
+    if (warp == kDgMmaWarp) {
+      // =========================== MMA issuer (whole warp walks the loops, lane 0 issues) ===========================
       const uint32_t idesc = idesc_f16_f32(kTcTileM, Nf);
       const int ksteps = Kc >> 4;
       uint32_t a_buf = 0, a_use = 0;  // accumulator buffer and how often it has been used
@@ -439,16 +439,19 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
             tc_fence_after();
             const uint32_t a0 = smem_u32(sm.stage_base + (size_t)sidx * P.stage_bytes);
             const uint32_t b0 = a0 + kBwdPieces * P.a_bytes;
+            if (lane == 0) {
 #pragma unroll
-            for (int pc = 0; pc < kBwdPieces; ++pc)
-              for (int ks = 0; ks < ksteps && !(P.dbg & 1); ++ks) {
-                const uint64_t adesc = make_smem_desc(a0 + pc * P.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
-                const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
-                umma_f16(d_tmem, adesc, bdesc, idesc, (k | pc | ks) != 0 ? 1u : 0u);
-              }
-            umma_commit(sm.empty0 + 8 * sidx);
+              for (int pc = 0; pc < kBwdPieces; ++pc)
+                for (int ks = 0; ks < ksteps && !(P.dbg & 1); ++ks) {
+                  const uint64_t adesc = make_smem_desc(a0 + pc * P.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
+                  const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
+                  umma_f16(d_tmem, adesc, bdesc, idesc, (k | pc | ks) != 0 ? 1u : 0u);
+                }
+              umma_commit(sm.empty0 + 8 * sidx);
+              if (k == NS - 1) umma_commit(sm.tfull0 + 8 * buf);
+            }
+            __syncwarp();
           }
-          umma_commit(sm.tfull0 + 8 * buf);
         }
       }
     }

@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const Smem sm = carve(smem_raw, P);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // (provably warp-uniform)
 
   if (threadIdx.x == 0) {
     for (int sidx = 0; sidx < P.stages; ++sidx) {
@@ -600,16 +600,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
   } else if (warp >= kMmaWarp) {
     // =========================== MMA issuer ===========================
     reg_dealloc<kRegsMma>();
-    if (warp == kMmaWarp && lane == 0) {
-      const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0;
+    if (warp == kMmaWarp) {
+      // (the whole warp walks the loops: uniform control flow keeps descriptors and counters in uniform registers -- a
+      // single-lane branch made the compiler wrap every MMA in an elect / broadcast loop; lane 0 issues)
+      const bool dbg = kTimers && P.debug != nullptr && blockIdx.x == 0 && lane == 0;
       long long d_full = 0, d_tempty = 0, t_begin = CIMQ_T0();
       const uint32_t idesc = idesc_i8_u8s8(kTcTileM, NROWS);
       const uint32_t sbo = 8u * (uint32_t)P.Kp;
-      uint32_t it = 0, acc_it = 0;
+      uint32_t acc_it = 0;
+      int m_sidx = 0;  // pipeline stage and its use count as running counters (no division by a run-time value)
+      uint32_t m_use = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int i = 0; i < g.NX; ++i, ++it) {
-          const int sidx = it % P.stages;
-          const uint32_t use = it / P.stages;
+        for (int i = 0; i < g.NX; ++i) {
+          const int sidx = m_sidx;
+          const uint32_t use = m_use;
+          if (++m_sidx == P.stages) { m_sidx = 0; ++m_use; }
           const int rows = min(rows_full, g.F - i * g.xbar);
           const int ksteps = (rows + 31) >> 5;
           long long t0 = CIMQ_T0();
@@ -625,14 +630,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams P) 
             d_tempty += CIMQ_T0() - t2;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * NROWS;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t adesc = make_smem_desc(a0 + j * P.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
-              const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
-              umma_i8(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+            if (lane == 0) {
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t adesc = make_smem_desc(a0 + j * P.a_bytes + ks * 2 * kTcLBO, kTcLBO, sbo);
+                const uint64_t bdesc = make_smem_desc(b0 + ks * 2 * kTcLBO, kTcLBO, sbo);
+                umma_i8(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+              }
+              umma_commit(sm.tfull0 + 8 * buf);  // accumulator of digit plane j complete -> epilogue
+              if (j == NSA - 1) umma_commit(sm.empty0 + 8 * sidx);  // all MMAs reading this stage complete -> producers
             }
-            umma_commit(sm.tfull0 + 8 * buf);  // accumulator of digit plane j complete -> epilogue
+            __syncwarp();
           }
-          umma_commit(sm.empty0 + 8 * sidx);  // all MMAs reading this stage complete -> producers
         }
       }
       if (dbg) { P.debug[4] = d_full; P.debug[5] = d_tempty; P.debug[6] = clock64() - t_begin; }
