@@ -251,7 +251,7 @@ def lsq_backward(grad_xq, x, s_elem, qn: int, qp: int, g: float):
     ws = torch.empty(load().cimq_lsq_backward_workspace_bytes(x.numel()), dtype=torch.uint8, device=x.device)
     _check(load().cimq_lsq_backward(_ptr(grad_xq), _ptr(x), x.numel(), _ptr(s_elem), qn, qp, g, _ptr(gx),
                                     _ptr(galpha), _ptr(ws), _stream()))
-    _count(1)  # (the last block to finish adds the per-block partials)
+    _count(2)
     return gx, galpha
 
 

@@ -4,7 +4,6 @@
 // Roofline: forward moves 5 B/element (4 read + 1 written), backward 12 B/element
 // (grad + x read, grad written).  Access is 128-bit vectorised and fully coalesced; each thread
 // keeps several independent 16-byte loads in flight.
-#include <atomic>
 #include "cimq_common.cuh"
 #include "lsq_code.cuh"
 
@@ -113,17 +112,12 @@ __device__ __forceinline__ double block_sum(double v) {
   return v;  // valid in thread 0
 }
 
-constexpr int kDoneRing = 64;
-__device__ unsigned int g_lsq_done[kDoneRing];
-
 // 8 elements per thread per iteration.  Writes one fp64 partial of sum(g * (q - u*mask)) per block.
 __global__ void __launch_bounds__(kThreads) lsq_backward_kernel(const float *__restrict__ gq,
                                                                 const float *__restrict__ x, int64_t n,
                                                                 const float *__restrict__ sp, float qn, float qp,
                                                                 float *__restrict__ gx,
-                                                                double *__restrict__ partials, int vec_ok,
-                                                                float gscale, float *__restrict__ galpha,
-                                                                unsigned int *__restrict__ done) {
+                                                                double *__restrict__ partials, int vec_ok) {
   const StepSize s = load_step(sp);
   float acc = 0.0f;
   const int64_t n8 = vec_ok ? n / 8 : 0;
@@ -152,24 +146,18 @@ __global__ void __launch_bounds__(kThreads) lsq_backward_kernel(const float *__r
     gx[i] = o;
   }
   double tot = block_sum((double)acc);
-  // The block that finishes LAST adds the partials (in index order, whichever block it is: deterministic) -- the
-  // separate one-block finish kernel was a launch per quantiser and step (38 per ResNet-20 step).
-  __shared__ bool last;
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = tot;
-    __threadfence();  // the partial is visible before the ticket
-    last = atomicAdd(done, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
+  if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+  // (Measured: letting the block that finishes last add the partials -- a ticket counter instead of the one-block
+  // kernel below -- saved nothing inside a captured step and cost 4 us here: 1184 same-address atomics at the tail.)
+}
+
+__global__ void __launch_bounds__(kThreads) lsq_backward_finish_kernel(const double *__restrict__ partials,
+                                                                       int nparts, float g,
+                                                                       float *__restrict__ galpha) {
   double v = 0.0;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) v += __ldcg(partials + i);
+  for (int i = threadIdx.x; i < nparts; i += kThreads) v += partials[i];
   v = block_sum(v);
-  if (threadIdx.x == 0) {
-    galpha[0] = (float)((double)gscale * v);
-    *done = 0u;  // ready for the next launch that is given this ticket counter
-  }
+  if (threadIdx.x == 0) galpha[0] = (float)((double)g * v);
 }
 
 inline int grid_for(int64_t work_items) {
@@ -228,13 +216,9 @@ int launch_lsq_backward(const float *gq, const float *x, int64_t n, const float 
                  reinterpret_cast<uintptr_t>(gx)) & 15u) == 0;
   int grid = grid_for((n + 7) / 8);
   double *partials = reinterpret_cast<double *>(ws);
-  // ticket counters of the last-block reduction: a ring in device memory (zero at load, reset by their kernel), one
-  // per launch in flight -- launches that share a counter must not overlap (64 consecutive launches never do)
-  unsigned int *ring = nullptr;
-  CIMQ_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void **>(&ring), g_lsq_done));
-  static std::atomic<unsigned int> next_ticket{0};
-  unsigned int *done = ring + (next_ticket.fetch_add(1) % kDoneRing);
-  lsq_backward_kernel<<<grid, kThreads, 0, st>>>(gq, x, n, s, (float)qn, (float)qp, gx, partials, vec_ok, g, galpha, done);
+  lsq_backward_kernel<<<grid, kThreads, 0, st>>>(gq, x, n, s, (float)qn, (float)qp, gx, partials, vec_ok);
+  CIMQ_CUDA_OK(cudaGetLastError());
+  lsq_backward_finish_kernel<<<1, kThreads, 0, st>>>(partials, grid, g, galpha);
   CIMQ_CUDA_OK(cudaGetLastError());
   return 0;
 }
