@@ -72,6 +72,7 @@ V2_CASES = [
     (32, 64, 8, 2, 1, 2, 64, 1, 3),       # two digit planes
     (64, 128, 8, 3, 1, 3, 128, 1.5, 3),   # two channel tiles, ragged last pixel tile (192 pixels)
     (48, 32, 8, 2, 1, 3, 128, 1.5, 1),    # 1x1 kernel: generic producer
+    (16, 16, 4, 8, 1, 3, 128, 1.5, 3),    # 4x4 images (L = 16): generic gather / fold, alpha-grad on the plane-per-thread kernel
 ]
 
 
@@ -121,6 +122,38 @@ def test_v2_forward_backward_against_oracle(case):
                 assert rel_err(gwq.cpu().numpy().reshape(ref_gw.shape), ref_gw) < TOL
                 if cfg.has_alpha_cim:
                     assert rel_err(galpha.cpu().numpy(), ref_ga) < TOL
+
+
+def test_full_size_v2_backward_equals_v1():
+    """The microbench layer at FULL size (B=256: 2048 pixel tiles, the non-split grad_out scale pass, many tiles per
+    CTA in every kernel): the oracle is too slow there, so the v2 backward (byte planes, two fp16 pieces of grad_out)
+    is compared with the v1 backward (uint32 state words, three bf16 terms) on the same inputs -- two independent
+    kernel generations that both pass the oracle at small sizes."""
+    L = _lib()
+    B, C, HW = 256, 64, 32
+    spec = L.LayerSpec(B, C, HW, C, 3, 1, 1, 3, 1, 3, 1, 128, 1.5)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.relu(torch.randn(B, C, HW, HW, device="cuda", generator=g))
+    w = torch.randn(C, C * 9, device="cuda", generator=g) * (2.0 / (C * 9)) ** 0.5
+    s = torch.stack([2 * x.abs().mean() / 7 ** 0.5, 2 * w.abs().mean() / 3 ** 0.5]).float()
+    xc = L.lsq_quantize(x, s[0:1], 0, 7)
+    wc = L.lsq_quantize(w, s[1:2], -4, 3)
+    mask = torch.tensor([[1, 2, 4], [2, 4, 8], [4, 8, 16]], dtype=torch.int8, device="cuda")
+    sums = L.conv_psum_abs_sums(spec, xc, wc).double()
+    a0 = (2.0 * sums / (B * HW * HW) * float(s[0]) * float(s[1])).float().clamp_min(1e-6).contiguous()
+    aq, aux = L.alpha_quantize(a0, 1, 255)
+    table = L.adc_table(spec, s, aq, mask, alpha_scale=aux[0:1].clone())
+    wdig, wtiles = L.weight_prepare(spec, wc)
+    go = torch.randn(B, C, HW * HW, device="cuda", generator=g)
+    res = {}
+    for gen, flags in (("v1", 0), ("v2", L.FLAG_V2)):
+        out, state = L.conv_forward(spec, xc, wc, wtiles, table, s, mask, save_state=True, flags=flags)
+        res[gen] = (out,) + tuple(L.conv_backward(spec, go, xc, wdig, wtiles, state, s, mask, need_alpha=True))
+        del state
+    torch.cuda.synchronize()
+    for name, a, b in zip(("out", "grad_x", "grad_w", "grad_alpha"), res["v1"], res["v2"]):
+        err = ((a.double() - b.double()).abs().max() / a.double().abs().max()).item()
+        assert err < 2e-5, (name, err)
 
 
 @pytest.mark.parametrize("name", golden_names())
