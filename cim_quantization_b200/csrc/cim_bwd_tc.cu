@@ -931,6 +931,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
           const int lo = cinf.x, rows = cinf.y, c_lo = cinf.z;
           const uint32_t xinf = xt_row[(i - i_begin) * 128 + fr];
           const bool frow = (xinf >> 31) != 0;
+          // (Measured: letting warps whose 32 rows all lie past the chunk's last row -- the 16- / 32-row last crossbar of
+          // a 16- / 32-channel layer -- skip gather and stores changed nothing: 701 -> 700 us at 16 channels.)
           const int ci = (int)(xinf & 0xffffu), ky = (int)((xinf >> 16) & 0xffu), kx = (int)((xinf >> 24) & 0x7fu);
           const int st_next = (i + 1) / P.sdiv, st_first = i_begin / P.sdiv;  // state (crossbar) index of the next chunk
           uint8_t *raw = cv.raw + (size_t)(chunk_it & 1) * P.raw_bytes;
