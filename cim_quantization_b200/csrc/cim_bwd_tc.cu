@@ -1298,6 +1298,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_weight_tc_kernel(const BwdPar
     if (warp == kMmaWarp && has_work) {  // the whole warp walks the loop (uniform control flow); lane 0 issues
       const uint32_t idesc = V2 ? idesc_f16_f32(128, Kc) : idesc_bf16_f32(128, Kc);
       constexpr int kPieces = V2 ? v2::kBwdPieces : 3;  // terms of the real-valued operand
+      // (Measured: the two v2 piece tiles are contiguous and can be ONE B operand of N = 2 * Kc rows -- half the MMAs,
+      // the X tile read once, the epilogue adds the two column halves; where tensor memory allows it (16 / 32
+      // channels) that took 703 -> 698 us and 327 -> 323 us: the MMA count does not bound this kernel.  Not kept.)
       uint32_t it = 0;
       int m_sidx = 0;
       uint32_t m_phase = 0;
