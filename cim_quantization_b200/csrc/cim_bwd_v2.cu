@@ -457,6 +457,9 @@ __global__ void __launch_bounds__(kDgThreads, 1) bwd_input_v2_kernel(const DgPar
     }
     else if (warp == kDgMmaWarp + 1 && lane == 0 && P.dbulk) {
       // =========================== D-byte loader ===========================
+      // (Measured dead end: the producers' 16-byte reads of these rows are 4-way bank conflicted at Kc = 64 (row pitch
+      // 64 bytes; ncu: 16 wavefronts per LDS.128).  One bulk copy PER ROW into rows of Kc + 16 bytes removes the
+      // conflicts and costs far more than it saves: 128 small copies per chunk, dgrad 235 -> 350 us.)
       uint32_t chunk_it = 0;
       for (int mt = blockIdx.x; mt < P.mtiles; mt += gridDim.x) {
         const int64_t m0 = (int64_t)mt * kTcTileM;
